@@ -1,0 +1,123 @@
+/* stereo_b200.h -- C ABI of libstereo_b200.so
+ *
+ * B200-native (sm_100a) replacement for the data-parallel hot path of
+ * johannesu/stereo: the TRW-S and QPBO fusion solvers behind trws.m / rd.m and
+ * the cost-volume / unary / pairwise array builders of dispmap_*.m.
+ *
+ * Conventions
+ *  - plain C, host pointers unless a name says `_dev`; MATLAB (column-major)
+ *    layouts exactly as the reference mex gateways receive them;
+ *  - every entry point returns 0 on success and a negative SB_E* code on
+ *    failure; sb_last_error() returns the message (thread-local);
+ *  - there is NO CPU fallback: without a CUDA device every compute entry
+ *    point fails with SB_ENODEV;
+ *  - node index u = r + H*c (0-based, column-major; dispmap_super.m:281-282);
+ *    pairwise terms in the order of dispmap_super.construct_neighborhood
+ *    (dispmap_super.m:279-302): vertical down, vertical up, horizontal right,
+ *    horizontal left, each column-major over the start node.
+ *
+ * Each declaration cites the reference interface it replaces.
+ */
+#ifndef STEREO_B200_H
+#define STEREO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_OK        0
+#define SB_EINVAL   -1   /* bad argument (the reference ASSERTs, cppmatrix.h:20-24)      */
+#define SB_ENODEV   -2   /* no CUDA device / driver                                      */
+#define SB_ECUDA    -3   /* CUDA runtime error                                           */
+#define SB_ENOTGRID -4   /* connectivity is not the 4-connected grid of dispmap_super    */
+#define SB_ENOMEM   -5   /* device memory exhausted                                      */
+#define SB_EUNSUP   -6   /* unsupported size (e.g. more than SB_MAX_LABELS labels)       */
+
+#define SB_MAX_LABELS 256
+
+#if defined(__GNUC__)
+#define SB_API __attribute__((visibility("default")))
+#else
+#define SB_API
+#endif
+
+/* ---------------------------------------------------------------- library */
+
+/* "stereo_b200 x.y (sm_100a)" */
+SB_API const char *sb_version(void);
+/* message of the last failing call on this thread ("" if none) */
+SB_API const char *sb_last_error(void);
+/* number of visible CUDA devices (0 if none; never fails) */
+SB_API int sb_device_count(void);
+/* select the device used by subsequent calls of this thread's process */
+SB_API int sb_set_device(int device);
+/* number of kernels launched by the library since load (bench.py gpu_launches) */
+SB_API int64_t sb_kernel_launches(void);
+
+/* ---------------------------------------------------------------- options */
+
+/* Arithmetic type of the TRW-S message sweep.  SB_F32 is the product path
+ * (north star: energies within 1e-4 relative of the reference's doubles);
+ * SB_F64 runs the same kernels in double for tight parity checks. */
+#define SB_F32 0
+#define SB_F64 1
+
+typedef struct sb_trws_options {
+    double maxiter;       /* trws_mex.cpp:39  default 1000 */
+    double max_relgap;    /* trws_mex.cpp:40  default 0    */
+    int    precision;     /* SB_F32 (default) | SB_F64     */
+    int    fuse_rounding; /* 1 (default): primal rounding of iteration t rides in the
+                             forward sweep of t+1; 0: separate sweep   */
+    int    reserved[6];
+} sb_trws_options;
+
+SB_API void sb_trws_default_options(sb_trws_options *opt);
+
+typedef struct sb_trws_timing {
+    double setup_ms;       /* upload, conversion, rank tables, schedule               */
+    double solve_ms;       /* all sweeps (CUDA events on the solver stream)           */
+    double sweep_ms_avg;   /* solve_ms / iterations                                   */
+    double download_ms;
+    int64_t kernel_launches;
+    int64_t reserved[3];
+} sb_trws_timing;
+
+/* ---------------------------------------------------------------- TRW-S */
+
+/* Replaces mexFunction of cpp/trws_mex.cpp:149-163 (called from trws.m:33).
+ *   kernel   1 = truncated linear (TypeStereoLinear), 2 = truncated quadratic
+ *            (TypeStereoQuadratic); anything else -> SB_EINVAL ("Unsupported kernel")
+ *   unary    L x N  (label fastest)                       trws_mex.cpp:31
+ *   conn     2 x E  uint32, 0-based: conn[2p]=tail, conn[2p+1]=head
+ *   q        L x E  positions of the head's labels        trws_mex.cpp:33,101-105
+ *   qprim    L x E  positions of the tail's labels        trws_mex.cpp:34,107-111
+ *   alphas   E      per-term weight                       trws_mex.cpp:35
+ *   tol      lambda (truncation)                          trws_mex.cpp:36-37
+ * Pairwise term p: V(k_tail,k_head) = alphas[p]*min(|q[k_head,p]-qprim[k_tail,p]|^kernel, tol)
+ * Outputs (trws_mex.cpp:134-143): labels N doubles, 1-BASED; energy; lower bound;
+ * iterations.  `timing` may be NULL.
+ * The connectivity must be the dispmap_super grid (both directions of every
+ * neighbour pair, reference order); otherwise SB_ENOTGRID. */
+SB_API int sb_trws_solve(int kernel, int L, int64_t N, int64_t E,
+                  const double *unary, const uint32_t *conn,
+                  const double *q, const double *qprim,
+                  const double *alphas, double tol,
+                  const sb_trws_options *opt,
+                  double *labels, double *energy, double *lower_bound,
+                  double *iterations, sb_trws_timing *timing);
+
+/* Node ordering of MRFEnergy::SetAutomaticOrdering (cpp/trw-s/ordering.cpp:7-157)
+ * on the H x W grid: ordering[r + H*c] in [0, H*W).  Closed form for H,W >= 4
+ * (SURVEY Appendix A.1), literal greedy scan otherwise.  Host-only. */
+SB_API int sb_trws_grid_ordering(int H, int W, int32_t *ordering);
+
+/* Infer (H, W) from a connectivity list and verify it is the reference grid.
+ * Host-only.  Returns SB_ENOTGRID when it is not. */
+SB_API int sb_grid_from_connectivity(int64_t N, int64_t E, const uint32_t *conn, int *H, int *W);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STEREO_B200_H */

@@ -1,0 +1,194 @@
+"""ctypes access to the parity oracles.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module; nothing under stereo_b200/ does.
+
+Two oracles sit behind the same function names:
+
+* ``kind == "reference"``: oracle/_ref/libref_*.so, the UNMODIFIED reference
+  C++ (cpp/trws_mex.cpp, cpp/rd_mex.cpp, imrender/vgg/vgg_interp2.cxx and the
+  vendored TRW-S / QPBO sources) compiled by oracle/Makefile against the fake
+  mex.h.  Built in the container that has /root/reference; the .so files
+  travel to the GPU box.
+* ``kind == "port"``: oracle/_build/libsb_oracle.so, our plain-C restatement
+  (oracle/*.c); always buildable.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import POINTER, c_double, c_int, c_int32, c_int64, c_uint32
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+PORT_DIR = os.path.join(HERE, "_build")
+
+_dp = POINTER(c_double)
+_up = POINTER(c_uint32)
+_ip = POINTER(c_int32)
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(t)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def build(ref: bool = True, port: bool = True) -> None:
+    """(Re)build the oracle libraries (make is incremental)."""
+    if port:
+        subprocess.check_call(["make", "-s", "-C", HERE, "port"])
+    if ref and os.path.isdir("/root/reference"):
+        subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+
+
+_cache: dict = {}
+
+
+def _load(path):
+    if path not in _cache:
+        _cache[path] = ctypes.CDLL(path)
+    return _cache[path]
+
+
+def have_ref(name: str = "trws") -> bool:
+    return os.path.exists(os.path.join(REF_DIR, f"libref_{name}.so"))
+
+
+def have_port() -> bool:
+    return os.path.exists(os.path.join(PORT_DIR, "libsb_oracle.so"))
+
+
+def _ref(name):
+    return _load(os.path.join(REF_DIR, f"libref_{name}.so"))
+
+
+def _port():
+    if not have_port():
+        build(ref=False, port=True)
+    return _load(os.path.join(PORT_DIR, "libsb_oracle.so"))
+
+
+# ----------------------------------------------------------------------------
+# TRW-S
+# ----------------------------------------------------------------------------
+_TRWS_ARGS = [c_int, c_int, c_int64, c_int64, _dp, _up, _dp, _dp, _dp, c_double,
+              c_double, c_double, _dp, _dp, _dp, _dp]
+
+
+def trws_solve(kernel, unary, conn, q, qprim, alphas, tol, maxiter=1000, max_relgap=0.0,
+               kind="reference"):
+    """trws_mex ABI (cpp/trws_mex.cpp:27-163): unary LxN, conn 2xE (0-based),
+    q/qprim LxE, alphas E -- all in MATLAB (column-major) layout, i.e. numpy
+    arrays of shape (N,L), (E,2), (E,L), (E,).  Returns (labels 1-based int64[N],
+    energy, lower_bound, iterations)."""
+    unary = _f64(unary)
+    q = _f64(q)
+    qprim = _f64(qprim)
+    alphas = _f64(alphas)
+    conn = np.ascontiguousarray(conn, dtype=np.uint32)
+    N, L = unary.shape
+    E = conn.shape[0]
+    assert conn.shape == (E, 2) and q.shape == (E, L) and qprim.shape == (E, L) and alphas.shape == (E,)
+    labels = np.zeros(N, dtype=np.float64)
+    out = (c_double * 3)()
+    if kind == "reference":
+        fn = _ref("trws").ref_trws_solve
+    else:
+        fn = _port().port_trws_solve
+    fn.argtypes = _TRWS_ARGS
+    fn.restype = c_int
+    rc = fn(int(kernel), L, N, E, _ptr(unary, _dp), _ptr(conn, _up), _ptr(q, _dp), _ptr(qprim, _dp),
+            _ptr(alphas, _dp), float(tol), float(maxiter), float(max_relgap), _ptr(labels, _dp),
+            ctypes.cast(ctypes.byref(out, 0), _dp), ctypes.cast(ctypes.byref(out, 8), _dp),
+            ctypes.cast(ctypes.byref(out, 16), _dp))
+    if rc != 0:
+        raise RuntimeError(f"oracle trws_solve ({kind}) failed rc={rc}")
+    return labels.astype(np.int64), out[0], out[1], int(out[2])
+
+
+def trws_ordering(H, W, kind="reference"):
+    """Node ordering (m_ordering) of SetAutomaticOrdering (ordering.cpp:7-157) on
+    the H x W grid; returned as an (H, W) int32 array."""
+    out = np.zeros(H * W, dtype=np.int32)
+    fn = _ref("trws").ref_trws_ordering if kind == "reference" else _port().port_trws_ordering
+    fn.argtypes = [c_int, c_int, _ip]
+    fn.restype = c_int
+    if fn(H, W, _ptr(out, _ip)) != 0:
+        raise RuntimeError("oracle ordering failed")
+    return out.reshape(W, H).T.copy()
+
+
+def trws_update_message(kernel, Di, msg, stored0, stored1, alpha, lam, gamma, dir_, swapped,
+                        kind="reference"):
+    """One Edge::UpdateMessage (typeStereoLinear.h:329-487 /
+    typeStereoQuadratic.h:329-501).  Returns (new message, vMin)."""
+    Di = _f64(Di)
+    msg = _f64(msg).copy()
+    s0 = _f64(stored0)
+    s1 = _f64(stored1)
+    L = Di.shape[0]
+    o0 = np.argsort(s0, kind="stable").astype(np.int32)
+    o1 = np.argsort(s1, kind="stable").astype(np.int32)
+    vmin = c_double()
+    fn = _ref("trws").ref_trws_update_message if kind == "reference" else _port().port_trws_update_message
+    fn.argtypes = [c_int, c_int, _dp, _dp, _dp, _dp, _ip, _ip, c_double, c_double, c_double, c_int, c_int, _dp]
+    fn.restype = c_int
+    rc = fn(int(kernel), L, _ptr(Di, _dp), _ptr(msg, _dp), _ptr(s0, _dp), _ptr(s1, _dp), _ptr(o0, _ip),
+            _ptr(o1, _ip), float(alpha), float(lam), float(gamma), int(dir_), int(swapped), ctypes.byref(vmin))
+    if rc != 0:
+        raise RuntimeError("oracle update_message failed")
+    return msg, vmin.value
+
+
+# ----------------------------------------------------------------------------
+# QPBO / roof duality
+# ----------------------------------------------------------------------------
+def rd_solve(U0, U1, E00, E01, E10, E11, conn, improve=False, kind="reference"):
+    """rd_mex ABI (cpp/rd_mex.cpp:14-100).  conn is (E,2) 0-based.  Returns
+    (labels float64[N] in {0,1,<0}, energy, lower_bound, num_unlabelled)."""
+    U0, U1, E00, E01, E10, E11 = (_f64(x).ravel() for x in (U0, U1, E00, E01, E10, E11))
+    conn = np.ascontiguousarray(conn, dtype=np.uint32)
+    N = U0.shape[0]
+    E = conn.shape[0]
+    labels = np.zeros(N, dtype=np.float64)
+    out = (c_double * 3)()
+    fn = _ref("rd").ref_rd_solve if kind == "reference" else _port().port_rd_solve
+    fn.argtypes = [c_int64, c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _up, c_int, _dp, _dp, _dp, _dp]
+    fn.restype = c_int
+    rc = fn(N, E, _ptr(U0, _dp), _ptr(U1, _dp), _ptr(E00, _dp), _ptr(E01, _dp), _ptr(E10, _dp), _ptr(E11, _dp),
+            _ptr(conn, _up), int(bool(improve)), _ptr(labels, _dp),
+            ctypes.cast(ctypes.byref(out, 0), _dp), ctypes.cast(ctypes.byref(out, 8), _dp),
+            ctypes.cast(ctypes.byref(out, 16), _dp))
+    if rc != 0:
+        raise RuntimeError(f"oracle rd_solve ({kind}) failed rc={rc}")
+    return labels, out[0], out[1], out[2]
+
+
+# ----------------------------------------------------------------------------
+# vgg_interp2 (linear)
+# ----------------------------------------------------------------------------
+def interp2_linear(A, X, Y, oobv, kind="reference"):
+    """vgg_interp2(A, X, Y, 'linear', oobv) (vgg_interp2.cxx:246-322).
+    A: (h, w, c) array; X, Y: n 1-based coordinates.  Returns (n, c)."""
+    A = np.asarray(A, dtype=np.float64)
+    if A.ndim == 2:
+        A = A[:, :, None]
+    h, w, c = A.shape
+    Af = np.asfortranarray(A)
+    X = _f64(X).ravel()
+    Y = _f64(Y).ravel()
+    n = X.shape[0]
+    out = np.zeros((c, n), dtype=np.float64)
+    fn = _ref("interp2").ref_interp2_linear if kind == "reference" else _port().port_interp2_linear
+    fn.argtypes = [_dp, c_int, c_int, c_int, _dp, _dp, c_int64, c_double, _dp]
+    fn.restype = c_int
+    rc = fn(Af.ctypes.data_as(_dp), h, w, c, _ptr(X, _dp), _ptr(Y, _dp), n, float(oobv), _ptr(out, _dp))
+    if rc != 0:
+        raise RuntimeError("oracle interp2 failed")
+    return out.T.copy()

@@ -1,0 +1,70 @@
+"""ctypes binding of libstereo_b200.so (include/stereo_b200.h).
+
+The library is the product: there is no Python or CPU fallback.  If the shared
+object is missing, importing the bound functions raises; if it loads but no CUDA
+device is visible every compute call returns SB_ENODEV and we raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int64, c_uint32
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libstereo_b200.so")
+
+SB_OK, SB_EINVAL, SB_ENODEV, SB_ECUDA, SB_ENOTGRID, SB_ENOMEM, SB_EUNSUP = 0, -1, -2, -3, -4, -5, -6
+SB_F32, SB_F64 = 0, 1
+SB_MAX_LABELS = 256
+
+_dp = POINTER(c_double)
+_up = POINTER(c_uint32)
+_ip = POINTER(c_int32)
+
+
+class SbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"stereo_b200 error {code}: {msg}")
+        self.code = code
+
+
+class TrwsOptions(Structure):
+    _fields_ = [("maxiter", c_double), ("max_relgap", c_double), ("precision", c_int),
+                ("fuse_rounding", c_int), ("reserved", c_int * 6)]
+
+
+class TrwsTiming(Structure):
+    _fields_ = [("setup_ms", c_double), ("solve_ms", c_double), ("sweep_ms_avg", c_double),
+                ("download_ms", c_double), ("kernel_launches", c_int64), ("reserved", c_int64 * 3)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libstereo_b200.so (built by stereo_b200/csrc/Makefile) or fail loudly."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: build it with `make -C stereo_b200/csrc` "
+                "(or python -c 'import __graft_entry__ as g; g.build()'). There is no fallback path.")
+        L = ctypes.CDLL(LIB_PATH)
+        L.sb_version.restype = c_char_p
+        L.sb_last_error.restype = c_char_p
+        L.sb_device_count.restype = c_int
+        L.sb_set_device.argtypes = [c_int]
+        L.sb_kernel_launches.restype = c_int64
+        L.sb_trws_default_options.argtypes = [POINTER(TrwsOptions)]
+        L.sb_trws_default_options.restype = None
+        L.sb_trws_solve.argtypes = [c_int, c_int, c_int64, c_int64, _dp, _up, _dp, _dp, _dp, c_double,
+                                    POINTER(TrwsOptions), _dp, _dp, _dp, _dp, POINTER(TrwsTiming)]
+        L.sb_trws_grid_ordering.argtypes = [c_int, c_int, _ip]
+        L.sb_grid_from_connectivity.argtypes = [c_int64, c_int64, _up, POINTER(c_int), POINTER(c_int)]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != SB_OK:
+        raise SbError(rc, lib().sb_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,23 @@
+// trws_order.h -- host-side grid / ordering / schedule helpers (trws_order.cpp).
+#pragma once
+#include <stdint.h>
+#include <cmath>
+#include <vector>
+#include "sb_common.h"
+
+namespace sb {
+
+// Pairwise terms of the H x W grid in dispmap_super.construct_neighborhood order.
+void grid_terms(int H, int W, std::vector<int32_t> &tail, std::vector<int32_t> &head);
+// True (and H, W set) iff conn is exactly that grid.
+bool grid_from_connectivity(int64_t N, int64_t E, const uint32_t *conn, int &H, int &W);
+// ordering.cpp:24-152 on an arbitrary term list; false where the reference would crash.
+bool greedy_ordering(int64_t N, const std::vector<int32_t> &tail, const std::vector<int32_t> &head,
+                     std::vector<int32_t> &ordering);
+// SetAutomaticOrdering on the grid (closed form for H,W >= 4).
+bool grid_ordering(int H, int W, std::vector<int32_t> &ordering);
+// Level-sorted dispatch list of the orientation DAG.
+void build_schedule(int H, int W, const std::vector<int32_t> &ordering, std::vector<int32_t> &sched,
+                    int32_t &num_levels);
+
+} // namespace sb

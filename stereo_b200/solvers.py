@@ -1,0 +1,108 @@
+"""Host-side mirrors of the reference's solver wrappers rd.m and trws.m.
+
+Same names, argument order, argument meaning and error behaviour as the MATLAB
+wrappers; arrays use MATLAB shapes (e.g. ``unary`` is L x N, ``connectivity`` is
+2 x E and 1-BASED exactly as dispmap_super builds it) so code reads like the
+reference's.  Everything is forwarded to the C ABI of libstereo_b200.so, which
+runs on the GPU; nothing is computed here.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_double, c_int
+
+import numpy as np
+
+from . import _lib
+from ._lib import SB_F32, SB_F64, TrwsOptions, TrwsTiming, _dp, _ip, _up, check, lib
+
+
+def _f(a):
+    """float64, column-major (MATLAB) memory."""
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+def _opt(options, key, default):
+    if options is None:
+        return default
+    if isinstance(options, dict):
+        return options.get(key, default)
+    return getattr(options, key, default)
+
+
+last_timing: dict = {}
+
+
+def trws(kernel, unary, connectivity, q, qprim, alphas, tol, options=None):
+    """[solution, energy, lower_bound, iterations] = trws(kernel, unary, connectivity, q, qprim,
+    alphas, tol, options)  -- trws.m:2-33.
+
+    kernel: 1 (truncated linear) or 2 (truncated quadratic).  unary: L x N.
+    connectivity: 2 x E, 1-based.  q, qprim: L x E.  alphas: E.  tol: scalar.
+    options: dict/object with ``maxiter`` (default 1000) and ``max_relgap`` (default 0)
+    (trws_mex.cpp:38-40); extra keys ``precision`` ("f32"|"f64") and ``fuse_rounding``.
+    Returns (solution N float64 1-based, energy, lower_bound, iterations).
+    """
+    unary = _f(unary)
+    q = _f(q)
+    qprim = _f(qprim)
+    alphas = _f(np.asarray(alphas).reshape(-1))
+    connectivity = np.asarray(connectivity)
+    # trws.m:5-6
+    assert connectivity.size == 0 or connectivity.min() > 0
+    assert connectivity.size == 0 or connectivity.max() <= unary.size
+    kernel = int(np.int32(kernel))
+    # trws.m:9-15
+    if np.isnan(q).any():
+        raise ValueError("q contains NaN")
+    if np.isnan(qprim).any():
+        raise ValueError("qprim contains NaN")
+    L, N = unary.shape
+    # trws_mex.cpp:42-52
+    assert connectivity.shape[0] == 2
+    E = connectivity.shape[1]
+    assert q.shape[1] == qprim.shape[1] == E
+    assert q.shape[0] == L and qprim.shape[0] == L
+    assert alphas.shape[0] == E
+    assert np.size(tol) == 1
+    conn0 = np.asfortranarray(connectivity.astype(np.int64) - 1, dtype=np.uint32)  # trws.m:33
+
+    opt = TrwsOptions()
+    lib().sb_trws_default_options(ctypes.byref(opt))
+    opt.maxiter = float(_opt(options, "maxiter", 1000))
+    opt.max_relgap = float(_opt(options, "max_relgap", 0))
+    prec = _opt(options, "precision", "f32")
+    opt.precision = SB_F64 if prec in ("f64", SB_F64, "double") and prec != 0 else SB_F32
+    opt.fuse_rounding = int(bool(_opt(options, "fuse_rounding", True)))
+
+    solution = np.zeros(N, dtype=np.float64)
+    e = c_double()
+    lb = c_double()
+    it = c_double()
+    tm = TrwsTiming()
+    rc = lib().sb_trws_solve(kernel, L, N, E, unary.ctypes.data_as(_dp), conn0.ctypes.data_as(_up),
+                             q.ctypes.data_as(_dp), qprim.ctypes.data_as(_dp), alphas.ctypes.data_as(_dp),
+                             float(np.asarray(tol).reshape(-1)[0]), ctypes.byref(opt), solution.ctypes.data_as(_dp),
+                             ctypes.byref(e), ctypes.byref(lb), ctypes.byref(it), ctypes.byref(tm))
+    check(rc)
+    last_timing.clear()
+    last_timing.update(setup_ms=tm.setup_ms, solve_ms=tm.solve_ms, sweep_ms_avg=tm.sweep_ms_avg,
+                       download_ms=tm.download_ms, kernel_launches=tm.kernel_launches)
+    return solution, e.value, lb.value, it.value
+
+
+def trws_grid_ordering(H, W):
+    """m_ordering of SetAutomaticOrdering (ordering.cpp:7-157) on the H x W grid, as (H, W) int32."""
+    out = np.zeros(H * W, dtype=np.int32)
+    check(lib().sb_trws_grid_ordering(int(H), int(W), out.ctypes.data_as(_ip)))
+    return out.reshape(W, H).T.copy()
+
+
+def grid_from_connectivity(connectivity0, N):
+    """(H, W) of a 0-based 2 x E connectivity list, or raises SbError(SB_ENOTGRID)."""
+    conn0 = np.asfortranarray(connectivity0, dtype=np.uint32)
+    H = c_int()
+    W = c_int()
+    check(lib().sb_grid_from_connectivity(int(N), conn0.shape[1], conn0.ctypes.data_as(_up), ctypes.byref(H),
+                                          ctypes.byref(W)))
+    return H.value, W.value

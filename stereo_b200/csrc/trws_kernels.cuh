@@ -10,11 +10,16 @@
 // Execution model (DESIGN.md "K5"):
 //   * one warp owns one node at a time; the L labels of every per-node vector
 //     are blocked over the lanes (label = lane*K + k, K = LP/32 in registers);
-//   * nodes are dispatched from a level-sorted list of the reference's own
-//     orientation DAG through an atomic ticket; a warp starts a node once the
-//     epoch flags of the neighbours it depends on are published
-//     (release/acquire through L2), so a whole sweep is ONE persistent launch
-//     with no grid barriers and the results equal the sequential sweep's;
+//   * work is dispatched in STRIPS (trws_order.cpp: the boundary ring, then one
+//     strip per interior row) through an atomic ticket; a warp walks its strip
+//     node by node, keeps the two messages it just sent to the next node of the
+//     strip in registers (no round trip for the in-strip dependency) and waits
+//     on epoch flags (release/acquire through L2) only for neighbours owned by
+//     other strips -- normally satisfied long before.  A whole sweep is ONE
+//     persistent launch with no grid barriers, and because it honours the
+//     reference's orientation DAG its results equal the sequential sweep's;
+//   * while a node is processed the operands of the next one are prefetched
+//     into L2 (prefetch.global.L2);
 //   * the min-plus update is O(L): labels are visited in the order of their
 //     (irregular) positions through iteration-invariant uint8 rank tables, the
 //     two directional distance transforms are warp-shuffle scans over
@@ -51,8 +56,11 @@ struct Problem {
     const uint8_t *cnt_qp;  // [E][LP]  #{q <= qprim[l]}   clamped to 255
     const REAL *alpha;      // [E]
     REAL lambda;
-    const int32_t *order;   // [N] m_ordering
-    const int32_t *sched;   // [N] level-sorted dispatch list
+    const uint8_t *info;    // [N] incidence byte: valid mask | lower mask << 4 (trws_order.cpp)
+    const int32_t *nodes;   // [N] forward-sweep strips, concatenated (backward = reverse)
+    const int32_t *strip_ptr; // [S+1]
+    int S;
+    int active_warps;       // warps per CTA that take strips (spreads few strips over all SMs)
     int32_t *done;          // [N] epoch flags
     int32_t *sol;           // [N] rounded labels (0-based)
     int *ticket;            // dispatch counter (zeroed before each launch)
@@ -453,6 +461,58 @@ __device__ __forceinline__ Incidence incidence(int d, int r, int c, long long u,
 }
 
 // ---------------------------------------------------------------- the sweep
+
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// direction (0 up, 1 down, 2 left, 3 right) from node u to node v, or -1
+__device__ __forceinline__ int direction_to(long long u, long long v, int H)
+{
+    const long long d = v - u;
+    return d == -1 ? 0 : d == 1 ? 1 : d == -H ? 2 : d == H ? 3 : -1;
+}
+
+// Pull the operands node `u` will need (its unary row and, for every term it sends on,
+// the old message, both position rows, the rank row and the merge-count row) into L2.
+template <typename REAL, int K, int PASS>
+__device__ __forceinline__ void prefetch_node(const Problem<REAL> &p, long long u, int lane)
+{
+    constexpr int LP = 32 * K;
+    constexpr int LR = (LP * (int)sizeof(REAL) + 127) / 128; // 128B lines per REAL row
+    constexpr int LB = (LP + 127) / 128;                     // lines per byte row
+    const unsigned info = __ldg(p.info + u);
+    const unsigned valid = info & 15u, lower = info >> 4;
+    const unsigned send_mask = (PASS == PASS_FWD) ? (valid & ~lower) : lower;
+    const int r = (int)(u % p.H), c = (int)(u / p.H);
+    if (lane < LR) prefetch_l2(reinterpret_cast<const char *>(p.D + u * LP) + lane * 128);
+#pragma unroll 1
+    for (int d = 0; d < 4; d++) {
+        if (!((send_mask >> d) & 1u)) continue;
+        const Incidence I = incidence(d, r, c, u, p.H, p.W, p.nV, p.nH);
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const long long row = I.term[j] * LP;
+            for (int i = lane; i < 3 * LR + 2 * LB; i += 32) {
+                const char *base;
+                int line;
+                if (i < 3 * LR) {
+                    const int a = i / LR;
+                    line = i % LR;
+                    base = reinterpret_cast<const char *>((a == 0 ? (const REAL *)p.msg : a == 1 ? p.posq : p.posqp) + row);
+                } else {
+                    const int a = (i - 3 * LR) / LB;
+                    line = (i - 3 * LR) % LB;
+                    base = reinterpret_cast<const char *>(
+                        (a == 0 ? (I.tail[j] ? p.rank_qp : p.rank_q) : (I.tail[j] ? p.cnt_q : p.cnt_qp)) + row);
+                }
+                prefetch_l2(base + line * 128);
+            }
+        }
+    }
+}
+
 template <typename REAL, int K, int KERN, int PASS, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) sweep_kernel(const Problem<REAL> p)
 {
@@ -461,7 +521,7 @@ __global__ void __launch_bounds__(WARPS * 32) sweep_kernel(const Problem<REAL> p
     const int warp = threadIdx.x >> 5;
     Pair<REAL> *P = reinterpret_cast<Pair<REAL> *>(smem_raw) + (size_t)warp * scratch_pairs<K>();
     const REAL BIG = Lim<REAL>::big();
-    const int LP = 32 * K;
+    constexpr int LP = 32 * K;
     if (lane == 0) {
         Pair<REAL> t;
         t.a = BIG;
@@ -474,160 +534,185 @@ __global__ void __launch_bounds__(WARPS * 32) sweep_kernel(const Problem<REAL> p
     const bool do_send = (PASS == PASS_BWD) || (p.mode & MODE_SEND);
     const bool do_round = (PASS == PASS_FWD) && (p.mode & MODE_ROUND);
     double acc_energy = 0.0, acc_lb = 0.0;
+    if (warp >= p.active_warps) return;
 
     for (;;) {
-        long long t = 0;
-        if (lane == 0) t = atomicAdd(p.ticket, 1);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= p.N) break;
-        const long long u = (PASS == PASS_BWD) ? p.sched[p.N - 1 - t] : p.sched[t];
-        const int r = (int)(u % p.H), c = (int)(u / p.H);
-        const int my_ord = p.order[u];
-
-        // orientation of the four neighbour pairs and gamma = 1/max(nF, nB)
-        // (treeProbabilities.cpp:28-45; two terms per neighbour)
-        unsigned lower_mask = 0, valid_mask = 0;
+        int ts = 0;
+        if (lane == 0) ts = atomicAdd(p.ticket, 1);
+        ts = __shfl_sync(0xffffffffu, ts, 0);
+        if (ts >= p.S) break;
+        // the backward sweep runs the forward schedule in reverse
+        const int fs = (PASS == PASS_BWD) ? p.S - 1 - ts : ts;
+        const int sb = __ldg(p.strip_ptr + fs), se = __ldg(p.strip_ptr + fs + 1);
+        const int step = (PASS == PASS_BWD) ? -1 : 1;
+        int idx = (PASS == PASS_BWD) ? se - 1 : sb;
+        long long u = (se > sb) ? __ldg(p.nodes + idx) : -1;
+        long long u_prev = -1;
+        bool carry_valid = false;
+        REAL carry0[K], carry1[K]; // messages this warp just sent to u on the pair's terms 0 / 1
 #pragma unroll
-        for (int d = 0; d < 4; d++) {
-            const Incidence I = incidence(d, r, c, u, p.H, p.W, p.nV, p.nH);
-            if (I.valid) {
-                valid_mask |= 1u << d;
-                if (p.order[I.nb] < my_ord) lower_mask |= 1u << d;
+        for (int k = 0; k < K; k++) carry0[k] = carry1[k] = REAL(0);
+
+        for (int n = se - sb; n > 0; n--, idx += step) {
+            const long long u_next = (n > 1) ? (long long)__ldg(p.nodes + idx + step) : -1;
+            if (u_next >= 0) prefetch_node<REAL, K, PASS>(p, u_next, lane);
+            const int r = (int)(u % p.H), c = (int)(u / p.H);
+            const unsigned info = __ldg(p.info + u);
+            const unsigned valid_mask = info & 15u, lower_mask = info >> 4;
+            // gamma = 1/max(nF, nB), two terms per neighbour (treeProbabilities.cpp:28-45)
+            const int nB = 2 * __popc(lower_mask), nF = 2 * __popc(valid_mask & ~lower_mask);
+            const REAL gamma = REAL(1) / REAL(max(1, max(nF, nB)));
+            const unsigned dep_mask = (PASS == PASS_FWD) ? lower_mask : (valid_mask & ~lower_mask);
+            const unsigned send_mask = (PASS == PASS_FWD) ? (valid_mask & ~lower_mask) : lower_mask;
+            const int d_prev = carry_valid ? direction_to(u, u_prev, p.H) : -1;
+            const int d_next = (u_next >= 0) ? direction_to(u, u_next, p.H) : -1;
+
+            // wait for the neighbours this node depends on that other strips own
+            if (lane < 4 && ((dep_mask >> lane) & 1u) && lane != d_prev) {
+                const Incidence I = incidence(lane, r, c, u, p.H, p.W, p.nV, p.nH);
+                while (ld_acquire(p.done + I.nb) < p.epoch) __nanosleep(20);
             }
-        }
-        const int nB = 2 * __popc(lower_mask), nF = 2 * __popc(valid_mask & ~lower_mask);
-        const REAL gamma = REAL(1) / REAL(max(1, max(nF, nB)));
-        // neighbours this node waits for / sends to in this pass
-        const unsigned dep_mask = (PASS == PASS_FWD) ? lower_mask : (valid_mask & ~lower_mask);
-        const unsigned send_mask = (PASS == PASS_FWD) ? (valid_mask & ~lower_mask) : lower_mask;
+            __syncwarp();
 
-        if (lane < 4 && ((dep_mask >> lane) & 1u)) {
-            const Incidence I = incidence(lane, r, c, u, p.H, p.W, p.nV, p.nH);
-            while (ld_acquire(p.done + I.nb) < p.epoch) __nanosleep(32);
-        }
-        __syncwarp();
+            REAL Di[K];
+            VecIO<REAL, K>::load_ro(Di, p.D + u * LP + lane * K);
 
-        REAL Di[K];
-        VecIO<REAL, K>::load_ro(Di, p.D + u * LP + lane * K);
-
-        if (do_round) {
-            // minimize.cpp:240-260: DiB = D + sum_{lower nb} V(x_nb, .), Dr = DiB + forward messages
-            REAL DiB[K], Dr[K];
+            if (do_round) {
+                // minimize.cpp:240-260: DiB = D + sum_{lower nb} V(x_nb, .), Dr = DiB + forward messages
+                REAL DiB[K], Dr[K];
 #pragma unroll
-            for (int k = 0; k < K; k++) DiB[k] = Di[k];
+                for (int k = 0; k < K; k++) DiB[k] = Di[k];
 #pragma unroll 1
-            for (int e = 0; e < 8; e++) {
-                const int d = e >> 1, j = e & 1;
-                if (!((lower_mask >> d) & 1u)) continue;
-                const Incidence I = incidence(d, r, c, u, p.H, p.W, p.nV, p.nH);
-                const long long tm = I.term[j];
-                const REAL *mine = (I.tail[j] ? p.posqp : p.posq) + tm * LP;
-                const REAL *theirs = (I.tail[j] ? p.posq : p.posqp) + tm * LP;
-                const int xs = __ldcg(p.sol + I.nb);
-                const REAL pos_nb = theirs[xs];
-                const REAL al = p.alpha[tm];
-                REAL mp[K];
-                VecIO<REAL, K>::load_ro(mp, mine + lane * K);
+                for (int e = 0; e < 8; e++) {
+                    const int d = e >> 1, j = e & 1;
+                    if (!((lower_mask >> d) & 1u)) continue;
+                    const Incidence I = incidence(d, r, c, u, p.H, p.W, p.nV, p.nH);
+                    const long long tm = I.term[j];
+                    const REAL *mine = (I.tail[j] ? p.posqp : p.posq) + tm * LP;
+                    const REAL *theirs = (I.tail[j] ? p.posq : p.posqp) + tm * LP;
+                    const int xs = __ldcg(p.sol + I.nb);
+                    const REAL pos_nb = theirs[xs];
+                    const REAL al = p.alpha[tm];
+                    REAL mp[K];
+                    VecIO<REAL, K>::load_ro(mp, mine + lane * K);
 #pragma unroll
-                for (int k = 0; k < K; k++) DiB[k] += al * smooth<REAL, KERN>(mp[k] - pos_nb, p.lambda);
-            }
+                    for (int k = 0; k < K; k++) DiB[k] += al * smooth<REAL, KERN>(mp[k] - pos_nb, p.lambda);
+                }
 #pragma unroll
-            for (int k = 0; k < K; k++) Dr[k] = DiB[k];
+                for (int k = 0; k < K; k++) Dr[k] = DiB[k];
 #pragma unroll 1
-            for (int e = 0; e < 8; e++) {
-                const int d = e >> 1, j = e & 1;
-                if (!(((valid_mask & ~lower_mask) >> d) & 1u)) continue;
-                const Incidence I = incidence(d, r, c, u, p.H, p.W, p.nV, p.nH);
-                REAL mm[K];
-                VecIO<REAL, K>::load_cg(mm, p.msg + I.term[j] * LP + lane * K);
-#pragma unroll
-                for (int k = 0; k < K; k++) Dr[k] += mm[k];
-            }
-            // Vector::ComputeMin: first minimum in label order (typeStereoLinear.h:238-252)
-            REAL best = BIG;
-            int bi = 0x7fffffff;
-            REAL bDiB = REAL(0);
-#pragma unroll
-            for (int k = 0; k < K; k++) {
-                const int lbl = lane * K + k;
-                if (lbl < p.L && Dr[k] < best) {
-                    best = Dr[k];
-                    bi = lbl;
-                    bDiB = DiB[k];
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const REAL ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                const REAL od = __shfl_xor_sync(0xffffffffu, bDiB, o);
-                if (ob < best || (ob == best && oi < bi)) {
-                    best = ob;
-                    bi = oi;
-                    bDiB = od;
-                }
-            }
-            if (lane == 0) {
-                p.sol[u] = bi;
-                acc_energy += (double)bDiB;
-            }
-        }
-
-        if (do_send) {
-            // Di = D + all incident messages (minimize.cpp:38-46 / 69-77)
-#pragma unroll
-            for (int e = 0; e < 8; e++) {
-                const int d = e >> 1, j = e & 1;
-                if ((valid_mask >> d) & 1u) {
+                for (int e = 0; e < 8; e++) {
+                    const int d = e >> 1, j = e & 1;
+                    if (!(((valid_mask & ~lower_mask) >> d) & 1u)) continue;
                     const Incidence I = incidence(d, r, c, u, p.H, p.W, p.nV, p.nH);
                     REAL mm[K];
                     VecIO<REAL, K>::load_cg(mm, p.msg + I.term[j] * LP + lane * K);
 #pragma unroll
-                    for (int k = 0; k < K; k++) Di[k] += mm[k];
+                    for (int k = 0; k < K; k++) Dr[k] += mm[k];
+                }
+                // Vector::ComputeMin: first minimum in label order (typeStereoLinear.h:238-252)
+                REAL best = BIG;
+                int bi = 0x7fffffff;
+                REAL bDiB = REAL(0);
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    const int lbl = lane * K + k;
+                    if (lbl < p.L && Dr[k] < best) {
+                        best = Dr[k];
+                        bi = lbl;
+                        bDiB = DiB[k];
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const REAL ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    const REAL od = __shfl_xor_sync(0xffffffffu, bDiB, o);
+                    if (ob < best || (ob == best && oi < bi)) {
+                        best = ob;
+                        bi = oi;
+                        bDiB = od;
+                    }
+                }
+                if (lane == 0) {
+                    p.sol[u] = bi;
+                    acc_energy += (double)bDiB;
                 }
             }
-            if (PASS == PASS_BWD) {
-                // ComputeAndSubtractMin + lower bound (minimize.cpp:79-81)
-                REAL vmin = BIG;
-#pragma unroll
-                for (int k = 0; k < K; k++)
-                    if (lane * K + k < p.L) vmin = min(vmin, Di[k]);
-                vmin = warp_min(vmin);
-#pragma unroll
-                for (int k = 0; k < K; k++) Di[k] -= vmin;
-                acc_lb += (double)vmin;
-            }
-#pragma unroll 1
-            for (int e = 0; e < 8; e++) {
-                const int d = e >> 1, j = e & 1;
-                if (!((send_mask >> d) & 1u)) continue;
-                const Incidence I = incidence(d, r, c, u, p.H, p.W, p.nV, p.nH);
-                const long long tm = I.term[j];
-                const long long off = tm * LP + lane * K;
-                // sender's positions: qprim if I am the tail of the term, else q
-                // (typeStereoLinear.h:343-357 with Swap(), MRFEnergy.cpp:200-203)
-                REAL m[K], s[K], x[K];
-                uint8_t rk[K], cn[K];
-                VecIO<REAL, K>::load_cg(m, p.msg + off);
-                VecIO<REAL, K>::load_ro(s, (I.tail[j] ? p.posqp : p.posq) + off);
-                VecIO<REAL, K>::load_ro(x, (I.tail[j] ? p.posq : p.posqp) + off);
-                ByteIO<K>::load(rk, (I.tail[j] ? p.rank_qp : p.rank_q) + off);
-                ByteIO<K>::load(cn, (I.tail[j] ? p.cnt_q : p.cnt_qp) + off);
-                const REAL al = p.alpha[tm];
-                REAL vmin;
-                if constexpr (KERN == 1)
-                    vmin = update_linear<REAL, K>(gamma, al, p.lambda, p.L, lane, Di, m, s, rk, x, cn, P);
-                else
-                    vmin = update_quadratic<REAL, K>(gamma, al, p.lambda, p.L, lane, Di, m, s, rk, x, cn, P);
-                VecIO<REAL, K>::store(p.msg + off, m);
-                if (PASS == PASS_BWD) acc_lb += (double)vmin;
-            }
-        }
 
-        // publish: all of this warp's stores happen-before the flag
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) st_release(p.done + u, p.epoch);
+            if (do_send) {
+                // Di = D + all incident messages (minimize.cpp:38-46 / 69-77); the pair just
+                // sent by this warp from the previous node of the strip comes from registers
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const int d = e >> 1, j = e & 1;
+                    if (!((valid_mask >> d) & 1u)) continue;
+                    if (d == d_prev) {
+#pragma unroll
+                        for (int k = 0; k < K; k++) Di[k] += (j ? carry1[k] : carry0[k]);
+                    } else {
+                        const Incidence I = incidence(d, r, c, u, p.H, p.W, p.nV, p.nH);
+                        REAL mm[K];
+                        VecIO<REAL, K>::load_cg(mm, p.msg + I.term[j] * LP + lane * K);
+#pragma unroll
+                        for (int k = 0; k < K; k++) Di[k] += mm[k];
+                    }
+                }
+                if (PASS == PASS_BWD) {
+                    // ComputeAndSubtractMin + lower bound (minimize.cpp:79-81)
+                    REAL vmin = BIG;
+#pragma unroll
+                    for (int k = 0; k < K; k++)
+                        if (lane * K + k < p.L) vmin = min(vmin, Di[k]);
+                    vmin = warp_min(vmin);
+#pragma unroll
+                    for (int k = 0; k < K; k++) Di[k] -= vmin;
+                    acc_lb += (double)vmin;
+                }
+                carry_valid = false;
+#pragma unroll 1
+                for (int e = 0; e < 8; e++) {
+                    const int d = e >> 1, j = e & 1;
+                    if (!((send_mask >> d) & 1u)) continue;
+                    const Incidence I = incidence(d, r, c, u, p.H, p.W, p.nV, p.nH);
+                    const long long tm = I.term[j];
+                    const long long off = tm * LP + lane * K;
+                    // sender's positions: qprim if I am the tail of the term, else q
+                    // (typeStereoLinear.h:343-357 with Swap(), MRFEnergy.cpp:200-203)
+                    REAL m[K], s[K], x[K];
+                    uint8_t rk[K], cn[K];
+                    VecIO<REAL, K>::load_cg(m, p.msg + off);
+                    VecIO<REAL, K>::load_ro(s, (I.tail[j] ? p.posqp : p.posq) + off);
+                    VecIO<REAL, K>::load_ro(x, (I.tail[j] ? p.posq : p.posqp) + off);
+                    ByteIO<K>::load(rk, (I.tail[j] ? p.rank_qp : p.rank_q) + off);
+                    ByteIO<K>::load(cn, (I.tail[j] ? p.cnt_q : p.cnt_qp) + off);
+                    const REAL al = p.alpha[tm];
+                    REAL vmin;
+                    if constexpr (KERN == 1)
+                        vmin = update_linear<REAL, K>(gamma, al, p.lambda, p.L, lane, Di, m, s, rk, x, cn, P);
+                    else
+                        vmin = update_quadratic<REAL, K>(gamma, al, p.lambda, p.L, lane, Di, m, s, rk, x, cn, P);
+                    VecIO<REAL, K>::store(p.msg + off, m);
+                    if (PASS == PASS_BWD) acc_lb += (double)vmin;
+                    if (d == d_next) {
+                        carry_valid = true;
+#pragma unroll
+                        for (int k = 0; k < K; k++) {
+                            if (j) carry1[k] = m[k];
+                            else carry0[k] = m[k];
+                        }
+                    }
+                }
+            } else {
+                carry_valid = false;
+            }
+
+            // publish: this warp's stores happen-before the flag (syncwarp + release)
+            __syncwarp();
+            if (lane == 0) st_release(p.done + u, p.epoch);
+            u_prev = u;
+            u = u_next;
+        }
     }
     if (lane == 0) {
         if (acc_energy != 0.0) atomicAdd(p.acc + 0, acc_energy);

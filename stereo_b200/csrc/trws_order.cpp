@@ -157,38 +157,85 @@ bool grid_ordering(int H, int W, std::vector<int32_t> &ordering)
     return greedy_ordering(N, tail, head, ordering);
 }
 
-// Longest-path levels of the DAG "lower ordering -> higher ordering" on the grid
-// and the level-sorted dispatch list (ties by ordering).  A node's forward sweep
-// may run once all lower-ordered neighbours are done (minimize.cpp:36-62 visits
-// nodes by m_ordering; only messages on incident edges are read or written).
-void build_schedule(int H, int W, const std::vector<int32_t> &ordering, std::vector<int32_t> &sched,
-                    int32_t &num_levels)
+// Per-node incidence byte: bit d (0 up, 1 down, 2 left, 3 right) = neighbour exists,
+// bit 4+d = that neighbour has a LOWER ordering (its terms are backward edges of this
+// node, MRFEnergy.cpp:188-219).  gamma and the send / wait sets follow from it.
+void build_node_info(int H, int W, const std::vector<int32_t> &ordering, std::vector<uint8_t> &info)
 {
     const int64_t N = (int64_t)H * W;
-    std::vector<int32_t> inv(N), level(N, 0);
-    for (int64_t u = 0; u < N; u++) inv[ordering[u]] = (int32_t)u;
-    int32_t maxl = 0;
-    for (int64_t o = 0; o < N; o++) {
-        const int64_t u = inv[o];
-        const int r = (int)(u % H), c = (int)(u / H);
-        int32_t l = 0;
-        auto dep = [&](int64_t v) { if (ordering[v] < o) l = std::max(l, level[v] + 1); };
-        if (r > 0) dep(u - 1);
-        if (r < H - 1) dep(u + 1);
-        if (c > 0) dep(u - H);
-        if (c < W - 1) dep(u + H);
-        level[u] = l;
-        maxl = std::max(maxl, l);
-    }
-    num_levels = maxl + 1;
-    // counting sort by level, stable in ordering
-    std::vector<int64_t> start(num_levels + 1, 0);
-    for (int64_t u = 0; u < N; u++) start[level[u] + 1]++;
-    for (int32_t l = 0; l < num_levels; l++) start[l + 1] += start[l];
-    sched.resize(N);
-    for (int64_t o = 0; o < N; o++) {
-        const int64_t u = inv[o];
-        sched[start[level[u]]++] = (int32_t)u;
+    info.resize(N);
+    for (int c = 0; c < W; c++)
+        for (int r = 0; r < H; r++) {
+            const int64_t u = r + (int64_t)H * c;
+            const int32_t o = ordering[u];
+            unsigned b = 0;
+            if (r > 0) { b |= 1u; if (ordering[u - 1] < o) b |= 16u; }
+            if (r < H - 1) { b |= 2u; if (ordering[u + 1] < o) b |= 32u; }
+            if (c > 0) { b |= 4u; if (ordering[u - H] < o) b |= 64u; }
+            if (c < W - 1) { b |= 8u; if (ordering[u + H] < o) b |= 128u; }
+            info[u] = (uint8_t)b;
+        }
+}
+
+// Dispatch schedule of one sweep: a list of STRIPS, each a run of nodes one warp
+// processes back to back.  A node's forward sweep may run once all lower-ordered
+// neighbours are done (minimize.cpp:36-62 visits nodes by m_ordering; only messages on
+// incident edges are read or written), so any dispatch order in which a strip only
+// waits for strips dispatched before it (plus the one documented exception below)
+// reproduces the sequential sweep.
+//   regular grids (H,W >= 4): strip 0 is the boundary ring in ordering sequence (a serial
+//     chain: every ring node's predecessor is its neighbour), strips 1..H-2 are the
+//     interior rows, swept right to left; row r only waits for the ring and row r-1,
+//     except that (H-3,1) -- the last node of the ordering -- waits for (H-2,1);
+//   other grids: one node per strip, sorted by longest-path level of the DAG.
+// The backward sweep uses the exact reverse (strips and nodes within strips).
+void build_schedule(int H, int W, const std::vector<int32_t> &ordering, Schedule &s)
+{
+    const int64_t N = (int64_t)H * W;
+    s.nodes.clear();
+    s.strip_ptr.clear();
+    s.nodes.reserve(N);
+    if (H >= 4 && W >= 4) {
+        const int64_t ring = 2LL * H + 2LL * W - 4;
+        std::vector<int32_t> ringnodes(ring);
+        auto put = [&](int r, int c) { const int64_t u = r + (int64_t)H * c; ringnodes[ordering[u]] = (int32_t)u; };
+        for (int r = 0; r < H; r++) { put(r, 0); put(r, W - 1); }
+        for (int c = 1; c < W - 1; c++) { put(0, c); put(H - 1, c); }
+        s.strip_ptr.push_back(0);
+        s.nodes.insert(s.nodes.end(), ringnodes.begin(), ringnodes.end());
+        for (int r = 1; r <= H - 2; r++) {
+            s.strip_ptr.push_back((int64_t)s.nodes.size());
+            for (int c = W - 2; c >= 1; c--) s.nodes.push_back((int32_t)(r + (int64_t)H * c));
+        }
+        s.strip_ptr.push_back((int64_t)s.nodes.size());
+        s.regular = true;
+    } else {
+        std::vector<int32_t> inv(N), level(N, 0);
+        for (int64_t u = 0; u < N; u++) inv[ordering[u]] = (int32_t)u;
+        int32_t maxl = 0;
+        for (int64_t o = 0; o < N; o++) {
+            const int64_t u = inv[o];
+            const int r = (int)(u % H), c = (int)(u / H);
+            int32_t l = 0;
+            auto dep = [&](int64_t v) { if (ordering[v] < o) l = std::max(l, level[v] + 1); };
+            if (r > 0) dep(u - 1);
+            if (r < H - 1) dep(u + 1);
+            if (c > 0) dep(u - H);
+            if (c < W - 1) dep(u + H);
+            level[u] = l;
+            maxl = std::max(maxl, l);
+        }
+        std::vector<int64_t> start(maxl + 2, 0);
+        for (int64_t u = 0; u < N; u++) start[level[u] + 1]++;
+        for (int32_t l = 0; l <= maxl; l++) start[l + 1] += start[l];
+        s.nodes.resize(N);
+        for (int64_t o = 0; o < N; o++) {
+            const int64_t u = inv[o];
+            s.nodes[start[level[u]]++] = (int32_t)u;
+        }
+        s.strip_ptr.resize(N + 1);
+        for (int64_t i = 0; i <= N; i++) s.strip_ptr[i] = i;
+        s.regular = false;
     }
 }
 

@@ -16,8 +16,14 @@ bool greedy_ordering(int64_t N, const std::vector<int32_t> &tail, const std::vec
                      std::vector<int32_t> &ordering);
 // SetAutomaticOrdering on the grid (closed form for H,W >= 4).
 bool grid_ordering(int H, int W, std::vector<int32_t> &ordering);
-// Level-sorted dispatch list of the orientation DAG.
-void build_schedule(int H, int W, const std::vector<int32_t> &ordering, std::vector<int32_t> &sched,
-                    int32_t &num_levels);
+// Per-node incidence byte (valid mask | lower mask << 4).
+void build_node_info(int H, int W, const std::vector<int32_t> &ordering, std::vector<uint8_t> &info);
+// Strip schedule of the forward sweep (the backward sweep runs it in reverse).
+struct Schedule {
+    std::vector<int32_t> nodes;      // concatenated strips
+    std::vector<int64_t> strip_ptr;  // strip s = nodes[strip_ptr[s] .. strip_ptr[s+1])
+    bool regular = false;            // ring + interior rows (H,W >= 4)
+};
+void build_schedule(int H, int W, const std::vector<int32_t> &ordering, Schedule &s);
 
 } // namespace sb

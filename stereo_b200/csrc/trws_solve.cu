@@ -10,6 +10,7 @@
 #include <vector>
 #include <chrono>
 #include <cstring>
+#include <algorithm>
 
 namespace sb {
 namespace trws {
@@ -54,21 +55,27 @@ void solve_typed(int kernel, int L, int64_t N, int64_t E, int H, int W, const do
     SB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
 
     // ---- host graph logic: ordering + dispatch schedule
-    std::vector<int32_t> order, sched;
+    std::vector<int32_t> order;
     SB_REQUIRE(grid_ordering(H, W, order), SB_EINVAL,
                "sb_trws_solve: %dx%d grid has no valid automatic ordering (the reference crashes on it)", H, W);
-    int32_t num_levels = 0;
-    build_schedule(H, W, order, sched, num_levels);
+    std::vector<uint8_t> info;
+    build_node_info(H, W, order, info);
+    Schedule sched;
+    build_schedule(H, W, order, sched);
+    const int S = (int)sched.strip_ptr.size() - 1;
+    std::vector<int32_t> strip_ptr32(sched.strip_ptr.begin(), sched.strip_ptr.end());
 
     // ---- device state
     DevBuf<REAL> dD((size_t)N * LP), dMsg((size_t)E * LP), dPosQ((size_t)E * LP), dPosQp((size_t)E * LP), dAlpha((size_t)E);
     DevBuf<uint8_t> dRankQ((size_t)E * LP), dRankQp((size_t)E * LP), dCntQ((size_t)E * LP), dCntQp((size_t)E * LP);
-    DevBuf<int32_t> dOrder((size_t)N), dSched((size_t)N), dDone((size_t)N), dSol((size_t)N);
+    DevBuf<int32_t> dNodes((size_t)N), dStripPtr((size_t)S + 1), dDone((size_t)N), dSol((size_t)N);
+    DevBuf<uint8_t> dInfo((size_t)N);
     DevBuf<Ctrl> dCtrl(1);
     DevBuf<int> dBad(1);
 
-    SB_CUDA(cudaMemcpyAsync(dOrder.p, order.data(), (size_t)N * 4, cudaMemcpyHostToDevice, stream));
-    SB_CUDA(cudaMemcpyAsync(dSched.p, sched.data(), (size_t)N * 4, cudaMemcpyHostToDevice, stream));
+    SB_CUDA(cudaMemcpyAsync(dNodes.p, sched.nodes.data(), (size_t)N * 4, cudaMemcpyHostToDevice, stream));
+    SB_CUDA(cudaMemcpyAsync(dStripPtr.p, strip_ptr32.data(), ((size_t)S + 1) * 4, cudaMemcpyHostToDevice, stream));
+    SB_CUDA(cudaMemcpyAsync(dInfo.p, info.data(), (size_t)N, cudaMemcpyHostToDevice, stream));
     SB_CUDA(cudaMemsetAsync(dDone.p, 0, (size_t)N * 4, stream));
     SB_CUDA(cudaMemsetAsync(dSol.p, 0, (size_t)N * 4, stream));
     SB_CUDA(cudaMemsetAsync(dMsg.p, 0, dMsg.bytes(), stream)); // ZeroMessages, MRFEnergy.cpp:115-131
@@ -112,7 +119,8 @@ void solve_typed(int kernel, int L, int64_t N, int64_t E, int H, int W, const do
     P.D = dD.p; P.msg = dMsg.p; P.posq = dPosQ.p; P.posqp = dPosQp.p;
     P.rank_q = dRankQ.p; P.rank_qp = dRankQp.p; P.cnt_q = dCntQ.p; P.cnt_qp = dCntQp.p;
     P.alpha = dAlpha.p; P.lambda = (REAL)tol;
-    P.order = dOrder.p; P.sched = dSched.p; P.done = dDone.p; P.sol = dSol.p;
+    P.info = dInfo.p; P.nodes = dNodes.p; P.strip_ptr = dStripPtr.p; P.S = S;
+    P.done = dDone.p; P.sol = dSol.p;
     P.ticket = &dCtrl.p->ticket; P.acc = dCtrl.p->acc;
 
     const int wpb = ops->sweep_warps_per_block();
@@ -120,11 +128,16 @@ void solve_typed(int kernel, int L, int64_t N, int64_t E, int H, int W, const do
         const int bps = ops->sweep_blocks_per_sm(precision, kernel, pass);
         SB_REQUIRE(bps >= 1, SB_ECUDA, "sb_trws_solve: sweep kernel does not fit on an SM");
         long long g = (long long)bps * num_sms;
-        const long long need = (N + wpb - 1) / wpb;
-        if (g > need) g = need;
+        if (g > S) g = S;
         return (int)(g < 1 ? 1 : g);
     };
     const int grid_fwd = grid_for(PASS_FWD), grid_bwd = grid_for(PASS_BWD);
+    auto active_for = [&](int grid) {
+        // at least two strip-walking warps in flight (trws_order.cpp: row H-3 waits for row H-2)
+        long long a = ((long long)S + grid - 1) / grid;
+        if ((long long)grid * a < 2) a = 2;
+        return (int)std::min<long long>(a, wpb);
+    };
 
     int epoch = 0;
     Ctrl hc;
@@ -135,6 +148,7 @@ void solve_typed(int kernel, int L, int64_t N, int64_t E, int H, int W, const do
         SweepLaunch sl;
         sl.precision = precision; sl.kern = kernel; sl.pass = pass; sl.problem = &P;
         sl.grid = pass == PASS_FWD ? grid_fwd : grid_bwd; sl.stream = stream;
+        P.active_warps = active_for(sl.grid);
         ops->sweep(sl);
         SB_CUDA(cudaMemcpyAsync(&hc, dCtrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
         SB_CUDA(cudaStreamSynchronize(stream));

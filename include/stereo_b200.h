@@ -81,7 +81,10 @@ typedef struct sb_trws_timing {
     double sweep_ms_avg;   /* solve_ms / iterations                                   */
     double download_ms;
     int64_t kernel_launches;
-    int64_t reserved[3];
+    double sweep_kernel_ms;       /* sum of the sweep kernels' own durations (CUDA events
+                                     around each launch on the solver stream)            */
+    int64_t sweep_kernel_launches;
+    int64_t reserved[1];
 } sb_trws_timing;
 
 /* ---------------------------------------------------------------- TRW-S */
@@ -107,6 +110,29 @@ SB_API int sb_trws_solve(int kernel, int L, int64_t N, int64_t E,
                   const sb_trws_options *opt,
                   double *labels, double *energy, double *lower_bound,
                   double *iterations, sb_trws_timing *timing);
+
+/* Resident-solver form of the same path, for callers that keep the problem in HBM
+ * across calls (bench.py; dispmap_super.simultaneous_fusion re-solves):
+ *   sb_trws_create     = the graph build of solve_mrf, cpp/trws_mex.cpp:58-121
+ *                        (AddNode / AddEdge / SetAutomaticOrdering) -- uploads and
+ *                        converts the inputs, builds rank tables and the schedule;
+ *   sb_trws_reset      = MRFEnergy::ZeroMessages, cpp/trw-s/MRFEnergy.cpp:115-131;
+ *   sb_trws_minimize   = MRFEnergy::Minimize_TRW_S, cpp/trw-s/minimize.cpp:7-116
+ *                        (continues from the current messages, like the reference);
+ *   sb_trws_get_labels = the GetSolution loop, cpp/trws_mex.cpp:134-139 (1-based);
+ *   sb_trws_destroy    = delete mrf, cpp/trws_mex.cpp:146. */
+typedef struct sb_trws_solver sb_trws_solver;
+SB_API int sb_trws_create(int kernel, int L, int64_t N, int64_t E,
+                   const double *unary, const uint32_t *conn,
+                   const double *q, const double *qprim,
+                   const double *alphas, double tol,
+                   const sb_trws_options *opt, sb_trws_solver **out);
+SB_API int sb_trws_reset(sb_trws_solver *s);
+SB_API int sb_trws_minimize(sb_trws_solver *s, double maxiter, double max_relgap,
+                     double *energy, double *lower_bound, double *iterations,
+                     sb_trws_timing *timing);
+SB_API int sb_trws_get_labels(sb_trws_solver *s, double *labels);
+SB_API void sb_trws_destroy(sb_trws_solver *s);
 
 /* Node ordering of MRFEnergy::SetAutomaticOrdering (cpp/trw-s/ordering.cpp:7-157)
  * on the H x W grid: ordering[r + H*c] in [0, H*W).  Closed form for H,W >= 4

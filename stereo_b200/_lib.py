@@ -35,7 +35,8 @@ class TrwsOptions(Structure):
 
 class TrwsTiming(Structure):
     _fields_ = [("setup_ms", c_double), ("solve_ms", c_double), ("sweep_ms_avg", c_double),
-                ("download_ms", c_double), ("kernel_launches", c_int64), ("reserved", c_int64 * 3)]
+                ("download_ms", c_double), ("kernel_launches", c_int64), ("sweep_kernel_ms", c_double),
+                ("sweep_kernel_launches", c_int64), ("reserved", c_int64 * 1)]
 
 
 _lib = None
@@ -59,6 +60,13 @@ def lib():
         L.sb_trws_default_options.restype = None
         L.sb_trws_solve.argtypes = [c_int, c_int, c_int64, c_int64, _dp, _up, _dp, _dp, _dp, c_double,
                                     POINTER(TrwsOptions), _dp, _dp, _dp, _dp, POINTER(TrwsTiming)]
+        L.sb_trws_create.argtypes = [c_int, c_int, c_int64, c_int64, _dp, _up, _dp, _dp, _dp, c_double,
+                                     POINTER(TrwsOptions), POINTER(ctypes.c_void_p)]
+        L.sb_trws_reset.argtypes = [ctypes.c_void_p]
+        L.sb_trws_minimize.argtypes = [ctypes.c_void_p, c_double, c_double, _dp, _dp, _dp, POINTER(TrwsTiming)]
+        L.sb_trws_get_labels.argtypes = [ctypes.c_void_p, _dp]
+        L.sb_trws_destroy.argtypes = [ctypes.c_void_p]
+        L.sb_trws_destroy.restype = None
         L.sb_trws_grid_ordering.argtypes = [c_int, c_int, _ip]
         L.sb_grid_from_connectivity.argtypes = [c_int64, c_int64, _up, POINTER(c_int), POINTER(c_int)]
         _lib = L

@@ -29,6 +29,13 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "trws_sched.h"
+
+// Build-time switches for timing experiments (make EXTRA=-DSB_TRWS_INSTRUMENT=1): per-phase
+// cycle counters (SB_TRWS_PROFILE) and work-skipping bisection flags (SB_TRWS_DEBUG).
+#ifndef SB_TRWS_INSTRUMENT
+#define SB_TRWS_INSTRUMENT 0
+#endif
 
 namespace sb {
 namespace trws {
@@ -56,17 +63,18 @@ struct Problem {
     const uint8_t *cnt_qp;  // [E][LP]  #{q <= qprim[l]}   clamped to 255
     const REAL *alpha;      // [E]
     REAL lambda;
-    const uint8_t *info;    // [N] incidence byte: valid mask | lower mask << 4 (trws_order.cpp)
-    const int32_t *nodes;   // [N] forward-sweep strips, concatenated (backward = reverse)
-    const int32_t *strip_ptr; // [S+1]
+    const SegWarp *segs;    // segment descriptors of THIS pass (trws_sched.h): [nseg][NCW]
+    const int32_t *seg_ptr; // [S+1] segments of each forward strip
+    const int32_t *strip_ptr; // [S+1] node count prefix of the forward strips
     int S;
-    int active_warps;       // warps per CTA that take strips (spreads few strips over all SMs)
-    int32_t *done;          // [N] epoch flags
+    int32_t *progress;      // [S] nodes of each strip completed in this pass (zeroed per launch)
     int32_t *sol;           // [N] rounded labels (0-based)
+    REAL *selpos;           // [E] position of the sender's rounded label on each forward term
+    long long *prof;        // optional [2][8] cycle counters (SB_TRWS_PROFILE), else null
     int *ticket;            // dispatch counter (zeroed before each launch)
     double *acc;            // [0] energy  [1] lower bound (zeroed before each launch)
-    int epoch;
     int mode;               // PASS_FWD only: MODE_SEND | MODE_ROUND
+    int debug;              // SB_TRWS_DEBUG bisection switches (timing experiments only; 0 in production)
 };
 
 // ---------------------------------------------------------------- helpers
@@ -87,6 +95,19 @@ template <typename T> __device__ __forceinline__ T warp_min(T v)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
+}
+// sm_100a: one-instruction warp minimum for fp32 (CREDUX.MIN.F32)
+template <> __device__ __forceinline__ float warp_min<float>(float v)
+{
+    float r;
+    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ int warp_min_s32(int v)
+{
+    int r;
+    asm volatile("redux.sync.min.s32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+    return r;
 }
 
 // Register <-> 32-bit word views of REAL (no address-taken locals: everything stays in registers).
@@ -417,304 +438,627 @@ template <typename REAL, int KERN> __device__ __forceinline__ REAL smooth(REAL d
     else return min(d * d, lambda);
 }
 
-// ---------------------------------------------------------------- incidence on the grid
-// Direction d: 0 up (r-1), 1 down (r+1), 2 left (c-1), 3 right (c+1).
-// j = 0/1 selects the two terms of the neighbour pair.  Term order follows
-// dispmap_super.m:284-294.
-struct Incidence {
-    long long nb;     // neighbour node
-    long long term[2];
-    bool tail[2];     // am I the tail (conn(0,p)) of term[j]?
-    bool valid;
-};
-
-__device__ __forceinline__ Incidence incidence(int d, int r, int c, long long u, int H, int W,
-                                               long long nV, long long nH)
-{
-    Incidence I;
-    if (d == 0) {
-        I.valid = r > 0;
-        I.nb = u - 1;
-        I.term[0] = (long long)c * (H - 1) + (r - 1); // VD(r-1,c): tail = nb
-        I.term[1] = I.term[0] + nV;                   // VU(r-1,c): tail = me
-        I.tail[0] = false; I.tail[1] = true;
-    } else if (d == 1) {
-        I.valid = r < H - 1;
-        I.nb = u + 1;
-        I.term[0] = (long long)c * (H - 1) + r;       // VD(r,c): tail = me
-        I.term[1] = I.term[0] + nV;                   // VU(r,c): tail = nb
-        I.tail[0] = true; I.tail[1] = false;
-    } else if (d == 2) {
-        I.valid = c > 0;
-        I.nb = u - H;
-        I.term[0] = 2 * nV + (long long)(c - 1) * H + r; // HR(r,c-1): tail = nb
-        I.term[1] = I.term[0] + nH;                      // HL(r,c-1): tail = me
-        I.tail[0] = false; I.tail[1] = true;
-    } else {
-        I.valid = c < W - 1;
-        I.nb = u + H;
-        I.term[0] = 2 * nV + (long long)c * H + r;       // HR(r,c): tail = me
-        I.term[1] = I.term[0] + nH;                      // HL(r,c): tail = nb
-        I.tail[0] = true; I.tail[1] = false;
-    }
-    return I;
-}
-
-// ---------------------------------------------------------------- the sweep
+// ---------------------------------------------------------------- small PTX helpers
 
 __device__ __forceinline__ void prefetch_l2(const void *p)
 {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
-
-// direction (0 up, 1 down, 2 left, 3 right) from node u to node v, or -1
-__device__ __forceinline__ int direction_to(long long u, long long v, int H)
+// Progress watermarks: the producer fences then stores its strip's count, consumers poll
+// with a relaxed (L2) load and read the published data with L2-coherent accesses only
+// (ld.cg / cp.async.cg).
+__device__ __forceinline__ int ld_flag(const int32_t *p)
 {
-    const long long d = v - u;
-    return d == -1 ? 0 : d == 1 ? 1 : d == -H ? 2 : d == H ? 3 : -1;
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void publish_flag(int32_t *p, int v)
+{
+    asm volatile("fence.acq_rel.gpu;\n\tst.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+// step barrier of the NCW compute warps (the auxiliary warp is not paced by it)
+__device__ __forceinline__ void step_barrier()
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(128) : "memory");
+}
+__device__ __forceinline__ void st_release_cta(int *smem, int v)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_cta(const int *smem)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(smem);
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
 }
 
-// Pull the operands node `u` will need (its unary row and, for every term it sends on,
-// the old message, both position rows, the rank row and the merge-count row) into L2.
-template <typename REAL, int K, int PASS>
-__device__ __forceinline__ void prefetch_node(const Problem<REAL> &p, long long u, int lane)
+// One LP-row global -> shared, 16 bytes per lane per round (LDGSTS, L2-coherent).
+template <typename REAL, int K> __device__ __forceinline__ void row_async(REAL *dst, const REAL *src, int lane)
 {
-    constexpr int LP = 32 * K;
-    constexpr int LR = (LP * (int)sizeof(REAL) + 127) / 128; // 128B lines per REAL row
-    constexpr int LB = (LP + 127) / 128;                     // lines per byte row
-    const unsigned info = __ldg(p.info + u);
-    const unsigned valid = info & 15u, lower = info >> 4;
-    const unsigned send_mask = (PASS == PASS_FWD) ? (valid & ~lower) : lower;
-    const int r = (int)(u % p.H), c = (int)(u / p.H);
-    if (lane < LR) prefetch_l2(reinterpret_cast<const char *>(p.D + u * LP) + lane * 128);
-#pragma unroll 1
-    for (int d = 0; d < 4; d++) {
-        if (!((send_mask >> d) & 1u)) continue;
-        const Incidence I = incidence(d, r, c, u, p.H, p.W, p.nV, p.nH);
+    constexpr int CH = 32 * K * (int)sizeof(REAL) / 16;
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const long long row = I.term[j] * LP;
-            for (int i = lane; i < 3 * LR + 2 * LB; i += 32) {
-                const char *base;
-                int line;
-                if (i < 3 * LR) {
-                    const int a = i / LR;
-                    line = i % LR;
-                    base = reinterpret_cast<const char *>((a == 0 ? (const REAL *)p.msg : a == 1 ? p.posq : p.posqp) + row);
-                } else {
-                    const int a = (i - 3 * LR) / LB;
-                    line = (i - 3 * LR) % LB;
-                    base = reinterpret_cast<const char *>(
-                        (a == 0 ? (I.tail[j] ? p.rank_qp : p.rank_q) : (I.tail[j] ? p.cnt_q : p.cnt_qp)) + row);
-                }
-                prefetch_l2(base + line * 128);
+    for (int ch = lane; ch < CH; ch += 32)
+        cp_async16(reinterpret_cast<char *>(dst) + ch * 16, reinterpret_cast<const char *>(src) + ch * 16);
+}
+
+// K consecutive REALs per lane from / to a shared-memory row.
+template <typename REAL, int K> __device__ __forceinline__ void row_lds(REAL (&r)[K], const REAL *row, int lane)
+{
+    constexpr int BYTES = K * (int)sizeof(REAL);
+    if constexpr (BYTES % 16 == 0) {
+        const float4 *q = reinterpret_cast<const float4 *>(row + lane * K);
+#pragma unroll
+        for (int i = 0; i < BYTES / 16; i++) {
+            const float4 v = q[i];
+            if constexpr (sizeof(REAL) == 4) {
+                r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+            } else {
+                r[2 * i] = __hiloint2double(__float_as_int(v.y), __float_as_int(v.x));
+                r[2 * i + 1] = __hiloint2double(__float_as_int(v.w), __float_as_int(v.z));
             }
         }
+    } else if constexpr (BYTES % 8 == 0) {
+        const float2 *q = reinterpret_cast<const float2 *>(row + lane * K);
+#pragma unroll
+        for (int i = 0; i < BYTES / 8; i++) {
+            const float2 v = q[i];
+            if constexpr (sizeof(REAL) == 4) {
+                r[2 * i] = v.x; r[2 * i + 1] = v.y;
+            } else {
+                r[i] = __hiloint2double(__float_as_int(v.y), __float_as_int(v.x));
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; k++) r[k] = row[lane * K + k];
+    }
+}
+template <typename REAL, int K> __device__ __forceinline__ void row_sts(REAL *row, const REAL (&r)[K], int lane)
+{
+    constexpr int BYTES = K * (int)sizeof(REAL);
+    if constexpr (BYTES % 16 == 0) {
+        float4 *q = reinterpret_cast<float4 *>(row + lane * K);
+#pragma unroll
+        for (int i = 0; i < BYTES / 16; i++) {
+            float4 v;
+            if constexpr (sizeof(REAL) == 4) {
+                v.x = r[4 * i]; v.y = r[4 * i + 1]; v.z = r[4 * i + 2]; v.w = r[4 * i + 3];
+            } else {
+                v.x = __int_as_float(__double2loint(r[2 * i])); v.y = __int_as_float(__double2hiint(r[2 * i]));
+                v.z = __int_as_float(__double2loint(r[2 * i + 1])); v.w = __int_as_float(__double2hiint(r[2 * i + 1]));
+            }
+            q[i] = v;
+        }
+    } else if constexpr (BYTES % 8 == 0) {
+        float2 *q = reinterpret_cast<float2 *>(row + lane * K);
+#pragma unroll
+        for (int i = 0; i < BYTES / 8; i++) {
+            float2 v;
+            if constexpr (sizeof(REAL) == 4) {
+                v.x = r[2 * i]; v.y = r[2 * i + 1];
+            } else {
+                v.x = __int_as_float(__double2loint(r[i])); v.y = __int_as_float(__double2hiint(r[i]));
+            }
+            q[i] = v;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; k++) row[lane * K + k] = r[k];
     }
 }
 
-template <typename REAL, int K, int KERN, int PASS, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) sweep_kernel(const Problem<REAL> p)
+// ---------------------------------------------------------------- the sweep
+//
+// CTA = NCW compute warps + 1 auxiliary warp; a CTA walks one strip at a time,
+// driven by the segment descriptors of trws_sched.h (no grid arithmetic here).
+// A node is processed in one STEP (two when it sends on more than NCW terms):
+//
+//   phase A (before the step's barrier), per compute warp: sum what this warp
+//     fetched for the node -- the old message of its own send term (registers,
+//     loaded one step ahead), rows that arrived in its landing buffers through
+//     cp.async (the unary row, dependency messages published by other strips,
+//     position rows for the rounding) -- into partial rows in shared memory;
+//   barrier (compute warps only);
+//   phase B: every compute warp issues the loads of the NEXT step, forms Di
+//     (minimize.cpp:38-46 / 69-77) from the partial rows plus the two messages
+//     the CTA sent to this node in the previous step (carry rows in shared
+//     memory), rounds the node when the pass carries the primal sweep
+//     (minimize.cpp:240-260), runs the min-plus update of its own term and
+//     stores it.
+//   The auxiliary warp watches the compute warps' completion counters,
+//   publishes the strip's progress watermark (gpu-scope fence + store, far too
+//   slow for the dependent chain) and pulls the operands of the nodes ahead
+//   into L2.
+//
+// Shared rows are double buffered by node parity, so one barrier per step is
+// enough.
+
+constexpr int NCW = SCHED_NCW;
+constexpr int CTA_THREADS = (NCW + 1) * 32;
+constexpr int SLOTS = SCHED_SLOTS; // landing rows per compute warp
+constexpr int ROWS_PER_PAR = 17;   // RM[4] RX[4] RB[4] DR CM[2] CC[2]
+constexpr int PF_DIST = 6;
+
+enum { R_RM = 0, R_RX = 4, R_RB = 8, R_DR = 12, R_CM = 13, R_CC = 15 };
+
+template <typename REAL, int K> __host__ __device__ constexpr size_t sweep_smem_bytes()
+{
+    return (size_t)(2 * ROWS_PER_PAR + NCW * SLOTS) * 32 * K * sizeof(REAL) +
+           (size_t)NCW * scratch_pairs<K>() * sizeof(Pair<REAL>);
+}
+
+template <typename REAL, int K> struct OwnTerm {
+    REAL m[K], s[K], x[K];
+    uint8_t rk[K], cn[K];
+    REAL alpha;
+    long long term;
+    int flags;       // OWN_*
+};
+
+template <typename REAL, int K, int KERN, int PASS>
+__global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_ticket;
+    __shared__ int s_wdone[NCW]; // nodes of the current strip each compute warp has completed
+    __shared__ __align__(16) SegWarp s_desc[NCW][2];
+    constexpr int LP = 32 * K;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    Pair<REAL> *P = reinterpret_cast<Pair<REAL> *>(smem_raw) + (size_t)warp * scratch_pairs<K>();
+    const bool is_aux = (warp == NCW);
+    REAL *rows = reinterpret_cast<REAL *>(smem_raw);
+    REAL *landing = rows + (size_t)2 * ROWS_PER_PAR * LP + (size_t)(is_aux ? 0 : warp) * SLOTS * LP;
+    Pair<REAL> *P = reinterpret_cast<Pair<REAL> *>(rows + (size_t)(2 * ROWS_PER_PAR + NCW * SLOTS) * LP) +
+                    (size_t)(is_aux ? 0 : warp) * scratch_pairs<K>();
     const REAL BIG = Lim<REAL>::big();
-    constexpr int LP = 32 * K;
-    if (lane == 0) {
+    if (!is_aux && lane == 0) {
         Pair<REAL> t;
         t.a = BIG;
         t.b = REAL(0);
         P[0] = t;
         P[phys<K>(LP)] = t;
     }
-    __syncwarp();
-
     const bool do_send = (PASS == PASS_BWD) || (p.mode & MODE_SEND);
     const bool do_round = (PASS == PASS_FWD) && (p.mode & MODE_ROUND);
+    const SegWarp *const segs = p.segs;
     double acc_energy = 0.0, acc_lb = 0.0;
-    if (warp >= p.active_warps) return;
+
+    auto row_ptr = [&](int par, int r) -> REAL * { return rows + (size_t)(par * ROWS_PER_PAR + r) * LP; };
+    auto slot_active = [&](int kind) -> bool {
+        const int k = kind & 255;
+        return k == S_D || k == S_STAT || (k == S_DYN && do_send) || (k == S_RND && do_round);
+    };
 
     for (;;) {
-        int ts = 0;
-        if (lane == 0) ts = atomicAdd(p.ticket, 1);
-        ts = __shfl_sync(0xffffffffu, ts, 0);
+        if (threadIdx.x == 0) s_ticket = atomicAdd(p.ticket, 1);
+        __syncthreads(); // the auxiliary warp has published the previous strip completely
+        const int ts = s_ticket;
+        if (threadIdx.x < NCW) s_wdone[threadIdx.x] = 0;
+        __syncthreads();
         if (ts >= p.S) break;
         // the backward sweep runs the forward schedule in reverse
         const int fs = (PASS == PASS_BWD) ? p.S - 1 - ts : ts;
-        const int sb = __ldg(p.strip_ptr + fs), se = __ldg(p.strip_ptr + fs + 1);
-        const int step = (PASS == PASS_BWD) ? -1 : 1;
-        int idx = (PASS == PASS_BWD) ? se - 1 : sb;
-        long long u = (se > sb) ? __ldg(p.nodes + idx) : -1;
-        long long u_prev = -1;
-        bool carry_valid = false;
-        REAL carry0[K], carry1[K]; // messages this warp just sent to u on the pair's terms 0 / 1
+        const int sg0 = __ldg(p.seg_ptr + fs), sg1 = __ldg(p.seg_ptr + fs + 1);
+        const int n_nodes = __ldg(p.strip_ptr + fs + 1) - __ldg(p.strip_ptr + fs);
+        if (sg1 <= sg0) continue;
+
+        if (is_aux) {
+            // ------------------------------------------------------------ auxiliary warp
+            int published = 0;
+            int pf_seg = sg0, pf_i = 0, pf_node = 0;     // next node to prefetch: segment, index in it, index in strip
+            int pf_n = __ldg(&segs[(size_t)pf_seg * NCW].n);
+            while (published < n_nodes) {
+                int c = (lane < NCW) ? ld_acquire_cta(s_wdone + lane) : 0x7fffffff;
 #pragma unroll
-        for (int k = 0; k < K; k++) carry0[k] = carry1[k] = REAL(0);
-
-        for (int n = se - sb; n > 0; n--, idx += step) {
-            const long long u_next = (n > 1) ? (long long)__ldg(p.nodes + idx + step) : -1;
-            if (u_next >= 0) prefetch_node<REAL, K, PASS>(p, u_next, lane);
-            const int r = (int)(u % p.H), c = (int)(u / p.H);
-            const unsigned info = __ldg(p.info + u);
-            const unsigned valid_mask = info & 15u, lower_mask = info >> 4;
-            // gamma = 1/max(nF, nB), two terms per neighbour (treeProbabilities.cpp:28-45)
-            const int nB = 2 * __popc(lower_mask), nF = 2 * __popc(valid_mask & ~lower_mask);
-            const REAL gamma = REAL(1) / REAL(max(1, max(nF, nB)));
-            const unsigned dep_mask = (PASS == PASS_FWD) ? lower_mask : (valid_mask & ~lower_mask);
-            const unsigned send_mask = (PASS == PASS_FWD) ? (valid_mask & ~lower_mask) : lower_mask;
-            const int d_prev = carry_valid ? direction_to(u, u_prev, p.H) : -1;
-            const int d_next = (u_next >= 0) ? direction_to(u, u_next, p.H) : -1;
-
-            // wait for the neighbours this node depends on that other strips own
-            if (lane < 4 && ((dep_mask >> lane) & 1u) && lane != d_prev) {
-                const Incidence I = incidence(lane, r, c, u, p.H, p.W, p.nV, p.nH);
-                while (ld_acquire(p.done + I.nb) < p.epoch) __nanosleep(20);
-            }
-            __syncwarp();
-
-            REAL Di[K];
-            VecIO<REAL, K>::load_ro(Di, p.D + u * LP + lane * K);
-
-            if (do_round) {
-                // minimize.cpp:240-260: DiB = D + sum_{lower nb} V(x_nb, .), Dr = DiB + forward messages
-                REAL DiB[K], Dr[K];
-#pragma unroll
-                for (int k = 0; k < K; k++) DiB[k] = Di[k];
-#pragma unroll 1
-                for (int e = 0; e < 8; e++) {
-                    const int d = e >> 1, j = e & 1;
-                    if (!((lower_mask >> d) & 1u)) continue;
-                    const Incidence I = incidence(d, r, c, u, p.H, p.W, p.nV, p.nH);
-                    const long long tm = I.term[j];
-                    const REAL *mine = (I.tail[j] ? p.posqp : p.posq) + tm * LP;
-                    const REAL *theirs = (I.tail[j] ? p.posq : p.posqp) + tm * LP;
-                    const int xs = __ldcg(p.sol + I.nb);
-                    const REAL pos_nb = theirs[xs];
-                    const REAL al = p.alpha[tm];
-                    REAL mp[K];
-                    VecIO<REAL, K>::load_ro(mp, mine + lane * K);
-#pragma unroll
-                    for (int k = 0; k < K; k++) DiB[k] += al * smooth<REAL, KERN>(mp[k] - pos_nb, p.lambda);
+                for (int o = 2; o > 0; o >>= 1) c = min(c, __shfl_xor_sync(0xffffffffu, c, o));
+                c = __shfl_sync(0xffffffffu, c, 0);
+                if (c > published) {
+                    if (lane == 0) publish_flag(p.progress + fs, c);
+                    published = c;
                 }
-#pragma unroll
-                for (int k = 0; k < K; k++) Dr[k] = DiB[k];
-#pragma unroll 1
-                for (int e = 0; e < 8; e++) {
-                    const int d = e >> 1, j = e & 1;
-                    if (!(((valid_mask & ~lower_mask) >> d) & 1u)) continue;
-                    const Incidence I = incidence(d, r, c, u, p.H, p.W, p.nV, p.nH);
-                    REAL mm[K];
-                    VecIO<REAL, K>::load_cg(mm, p.msg + I.term[j] * LP + lane * K);
-#pragma unroll
-                    for (int k = 0; k < K; k++) Dr[k] += mm[k];
+                const int pf_end = min(n_nodes, c + 1 + PF_DIST);
+                if (pf_node >= pf_end) {
+                    if (published < n_nodes) __nanosleep(40);
+                    continue;
                 }
-                // Vector::ComputeMin: first minimum in label order (typeStereoLinear.h:238-252)
-                REAL best = BIG;
-                int bi = 0x7fffffff;
-                REAL bDiB = REAL(0);
-#pragma unroll
-                for (int k = 0; k < K; k++) {
-                    const int lbl = lane * K + k;
-                    if (lbl < p.L && Dr[k] < best) {
-                        best = Dr[k];
-                        bi = lbl;
-                        bDiB = DiB[k];
+                for (; pf_node < pf_end; pf_node++) {
+                    if (pf_node > c) {
+                        // rows of node (pf_seg, pf_i): lanes 0..3 take the four warps' own terms,
+                        // lanes 4..19 the sixteen slots
+                        constexpr int LR = (LP * (int)sizeof(REAL) + 127) / 128;
+                        constexpr int LB = (LP + 127) / 128;
+                        const SegWarp *g = segs + (size_t)pf_seg * NCW;
+                        if (lane < NCW) {
+                            for (int h = 0; h < 2; h++) {
+                                const SegOwn o = g[lane].own[h];
+                                if (!(o.flags & OWN_HAS)) continue;
+                                const long long row = (o.term0 + (long long)pf_i * o.tstride) * LP;
+                                const bool tail = (o.flags & OWN_TAIL) != 0;
+                                for (int t = 0; t < LR; t++) {
+                                    prefetch_l2(reinterpret_cast<const char *>(p.msg + row) + t * 128);
+                                    prefetch_l2(reinterpret_cast<const char *>(p.posq + row) + t * 128);
+                                    prefetch_l2(reinterpret_cast<const char *>(p.posqp + row) + t * 128);
+                                }
+                                for (int t = 0; t < LB; t++) {
+                                    prefetch_l2(reinterpret_cast<const char *>((tail ? p.rank_qp : p.rank_q) + row) + t * 128);
+                                    prefetch_l2(reinterpret_cast<const char *>((tail ? p.cnt_q : p.cnt_qp) + row) + t * 128);
+                                }
+                            }
+                        } else if (lane < NCW + NCW * SLOTS) {
+                            const SegSlot sl = g[(lane - NCW) >> 2].slot[(lane - NCW) & 3];
+                            const int kind = sl.kind & 255;
+                            const long long row = (sl.term0 + (long long)pf_i * sl.tstride) * LP;
+                            const REAL *base = nullptr;
+                            if (kind == S_D) base = p.D + row;
+                            else if (kind == S_STAT) base = p.msg + row;
+                            else if (kind == S_RND && do_round) base = ((sl.kind & 256) ? p.posqp : p.posq) + row;
+                            if (base)
+                                for (int t = 0; t < LR; t++) prefetch_l2(reinterpret_cast<const char *>(base) + t * 128);
+                        }
                     }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const REAL ob = __shfl_xor_sync(0xffffffffu, best, o);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                    const REAL od = __shfl_xor_sync(0xffffffffu, bDiB, o);
-                    if (ob < best || (ob == best && oi < bi)) {
-                        best = ob;
-                        bi = oi;
-                        bDiB = od;
+                    if (++pf_i >= pf_n) {
+                        pf_i = 0;
+                        pf_seg++;
+                        pf_n = (pf_seg < sg1) ? __ldg(&segs[(size_t)pf_seg * NCW].n) : 0x7fffffff;
                     }
-                }
-                if (lane == 0) {
-                    p.sol[u] = bi;
-                    acc_energy += (double)bDiB;
                 }
             }
+            continue;
+        }
 
-            if (do_send) {
-                // Di = D + all incident messages (minimize.cpp:38-46 / 69-77); the pair just
-                // sent by this warp from the previous node of the strip comes from registers
+        // ---------------------------------------------------------------- compute warps
+        const int w = warp;
+        // optional phase timers (warp 0 only): 0 flag spin, 1 rest of phase A, 2 barrier, 3 prepare,
+        // 4 B1 (Di / rounding), 5 resolve, 6 update + stores, 7 steps
+        long long tprof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const bool prof_on = SB_TRWS_INSTRUMENT && (p.prof != nullptr) && w == 0;
+        long long tclk = prof_on ? clock64() : 0;
+        auto tick = [&](int which) {
+            if (prof_on) {
+                const long long now = clock64();
+                tprof[which] += now - tclk;
+                tclk = now;
+            }
+        };
+
+        // descriptor of segment sg -> s_desc[w][buf] (12 lanes x 16 bytes, own warp only)
+        auto fetch_desc = [&](int sg, int buf) {
+            if (lane < (int)sizeof(SegWarp) / 16)
+                cp_async16(reinterpret_cast<char *>(&s_desc[w][buf]) + lane * 16,
+                           reinterpret_cast<const char *>(segs + (size_t)sg * NCW + w) + lane * 16);
+        };
+
+        OwnTerm<REAL, K> own;       // operands of this warp's term in the current step
+        own.flags = 0;
+        // per-slot bookkeeping of the node whose rows are in flight / in the landing buffers
+        int slot_kind[SLOTS], slot_flag[SLOTS], slot_need[SLOTS], slot_fv[SLOTS];
+        REAL slot_alpha[SLOTS], slot_sel[SLOTS];
+        long long slot_term[SLOTS];
 #pragma unroll
-                for (int e = 0; e < 8; e++) {
-                    const int d = e >> 1, j = e & 1;
-                    if (!((valid_mask >> d) & 1u)) continue;
-                    if (d == d_prev) {
+        for (int q = 0; q < SLOTS; q++) { slot_kind[q] = S_NONE; slot_flag[q] = -1; slot_need[q] = 0; slot_fv[q] = 0; slot_alpha[q] = REAL(0); slot_sel[q] = REAL(0); slot_term[q] = 0; }
+        REAL Di[K];
 #pragma unroll
-                        for (int k = 0; k < K; k++) Di[k] += (j ? carry1[k] : carry0[k]);
-                    } else {
-                        const Incidence I = incidence(d, r, c, u, p.H, p.W, p.nV, p.nH);
-                        REAL mm[K];
-                        VecIO<REAL, K>::load_cg(mm, p.msg + I.term[j] * LP + lane * K);
+        for (int k = 0; k < K; k++) Di[k] = REAL(0);
+        int xs = 0;   // rounded label of the current node
+
+        // prepare(): first part of issuing the loads of a step (node i of the segment
+        // described by g, half `half`): own-term operands into registers, static rows into the
+        // landing buffers, and -- without branching on them yet -- the progress counters that
+        // guard the dependency rows.
+        auto prepare = [&](const SegWarp *g, int i, int half, OwnTerm<REAL, K> &o) {
+            const SegOwn so = g->own[half];
+            o.flags = so.flags;
+            if (so.flags & OWN_HAS) {
+                o.term = so.term0 + (long long)i * so.tstride;
+                const long long off = o.term * LP + lane * K;
+                const bool tail = (so.flags & OWN_TAIL) != 0;
+                if (SB_TRWS_INSTRUMENT && (p.debug & 4)) {
 #pragma unroll
-                        for (int k = 0; k < K; k++) Di[k] += mm[k];
-                    }
-                }
-                if (PASS == PASS_BWD) {
-                    // ComputeAndSubtractMin + lower bound (minimize.cpp:79-81)
-                    REAL vmin = BIG;
-#pragma unroll
-                    for (int k = 0; k < K; k++)
-                        if (lane * K + k < p.L) vmin = min(vmin, Di[k]);
-                    vmin = warp_min(vmin);
-#pragma unroll
-                    for (int k = 0; k < K; k++) Di[k] -= vmin;
-                    acc_lb += (double)vmin;
-                }
-                carry_valid = false;
-#pragma unroll 1
-                for (int e = 0; e < 8; e++) {
-                    const int d = e >> 1, j = e & 1;
-                    if (!((send_mask >> d) & 1u)) continue;
-                    const Incidence I = incidence(d, r, c, u, p.H, p.W, p.nV, p.nH);
-                    const long long tm = I.term[j];
-                    const long long off = tm * LP + lane * K;
+                    for (int k = 0; k < K; k++) { o.m[k] = REAL(0); o.s[k] = REAL(k); o.x[k] = REAL(k); o.rk[k] = (uint8_t)(lane * K + k); o.cn[k] = (uint8_t)(lane * K + k); }
+                    o.alpha = REAL(1);
+                } else {
                     // sender's positions: qprim if I am the tail of the term, else q
                     // (typeStereoLinear.h:343-357 with Swap(), MRFEnergy.cpp:200-203)
-                    REAL m[K], s[K], x[K];
-                    uint8_t rk[K], cn[K];
-                    VecIO<REAL, K>::load_cg(m, p.msg + off);
-                    VecIO<REAL, K>::load_ro(s, (I.tail[j] ? p.posqp : p.posq) + off);
-                    VecIO<REAL, K>::load_ro(x, (I.tail[j] ? p.posq : p.posqp) + off);
-                    ByteIO<K>::load(rk, (I.tail[j] ? p.rank_qp : p.rank_q) + off);
-                    ByteIO<K>::load(cn, (I.tail[j] ? p.cnt_q : p.cnt_qp) + off);
-                    const REAL al = p.alpha[tm];
-                    REAL vmin;
-                    if constexpr (KERN == 1)
-                        vmin = update_linear<REAL, K>(gamma, al, p.lambda, p.L, lane, Di, m, s, rk, x, cn, P);
-                    else
-                        vmin = update_quadratic<REAL, K>(gamma, al, p.lambda, p.L, lane, Di, m, s, rk, x, cn, P);
-                    VecIO<REAL, K>::store(p.msg + off, m);
-                    if (PASS == PASS_BWD) acc_lb += (double)vmin;
-                    if (d == d_next) {
-                        carry_valid = true;
+                    VecIO<REAL, K>::load_cg(o.m, p.msg + off);
+                    VecIO<REAL, K>::load_ro(o.s, (tail ? p.posqp : p.posq) + off);
+                    VecIO<REAL, K>::load_ro(o.x, (tail ? p.posq : p.posqp) + off);
+                    ByteIO<K>::load(o.rk, (tail ? p.rank_qp : p.rank_q) + off);
+                    ByteIO<K>::load(o.cn, (tail ? p.cnt_q : p.cnt_qp) + off);
+                    o.alpha = __ldg(p.alpha + o.term);
+                }
+            }
+            if (half == 0) {
 #pragma unroll
-                        for (int k = 0; k < K; k++) {
-                            if (j) carry1[k] = m[k];
-                            else carry0[k] = m[k];
+                for (int q = 0; q < SLOTS; q++) {
+                    const SegSlot sl = g->slot[q];
+                    const int kind = slot_active(sl.kind) ? sl.kind : (int)S_NONE;
+                    slot_kind[q] = kind;
+                    slot_flag[q] = -1;
+                    if (kind == S_NONE) continue;
+                    const long long term = sl.term0 + (long long)i * sl.tstride;
+                    slot_term[q] = term;
+                    REAL *dst = landing + (size_t)q * LP;
+                    const int k = kind & 255;
+                    if (k == S_D) {
+                        row_async<REAL, K>(dst, p.D + term * LP, lane);
+                    } else if (k == S_STAT) {
+                        row_async<REAL, K>(dst, p.msg + term * LP, lane);
+                    } else {
+                        slot_flag[q] = sl.strip;
+                        slot_need[q] = sl.need0 + i * sl.dneed;
+                        slot_fv[q] = ld_flag(p.progress + sl.strip);
+                        if (k == S_RND) { // my positions on the term now, the neighbour's selected position later
+                            row_async<REAL, K>(dst, ((kind & 256) ? p.posqp : p.posq) + term * LP, lane);
+                            slot_alpha[q] = __ldg(p.alpha + term);
                         }
                     }
                 }
-            } else {
-                carry_valid = false;
             }
+        };
+        // resolve(): second part -- dependency rows whose counter was already high enough are
+        // fetched now; the others are left to phase A of their step.
+        auto resolve = [&]() {
+#pragma unroll
+            for (int q = 0; q < SLOTS; q++) {
+                if (slot_flag[q] >= 0 && slot_fv[q] >= slot_need[q]) {
+                    if ((slot_kind[q] & 255) == S_DYN) row_async<REAL, K>(landing + (size_t)q * LP, p.msg + slot_term[q] * LP, lane);
+                    else slot_sel[q] = __ldcg(p.selpos + slot_term[q]);
+                    slot_flag[q] = -1;
+                }
+            }
+        };
 
-            // publish: this warp's stores happen-before the flag (syncwarp + release)
+        // first descriptor (blocking), the one after it in the background
+        int sg = sg0, buf = 0;
+        fetch_desc(sg, 0);
+        cp_async_wait_all();
+        __syncwarp();
+        if (sg + 1 < sg1) fetch_desc(sg + 1, 1);
+        const SegWarp *g = &s_desc[w][0];
+        int seg_n = g->n, seg_i = 0;
+        prepare(g, 0, 0, own);
+        resolve();
+
+        for (int node = 0; node < n_nodes; node++) {
+            const int u = g->u0 + seg_i * g->du;
+            const int par = node & 1;
+            const REAL gamma = REAL(1) / REAL(g->gamma_den);
+            const int halves = g->halves;
+            const bool use_carry = g->use_carry != 0;
+            // where the next node lives
+            const bool seg_last = (seg_i + 1 >= seg_n);
+            const bool has_next = (node + 1 < n_nodes);
+            const SegWarp *gn = seg_last ? &s_desc[w][buf ^ 1] : g;
+            const int in = seg_last ? 0 : seg_i + 1;
+
+            for (int half = 0; half < halves; half++) {
+                tick(6);
+                if (half == 0) {
+                    // ---------------- phase A: resolve pending dependencies, sum into partial rows
+#pragma unroll
+                    for (int q = 0; q < SLOTS; q++) {
+                        if (slot_flag[q] >= 0) {
+                            while (ld_flag(p.progress + slot_flag[q]) < slot_need[q]) __nanosleep(32);
+                            if ((slot_kind[q] & 255) == S_DYN) row_async<REAL, K>(landing + (size_t)q * LP, p.msg + slot_term[q] * LP, lane);
+                            else slot_sel[q] = __ldcg(p.selpos + slot_term[q]);
+                            slot_flag[q] = -1;
+                        }
+                    }
+                    tick(0);
+                    cp_async_wait_all();
+                    __syncwarp();
+                    REAL rm[K], rx[K], rb[K];
+#pragma unroll
+                    for (int k = 0; k < K; k++) {
+                        rm[k] = (own.flags & OWN_HAS) ? own.m[k] : REAL(0);
+                        rx[k] = REAL(0);
+                        rb[k] = REAL(0);
+                    }
+#pragma unroll
+                    for (int q = 0; q < SLOTS; q++) {
+                        const int k0 = slot_kind[q] & 255;
+                        if (k0 == S_NONE) continue;
+                        REAL v[K];
+                        row_lds<REAL, K>(v, landing + (size_t)q * LP, lane);
+                        if (k0 == S_D) {
+                            row_sts<REAL, K>(row_ptr(par, R_DR), v, lane);
+                        } else if (k0 == S_STAT) {
+#pragma unroll
+                            for (int k = 0; k < K; k++) rm[k] += v[k];
+                        } else if (k0 == S_DYN) {
+#pragma unroll
+                            for (int k = 0; k < K; k++) rx[k] += v[k];
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < K; k++) rb[k] += slot_alpha[q] * smooth<REAL, KERN>(v[k] - slot_sel[q], p.lambda);
+                        }
+                    }
+                    row_sts<REAL, K>(row_ptr(par, R_RM + w), rm, lane);
+                    if (do_send) row_sts<REAL, K>(row_ptr(par, R_RX + w), rx, lane);
+                    if (do_round) row_sts<REAL, K>(row_ptr(par, R_RB + w), rb, lane);
+                }
+                tick(1);
+                step_barrier();
+                tick(2);
+                // ---------------- issue the loads of the next step (part 1)
+                OwnTerm<REAL, K> nxt;
+                nxt.flags = 0;
+                const bool last_half = (half + 1 == halves);
+                if (!last_half) prepare(g, seg_i, half + 1, nxt);
+                else if (has_next) prepare(gn, in, 0, nxt);
+                tick(3);
+                if (half == 0) {
+                    // ---------------- phase B1: Di (and the rounding) from the partial rows
+                    REAL dsum[K], msum[K];
+                    row_lds<REAL, K>(dsum, row_ptr(par, R_DR), lane);
+#pragma unroll
+                    for (int k = 0; k < K; k++) msum[k] = REAL(0);
+#pragma unroll
+                    for (int ww = 0; ww < NCW; ww++) {
+                        REAL v[K];
+                        row_lds<REAL, K>(v, row_ptr(par, R_RM + ww), lane);
+#pragma unroll
+                        for (int k = 0; k < K; k++) msum[k] += v[k];
+                    }
+                    if (do_round) {
+                        // minimize.cpp:240-260: DiB = D + sum_{lower nb} V(x_nb, .), Dr = DiB + forward messages
+                        REAL dib[K];
+#pragma unroll
+                        for (int k = 0; k < K; k++) dib[k] = dsum[k];
+#pragma unroll
+                        for (int ww = 0; ww < NCW; ww++) {
+                            REAL v[K];
+                            row_lds<REAL, K>(v, row_ptr(par, R_RB + ww), lane);
+#pragma unroll
+                            for (int k = 0; k < K; k++) dib[k] += v[k];
+                        }
+                        if (use_carry) {
+#pragma unroll
+                            for (int jj = 0; jj < 2; jj++) {
+                                REAL v[K];
+                                row_lds<REAL, K>(v, row_ptr(par, R_CC + jj), lane);
+#pragma unroll
+                                for (int k = 0; k < K; k++) dib[k] += v[k];
+                            }
+                        }
+                        // Vector::ComputeMin: first minimum in label order (typeStereoLinear.h:238-252)
+                        REAL best = BIG;
+                        int bi = 0x7fffffff;
+                        REAL bdib = REAL(0);
+#pragma unroll
+                        for (int k = 0; k < K; k++) {
+                            const int lbl = lane * K + k;
+                            const REAL dr = dib[k] + msum[k];
+                            if (lbl < p.L && dr < best) { best = dr; bi = lbl; bdib = dib[k]; }
+                        }
+                        // first minimum over the warp: value, then the smallest label attaining it
+                        const REAL wbest = warp_min(best);
+                        bi = warp_min_s32(best == wbest ? bi : 0x7fffffff);
+                        {
+                            REAL dv = dib[0];
+#pragma unroll
+                            for (int k = 1; k < K; k++)
+                                if (k == bi % K) dv = dib[k];
+                            bdib = __shfl_sync(0xffffffffu, dv, bi / K);
+                        }
+                        xs = bi;
+                        if (w == 0 && lane == 0) {
+                            p.sol[u] = bi;
+                            acc_energy += (double)bdib;
+                        }
+                    }
+                    if (do_send) {
+                        // Di = D + all incident messages (minimize.cpp:38-46 / 69-77)
+#pragma unroll
+                        for (int k = 0; k < K; k++) Di[k] = dsum[k] + msum[k];
+#pragma unroll
+                        for (int ww = 0; ww < NCW; ww++) {
+                            REAL v[K];
+                            row_lds<REAL, K>(v, row_ptr(par, R_RX + ww), lane);
+#pragma unroll
+                            for (int k = 0; k < K; k++) Di[k] += v[k];
+                        }
+                        if (use_carry) {
+#pragma unroll
+                            for (int jj = 0; jj < 2; jj++) {
+                                REAL v[K];
+                                row_lds<REAL, K>(v, row_ptr(par, R_CM + jj), lane);
+#pragma unroll
+                                for (int k = 0; k < K; k++) Di[k] += v[k];
+                            }
+                        }
+                        if (PASS == PASS_BWD) {
+                            // ComputeAndSubtractMin + lower bound (minimize.cpp:79-81)
+                            REAL vmin = BIG;
+#pragma unroll
+                            for (int k = 0; k < K; k++)
+                                if (lane * K + k < p.L) vmin = min(vmin, Di[k]);
+                            vmin = warp_min(vmin);
+#pragma unroll
+                            for (int k = 0; k < K; k++) Di[k] -= vmin;
+                            if (w == 0) acc_lb += (double)vmin;
+                        }
+                    }
+                }
+
+                // ---------------- issue the loads of the next step (part 2: flag-dependent rows)
+                tick(4);
+                if (last_half && has_next) resolve();
+                tick(5);
+
+                // ---------------- phase B5: min-plus update of this warp's term
+                if (own.flags & OWN_HAS) {
+                    const bool to_next = (own.flags & OWN_TO_NEXT) != 0;
+                    const int oj = (own.flags & OWN_J) ? 1 : 0;
+                    if (do_round) {
+                        // position of the rounded label on this term, for the receiver's rounding
+                        REAL sv = own.s[0];
+#pragma unroll
+                        for (int k = 1; k < K; k++)
+                            if (k == xs % K) sv = own.s[k];
+                        sv = __shfl_sync(0xffffffffu, sv, xs / K);
+                        if (lane == 0) __stcg(p.selpos + own.term, sv);
+                        if (to_next) {
+                            REAL cc[K];
+#pragma unroll
+                            for (int k = 0; k < K; k++) cc[k] = own.alpha * smooth<REAL, KERN>(own.x[k] - sv, p.lambda);
+                            row_sts<REAL, K>(row_ptr(par ^ 1, R_CC + oj), cc, lane);
+                        }
+                    }
+                    if (do_send) {
+                        REAL vmin = REAL(0);
+                        if (SB_TRWS_INSTRUMENT && (p.debug & 2)) {
+#pragma unroll
+                            for (int k = 0; k < K; k++) own.m[k] = Di[k] * gamma - own.m[k];
+                        } else if constexpr (KERN == 1)
+                            vmin = update_linear<REAL, K>(gamma, own.alpha, p.lambda, p.L, lane, Di, own.m, own.s, own.rk, own.x, own.cn, P);
+                        else
+                            vmin = update_quadratic<REAL, K>(gamma, own.alpha, p.lambda, p.L, lane, Di, own.m, own.s, own.rk, own.x, own.cn, P);
+                        if (!(SB_TRWS_INSTRUMENT && (p.debug & 1))) VecIO<REAL, K>::store(p.msg + own.term * LP + lane * K, own.m);
+                        if (PASS == PASS_BWD) acc_lb += (double)vmin;
+                        if (to_next) row_sts<REAL, K>(row_ptr(par ^ 1, R_CM + oj), own.m, lane);
+                    }
+                }
+                own = nxt;
+            }
+            // this warp's stores for the node are issued: tell the auxiliary warp
             __syncwarp();
-            if (lane == 0) st_release(p.done + u, p.epoch);
-            u_prev = u;
-            u = u_next;
+            if (lane == 0) st_release_cta(s_wdone + w, node + 1);
+            if (prof_on) tprof[7] += 1;
+            // advance to the next node / segment
+            if (seg_last) {
+                if (has_next) {
+                    sg++;
+                    buf ^= 1;
+                    g = &s_desc[w][buf];
+                    seg_n = g->n;
+                    seg_i = 0;
+                    if (sg + 1 < sg1) fetch_desc(sg + 1, buf ^ 1);
+                }
+            } else {
+                seg_i++;
+            }
+        }
+        if (prof_on && lane == 0) {
+            tick(6);
+            const int grp = (fs == 0) ? 0 : 1; // strip 0 is the boundary ring on regular grids
+#pragma unroll
+            for (int q = 0; q < 8; q++) atomicAdd((unsigned long long *)p.prof + grp * 8 + q, (unsigned long long)tprof[q]);
         }
     }
-    if (lane == 0) {
+    if (!is_aux && lane == 0) {
         if (acc_energy != 0.0) atomicAdd(p.acc + 0, acc_energy);
         if (acc_lb != 0.0) atomicAdd(p.acc + 1, acc_lb);
     }

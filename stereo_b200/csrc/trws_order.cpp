@@ -10,6 +10,8 @@
 #include "trws_order.h"
 #include <algorithm>
 #include <numeric>
+#include <cstring>
+#include <cstdlib>
 
 namespace sb {
 
@@ -237,6 +239,202 @@ void build_schedule(int H, int W, const std::vector<int32_t> &ordering, Schedule
         for (int64_t i = 0; i <= N; i++) s.strip_ptr[i] = i;
         s.regular = false;
     }
+}
+
+
+// ---------------------------------------------------------------------------
+// Segment descriptors (trws_sched.h).
+namespace {
+
+struct NodeDesc {
+    int u, halves, gamma_den, use_carry;
+    struct Own { long long term; int flags; } own[trws::SCHED_NCW][2];
+    struct Slot { long long term; int kind; int strip; int need; } slot[trws::SCHED_NCW][trws::SCHED_SLOTS];
+};
+
+struct Inc { int nb; long long term; bool tail; };
+
+// Terms between node (r, c) and its neighbour in direction d (0 up, 1 down, 2 left,
+// 3 right); j picks the term of the pair.  Order of dispmap_super.m:284-294.
+inline Inc incidence(int d, int j, int r, int c, int u, int H, long long nV, long long nH)
+{
+    Inc I;
+    if (d == 0) { I.nb = u - 1; I.term = (long long)c * (H - 1) + (r - 1) + (j ? nV : 0); I.tail = (j == 1); }
+    else if (d == 1) { I.nb = u + 1; I.term = (long long)c * (H - 1) + r + (j ? nV : 0); I.tail = (j == 0); }
+    else if (d == 2) { I.nb = u - H; I.term = 2 * nV + (long long)(c - 1) * H + r + (j ? nH : 0); I.tail = (j == 1); }
+    else { I.nb = u + H; I.term = 2 * nV + (long long)c * H + r + (j ? nH : 0); I.tail = (j == 0); }
+    return I;
+}
+
+inline int direction_to(int u, int v, int H)
+{
+    const int d = v - u;
+    return d == -1 ? 0 : d == 1 ? 1 : d == -H ? 2 : d == H ? 3 : -1;
+}
+
+} // namespace
+
+void build_pass_plan(int H, int W, const std::vector<uint8_t> &info, const Schedule &s, int pass, PassPlan &plan)
+{
+    using namespace trws;
+    const int64_t N = (int64_t)H * W;
+    const long long nV = (long long)(H - 1) * W, nH = (long long)H * (W - 1);
+    const int S = (int)s.strip_ptr.size() - 1;
+    // where every node sits: strip and index within the strip (forward order)
+    std::vector<int32_t> strip_of((size_t)N), idx_of((size_t)N);
+    for (int fs = 0; fs < S; fs++)
+        for (int64_t k = s.strip_ptr[fs]; k < s.strip_ptr[fs + 1]; k++) {
+            strip_of[s.nodes[k]] = fs;
+            idx_of[s.nodes[k]] = (int32_t)(k - s.strip_ptr[fs]);
+        }
+    auto need_of = [&](int v) {
+        const int fs = strip_of[v];
+        const int len = (int)(s.strip_ptr[fs + 1] - s.strip_ptr[fs]);
+        return pass == 0 ? idx_of[v] + 1 : len - idx_of[v];
+    };
+    auto describe = [&](int u, int u_prev, int u_next, NodeDesc &nd) {
+        std::memset(&nd, 0, sizeof(nd));
+        for (int w = 0; w < SCHED_NCW; w++)
+            for (int q = 0; q < SCHED_SLOTS; q++) nd.slot[w][q].strip = -1;
+        const int r = u % H, c = u / H;
+        const unsigned valid = info[u] & 15u, lower = info[u] >> 4;
+        const unsigned send_mask = pass == 0 ? (valid & ~lower) : lower;
+        const unsigned dep_mask = pass == 0 ? lower : (valid & ~lower);
+        int d_prev = u_prev >= 0 ? direction_to(u, u_prev, H) : -1;
+        if (d_prev >= 0 && !((dep_mask >> d_prev) & 1u)) d_prev = -1;
+        int d_next = u_next >= 0 ? direction_to(u, u_next, H) : -1;
+        if (d_next >= 0 && !((send_mask >> d_next) & 1u)) d_next = -1;
+        nd.u = u;
+        const int nB = 2 * __builtin_popcount(lower), nF = 2 * __builtin_popcount(valid & ~lower);
+        nd.gamma_den = std::max(1, std::max(nF, nB));
+        nd.use_carry = d_prev >= 0;
+        const int ns = 2 * __builtin_popcount(send_mask);
+        nd.halves = ns > SCHED_NCW ? 2 : 1;
+        int n = 0, si = 0;
+        auto add_item = [&](int kind, long long term, bool tail, int strip, int need) {
+            const int w = n & 3, q = n >> 2;
+            SB_REQUIRE(q < SCHED_SLOTS, SB_EUNSUP, "trws schedule: too many rows per warp");
+            nd.slot[w][q].term = term;
+            nd.slot[w][q].kind = kind | (tail ? 256 : 0);
+            nd.slot[w][q].strip = strip;
+            nd.slot[w][q].need = need;
+            n++;
+        };
+        add_item(S_D, u, false, -1, 0);
+        for (int e = 0; e < 8; e++) {
+            const int d = e >> 1, j = e & 1;
+            if (!((valid >> d) & 1u)) continue;
+            const Inc I = incidence(d, j, r, c, u, H, nV, nH);
+            if ((send_mask >> d) & 1u) {
+                NodeDesc::Own &o = nd.own[si & 3][si >> 2];
+                o.term = I.term;
+                o.flags = OWN_HAS | (I.tail ? OWN_TAIL : 0) | (d == d_next ? OWN_TO_NEXT : 0) | (j ? OWN_J : 0);
+                if (si >= SCHED_NCW) add_item(S_STAT, I.term, false, -1, 0);
+                si++;
+            } else if (d != d_prev) {
+                add_item(S_DYN, I.term, false, strip_of[I.nb], need_of(I.nb));
+            }
+        }
+        if (pass == 0)
+            for (int e = 0; e < 8; e++) {
+                const int d = e >> 1, j = e & 1;
+                if (((lower >> d) & 1u) && d != d_prev) {
+                    const Inc I = incidence(d, j, r, c, u, H, nV, nH);
+                    add_item(S_RND, I.term, I.tail, strip_of[I.nb], need_of(I.nb));
+                }
+            }
+    };
+    auto same_structure = [&](const NodeDesc &a, const NodeDesc &b) {
+        if (a.halves != b.halves || a.gamma_den != b.gamma_den || a.use_carry != b.use_carry) return false;
+        for (int w = 0; w < SCHED_NCW; w++) {
+            for (int h = 0; h < 2; h++)
+                if (a.own[w][h].flags != b.own[w][h].flags) return false;
+            for (int q = 0; q < SCHED_SLOTS; q++)
+                if (a.slot[w][q].kind != b.slot[w][q].kind || a.slot[w][q].strip != b.slot[w][q].strip) return false;
+        }
+        return true;
+    };
+
+    plan.segs.clear();
+    plan.seg_ptr.assign((size_t)S + 1, 0);
+    NodeDesc first, nd;
+    long long d_u = 0, d_own[SCHED_NCW][2], d_term[SCHED_NCW][SCHED_SLOTS], d_need[SCHED_NCW][SCHED_SLOTS];
+    int seg_n = 0;
+    auto flush = [&]() {
+        if (!seg_n) return;
+        for (int w = 0; w < SCHED_NCW; w++) {
+            SegWarp g;
+            std::memset(&g, 0, sizeof(g));
+            g.u0 = first.u; g.du = (int)d_u; g.n = seg_n;
+            g.halves = first.halves; g.gamma_den = first.gamma_den; g.use_carry = first.use_carry;
+            for (int h = 0; h < 2; h++) {
+                g.own[h].term0 = first.own[w][h].term;
+                g.own[h].tstride = (int)d_own[w][h];
+                g.own[h].flags = first.own[w][h].flags;
+            }
+            for (int q = 0; q < SCHED_SLOTS; q++) {
+                g.slot[q].term0 = first.slot[w][q].term;
+                g.slot[q].tstride = (int)d_term[w][q];
+                g.slot[q].kind = first.slot[w][q].kind;
+                g.slot[q].strip = first.slot[w][q].strip;
+                g.slot[q].need0 = first.slot[w][q].need;
+                g.slot[q].dneed = (int)d_need[w][q];
+            }
+            plan.segs.push_back(g);
+        }
+        seg_n = 0;
+    };
+    for (int fs = 0; fs < S; fs++) {
+        plan.seg_ptr[fs] = (int32_t)(plan.segs.size() / SCHED_NCW);
+        const int64_t sb = s.strip_ptr[fs], se = s.strip_ptr[fs + 1];
+        const int64_t len = se - sb;
+        auto node_at = [&](int64_t i) { return (int)s.nodes[pass == 0 ? sb + i : se - 1 - i]; };
+        for (int64_t i = 0; i < len; i++) {
+            describe(node_at(i), i > 0 ? node_at(i - 1) : -1, i + 1 < len ? node_at(i + 1) : -1, nd);
+            bool extend = false;
+            if (seg_n >= 1 && same_structure(first, nd)) {
+                extend = true;
+                if (seg_n == 1) {
+                    d_u = (long long)nd.u - first.u;
+                    for (int w = 0; w < SCHED_NCW; w++) {
+                        for (int h = 0; h < 2; h++) d_own[w][h] = nd.own[w][h].term - first.own[w][h].term;
+                        for (int q = 0; q < SCHED_SLOTS; q++) {
+                            d_term[w][q] = nd.slot[w][q].term - first.slot[w][q].term;
+                            d_need[w][q] = (long long)nd.slot[w][q].need - first.slot[w][q].need;
+                        }
+                    }
+                    // strides are stored as 32-bit ints
+                    for (int w = 0; w < SCHED_NCW && extend; w++) {
+                        for (int h = 0; h < 2; h++) if (std::llabs(d_own[w][h]) > INT32_MAX) extend = false;
+                        for (int q = 0; q < SCHED_SLOTS; q++) if (std::llabs(d_term[w][q]) > INT32_MAX) extend = false;
+                    }
+                } else {
+                    const long long k = seg_n;
+                    if ((long long)nd.u != first.u + k * d_u) extend = false;
+                    for (int w = 0; w < SCHED_NCW && extend; w++) {
+                        for (int h = 0; h < 2; h++)
+                            if (nd.own[w][h].term != first.own[w][h].term + k * d_own[w][h]) extend = false;
+                        for (int q = 0; q < SCHED_SLOTS; q++)
+                            if (nd.slot[w][q].term != first.slot[w][q].term + k * d_term[w][q] ||
+                                nd.slot[w][q].need != first.slot[w][q].need + k * d_need[w][q]) extend = false;
+                    }
+                }
+            }
+            if (extend) {
+                seg_n++;
+            } else {
+                flush();
+                first = nd;
+                d_u = 0;
+                std::memset(d_own, 0, sizeof(d_own));
+                std::memset(d_term, 0, sizeof(d_term));
+                std::memset(d_need, 0, sizeof(d_need));
+                seg_n = 1;
+            }
+        }
+        flush();
+    }
+    plan.seg_ptr[S] = (int32_t)(plan.segs.size() / SCHED_NCW);
 }
 
 } // namespace sb

@@ -1,0 +1,55 @@
+// trws_sched.h -- the data-driven sweep schedule shared by the host builder
+// (trws_order.cpp) and the sweep kernel (trws_kernels.cuh).
+//
+// A sweep visits the nodes in STRIPS (trws_order.cpp: the boundary ring, then one
+// strip per interior row).  Within a strip, runs of nodes that look alike -- same
+// incident-term structure, same dependencies, addresses advancing by constant
+// strides -- are folded into SEGMENTS, and everything a warp needs to process the
+// i-th node of a segment is `base + i * stride` of a few descriptor fields.  The
+// kernel therefore does no index arithmetic on the grid at all: which terms a node
+// sends on (MRFEnergy.cpp:188-219 orientation), which warp owns which term, which
+// rows have to be fetched and which progress counter guards them are all decided
+// here, once per problem.
+#pragma once
+#include <stdint.h>
+
+namespace sb {
+namespace trws {
+
+enum { SCHED_NCW = 4, SCHED_SLOTS = 4 };
+
+// kinds of rows a warp fetches for a node besides its own send term
+enum { S_NONE = 0, S_D = 1, S_STAT = 2, S_DYN = 3, S_RND = 4 };
+
+// own-term flags
+enum { OWN_HAS = 1, OWN_TAIL = 2, OWN_TO_NEXT = 4, OWN_J = 8 };
+
+struct SegOwn {            // the send term a warp owns in one half of a node (16 bytes)
+    long long term0;       // term of the segment's first node
+    int tstride;           // term increment per node
+    int flags;             // OWN_*
+};
+
+struct SegSlot {           // one extra row per node for this warp (32 bytes)
+    long long term0;       // term (S_D: node) of the segment's first node
+    int tstride;           // increment per node
+    int kind;              // S_*  | tail << 8 (S_RND: am I the tail of the term)
+    int strip;             // S_DYN / S_RND: progress counter that guards the row, else -1
+    int need0, dneed;      // ... and the count it must have reached: need0 + i * dneed
+    int pad;
+};
+
+struct SegWarp {           // per (segment, compute warp) record (192 bytes, 16-byte aligned)
+    int u0, du, n;         // nodes u0 + i * du, i in [0, n)
+    int halves;            // 2 when the nodes send on more than SCHED_NCW terms
+    int gamma_den;         // max(nF, nB): gamma = 1 / gamma_den (treeProbabilities.cpp:28-45)
+    int use_carry;         // the nodes receive the two messages of the previous strip node through shared memory
+    int pad[2];
+    SegOwn own[2];
+    SegSlot slot[SCHED_SLOTS];
+};
+
+static_assert(sizeof(SegWarp) == 192, "SegWarp layout");
+
+} // namespace trws
+} // namespace sb

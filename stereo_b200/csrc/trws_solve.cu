@@ -10,6 +10,7 @@
 #include <vector>
 #include <chrono>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 
 namespace sb {
@@ -29,6 +30,7 @@ struct Ctrl {
     int ticket;
     int pad;
     double acc[2];
+    // followed by int32 progress[S] (zeroed together with the rest before each launch)
 };
 
 double now_ms()
@@ -37,169 +39,263 @@ double now_ms()
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
+// Type-erased solver object behind the sb_trws_solver handle.
+struct SolverBase {
+    virtual ~SolverBase() {}
+    virtual void reset() = 0;
+    virtual void minimize(double maxiter, double max_relgap, double *energy, double *lb, double *iters,
+                          sb_trws_timing *timing) = 0;
+    virtual void labels(double *out) = 0;
+    double setup_ms = 0;
+};
+
 template <typename REAL>
-void solve_typed(int kernel, int L, int64_t N, int64_t E, int H, int W, const double *unary, const double *q,
-                 const double *qprim, const double *alphas, double tol, const sb_trws_options &opt,
-                 double *labels, double *energy_out, double *lb_out, double *iters_out, sb_trws_timing *timing)
-{
-    const int precision = sizeof(REAL) == 8 ? SB_F64 : SB_F32;
-    const KOps *ops = kops_for_labels(L);
-    SB_REQUIRE(ops, SB_EUNSUP, "sb_trws_solve: %d labels exceed SB_MAX_LABELS=%d", L, SB_MAX_LABELS);
-    const int K = ops->K, LP = 32 * K;
-    const int64_t launches0 = g_launches.load();
-    const double t_setup0 = now_ms();
-
+struct Solver : SolverBase {
+    int kernel, L, H, W, K, LP, S = 0, precision;
+    int64_t N, E;
+    bool fuse;
+    const KOps *ops;
     cudaStream_t stream = 0;
-    int dev = 0, num_sms = 0;
-    SB_CUDA(cudaGetDevice(&dev));
-    SB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-
-    // ---- host graph logic: ordering + dispatch schedule
-    std::vector<int32_t> order;
-    SB_REQUIRE(grid_ordering(H, W, order), SB_EINVAL,
-               "sb_trws_solve: %dx%d grid has no valid automatic ordering (the reference crashes on it)", H, W);
-    std::vector<uint8_t> info;
-    build_node_info(H, W, order, info);
-    Schedule sched;
-    build_schedule(H, W, order, sched);
-    const int S = (int)sched.strip_ptr.size() - 1;
-    std::vector<int32_t> strip_ptr32(sched.strip_ptr.begin(), sched.strip_ptr.end());
-
-    // ---- device state
-    DevBuf<REAL> dD((size_t)N * LP), dMsg((size_t)E * LP), dPosQ((size_t)E * LP), dPosQp((size_t)E * LP), dAlpha((size_t)E);
-    DevBuf<uint8_t> dRankQ((size_t)E * LP), dRankQp((size_t)E * LP), dCntQ((size_t)E * LP), dCntQp((size_t)E * LP);
-    DevBuf<int32_t> dNodes((size_t)N), dStripPtr((size_t)S + 1), dDone((size_t)N), dSol((size_t)N);
-    DevBuf<uint8_t> dInfo((size_t)N);
-    DevBuf<Ctrl> dCtrl(1);
-    DevBuf<int> dBad(1);
-
-    SB_CUDA(cudaMemcpyAsync(dNodes.p, sched.nodes.data(), (size_t)N * 4, cudaMemcpyHostToDevice, stream));
-    SB_CUDA(cudaMemcpyAsync(dStripPtr.p, strip_ptr32.data(), ((size_t)S + 1) * 4, cudaMemcpyHostToDevice, stream));
-    SB_CUDA(cudaMemcpyAsync(dInfo.p, info.data(), (size_t)N, cudaMemcpyHostToDevice, stream));
-    SB_CUDA(cudaMemsetAsync(dDone.p, 0, (size_t)N * 4, stream));
-    SB_CUDA(cudaMemsetAsync(dSol.p, 0, (size_t)N * 4, stream));
-    SB_CUDA(cudaMemsetAsync(dMsg.p, 0, dMsg.bytes(), stream)); // ZeroMessages, MRFEnergy.cpp:115-131
-    SB_CUDA(cudaMemsetAsync(dBad.p, 0, sizeof(int), stream));
-    {
-        // raw doubles -> padded REAL arrays + rank / merge-count tables
-        DevBuf<double> raw((size_t)N * L);
-        SB_CUDA(cudaMemcpyAsync(raw.p, unary, raw.bytes(), cudaMemcpyHostToDevice, stream));
-        const long long tot = (long long)N * LP;
-        convert_unary_kernel<REAL><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(raw.p, dD.p, L, LP, N);
-        SB_CUDA(cudaGetLastError());
-        count_launch();
-        SB_CUDA(cudaStreamSynchronize(stream));
-    }
-    if (E > 0) {
-        DevBuf<double> rawa((size_t)E);
-        SB_CUDA(cudaMemcpyAsync(rawa.p, alphas, rawa.bytes(), cudaMemcpyHostToDevice, stream));
-        convert_vec_kernel<REAL><<<(unsigned)((E + 255) / 256), 256, 0, stream>>>(rawa.p, dAlpha.p, E);
-        SB_CUDA(cudaGetLastError());
-        count_launch();
-        DevBuf<double> rq((size_t)E * L), rqp((size_t)E * L);
-        SB_CUDA(cudaMemcpyAsync(rq.p, q, rq.bytes(), cudaMemcpyHostToDevice, stream));
-        SB_CUDA(cudaMemcpyAsync(rqp.p, qprim, rqp.bytes(), cudaMemcpyHostToDevice, stream));
-        TablesLaunch tl;
-        tl.precision = precision;
-        tl.q = rq.p; tl.qp = rqp.p; tl.L = L; tl.E = E;
-        tl.posq = dPosQ.p; tl.posqp = dPosQp.p;
-        tl.rank_q = dRankQ.p; tl.rank_qp = dRankQp.p; tl.cnt_q = dCntQ.p; tl.cnt_qp = dCntQp.p;
-        tl.bad = dBad.p; tl.stream = stream;
-        ops->tables(tl);
-        int bad = 0;
-        SB_CUDA(cudaMemcpyAsync(&bad, dBad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
-        SB_CUDA(cudaStreamSynchronize(stream));
-        SB_REQUIRE(!bad, SB_EINVAL, "sb_trws_solve: q or qprim contains NaN (trws.m:9-15)");
-    }
-
+    DevBuf<REAL> dD, dMsg, dPosQ, dPosQp, dAlpha;
+    DevBuf<uint8_t> dRankQ, dRankQp, dCntQ, dCntQp;
+    DevBuf<SegWarp> dSegs[2];
+    DevBuf<int32_t> dSegPtr[2];
+    DevBuf<REAL> dSelPos;
+    DevBuf<int32_t> dStripPtr, dSol;
+    DevBuf<unsigned char> dCtrl;   // Ctrl + progress[S]
+    DevBuf<long long> dProf;
     Problem<REAL> P;
-    std::memset(&P, 0, sizeof(P));
-    P.H = H; P.W = W; P.L = L; P.LP = LP; P.N = N; P.E = E;
-    P.nV = (long long)(H - 1) * W; P.nH = (long long)H * (W - 1);
-    P.D = dD.p; P.msg = dMsg.p; P.posq = dPosQ.p; P.posqp = dPosQp.p;
-    P.rank_q = dRankQ.p; P.rank_qp = dRankQp.p; P.cnt_q = dCntQ.p; P.cnt_qp = dCntQp.p;
-    P.alpha = dAlpha.p; P.lambda = (REAL)tol;
-    P.info = dInfo.p; P.nodes = dNodes.p; P.strip_ptr = dStripPtr.p; P.S = S;
-    P.done = dDone.p; P.sol = dSol.p;
-    P.ticket = &dCtrl.p->ticket; P.acc = dCtrl.p->acc;
+    int grid_fwd = 1, grid_bwd = 1, wpb = 1, epoch = 0;
+    Ctrl *hc = nullptr; // pinned
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double kernel_ms = 0;
+    int64_t kernel_count = 0;
 
-    const int wpb = ops->sweep_warps_per_block();
-    auto grid_for = [&](int pass) {
-        const int bps = ops->sweep_blocks_per_sm(precision, kernel, pass);
-        SB_REQUIRE(bps >= 1, SB_ECUDA, "sb_trws_solve: sweep kernel does not fit on an SM");
-        long long g = (long long)bps * num_sms;
-        if (g > S) g = S;
-        return (int)(g < 1 ? 1 : g);
-    };
-    const int grid_fwd = grid_for(PASS_FWD), grid_bwd = grid_for(PASS_BWD);
-    auto active_for = [&](int grid) {
-        // at least two strip-walking warps in flight (trws_order.cpp: row H-3 waits for row H-2)
-        long long a = ((long long)S + grid - 1) / grid;
-        if ((long long)grid * a < 2) a = 2;
-        return (int)std::min<long long>(a, wpb);
-    };
+    Solver(int kernel_, int L_, int64_t N_, int64_t E_, int H_, int W_, const double *unary, const double *q,
+           const double *qprim, const double *alphas, double tol, const sb_trws_options &opt)
+        : kernel(kernel_), L(L_), H(H_), W(W_), N(N_), E(E_)
+    {
+        precision = sizeof(REAL) == 8 ? SB_F64 : SB_F32;
+        fuse = opt.fuse_rounding != 0;
+        ops = kops_for_labels(L);
+        SB_REQUIRE(ops, SB_EUNSUP, "sb_trws_solve: %d labels exceed SB_MAX_LABELS=%d", L, SB_MAX_LABELS);
+        K = ops->K;
+        LP = 32 * K;
+        const double t0 = now_ms();
+        int dev = 0, num_sms = 0;
+        SB_CUDA(cudaGetDevice(&dev));
+        SB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
 
-    int epoch = 0;
-    Ctrl hc;
-    auto run_pass = [&](int pass, int mode) {
-        SB_CUDA(cudaMemsetAsync(dCtrl.p, 0, sizeof(Ctrl), stream));
-        P.epoch = ++epoch;
+        // ---- host graph logic: ordering + dispatch schedule
+        std::vector<int32_t> order;
+        SB_REQUIRE(grid_ordering(H, W, order), SB_EINVAL,
+                   "sb_trws_solve: %dx%d grid has no valid automatic ordering (the reference crashes on it)", H, W);
+        std::vector<uint8_t> info;
+        build_node_info(H, W, order, info);
+        Schedule sched;
+        build_schedule(H, W, order, sched);
+        S = (int)sched.strip_ptr.size() - 1;
+        std::vector<int32_t> strip_ptr32(sched.strip_ptr.begin(), sched.strip_ptr.end());
+
+        // ---- device state
+        dD.alloc((size_t)N * LP); dMsg.alloc((size_t)E * LP); dPosQ.alloc((size_t)E * LP); dPosQp.alloc((size_t)E * LP);
+        dAlpha.alloc((size_t)E);
+        dRankQ.alloc((size_t)E * LP); dRankQp.alloc((size_t)E * LP); dCntQ.alloc((size_t)E * LP); dCntQp.alloc((size_t)E * LP);
+        dStripPtr.alloc((size_t)S + 1); dSol.alloc((size_t)N);
+        dSelPos.alloc((size_t)std::max<int64_t>(E, 1));
+        for (int pass = 0; pass < 2; pass++) {
+            PassPlan plan;
+            build_pass_plan(H, W, info, sched, pass, plan);
+            dSegs[pass].alloc(plan.segs.size());
+            dSegPtr[pass].alloc(plan.seg_ptr.size());
+            SB_CUDA(cudaMemcpy(dSegs[pass].p, plan.segs.data(), plan.segs.size() * sizeof(SegWarp), cudaMemcpyHostToDevice));
+            SB_CUDA(cudaMemcpy(dSegPtr[pass].p, plan.seg_ptr.data(), plan.seg_ptr.size() * 4, cudaMemcpyHostToDevice));
+        }
+        dCtrl.alloc(sizeof(Ctrl) + (size_t)S * 4);
+        DevBuf<int> dBad(1);
+        SB_CUDA(cudaMallocHost((void **)&hc, sizeof(Ctrl)));
+        SB_CUDA(cudaEventCreate(&ev0));
+        SB_CUDA(cudaEventCreate(&ev1));
+
+        SB_CUDA(cudaMemcpyAsync(dStripPtr.p, strip_ptr32.data(), ((size_t)S + 1) * 4, cudaMemcpyHostToDevice, stream));
+        SB_CUDA(cudaMemsetAsync(dSelPos.p, 0, dSelPos.bytes(), stream));
+        SB_CUDA(cudaMemsetAsync(dBad.p, 0, sizeof(int), stream));
+        {
+            // raw doubles -> padded REAL arrays + rank / merge-count tables
+            DevBuf<double> raw((size_t)N * L);
+            SB_CUDA(cudaMemcpyAsync(raw.p, unary, raw.bytes(), cudaMemcpyHostToDevice, stream));
+            const long long tot = (long long)N * LP;
+            convert_unary_kernel<REAL><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(raw.p, dD.p, L, LP, N);
+            SB_CUDA(cudaGetLastError());
+            count_launch();
+            SB_CUDA(cudaStreamSynchronize(stream));
+        }
+        if (E > 0) {
+            DevBuf<double> rawa((size_t)E);
+            SB_CUDA(cudaMemcpyAsync(rawa.p, alphas, rawa.bytes(), cudaMemcpyHostToDevice, stream));
+            convert_vec_kernel<REAL><<<(unsigned)((E + 255) / 256), 256, 0, stream>>>(rawa.p, dAlpha.p, E);
+            SB_CUDA(cudaGetLastError());
+            count_launch();
+            // q / qprim are uploaded and tabulated in slabs so the raw doubles never need 2*8*L*E bytes
+            const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(E, (int64_t)(256u << 20) / (8 * (int64_t)L)));
+            DevBuf<double> rq((size_t)slab * L), rqp((size_t)slab * L);
+            for (int64_t e0 = 0; e0 < E; e0 += slab) {
+                const int64_t ne = std::min<int64_t>(slab, E - e0);
+                SB_CUDA(cudaMemcpyAsync(rq.p, q + e0 * L, (size_t)ne * L * 8, cudaMemcpyHostToDevice, stream));
+                SB_CUDA(cudaMemcpyAsync(rqp.p, qprim + e0 * L, (size_t)ne * L * 8, cudaMemcpyHostToDevice, stream));
+                TablesLaunch tl;
+                tl.precision = precision;
+                tl.q = rq.p; tl.qp = rqp.p; tl.L = L; tl.E = ne;
+                tl.posq = dPosQ.p + e0 * LP; tl.posqp = dPosQp.p + e0 * LP;
+                tl.rank_q = dRankQ.p + e0 * LP; tl.rank_qp = dRankQp.p + e0 * LP;
+                tl.cnt_q = dCntQ.p + e0 * LP; tl.cnt_qp = dCntQp.p + e0 * LP;
+                tl.bad = dBad.p; tl.stream = stream;
+                ops->tables(tl);
+            }
+            int bad = 0;
+            SB_CUDA(cudaMemcpyAsync(&bad, dBad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            SB_CUDA(cudaStreamSynchronize(stream));
+            SB_REQUIRE(!bad, SB_EINVAL, "sb_trws_solve: q or qprim contains NaN (trws.m:9-15)");
+        }
+
+        std::memset(&P, 0, sizeof(P));
+        P.H = H; P.W = W; P.L = L; P.LP = LP; P.N = N; P.E = E;
+        P.nV = (long long)(H - 1) * W; P.nH = (long long)H * (W - 1);
+        P.D = dD.p; P.msg = dMsg.p; P.posq = dPosQ.p; P.posqp = dPosQp.p;
+        P.rank_q = dRankQ.p; P.rank_qp = dRankQp.p; P.cnt_q = dCntQ.p; P.cnt_qp = dCntQp.p;
+        P.alpha = dAlpha.p; P.lambda = (REAL)tol;
+        P.strip_ptr = dStripPtr.p; P.S = S;
+        P.sol = dSol.p; P.selpos = dSelPos.p;
+        Ctrl *ctrl = reinterpret_cast<Ctrl *>(dCtrl.p);
+        P.ticket = &ctrl->ticket; P.acc = ctrl->acc;
+        P.progress = reinterpret_cast<int32_t *>(dCtrl.p + sizeof(Ctrl));
+
+        if (const char *dbg = getenv("SB_TRWS_DEBUG")) P.debug = atoi(dbg);
+        if (getenv("SB_TRWS_PROFILE")) {
+            dProf.alloc(16);
+            SB_CUDA(cudaMemsetAsync(dProf.p, 0, 16 * sizeof(long long), stream));
+            P.prof = dProf.p;
+        }
+
+        wpb = ops->sweep_warps_per_block();
+        auto grid_for = [&](int pass) {
+            const int bps = ops->sweep_blocks_per_sm(precision, kernel, pass);
+            SB_REQUIRE(bps >= 1, SB_ECUDA, "sb_trws_solve: sweep kernel does not fit on an SM");
+            long long g = (long long)bps * num_sms;
+            if (g > S) g = S;
+            // two strip walkers must be in flight: (H-3,1) waits for (H-2,1) (trws_order.cpp)
+            SB_REQUIRE(S < 2 || g >= 2, SB_ECUDA, "sb_trws_solve: fewer than two resident CTAs");
+            return (int)(g < 1 ? 1 : g);
+        };
+        grid_fwd = grid_for(PASS_FWD);
+        grid_bwd = grid_for(PASS_BWD);
+        reset();
+        SB_CUDA(cudaStreamSynchronize(stream));
+        setup_ms = now_ms() - t0;
+    }
+
+    ~Solver() override
+    {
+        if (hc) cudaFreeHost(hc);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+    }
+
+    // ZeroMessages (MRFEnergy.cpp:115-131) + fresh epoch flags
+    void reset() override
+    {
+        SB_CUDA(cudaMemsetAsync(dSol.p, 0, (size_t)N * 4, stream));
+        SB_CUDA(cudaMemsetAsync(dMsg.p, 0, dMsg.bytes(), stream));
+        epoch = 0;
+    }
+
+    void run_pass(int pass, int mode)
+    {
+        SB_CUDA(cudaMemsetAsync(dCtrl.p, 0, dCtrl.bytes(), stream));
+        ++epoch;
         P.mode = mode;
+        P.segs = dSegs[pass == PASS_FWD ? 0 : 1].p;
+        P.seg_ptr = dSegPtr[pass == PASS_FWD ? 0 : 1].p;
         SweepLaunch sl;
         sl.precision = precision; sl.kern = kernel; sl.pass = pass; sl.problem = &P;
         sl.grid = pass == PASS_FWD ? grid_fwd : grid_bwd; sl.stream = stream;
-        P.active_warps = active_for(sl.grid);
+        SB_CUDA(cudaEventRecord(ev0, stream));
         ops->sweep(sl);
-        SB_CUDA(cudaMemcpyAsync(&hc, dCtrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
+        SB_CUDA(cudaEventRecord(ev1, stream));
+        SB_CUDA(cudaMemcpyAsync(hc, dCtrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
         SB_CUDA(cudaStreamSynchronize(stream));
-    };
-
-    const double t_setup1 = now_ms();
-    EventTimer timer(stream);
-    timer.start();
+        float ms = 0;
+        SB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        kernel_ms += ms;
+        kernel_count++;
+    }
 
     // minimize.cpp:31-113.  With fused rounding the energy of iteration t becomes
     // known inside the forward sweep of t+1; the outputs (labels, energy, bound,
     // count) are those of iteration t either way.
-    const int iter_max = (int)opt.maxiter;
-    const double relgap_max = opt.max_relgap;
-    const bool fuse = opt.fuse_rounding != 0;
-    double energy = 0, lb = 0;
-    int iterations = 0;
-    for (int it = 1;; it++) {
-        run_pass(PASS_FWD, MODE_SEND | ((fuse && it > 1) ? MODE_ROUND : 0));
-        if (fuse && it > 1) {
-            energy = hc.acc[0];
-            if ((energy - lb) / energy < relgap_max) { iterations = it - 1; break; }
+    void minimize(double maxiter, double max_relgap, double *energy_out, double *lb_out, double *iters_out,
+                  sb_trws_timing *timing) override
+    {
+        const int64_t launches0 = g_launches.load();
+        kernel_ms = 0;
+        kernel_count = 0;
+        EventTimer timer(stream);
+        timer.start();
+        const int iter_max = (int)maxiter;
+        double energy = 0, lb = 0;
+        int iterations = 0;
+        for (int it = 1;; it++) {
+            run_pass(PASS_FWD, MODE_SEND | ((fuse && it > 1) ? MODE_ROUND : 0));
+            if (fuse && it > 1) {
+                energy = hc->acc[0];
+                if ((energy - lb) / energy < max_relgap) { iterations = it - 1; break; }
+            }
+            run_pass(PASS_BWD, 0);
+            lb = hc->acc[1];
+            if (!fuse || it >= iter_max) {
+                run_pass(PASS_FWD, MODE_ROUND);
+                energy = hc->acc[0];
+                if (it >= iter_max || (energy - lb) / energy < max_relgap) { iterations = it; break; }
+            }
         }
-        run_pass(PASS_BWD, 0);
-        lb = hc.acc[1];
-        if (!fuse || it >= iter_max) {
-            run_pass(PASS_FWD, MODE_ROUND);
-            energy = hc.acc[0];
-            if (it >= iter_max || (energy - lb) / energy < relgap_max) { iterations = it; break; }
+        const double solve_ms = timer.stop_ms();
+        if (P.prof) {
+            long long h[16];
+            SB_CUDA(cudaMemcpy(h, dProf.p, sizeof(h), cudaMemcpyDeviceToHost));
+            SB_CUDA(cudaMemsetAsync(dProf.p, 0, sizeof(h), stream));
+            static const char *names[8] = {"flag-spin", "phaseA", "barrier", "prepare", "B1", "resolve", "update", "steps"};
+            for (int g = 0; g < 2; g++) {
+                fprintf(stderr, "[sb profile] %s:", g ? "rows" : "ring");
+                for (int q = 0; q < 7; q++) fprintf(stderr, " %s=%.0f", names[q], h[g * 8 + 7] ? (double)h[g * 8 + q] / (double)h[g * 8 + 7] : 0.0);
+                fprintf(stderr, " cycles/step over %lld steps\n", h[g * 8 + 7]);
+            }
+        }
+        *energy_out = energy;
+        *lb_out = lb;
+        *iters_out = (double)iterations;
+        if (timing) {
+            std::memset(timing, 0, sizeof(*timing));
+            timing->setup_ms = setup_ms;
+            timing->solve_ms = solve_ms;
+            timing->sweep_ms_avg = iterations ? solve_ms / iterations : 0;
+            timing->kernel_launches = g_launches.load() - launches0;
+            timing->sweep_kernel_ms = kernel_ms;
+            timing->sweep_kernel_launches = kernel_count;
         }
     }
-    const double solve_ms = timer.stop_ms();
 
-    const double t_dl0 = now_ms();
-    std::vector<int32_t> sol((size_t)N);
-    SB_CUDA(cudaMemcpy(sol.data(), dSol.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
-    for (int64_t u = 0; u < N; u++) labels[u] = (double)(sol[u] + 1); // trws_mex.cpp:138
-    *energy_out = energy;
-    *lb_out = lb;
-    *iters_out = (double)iterations;
-    if (timing) {
-        std::memset(timing, 0, sizeof(*timing));
-        timing->setup_ms = t_setup1 - t_setup0;
-        timing->solve_ms = solve_ms;
-        timing->sweep_ms_avg = iterations ? solve_ms / iterations : 0;
-        timing->download_ms = now_ms() - t_dl0;
-        timing->kernel_launches = g_launches.load() - launches0;
+    void labels(double *out) override
+    {
+        std::vector<int32_t> sol((size_t)N);
+        SB_CUDA(cudaMemcpy(sol.data(), dSol.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
+        for (int64_t u = 0; u < N; u++) out[u] = (double)(sol[u] + 1); // trws_mex.cpp:138
     }
-}
+};
 
 } // namespace
+
+double now_ms_public() { return now_ms(); }
+
 } // namespace trws
 } // namespace sb
 
@@ -215,18 +311,23 @@ void sb_trws_default_options(sb_trws_options *opt)
     opt->fuse_rounding = 1;
 }
 
-int sb_trws_solve(int kernel, int L, int64_t N, int64_t E, const double *unary, const uint32_t *conn,
-                  const double *q, const double *qprim, const double *alphas, double tol,
-                  const sb_trws_options *opt_in, double *labels, double *energy, double *lower_bound,
-                  double *iterations, sb_trws_timing *timing)
+struct sb_trws_solver {
+    sb::trws::SolverBase *impl;
+};
+
+int sb_trws_create(int kernel, int L, int64_t N, int64_t E, const double *unary, const uint32_t *conn,
+                   const double *q, const double *qprim, const double *alphas, double tol,
+                   const sb_trws_options *opt_in, sb_trws_solver **out)
 {
     return sb::guarded([&] {
+        SB_REQUIRE(out, SB_EINVAL, "sb_trws_create: null output");
+        *out = nullptr;
         // trws_mex.cpp:156-163
         SB_REQUIRE(kernel == 1 || kernel == 2, SB_EINVAL, "Unsupported kernel");
         // trws_mex.cpp:42-52
         SB_REQUIRE(L >= 1 && N >= 1 && E >= 0, SB_EINVAL, "sb_trws_solve: bad sizes L=%d N=%lld E=%lld", L,
                    (long long)N, (long long)E);
-        SB_REQUIRE(unary && labels && energy && lower_bound && iterations, SB_EINVAL, "sb_trws_solve: null pointer");
+        SB_REQUIRE(unary, SB_EINVAL, "sb_trws_solve: null pointer");
         SB_REQUIRE(E == 0 || (conn && q && qprim && alphas), SB_EINVAL, "sb_trws_solve: null pointer");
         SB_REQUIRE(N < (1LL << 31), SB_EUNSUP, "sb_trws_solve: too many nodes");
         sb_trws_options opt;
@@ -237,13 +338,70 @@ int sb_trws_solve(int kernel, int L, int64_t N, int64_t E, const double *unary, 
                    "sb_trws_solve: connectivity (N=%lld, E=%lld) is not the 4-connected dispmap_super grid; "
                    "general graphs are not supported on the GPU path", (long long)N, (long long)E);
         sb::require_device();
+        sb::trws::SolverBase *impl;
         if (opt.precision == SB_F64)
-            sb::trws::solve_typed<double>(kernel, L, N, E, H, W, unary, q, qprim, alphas, tol, opt, labels, energy,
-                                          lower_bound, iterations, timing);
+            impl = new sb::trws::Solver<double>(kernel, L, N, E, H, W, unary, q, qprim, alphas, tol, opt);
         else
-            sb::trws::solve_typed<float>(kernel, L, N, E, H, W, unary, q, qprim, alphas, tol, opt, labels, energy,
-                                         lower_bound, iterations, timing);
+            impl = new sb::trws::Solver<float>(kernel, L, N, E, H, W, unary, q, qprim, alphas, tol, opt);
+        *out = new sb_trws_solver{impl};
     });
+}
+
+int sb_trws_reset(sb_trws_solver *s)
+{
+    return sb::guarded([&] {
+        SB_REQUIRE(s && s->impl, SB_EINVAL, "sb_trws_reset: null solver");
+        s->impl->reset();
+    });
+}
+
+int sb_trws_minimize(sb_trws_solver *s, double maxiter, double max_relgap, double *energy, double *lower_bound,
+                     double *iterations, sb_trws_timing *timing)
+{
+    return sb::guarded([&] {
+        SB_REQUIRE(s && s->impl, SB_EINVAL, "sb_trws_minimize: null solver");
+        SB_REQUIRE(energy && lower_bound && iterations, SB_EINVAL, "sb_trws_minimize: null pointer");
+        s->impl->minimize(maxiter, max_relgap, energy, lower_bound, iterations, timing);
+    });
+}
+
+int sb_trws_get_labels(sb_trws_solver *s, double *labels)
+{
+    return sb::guarded([&] {
+        SB_REQUIRE(s && s->impl && labels, SB_EINVAL, "sb_trws_get_labels: null pointer");
+        s->impl->labels(labels);
+    });
+}
+
+void sb_trws_destroy(sb_trws_solver *s)
+{
+    if (!s) return;
+    delete s->impl;
+    delete s;
+}
+
+int sb_trws_solve(int kernel, int L, int64_t N, int64_t E, const double *unary, const uint32_t *conn,
+                  const double *q, const double *qprim, const double *alphas, double tol,
+                  const sb_trws_options *opt_in, double *labels, double *energy, double *lower_bound,
+                  double *iterations, sb_trws_timing *timing)
+{
+    sb_trws_solver *s = nullptr;
+    if (!labels || !energy || !lower_bound || !iterations) {
+        sb::set_last_error("sb_trws_solve: null pointer");
+        return SB_EINVAL;
+    }
+    int rc = sb_trws_create(kernel, L, N, E, unary, conn, q, qprim, alphas, tol, opt_in, &s);
+    if (rc != SB_OK) return rc;
+    sb_trws_options opt;
+    if (opt_in) opt = *opt_in; else sb_trws_default_options(&opt);
+    rc = sb_trws_minimize(s, opt.maxiter, opt.max_relgap, energy, lower_bound, iterations, timing);
+    if (rc == SB_OK) {
+        const double t0 = sb::trws::now_ms_public();
+        rc = sb_trws_get_labels(s, labels);
+        if (timing) timing->download_ms = sb::trws::now_ms_public() - t0;
+    }
+    sb_trws_destroy(s);
+    return rc;
 }
 
 } // extern "C"

@@ -33,16 +33,8 @@ def _opt(options, key, default):
 last_timing: dict = {}
 
 
-def trws(kernel, unary, connectivity, q, qprim, alphas, tol, options=None):
-    """[solution, energy, lower_bound, iterations] = trws(kernel, unary, connectivity, q, qprim,
-    alphas, tol, options)  -- trws.m:2-33.
-
-    kernel: 1 (truncated linear) or 2 (truncated quadratic).  unary: L x N.
-    connectivity: 2 x E, 1-based.  q, qprim: L x E.  alphas: E.  tol: scalar.
-    options: dict/object with ``maxiter`` (default 1000) and ``max_relgap`` (default 0)
-    (trws_mex.cpp:38-40); extra keys ``precision`` ("f32"|"f64") and ``fuse_rounding``.
-    Returns (solution N float64 1-based, energy, lower_bound, iterations).
-    """
+def _trws_args(kernel, unary, connectivity, q, qprim, alphas, tol):
+    """Argument checks of trws.m:5-15 and trws_mex.cpp:42-52; returns ctypes-ready arrays."""
     unary = _f(unary)
     q = _f(q)
     qprim = _f(qprim)
@@ -66,7 +58,10 @@ def trws(kernel, unary, connectivity, q, qprim, alphas, tol, options=None):
     assert alphas.shape[0] == E
     assert np.size(tol) == 1
     conn0 = np.asfortranarray(connectivity.astype(np.int64) - 1, dtype=np.uint32)  # trws.m:33
+    return kernel, L, N, E, unary, conn0, q, qprim, alphas, float(np.asarray(tol).reshape(-1)[0])
 
+
+def _trws_options(options):
     opt = TrwsOptions()
     lib().sb_trws_default_options(ctypes.byref(opt))
     opt.maxiter = float(_opt(options, "maxiter", 1000))
@@ -74,7 +69,28 @@ def trws(kernel, unary, connectivity, q, qprim, alphas, tol, options=None):
     prec = _opt(options, "precision", "f32")
     opt.precision = SB_F64 if prec in ("f64", SB_F64, "double") and prec != 0 else SB_F32
     opt.fuse_rounding = int(bool(_opt(options, "fuse_rounding", True)))
+    return opt
 
+
+def _timing_dict(tm):
+    return dict(setup_ms=tm.setup_ms, solve_ms=tm.solve_ms, sweep_ms_avg=tm.sweep_ms_avg,
+                download_ms=tm.download_ms, kernel_launches=tm.kernel_launches,
+                sweep_kernel_ms=tm.sweep_kernel_ms, sweep_kernel_launches=tm.sweep_kernel_launches)
+
+
+def trws(kernel, unary, connectivity, q, qprim, alphas, tol, options=None):
+    """[solution, energy, lower_bound, iterations] = trws(kernel, unary, connectivity, q, qprim,
+    alphas, tol, options)  -- trws.m:2-33.
+
+    kernel: 1 (truncated linear) or 2 (truncated quadratic).  unary: L x N.
+    connectivity: 2 x E, 1-based.  q, qprim: L x E.  alphas: E.  tol: scalar.
+    options: dict/object with ``maxiter`` (default 1000) and ``max_relgap`` (default 0)
+    (trws_mex.cpp:38-40); extra keys ``precision`` ("f32"|"f64") and ``fuse_rounding``.
+    Returns (solution N float64 1-based, energy, lower_bound, iterations).
+    """
+    kernel, L, N, E, unary, conn0, q, qprim, alphas, tol = _trws_args(kernel, unary, connectivity, q, qprim,
+                                                                      alphas, tol)
+    opt = _trws_options(options)
     solution = np.zeros(N, dtype=np.float64)
     e = c_double()
     lb = c_double()
@@ -82,13 +98,58 @@ def trws(kernel, unary, connectivity, q, qprim, alphas, tol, options=None):
     tm = TrwsTiming()
     rc = lib().sb_trws_solve(kernel, L, N, E, unary.ctypes.data_as(_dp), conn0.ctypes.data_as(_up),
                              q.ctypes.data_as(_dp), qprim.ctypes.data_as(_dp), alphas.ctypes.data_as(_dp),
-                             float(np.asarray(tol).reshape(-1)[0]), ctypes.byref(opt), solution.ctypes.data_as(_dp),
+                             tol, ctypes.byref(opt), solution.ctypes.data_as(_dp),
                              ctypes.byref(e), ctypes.byref(lb), ctypes.byref(it), ctypes.byref(tm))
     check(rc)
     last_timing.clear()
-    last_timing.update(setup_ms=tm.setup_ms, solve_ms=tm.solve_ms, sweep_ms_avg=tm.sweep_ms_avg,
-                       download_ms=tm.download_ms, kernel_launches=tm.kernel_launches)
+    last_timing.update(_timing_dict(tm))
     return solution, e.value, lb.value, it.value
+
+
+class TrwsSolver:
+    """Resident form of ``trws``: the MRFEnergy object of trws_mex.cpp:58-146 kept alive in HBM.
+    ``minimize`` continues from the current messages (Minimize_TRW_S, minimize.cpp:7-116),
+    ``reset`` is ZeroMessages (MRFEnergy.cpp:115-131)."""
+
+    def __init__(self, kernel, unary, connectivity, q, qprim, alphas, tol, options=None):
+        kernel, L, N, E, unary, conn0, q, qprim, alphas, tol = _trws_args(kernel, unary, connectivity, q, qprim,
+                                                                          alphas, tol)
+        self.N, self.L, self.E = N, L, E
+        opt = _trws_options(options)
+        self._h = ctypes.c_void_p()
+        check(lib().sb_trws_create(kernel, L, N, E, unary.ctypes.data_as(_dp), conn0.ctypes.data_as(_up),
+                                   q.ctypes.data_as(_dp), qprim.ctypes.data_as(_dp), alphas.ctypes.data_as(_dp),
+                                   tol, ctypes.byref(opt), ctypes.byref(self._h)))
+        self.timing = {}
+
+    def reset(self):
+        check(lib().sb_trws_reset(self._h))
+
+    def minimize(self, maxiter=1000, max_relgap=0.0):
+        e = c_double()
+        lb = c_double()
+        it = c_double()
+        tm = TrwsTiming()
+        check(lib().sb_trws_minimize(self._h, float(maxiter), float(max_relgap), ctypes.byref(e), ctypes.byref(lb),
+                                     ctypes.byref(it), ctypes.byref(tm)))
+        self.timing = _timing_dict(tm)
+        return e.value, lb.value, it.value
+
+    def labels(self):
+        out = np.zeros(self.N, dtype=np.float64)
+        check(lib().sb_trws_get_labels(self._h, out.ctypes.data_as(_dp)))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().sb_trws_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def trws_grid_ordering(H, W):

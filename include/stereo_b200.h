@@ -143,6 +143,67 @@ SB_API int sb_trws_grid_ordering(int H, int W, int32_t *ordering);
  * Host-only.  Returns SB_ENOTGRID when it is not. */
 SB_API int sb_grid_from_connectivity(int64_t N, int64_t E, const uint32_t *conn, int *H, int *W);
 
+/* ---------------------------------------------------------------- QPBO / roof duality */
+
+/* Replaces mexFunction of cpp/rd_mex.cpp:14-101 (called from rd.m:21).
+ *   U0, U1            N      unary cost of keeping / switching           rd_mex.cpp:24-25
+ *   E00,E01,E10,E11   E      pairwise tables, E_ab(p) = cost of (x_tail = a, x_head = b)
+ *   conn              2 x E  uint32, 0-based (rd.m:21 subtracts 1)        rd_mex.cpp:31
+ *   improve           QPBO-I on the nodes left unlabelled                 rd_mex.cpp:34,91-92
+ * Outputs (rd_mex.cpp:72-100): labels N doubles in {0, 1, negative = unlabelled}; energy of
+ * the labelling with unlabelled -> 0; roof-dual lower bound; number of nodes unlabelled
+ * after Solve + ComputeWeakPersistencies (before Improve).
+ * The connectivity must be the dispmap_super grid, else SB_ENOTGRID.  Improve draws its node
+ * permutation from libc rand() exactly like QPBO_extra.cpp:13-27. */
+SB_API int sb_rd_solve(int64_t N, int64_t E, const double *U0, const double *U1,
+                const double *E00, const double *E01, const double *E10, const double *E11,
+                const uint32_t *conn, int improve,
+                double *labels, double *energy, double *lower_bound, double *num_unlabelled);
+
+/* ------------------------------------------- cost volume / unary / pairwise builders
+ *
+ * The dense arrays dispmap_super.binary_fusion / simultaneous_fusion hand to rd() / trws()
+ * are produced by the methods below in the reference; each entry point replaces one of
+ * them.  Images are H x W x C doubles (MATLAB layout, values 0..255), planes are 4 x M
+ * ([a; b; c; d0] per column), points 2 x M ([x; y] = [column; row], 1-based).
+ * d_min / d_step are the disparity normalisation of dispmap_globalstereo.m:336-345
+ * (pass 0 and 1 for dispmap_ncc / dispmap_super). */
+
+/* dispmap_ncc.compute_ncc (dispmap_ncc.m:116-198): NCC volume H x W x D over the joint
+ * (2*patchsize+1)^2 x 3 window; the reference hard-codes patchsize = 2 (dispmap_ncc.m:24). */
+SB_API int sb_ncc_volume(int H, int W, int C, const double *im0, const double *im1,
+                  int D, const double *disparities, int patchsize, double *ncc_out);
+/* dispmap_ncc.best_disp_from_ncc (dispmap_ncc.m:208-221): WTA level + parabola refinement. */
+SB_API int sb_ncc_best_disp(int H, int W, int D, const double *ncc, const double *disparities,
+                     double *best_disp);
+/* dispmap_ncc.sample_ncc_from_disp (dispmap_ncc.m:222-245); with as_unary != 0 the output is
+ * unary_weight * (1 - nccs), i.e. dispmap_ncc.unary_cost (dispmap_ncc.m:107-115). */
+SB_API int sb_ncc_sample(int H, int W, int D, const double *ncc, const double *disparities,
+                  const double *disps, double unary_weight, int as_unary, double *out);
+/* dispmap_super.disparitymap_from_assignment (dispmap_super.m:318-328) and its override
+ * (dispmap_globalstereo.m:336-345); c == 0 -> SB_EINVAL "Infinite disparity". */
+SB_API int sb_plane_disparity(int64_t M, const double *planes, const double *points,
+                       double d_min, double d_step, double *out);
+/* vgg_interp2(A, X, Y, 'linear', oobv) (imrender/vgg/vgg_interp2.cxx:246-322); B is n x col. */
+SB_API int sb_interp2_linear(const double *A, int h, int w, int col, const double *X, const double *Y,
+                      int64_t n, double oobv, double *B);
+/* dispmap_globalstereo.unary_cost + ephoto (dispmap_globalstereo.m:355-375,405).
+ * P2 = self.P(:,:,2): the 4 x 3 transpose of the second camera matrix (:42). */
+SB_API int sb_photo_unary(int H, int W, int C, const double *im0, const double *im1, const double *P2,
+                   const double *planes, double d_min, double d_step, double col_thresh, double *U);
+/* dispmap_super.all_pairwise_costs (dispmap_super.m:226-262).  proposal == NULL computes E00
+ * only (the nargout == 1 form used by update_energy). */
+SB_API int sb_pairwise_tables(int H, int W, int kernel, const double *assignment, const double *proposal,
+                       const double *weights, double tol, double d_min, double d_step,
+                       double *E00, double *E01, double *E10, double *E11);
+/* q / qprim (L x E) of dispmap_super.simultaneous_fusion (dispmap_super.m:170-183);
+ * proposals = L consecutive 4 x N plane arrays. */
+SB_API int sb_fusion_positions(int H, int W, int L, const double *proposals, double d_min, double d_step,
+                        double *q, double *qprim);
+/* dispmap_super.update_energy (dispmap_super.m:263-274): sum(unary) + sum(E00). */
+SB_API int sb_energy(int H, int W, int kernel, const double *unary, const double *assignment,
+              const double *weights, double tol, double d_min, double d_step, double *energy);
+
 #ifdef __cplusplus
 }
 #endif

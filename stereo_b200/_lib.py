@@ -69,6 +69,17 @@ def lib():
         L.sb_trws_destroy.restype = None
         L.sb_trws_grid_ordering.argtypes = [c_int, c_int, _ip]
         L.sb_grid_from_connectivity.argtypes = [c_int64, c_int64, _up, POINTER(c_int), POINTER(c_int)]
+        ip, i64, dbl = c_int, c_int64, c_double
+        L.sb_rd_solve.argtypes = [c_int64, c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _up, c_int, _dp, _dp, _dp, _dp]
+        L.sb_ncc_volume.argtypes = [ip, ip, ip, _dp, _dp, ip, _dp, ip, _dp]
+        L.sb_ncc_best_disp.argtypes = [ip, ip, ip, _dp, _dp, _dp]
+        L.sb_ncc_sample.argtypes = [ip, ip, ip, _dp, _dp, _dp, dbl, ip, _dp]
+        L.sb_plane_disparity.argtypes = [i64, _dp, _dp, dbl, dbl, _dp]
+        L.sb_interp2_linear.argtypes = [_dp, ip, ip, ip, _dp, _dp, i64, dbl, _dp]
+        L.sb_photo_unary.argtypes = [ip, ip, ip, _dp, _dp, _dp, _dp, dbl, dbl, dbl, _dp]
+        L.sb_pairwise_tables.argtypes = [ip, ip, ip, _dp, _dp, _dp, dbl, dbl, dbl, _dp, _dp, _dp, _dp]
+        L.sb_fusion_positions.argtypes = [ip, ip, ip, _dp, dbl, dbl, _dp, _dp]
+        L.sb_energy.argtypes = [ip, ip, ip, _dp, _dp, _dp, dbl, dbl, dbl, _dp]
         _lib = L
     return _lib
 

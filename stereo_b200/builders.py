@@ -1,0 +1,129 @@
+"""ctypes wrappers of the cost-volume / unary / pairwise builders of libstereo_b200.so
+(include/stereo_b200.h).  Arrays use MATLAB shapes; everything is computed on the GPU."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from ._lib import _dp, check, lib
+
+
+def _f(a):
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+def ncc_volume(im0, im1, disparities, patchsize=2):
+    """dispmap_ncc.compute_ncc (dispmap_ncc.m:116-198) -> (H, W, D)."""
+    im0, im1 = _f(im0), _f(im1)
+    H, W, C = im0.shape
+    assert im1.shape == im0.shape
+    d = _f(np.asarray(disparities).reshape(-1))
+    out = np.zeros((H, W, d.size), dtype=np.float64, order="F")
+    check(lib().sb_ncc_volume(H, W, C, _p(im0), _p(im1), d.size, _p(d), int(patchsize), _p(out)))
+    return out
+
+
+def ncc_best_disp(ncc, disparities):
+    """dispmap_ncc.best_disp_from_ncc (dispmap_ncc.m:208-221) -> (H, W)."""
+    ncc = _f(ncc)
+    H, W, D = ncc.shape
+    d = _f(np.asarray(disparities).reshape(-1))
+    out = np.zeros((H, W), dtype=np.float64, order="F")
+    check(lib().sb_ncc_best_disp(H, W, D, _p(ncc), _p(d), _p(out)))
+    return out
+
+
+def ncc_sample(ncc, disparities, disps, unary_weight=1.0, as_unary=False):
+    """dispmap_ncc.sample_ncc_from_disp (dispmap_ncc.m:222-245); as_unary: dispmap_ncc.unary_cost."""
+    ncc = _f(ncc)
+    H, W, D = ncc.shape
+    d = _f(np.asarray(disparities).reshape(-1))
+    x = _f(np.asarray(disps).reshape(-1, order="F"))
+    out = np.zeros((H, W), dtype=np.float64, order="F")
+    check(lib().sb_ncc_sample(H, W, D, _p(ncc), _p(d), _p(x), float(unary_weight), int(bool(as_unary)), _p(out)))
+    return out
+
+
+def plane_disparity(planes, points, d_min=0.0, d_step=1.0):
+    """disparitymap_from_assignment (dispmap_super.m:318-328 / dispmap_globalstereo.m:336-345)."""
+    planes, points = _f(planes), _f(points)
+    M = planes.shape[1]
+    assert planes.shape[0] == 4 and points.shape == (2, M)
+    out = np.zeros(M, dtype=np.float64)
+    check(lib().sb_plane_disparity(M, _p(planes), _p(points), float(d_min), float(d_step), _p(out)))
+    return out
+
+
+def interp2_linear(A, X, Y, oobv):
+    """vgg_interp2(A, X, Y, 'linear', oobv) (vgg_interp2.cxx:246-322) -> (n, col)."""
+    A = _f(A)
+    if A.ndim == 2:
+        A = A[:, :, None]
+    h, w, col = A.shape
+    X, Y = _f(np.asarray(X).reshape(-1)), _f(np.asarray(Y).reshape(-1))
+    out = np.zeros((X.size, col), dtype=np.float64, order="F")
+    check(lib().sb_interp2_linear(_p(A), h, w, col, _p(X), _p(Y), X.size, float(oobv), _p(out)))
+    return out
+
+
+def photo_unary(im0, im1, P2, planes, d_min, d_step, col_thresh):
+    """dispmap_globalstereo.unary_cost (dispmap_globalstereo.m:355-375,405) -> N."""
+    im0, im1 = _f(im0), _f(im1)
+    if im0.ndim == 2:
+        im0, im1 = im0[:, :, None], im1[:, :, None]
+    H, W, C = im0.shape
+    P2 = _f(P2)
+    assert P2.shape == (4, 3)
+    planes = _f(planes)
+    out = np.zeros(H * W, dtype=np.float64)
+    check(lib().sb_photo_unary(H, W, C, _p(im0), _p(im1), _p(P2), _p(planes), float(d_min), float(d_step),
+                               float(col_thresh), _p(out)))
+    return out
+
+
+def pairwise_tables(H, W, kernel, assignment, proposal, weights, tol, d_min=0.0, d_step=1.0):
+    """dispmap_super.all_pairwise_costs (dispmap_super.m:236-262) -> E00, E01, E10, E11
+    (E00 only when proposal is None)."""
+    E = 2 * ((H - 1) * W + H * (W - 1))
+    a = _f(assignment)
+    w = _f(np.asarray(weights).reshape(-1))
+    assert a.shape == (4, H * W) and w.size == E
+    E00 = np.zeros(E)
+    if proposal is None:
+        check(lib().sb_pairwise_tables(H, W, int(kernel), _p(a), None, _p(w), float(tol), float(d_min), float(d_step),
+                                       _p(E00), None, None, None))
+        return E00
+    b = _f(proposal)
+    E01, E10, E11 = np.zeros(E), np.zeros(E), np.zeros(E)
+    check(lib().sb_pairwise_tables(H, W, int(kernel), _p(a), _p(b), _p(w), float(tol), float(d_min), float(d_step),
+                                   _p(E00), _p(E01), _p(E10), _p(E11)))
+    return E00, E01, E10, E11
+
+
+def fusion_positions(H, W, proposals, d_min=0.0, d_step=1.0):
+    """q, qprim (L x E) of dispmap_super.simultaneous_fusion (dispmap_super.m:170-183)."""
+    L = len(proposals)
+    E = 2 * ((H - 1) * W + H * (W - 1))
+    stack = np.empty((L, 4 * H * W), dtype=np.float64)
+    for l, pr in enumerate(proposals):
+        stack[l] = _f(pr).reshape(-1, order="F")
+    q = np.zeros((L, E), dtype=np.float64, order="F")
+    qp = np.zeros((L, E), dtype=np.float64, order="F")
+    check(lib().sb_fusion_positions(H, W, L, _p(stack), float(d_min), float(d_step), _p(q), _p(qp)))
+    return q, qp
+
+
+def energy(H, W, kernel, unary, assignment, weights, tol, d_min=0.0, d_step=1.0):
+    """dispmap_super.update_energy (dispmap_super.m:263-274)."""
+    u = _f(np.asarray(unary).reshape(-1))
+    a = _f(assignment)
+    w = _f(np.asarray(weights).reshape(-1))
+    e = ctypes.c_double()
+    check(lib().sb_energy(H, W, int(kernel), _p(u), _p(a), _p(w), float(tol), float(d_min), float(d_step),
+                          ctypes.byref(e)))
+    return e.value

@@ -1,0 +1,648 @@
+// qpbo.cu -- roof duality (QPBO) binary fusion on the GPU behind sb_rd_solve
+// (include/stereo_b200.h).  Replaces, for the 4-connected dispmap_super grid,
+//   mexFunction of cpp/rd_mex.cpp:14-101
+//   QPBO::AddPairwiseTerm / ComputeWeights / AddUnaryTerm   QPBO.cpp:408-507, QPBO.h:615-624,760-807
+//   QPBO::MergeParallelEdges                                QPBO.cpp:786-816, QPBO_extra.cpp:137-239
+//   QPBO::Solve / maxflow                                   QPBO.cpp:818-845, QPBO_maxflow.cpp:477-617
+//   QPBO::ComputeWeakPersistencies                          QPBO_postprocessing.cpp:10-120
+//   QPBO::Improve                                           QPBO_extra.cpp:1151-1232
+//   ComputeTwiceEnergy / ComputeTwiceLowerBound             QPBO.cpp:847-917
+//
+// Design.  The reference runs Boykov-Kolmogorov augmenting paths on a pointer graph; the
+// quantities it returns, however, are properties of the energy, not of the algorithm:
+//   * strong labels (Solve): label(i) = what_segment(i) unless it equals what_segment(i'),
+//     where what_segment(v) = 1 iff v is in the sink tree, i.e. iff v can still reach the
+//     sink in the residual graph of a maximum flow -- the same set for every maximum flow;
+//   * the roof-dual bound = constant + value of the maximum flow.
+// So the device runs a different max-flow: synchronous (Jacobi) push-relabel on the implicit
+// 2N-node grid network, fp64 capacities, one thread per node, periodic exact global relabelling
+// by parallel BFS from the sink.  Phase 1 (maximum preflow) already fixes the sink-reachable
+// set; the excess stranded on the source side is only returned (phase 2) when weak
+// persistencies have to be computed on a true flow.  The two directed terms of every
+// neighbour pair are summed into one table before the normal form (the reference merges them
+// afterwards, QPBO.cpp:786-816; the represented energy is the same).
+//
+// Layout: node v = u + side * N (side 1 = the mate i'), u = r + H*c.  Pair P: vertical pairs
+// (r,c)-(r+1,c) first, P = c*(H-1)+r, then horizontal pairs (r,c)-(r,c+1), P = nV + c*H + r;
+// i = first node of the pair.  Four residual capacities per pair:
+//   [0] i -> J0   [1] J0 -> i   [2] J1 -> i'   [3] i' -> J1
+// with (J0, J1) = (j, j') for a submodular pair and (j', j) otherwise (QPBO.cpp:458-500).
+#include "sb_common.h"
+#include <vector>
+#include <algorithm>
+#include <cstring>
+#include <cstdlib>
+#include <cmath>
+
+namespace sb {
+namespace qpbo {
+
+constexpr int HINF = 0x3fffffff;
+
+struct Graph {
+    int H, W;
+    long long N, nV, nH, nP;
+    double *tr0;      // [2N] initial signed terminal capacity (> 0: from the source, < 0: to the sink)
+    double *excess;   // [2N]
+    double *tsink;    // [2N] residual capacity v -> sink
+    double *tsrc;     // [2N] residual capacity v -> source (flow received from the source)
+    double *r;        // [nP][4]
+    double *pushed;   // [nP][4] flow sent over each arc in the current round
+    unsigned char *sub; // [nP]
+    int *h, *h2;      // [2N] labels (double buffered)
+    int *flag;        // device flags: [0] active, [1] changed
+};
+
+// ComputeWeights, QPBO.h:760-807
+__device__ __forceinline__ void compute_weights(double A, double B, double C, double D, double &ci, double &cj,
+                                                double &cij, double &cji)
+{
+    ci = D - A;
+    B -= A;
+    C -= D;
+    if (B < 0) {
+        ci += -B;
+        cj = B;
+        cji = B + C;
+        cij = 0;
+    } else if (C < 0) {
+        ci += C;
+        cj = -C;
+        cij = B + C;
+        cji = 0;
+    } else {
+        cj = 0;
+        cij = B;
+        cji = C;
+    }
+}
+
+// One thread per neighbour pair: sum the two directed terms, normal form, arc capacities.
+__global__ void build_pairs_kernel(Graph g, const double *__restrict__ E00, const double *__restrict__ E01,
+                                   const double *__restrict__ E10, const double *__restrict__ E11,
+                                   double *__restrict__ pair_ci, double *__restrict__ pair_cj,
+                                   double *__restrict__ pair_t00)
+{
+    const long long P = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (P >= g.nP) return;
+    long long p1, p2;
+    if (P < g.nV) { p1 = P; p2 = g.nV + P; }                 // VD, VU (dispmap_super.m:284-288)
+    else { p1 = 2 * g.nV + (P - g.nV); p2 = p1 + g.nH; }     // HR, HL (:290-294)
+    const double t00 = E00[p1] + E00[p2], t01 = E01[p1] + E10[p2], t10 = E10[p1] + E01[p2], t11 = E11[p1] + E11[p2];
+    double ci, cj, cij, cji;
+    const bool sub = (t01 + t10 >= t00 + t11);               // QPBO.cpp:433
+    if (sub) compute_weights(t00, t01, t10, t11, ci, cj, cij, cji);
+    else { compute_weights(t01, t00, t11, t10, ci, cj, cij, cji); cj = -cj; }
+    g.sub[P] = sub ? 1 : 0;
+    double *r = g.r + 4 * P;
+    r[0] = cij; r[1] = cji; r[2] = cij; r[3] = cji;
+    pair_ci[P] = ci;
+    pair_cj[P] = cj;
+    pair_t00[P] = t00;
+}
+
+// One thread per pixel: terminal capacity = unary difference + the pairs' contributions, in
+// a fixed order (up, down, left, right).
+__global__ void build_nodes_kernel(Graph g, const double *__restrict__ U0, const double *__restrict__ U1,
+                                   const double *__restrict__ pair_ci, const double *__restrict__ pair_cj)
+{
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= g.N) return;
+    const int H = g.H, W = g.W;
+    const int r = (int)(u % H), c = (int)(u / H);
+    double t = U1[u] - U0[u];
+    if (r > 0) t += pair_cj[(long long)c * (H - 1) + (r - 1)];
+    if (r < H - 1) t += pair_ci[(long long)c * (H - 1) + r];
+    if (c > 0) t += pair_cj[g.nV + (long long)(c - 1) * H + r];
+    if (c < W - 1) t += pair_ci[g.nV + (long long)c * H + r];
+    g.tr0[u] = t;
+    g.tr0[u + g.N] = -t;
+}
+
+__global__ void init_preflow_kernel(Graph g)
+{
+    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= 2 * g.N) return;
+    const double t = g.tr0[v];
+    g.excess[v] = t > 0 ? t : 0.0;
+    g.tsink[v] = t < 0 ? -t : 0.0;
+    g.tsrc[v] = t > 0 ? t : 0.0;
+    g.h[v] = 0;
+    g.h2[v] = 0;
+}
+
+// Arc of node v in grid direction d (0 up, 1 down, 2 left, 3 right): pair, this node's
+// outgoing slot (the incoming one is slot ^ 1) and the node at the other end.
+struct Arc { long long P; int slot; long long w; bool valid; };
+__device__ __forceinline__ Arc arc_of(const Graph &g, long long v, int d)
+{
+    Arc a;
+    const long long N = g.N;
+    const int side = v >= N ? 1 : 0;
+    const long long u = v - (side ? N : 0);
+    const int H = g.H, W = g.W;
+    const int r = (int)(u % H), c = (int)(u / H);
+    bool first;
+    long long other;
+    if (d == 0) { a.valid = r > 0; a.P = (long long)c * (H - 1) + (r - 1); first = false; other = u - 1; }
+    else if (d == 1) { a.valid = r < H - 1; a.P = (long long)c * (H - 1) + r; first = true; other = u + 1; }
+    else if (d == 2) { a.valid = c > 0; a.P = g.nV + (long long)(c - 1) * H + r; first = false; other = u - H; }
+    else { a.valid = c < W - 1; a.P = g.nV + (long long)c * H + r; first = true; other = u + H; }
+    if (!a.valid) { a.slot = 0; a.w = 0; return a; }
+    const bool sub = g.sub[a.P] != 0;
+    int oside;
+    if (first) {           // i / i'
+        a.slot = side ? 3 : 0;
+        oside = side ? (sub ? 1 : 0) : (sub ? 0 : 1);
+    } else {               // j / j'
+        const bool isJ0 = (side == 0) == sub;   // J0 = j if sub else j'
+        a.slot = isJ0 ? 1 : 2;
+        oside = isJ0 ? 0 : 1;
+    }
+    a.w = other + (oside ? N : 0);
+    return a;
+}
+
+// Push round: every active node sends along admissible arcs (label exactly one lower).
+// TO_SOURCE selects phase 2 (the stranded excess flows back to the source).
+template <bool TO_SOURCE> __global__ void push_kernel(Graph g)
+{
+    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= 2 * g.N) return;
+    double e = g.excess[v];
+    const int hv = g.h[v];
+    if (!(e > 0) || hv >= HINF) return;
+    double *term = TO_SOURCE ? g.tsrc : g.tsink;
+    const double tc = term[v];
+    if (tc > 0 && hv == 1) {
+        const double dl = fmin(e, tc);
+        term[v] = tc - dl;
+        e -= dl;
+    }
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+        if (!(e > 0)) break;
+        const Arc a = arc_of(g, v, d);
+        if (!a.valid) continue;
+        const double rr = g.r[4 * a.P + a.slot];
+        if (rr > 0 && g.h[a.w] == hv - 1) {
+            const double dl = fmin(e, rr);
+            g.r[4 * a.P + a.slot] = rr - dl;
+            e -= dl;
+            g.pushed[4 * a.P + a.slot] = dl;
+        }
+    }
+    g.excess[v] = e;
+}
+
+// Collect what the neighbours pushed, then relabel (Jacobi: reads h, writes h2).
+template <bool TO_SOURCE> __global__ void collect_relabel_kernel(Graph g)
+{
+    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= 2 * g.N) return;
+    double e = g.excess[v];
+    int minh = HINF;
+    const double tc = (TO_SOURCE ? g.tsrc : g.tsink)[v];
+    if (tc > 0) minh = 0;
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+        const Arc a = arc_of(g, v, d);
+        if (!a.valid) continue;
+        const long long in = 4 * a.P + (a.slot ^ 1);
+        const double dl = g.pushed[in];
+        double rr = g.r[4 * a.P + a.slot];
+        if (dl != 0.0) {
+            e += dl;
+            rr += dl;
+            g.r[4 * a.P + a.slot] = rr;
+            g.pushed[in] = 0.0;
+        }
+        if (rr > 0) minh = min(minh, g.h[a.w]);
+    }
+    g.excess[v] = e;
+    int hv = g.h[v];
+    if (e > 0 && hv < HINF) {
+        const int hn = minh >= HINF ? HINF : minh + 1;
+        if (hn > hv) hv = hn;
+        if (hv < HINF) g.flag[0] = 1;
+    }
+    g.h2[v] = hv;
+}
+
+// Exact labels: BFS distance to the terminal in the residual graph (relaxation sweeps).
+template <bool TO_SOURCE> __global__ void bfs_init_kernel(Graph g)
+{
+    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= 2 * g.N) return;
+    g.h[v] = ((TO_SOURCE ? g.tsrc : g.tsink)[v] > 0) ? 1 : HINF;
+}
+__global__ void bfs_sweep_kernel(Graph g)
+{
+    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= 2 * g.N) return;
+    int hv = g.h[v];
+    int best = hv;
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+        const Arc a = arc_of(g, v, d);
+        if (!a.valid) continue;
+        if (g.r[4 * a.P + a.slot] > 0) {
+            const int hw = g.h[a.w];
+            if (hw < HINF && hw + 1 < best) best = hw + 1;
+        }
+    }
+    if (best < hv) {
+        g.h[v] = best;
+        g.flag[1] = 1;
+    }
+}
+__global__ void any_active_kernel(Graph g)
+{
+    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= 2 * g.N) return;
+    if (g.excess[v] > 0 && g.h[v] < HINF) g.flag[0] = 1;
+}
+
+// label(i) = what_segment(i), -1 when it equals what_segment(i') (QPBO.cpp:839-843);
+// what_segment = 1 iff the node can reach the sink.
+__global__ void labels_kernel(Graph g, int *__restrict__ label)
+{
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= g.N) return;
+    const int a = g.h[u] < HINF ? 1 : 0, b = g.h[u + g.N] < HINF ? 1 : 0;
+    label[u] = (a == b) ? -1 : a;
+}
+
+// energy of a labelling (unlabelled -> 0), ComputeTwiceEnergy / 2 (QPBO.cpp:847-875)
+__global__ void energy_terms_kernel(long long N, long long E, const unsigned *__restrict__ conn,
+                                    const int *__restrict__ label, const double *__restrict__ U0,
+                                    const double *__restrict__ U1, const double *__restrict__ E00,
+                                    const double *__restrict__ E01, const double *__restrict__ E10,
+                                    const double *__restrict__ E11, double *__restrict__ out)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < N) {
+        out[t] = label[t] == 1 ? U1[t] : U0[t];
+    } else if (t < N + E) {
+        const long long p = t - N;
+        const int xi = label[conn[2 * p]] == 1, xj = label[conn[2 * p + 1]] == 1;
+        out[t] = xi ? (xj ? E11[p] : E10[p]) : (xj ? E01[p] : E00[p]);
+    }
+}
+
+__global__ void bound_terms_kernel(Graph g, const double *__restrict__ U0, const double *__restrict__ pair_t00,
+                                   double *__restrict__ out)
+{
+    // twice the initial bound: 2 Z + sum_i min(0, 2 t_i) - sum_nonsub 2 cij  (QPBO.cpp:897-917 on the
+    // initial reparameterisation), laid out as [N node terms][nP pair terms]
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < g.N) {
+        out[t] = 2.0 * U0[t] + fmin(0.0, 2.0 * g.tr0[t]);
+    } else if (t < g.N + g.nP) {
+        const long long P = t - g.N;
+        out[t] = 2.0 * pair_t00[P];
+    }
+}
+__global__ void flow_terms_kernel(Graph g, const double *__restrict__ r0, double *__restrict__ out)
+{
+    // flow into the sink per node; the non-submodular E00 caps are subtracted from the pair terms
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 2 * g.N) {
+        const double t0 = g.tr0[t];
+        out[t] = (t0 < 0 ? -t0 : 0.0) - g.tsink[t];
+    } else if (t < 2 * g.N + g.nP) {
+        const long long P = t - 2 * g.N;
+        out[t] = g.sub[P] ? 0.0 : -2.0 * r0[4 * P];
+    }
+}
+
+__global__ void reduce_kernel(const double *__restrict__ a, long long n, double *__restrict__ partial)
+{
+    __shared__ double sh[256];
+    double s = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        s += a[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+// add a unary term (0, delta) to node u on the device state (AddUnaryTerm in stage 1,
+// QPBO.h:615-624): tr(u) += delta, tr(u') -= delta, applied to the preflow state
+__global__ void add_unary_kernel(Graph g, long long u, double delta)
+{
+    if (blockIdx.x || threadIdx.x) return;
+    for (int s = 0; s < 2; s++) {
+        const long long v = u + (s ? g.N : 0);
+        double dl = s ? -delta : delta;
+        if (dl > 0) { // more source capacity: cancels sink residual first, the rest is new excess
+            const double c = fmin(dl, g.tsink[v]);
+            g.tsink[v] -= c;
+            g.excess[v] += dl - c;
+            g.tsrc[v] += dl - c;
+        } else if (dl < 0) { // more sink capacity: absorbs the node's excess first
+            dl = -dl;
+            const double c = fmin(dl, g.excess[v]);
+            g.excess[v] -= c;
+            g.tsink[v] += dl - c;
+        }
+    }
+}
+// DetermineSaturation(i) + 1 (QPBO_extra.cpp:242-254, 1178-1181) on the current residuals
+__global__ void saturation_kernel(Graph g, long long u, double *out)
+{
+    if (blockIdx.x || threadIdx.x) return;
+    // any value that exceeds everything the node's arcs and terminals can carry works; the
+    // reference takes max(c1, c2) + 1 over its own residuals
+    double c = g.excess[u] + g.tsink[u] + 1.0;
+    for (int d = 0; d < 4; d++) {
+        const Arc a = arc_of(g, u, d);
+        if (!a.valid) continue;
+        c += g.r[4 * a.P + a.slot] + g.r[4 * a.P + (a.slot ^ 1)];
+    }
+    *out = c;
+}
+
+inline unsigned nblk(long long n) { return (unsigned)std::max<long long>(1, (n + 255) / 256); }
+
+struct Solver {
+    Graph g;
+    DevBuf<double> tr0, excess, tsink, tsrc, r, pushed, r0;
+    DevBuf<unsigned char> sub;
+    DevBuf<int> h, h2, flag, label;
+    int *hflag = nullptr;
+    int64_t rounds = 0, relabels = 0;
+
+    ~Solver() { if (hflag) cudaFreeHost(hflag); }
+
+    void alloc(int H, int W)
+    {
+        g.H = H; g.W = W; g.N = (long long)H * W;
+        g.nV = (long long)(H - 1) * W; g.nH = (long long)H * (W - 1); g.nP = g.nV + g.nH;
+        const size_t n2 = (size_t)2 * g.N, np4 = (size_t)std::max<long long>(g.nP, 1) * 4;
+        tr0.alloc(n2); excess.alloc(n2); tsink.alloc(n2); tsrc.alloc(n2); r.alloc(np4); pushed.alloc(np4); r0.alloc(np4);
+        sub.alloc((size_t)std::max<long long>(g.nP, 1)); h.alloc(n2); h2.alloc(n2); flag.alloc(2); label.alloc((size_t)g.N);
+        g.tr0 = tr0.p; g.excess = excess.p; g.tsink = tsink.p; g.tsrc = tsrc.p; g.r = r.p; g.pushed = pushed.p;
+        g.sub = sub.p; g.h = h.p; g.h2 = h2.p; g.flag = flag.p;
+        SB_CUDA(cudaMallocHost((void **)&hflag, 2 * sizeof(int)));
+        SB_CUDA(cudaMemset(pushed.p, 0, pushed.bytes()));
+    }
+
+    // exact labels by BFS from the terminal; returns true if some node with excess can reach it
+    template <bool TO_SOURCE> bool global_relabel()
+    {
+        const unsigned nb = nblk(2 * g.N);
+        bfs_init_kernel<TO_SOURCE><<<nb, 256>>>(g);
+        count_launch();
+        for (;;) {
+            SB_CUDA(cudaMemsetAsync(flag.p, 0, 2 * sizeof(int)));
+            for (int k = 0; k < 16; k++) bfs_sweep_kernel<<<nb, 256>>>(g);
+            count_launch(16);
+            SB_CUDA(cudaMemcpy(hflag, flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+            if (!hflag[1]) break;
+        }
+        relabels++;
+        SB_CUDA(cudaMemsetAsync(flag.p, 0, 2 * sizeof(int)));
+        any_active_kernel<<<nb, 256>>>(g);
+        count_launch();
+        SB_CUDA(cudaMemcpy(hflag, flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+        return hflag[0] != 0;
+    }
+
+    // maximum preflow (phase 1) or return of the stranded excess (phase 2)
+    template <bool TO_SOURCE> void maxflow()
+    {
+        const unsigned nb = nblk(2 * g.N);
+        int burst = 32;
+        while (global_relabel<TO_SOURCE>()) {
+            // a burst of push / relabel rounds between two exact relabellings
+            for (int k = 0; k < burst; k++) {
+                push_kernel<TO_SOURCE><<<nb, 256>>>(g);
+                collect_relabel_kernel<TO_SOURCE><<<nb, 256>>>(g);
+                std::swap(g.h, g.h2);
+            }
+            count_launch(2 * burst);
+            rounds += burst;
+            SB_CUDA(cudaGetLastError());
+            burst = std::min(burst * 2, 512);
+        }
+    }
+};
+
+double device_sum(const double *d, long long n)
+{
+    const int nbk = 148 * 4;
+    DevBuf<double> part(nbk);
+    reduce_kernel<<<nbk, 256>>>(d, n, part.p);
+    SB_CUDA(cudaGetLastError());
+    count_launch();
+    std::vector<double> hh(nbk);
+    SB_CUDA(cudaMemcpy(hh.data(), part.p, nbk * sizeof(double), cudaMemcpyDeviceToHost));
+    double s = 0;
+    for (double v : hh) s += v;
+    return s;
+}
+
+// ComputeWeakPersistencies (QPBO_postprocessing.cpp:10-120) on the host for the nodes Solve
+// left unlabelled: Kosaraju's two depth-first passes over the residual graph restricted to
+// them, start nodes and region numbering in the reference's order (all i, then all i').
+void weak_persistencies(const Graph &g, const std::vector<double> &r, const std::vector<unsigned char> &sub,
+                        std::vector<int> &label)
+{
+    const long long N = g.N;
+    const int H = g.H, W = g.W;
+    auto arc_of_host = [&](long long v, int d, long long &P, int &slot, long long &w) -> bool {
+        const int side = v >= N ? 1 : 0;
+        const long long u = v - (side ? N : 0);
+        const int rr = (int)(u % H), c = (int)(u / H);
+        bool first;
+        long long other;
+        if (d == 0) { if (rr <= 0) return false; P = (long long)c * (H - 1) + (rr - 1); first = false; other = u - 1; }
+        else if (d == 1) { if (rr >= H - 1) return false; P = (long long)c * (H - 1) + rr; first = true; other = u + 1; }
+        else if (d == 2) { if (c <= 0) return false; P = g.nV + (long long)(c - 1) * H + rr; first = false; other = u - H; }
+        else { if (c >= W - 1) return false; P = g.nV + (long long)c * H + rr; first = true; other = u + H; }
+        const bool sb_ = sub[P] != 0;
+        int oside;
+        if (first) { slot = side ? 3 : 0; oside = side ? (sb_ ? 1 : 0) : (sb_ ? 0 : 1); }
+        else { const bool isJ0 = (side == 0) == sb_; slot = isJ0 ? 1 : 2; oside = isJ0 ? 0 : 1; }
+        w = other + (oside ? N : 0);
+        return true;
+    };
+    std::vector<int> region((size_t)2 * N, 0);
+    std::vector<char> visited((size_t)2 * N, 1);
+    bool any = false;
+    for (long long u = 0; u < N; u++)
+        if (label[u] < 0) { visited[u] = visited[u + N] = 0; region[u] = region[u + N] = -1; any = true; }
+    if (!any) return;
+    // first DFS: finishing order
+    std::vector<long long> order;
+    std::vector<std::pair<long long, int>> st;
+    for (long long s0 = 0; s0 < 2 * N; s0++) {
+        if (visited[s0]) continue;
+        visited[s0] = 1;
+        st.push_back({s0, 0});
+        while (!st.empty()) {
+            auto &top = st.back();
+            if (top.second >= 4) { order.push_back(top.first); st.pop_back(); continue; }
+            const int d = top.second++;
+            long long P, w; int slot;
+            if (!arc_of_host(top.first, d, P, slot, w)) continue;
+            if (!(r[4 * P + slot] > 0) || visited[w]) continue;
+            visited[w] = 1;
+            st.push_back({w, 0});
+        }
+    }
+    // second DFS over reversed arcs, most recently finished first
+    int component = 0;
+    for (long long k = (long long)order.size() - 1; k >= 0; k--) {
+        const long long s0 = order[k];
+        if (region[s0] > 0) continue;
+        region[s0] = ++component;
+        st.push_back({s0, 0});
+        while (!st.empty()) {
+            auto &top = st.back();
+            if (top.second >= 4) { st.pop_back(); continue; }
+            const int d = top.second++;
+            long long P, w; int slot;
+            if (!arc_of_host(top.first, d, P, slot, w)) continue;
+            if (!(r[4 * P + (slot ^ 1)] > 0) || region[w] >= 0) continue;
+            region[w] = component;
+            st.push_back({w, 0});
+        }
+    }
+    for (long long u = 0; u < N; u++)
+        if (label[u] < 0) {
+            if (region[u] > region[u + N]) label[u] = 0;
+            else if (region[u] < region[u + N]) label[u] = 1;
+        }
+}
+
+} // namespace qpbo
+
+bool grid_from_connectivity(int64_t N, int64_t E, const uint32_t *conn, int &H, int &W);
+
+} // namespace sb
+
+using namespace sb;
+using namespace sb::qpbo;
+
+extern "C" {
+
+int sb_rd_solve(int64_t N, int64_t E, const double *U0, const double *U1, const double *E00, const double *E01,
+                const double *E10, const double *E11, const uint32_t *conn, int improve, double *labels,
+                double *energy, double *lower_bound, double *num_unlabelled)
+{
+    return guarded([&] {
+        SB_REQUIRE(N >= 1 && E >= 0, SB_EINVAL, "sb_rd_solve: bad sizes N=%lld E=%lld", (long long)N, (long long)E);
+        SB_REQUIRE(U0 && U1 && labels && energy && lower_bound && num_unlabelled, SB_EINVAL, "sb_rd_solve: null pointer");
+        SB_REQUIRE(E == 0 || (E00 && E01 && E10 && E11 && conn), SB_EINVAL, "sb_rd_solve: null pointer");
+        SB_REQUIRE(N < (1LL << 30), SB_EUNSUP, "sb_rd_solve: too many nodes");
+        int H = 0, W = 0;
+        SB_REQUIRE(grid_from_connectivity(N, E, conn, H, W), SB_ENOTGRID,
+                   "sb_rd_solve: connectivity (N=%lld, E=%lld) is not the 4-connected dispmap_super grid; "
+                   "general graphs are not supported on the GPU path", (long long)N, (long long)E);
+        require_device();
+        Solver S;
+        S.alloc(H, W);
+        Graph &g = S.g;
+        DevBuf<double> dU0, dU1, dE[4], pci((size_t)std::max<long long>(g.nP, 1)), pcj((size_t)std::max<long long>(g.nP, 1)),
+            pt00((size_t)std::max<long long>(g.nP, 1));
+        DevBuf<unsigned> dconn;
+        auto up = [&](DevBuf<double> &b, const double *hsrc, size_t n) {
+            b.alloc(std::max<size_t>(n, 1));
+            if (n) SB_CUDA(cudaMemcpy(b.p, hsrc, n * 8, cudaMemcpyHostToDevice));
+        };
+        up(dU0, U0, (size_t)N); up(dU1, U1, (size_t)N);
+        up(dE[0], E00, (size_t)E); up(dE[1], E01, (size_t)E); up(dE[2], E10, (size_t)E); up(dE[3], E11, (size_t)E);
+        dconn.alloc((size_t)std::max<int64_t>(2 * E, 1));
+        if (E) SB_CUDA(cudaMemcpy(dconn.p, conn, (size_t)E * 8, cudaMemcpyHostToDevice));
+        if (g.nP) build_pairs_kernel<<<nblk(g.nP), 256>>>(g, dE[0].p, dE[1].p, dE[2].p, dE[3].p, pci.p, pcj.p, pt00.p);
+        build_nodes_kernel<<<nblk(N), 256>>>(g, dU0.p, dU1.p, pci.p, pcj.p);
+        init_preflow_kernel<<<nblk(2 * N), 256>>>(g);
+        SB_CUDA(cudaGetLastError());
+        count_launch(3);
+        SB_CUDA(cudaMemcpy(S.r0.p, S.r.p, S.r.bytes(), cudaMemcpyDeviceToDevice));
+
+        // ---- Solve(): maximum preflow, sink-reachable set, strong labels
+        S.maxflow<false>();
+        labels_kernel<<<nblk(N), 256>>>(g, S.label.p);
+        count_launch();
+        std::vector<int> lab((size_t)N);
+        SB_CUDA(cudaMemcpy(lab.data(), S.label.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
+
+        // ---- lower bound: (initial bound + flow value) / 2 (ComputeTwiceLowerBound, QPBO.cpp:897-917)
+        {
+            DevBuf<double> terms((size_t)(2 * N + g.nP));
+            bound_terms_kernel<<<nblk(N + g.nP), 256>>>(g, dU0.p, pt00.p, terms.p);
+            count_launch();
+            double twice = device_sum(terms.p, N + g.nP);
+            flow_terms_kernel<<<nblk(2 * N + g.nP), 256>>>(g, S.r0.p, terms.p);
+            count_launch();
+            twice += device_sum(terms.p, 2 * N + g.nP);
+            *lower_bound = twice / 2;
+        }
+
+        // ---- ComputeWeakPersistencies() on the nodes Solve left open
+        long long open_nodes = 0;
+        for (int64_t u = 0; u < N; u++) open_nodes += lab[u] < 0;
+        if (open_nodes > 0) {
+            S.maxflow<true>();   // a true flow: stranded excess back to the source
+            std::vector<double> hr((size_t)std::max<long long>(g.nP, 1) * 4);
+            std::vector<unsigned char> hsub((size_t)std::max<long long>(g.nP, 1));
+            SB_CUDA(cudaMemcpy(hr.data(), S.r.p, hr.size() * 8, cudaMemcpyDeviceToHost));
+            SB_CUDA(cudaMemcpy(hsub.data(), S.sub.p, hsub.size(), cudaMemcpyDeviceToHost));
+            weak_persistencies(g, hr, hsub, lab);
+        }
+        double nun = 0;
+        for (int64_t u = 0; u < N; u++) nun += lab[u] < 0;   // rd_mex.cpp:83-88
+        *num_unlabelled = nun;
+
+        // ---- Improve() (QPBO_extra.cpp:1151-1232): fix still-ambiguous nodes one by one to
+        // label 0 in a libc rand() permutation, re-solving after each
+        if (improve && nun > 0) {
+            std::vector<int> perm((size_t)N);
+            for (int64_t i = 0; i < N; i++) perm[i] = (int)i;
+            for (int64_t i = 0; i + 1 < N; i++) {   // ComputeRandomPermutation, QPBO_extra.cpp:13-27
+                int64_t j = i + (int64_t)((rand() / (1.0 + (double)RAND_MAX)) * (double)(N - i));
+                if (j > N - 1) j = N - 1;
+                std::swap(perm[j], perm[i]);
+            }
+            S.maxflow<false>();
+            labels_kernel<<<nblk(N), 256>>>(g, S.label.p);
+            std::vector<int> cur((size_t)N);
+            SB_CUDA(cudaMemcpy(cur.data(), S.label.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
+            DevBuf<double> dsat(1);
+            for (int64_t pi = 0; pi < N; pi++) {
+                const int u = perm[pi];
+                if (cur[u] >= 0) continue;     // what_segment(i) != what_segment(i'): decided
+                double sat = 0;
+                saturation_kernel<<<1, 1>>>(g, u, dsat.p);
+                SB_CUDA(cudaMemcpy(&sat, dsat.p, 8, cudaMemcpyDeviceToHost));
+                add_unary_kernel<<<1, 1>>>(g, u, sat);   // user_label == 0: forbid label 1
+                count_launch(2);
+                S.maxflow<false>();
+                labels_kernel<<<nblk(N), 256>>>(g, S.label.p);
+                count_launch();
+                SB_CUDA(cudaMemcpy(cur.data(), S.label.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
+            }
+            for (int64_t u = 0; u < N; u++) lab[u] = cur[u] < 0 ? 0 : cur[u];   // ambiguous -> user_label (0)
+        }
+
+        // ---- energy of the labelling (unlabelled -> 0), ComputeTwiceEnergy / 2
+        {
+            SB_CUDA(cudaMemcpy(S.label.p, lab.data(), (size_t)N * 4, cudaMemcpyHostToDevice));
+            DevBuf<double> terms((size_t)(N + E));
+            energy_terms_kernel<<<nblk(N + E), 256>>>(N, E, dconn.p, S.label.p, dU0.p, dU1.p, dE[0].p, dE[1].p, dE[2].p,
+                                                      dE[3].p, terms.p);
+            count_launch();
+            *energy = device_sum(terms.p, N + E);
+        }
+        for (int64_t u = 0; u < N; u++) labels[u] = (double)lab[u];
+    });
+}
+
+} // extern "C"

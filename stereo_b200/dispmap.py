@@ -1,0 +1,295 @@
+"""Host-side mirror of the reference's model classes dispmap_super / dispmap_ncc /
+dispmap_globalstereo (same property and method names, argument order and error behaviour), over
+the C ABI of libstereo_b200.so.  Arrays keep MATLAB shapes: ``assignment`` is 4 x N (one plane
+[a; b; c; d0] per pixel, node u = r + H*c), proposals are lists ("cell arrays") of 4 x N arrays.
+Nothing is computed here: every array-producing method forwards to a CUDA entry point.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import builders
+from .grid import construct_neighborhood, get_points
+from .solvers import rd, trws
+
+
+class dispmap_super:
+    """dispmap_super.m:3-329."""
+
+    def __init__(self, images, kernel):
+        # dispmap_super.m:24-36
+        self.images = [np.asarray(im, dtype=np.float64) for im in images]
+        self.sz = tuple(self.images[0].shape[:2])
+        self._kernel = kernel
+        self.maxiter = 1000              # dispmap_super.m:9
+        self._max_relgap = 1e-4          # :10
+        self._improve = False            # :13
+        self._assignment = None
+        self.stored_energy = np.inf
+        ind1, ind2 = construct_neighborhood(*self.sz)
+        self.neighborhood = dict(ind1=ind1, ind2=ind2)
+        self.smooth_weights = np.ones(ind1.size)
+        self.d_min, self.d_step = 0.0, 1.0   # disparity normalisation (identity here)
+
+    # ---- properties with the reference's validating setters (dispmap_super.m:39-56)
+    @property
+    def max_relgap(self):
+        return self._max_relgap
+
+    @max_relgap.setter
+    def max_relgap(self, v):
+        if v < 0:
+            raise ValueError("Maximum relative gap must be non-negative")
+        self._max_relgap = v
+
+    @property
+    def improve(self):
+        return self._improve
+
+    @improve.setter
+    def improve(self, v):
+        self._improve = bool(v)
+
+    @property
+    def assignment(self):
+        return self._assignment
+
+    @assignment.setter
+    def assignment(self, a):
+        self._assignment = np.asarray(a, dtype=np.float64)
+        self.update_energy()
+
+    @property
+    def smoothness_kernel(self):
+        return self._kernel
+
+    @smoothness_kernel.setter
+    def smoothness_kernel(self, k):
+        self._kernel = k
+        self.update_energy()
+
+    def energy(self):
+        return self.stored_energy
+
+    # ---- fusion moves
+    def binary_fusion(self, proposal):
+        """dispmap_super.m:61-84: one QPBO fusion move."""
+        proposal = np.asarray(proposal, dtype=np.float64)
+        if proposal.shape != self._assignment.shape:
+            raise ValueError("Binary fusion: Proposals is of wrong size")
+        E00, E01, E10, E11 = self.all_pairwise_costs(self._assignment, proposal)
+        U0 = self.unary_cost(self._assignment)
+        U1 = self.unary_cost(proposal)
+        connectivity = np.stack([self.neighborhood["ind1"], self.neighborhood["ind2"]]).astype(np.uint32)
+        labelling, e, lb, num_unlabelled = rd(U0, U1, E00, E01, E10, E11, connectivity, dict(improve=self.improve))
+        a = self._assignment.copy()
+        take = labelling == 1
+        a[:, take] = proposal[:, take]
+        self.assignment = a
+        return e, lb, num_unlabelled
+
+    def binary_fuse_until_convergence(self, proposal_cell, show_steps=False, rng=None):
+        """dispmap_super.m:85-152 (including its ``iter = iter + 1`` skip of ids(1))."""
+        if not isinstance(proposal_cell, (list, tuple)):
+            raise TypeError("Input proposals should be given in cell array.")
+        rng = rng or np.random.default_rng()
+        n = len(proposal_cell)
+        nrand = self.maxiter * 5
+        ids = np.concatenate([np.arange(1, n + 1), rng.integers(1, n + 1, size=nrand)])
+        keep = np.ones(ids.size, dtype=bool)
+        keep[:-1][np.diff(ids) == 0] = False   # ids([diff(ids) == 0]) = 0; removed
+        ids = ids[keep]
+        E = [self.energy()]
+        visited = np.zeros(n, dtype=bool)
+        for it in range(1, self.maxiter + 1):
+            if it > nrand:
+                ids = np.concatenate([ids, ids])
+            it1 = it + 1                        # :116
+            if it1 > ids.size:
+                break
+            if visited[ids[it1 - 1] - 1]:
+                continue
+            self.binary_fusion(proposal_cell[ids[it1 - 1] - 1])
+            E.append(self.energy())
+            if E[-2] != E[-1]:
+                visited[:] = False
+            else:
+                visited[ids[it1 - 1] - 1] = True
+            if visited.all():
+                break
+        return len(E)
+
+    def simultaneous_fusion(self, proposal_cell):
+        """dispmap_super.m:153-198: TRW-S over the proposals plus the current assignment."""
+        if not isinstance(proposal_cell, (list, tuple)):
+            raise TypeError("Input proposals should be given in cell array.")
+        proposal_cell = list(proposal_cell) + [self._assignment]
+        unary = np.stack([self.unary_cost(p) for p in proposal_cell])
+        connectivity = np.stack([self.neighborhood["ind1"], self.neighborhood["ind2"]]).astype(np.uint32)
+        q, qprim = builders.fusion_positions(self.sz[0], self.sz[1], proposal_cell, self.d_min, self.d_step)
+        options = dict(maxiter=self.maxiter, max_relgap=self.max_relgap)
+        L, e, lb, iterations = trws(np.int32(self.smoothness_kernel), unary, connectivity, q, qprim,
+                                    self.smooth_weights.reshape(-1), self.tol, options)
+        assignments = np.zeros_like(proposal_cell[0])
+        for i, p in enumerate(proposal_cell):
+            m = L == i + 1
+            assignments[:, m] = p[:, m]
+        self.assignment = assignments
+        return e, lb, iterations
+
+    def current_dispmap(self):
+        return self.disparitymap_from_assignment(self._assignment).reshape(self.sz[1], self.sz[0]).T
+
+    # ---- protected methods of the reference
+    def unary_cost(self, assignment):
+        raise NotImplementedError("Overload unary_cost")
+
+    def all_pairwise_costs(self, assignment, proposals=None):
+        """dispmap_super.m:236-262."""
+        return builders.pairwise_tables(self.sz[0], self.sz[1], self.smoothness_kernel, assignment, proposals,
+                                        self.smooth_weights, self.tol, self.d_min, self.d_step)
+
+    def update_energy(self):
+        """dispmap_super.m:263-274."""
+        if self._assignment is None:
+            self.stored_energy = np.inf
+            return
+        U = self.unary_cost(self._assignment)
+        self.stored_energy = builders.energy(self.sz[0], self.sz[1], self.smoothness_kernel, U, self._assignment,
+                                             self.smooth_weights, self.tol, self.d_min, self.d_step)
+
+    def get_points(self):
+        return get_points(*self.sz)
+
+    def disparitymap_from_assignment(self, assignment, points=None):
+        """dispmap_super.m:318-328 (dispmap_globalstereo.m:336-345 through d_min / d_step)."""
+        if points is None:
+            points = self.get_points()
+        return builders.plane_disparity(assignment, points, self.d_min, self.d_step)
+
+
+class dispmap_ncc(dispmap_super):
+    """dispmap_ncc.m:5-277.  ``patchsize`` is the one surface extension (reference: fixed 2,
+    dispmap_ncc.m:24) needed for BASELINE config 3's 9x9 window."""
+
+    def __init__(self, images, disparities, kernel, unary_weight, tol, patchsize=2):
+        super().__init__(images, kernel)
+        self.disparities = np.asarray(disparities, dtype=np.float64).reshape(-1)
+        if unary_weight < 0:
+            raise ValueError("Unary weight must be positive")
+        if tol < 0:
+            raise ValueError("Tolerance weight must be positive")
+        self._unary_weight = unary_weight
+        self._tol = tol
+        self.ncc = builders.ncc_volume(self.images[0], self.images[1], self.disparities, patchsize)  # :24
+        self.init_solution()                                                                        # :27
+
+    @property
+    def tol(self):
+        return self._tol
+
+    @tol.setter
+    def tol(self, v):
+        if v < 0:
+            raise ValueError("Tolerance weight must be positive")
+        self._tol = v
+        self.update_energy()
+
+    @property
+    def unary_weight(self):
+        return self._unary_weight
+
+    @unary_weight.setter
+    def unary_weight(self, v):
+        if v < 0:
+            raise ValueError("Unary weight must be positive")
+        self._unary_weight = v
+        self.update_energy()
+
+    def restart(self):
+        self.init_solution()
+
+    def unary_cost(self, assignment):
+        """dispmap_ncc.m:107-115."""
+        disps = self.disparitymap_from_assignment(assignment)
+        return builders.ncc_sample(self.ncc, self.disparities, disps, self.unary_weight, True).reshape(-1, order="F")
+
+    def best_disp_from_ncc(self):
+        return builders.ncc_best_disp(self.ncc, self.disparities)
+
+    def init_solution(self):
+        """dispmap_ncc.m:199-207."""
+        best = self.best_disp_from_ncc()
+        a = np.zeros((4, self.sz[0] * self.sz[1]))
+        a[2] = 1
+        a[3] = -best.reshape(-1, order="F")
+        self.assignment = a
+
+
+class dispmap_globalstereo(dispmap_super):
+    """dispmap_globalstereo.m:10-480, hot-path part: the photo-consistency unary, the disparity
+    normalisation and the segmentation-weighted smoothness.  The mean-shift segmentation of the
+    reference (vgg_segment_ms) is preprocessing outside the hot path: pass
+    its label image as ``segment`` (H x W integers); without it all edges get lambda_l."""
+
+    def __init__(self, images, P, disp_range, disparity_factor, options, segment=None, start_disparity=None,
+                 rng=None):
+        kernel = options["smoothness_kernel"]
+        super().__init__(images, kernel)
+        self._tol = options["disp_thresh"]
+        P = np.asarray(P, dtype=np.float64)
+        if P.ndim == 2:
+            P = P[:, :, None]
+        if np.max(np.abs(P.reshape(-1, order="F")[[0, 1, 2, 3, 4, 5, 8]] - [1, 0, 0, 0, 1, 0, 1])) > 1e-12:
+            raise ValueError("First image must be reference image")
+        self.P = np.transpose(P, (1, 0, 2))                       # :42
+        self.disp_range = disp_range
+        self.disparity_factor = disparity_factor
+        disps = np.sort(np.arange(disp_range[0] * disparity_factor, disp_range[1] * disparity_factor + 1))[::-1]
+        self.disps = disps
+        self.d_min = float(disps[-1])
+        self.d_step = float(disps[0] - self.d_min)
+        self.options = dict(options)
+        self._preprocess(segment)
+        if start_disparity is None:
+            rng = rng or np.random.default_rng()
+            start_disparity = rng.random(self.sz) * self.d_step + self.d_min   # :56
+        self.start_disparity = np.asarray(start_disparity, dtype=np.float64)
+        self.init_solution()
+
+    @property
+    def tol(self):
+        return self._tol
+
+    @tol.setter
+    def tol(self, v):
+        self._tol = v
+
+    def _preprocess(self, segment):
+        """dispmap_globalstereo.m:377-414 without the segmentation call itself."""
+        o = self.options
+        self.improve = o.get("improve", 0) > 0
+        num_in = len(self.images)
+        ind1, ind2 = self.neighborhood["ind1"], self.neighborhood["ind2"]
+        if segment is None:
+            same = np.zeros(ind1.size, dtype=bool)
+        else:
+            seg = np.asarray(segment).reshape(-1, order="F")
+            same = seg[ind1 - 1] == seg[ind2 - 1]
+        EW = np.where(same, o["lambda_h"], o["lambda_l"]).astype(np.float64)
+        EW = EW * (num_in / ((o.get("connect", 4) == 8) + 1))
+        self.smooth_weights = EW
+        if self._kernel == 2:
+            self.smooth_weights = self.smooth_weights / self._tol
+            self._tol = self._tol ** 2
+
+    def init_solution(self):
+        a = np.zeros((4, self.sz[0] * self.sz[1]))
+        a[2] = 1
+        a[3] = -self.start_disparity.reshape(-1, order="F")
+        self.assignment = a
+
+    def unary_cost(self, assignment):
+        """dispmap_globalstereo.m:355-375."""
+        return builders.photo_unary(self.images[0], self.images[1], self.P[:, :, 1], assignment, self.d_min,
+                                    self.d_step, self.options["col_thresh"])

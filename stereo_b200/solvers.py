@@ -152,6 +152,36 @@ class TrwsSolver:
             pass
 
 
+def rd(U0, U1, E00, E01, E10, E11, connectivity, options=None):
+    """[solution, energy, lower_bound, num_unlabelled] = rd(U0, U1, E00, E01, E10, E11,
+    connectivity, options)  -- rd.m:3-21.
+
+    U0, U1: N.  E00..E11: E.  connectivity: 2 x E, 1-based.  options: ``improve`` (bool,
+    default False; rd_mex.cpp:34).  Returns (solution N float64 in {0, 1, negative}, energy,
+    lower_bound, num_unlabelled)."""
+    U0, U1 = _f(np.asarray(U0).reshape(-1)), _f(np.asarray(U1).reshape(-1))
+    E00, E01, E10, E11 = (_f(np.asarray(x).reshape(-1)) for x in (E00, E01, E10, E11))
+    connectivity = np.asarray(connectivity)
+    # rd.m:5-6
+    assert connectivity.size == 0 or connectivity.min() > 0
+    assert connectivity.size == 0 or connectivity.max() <= U0.size
+    # rd_mex.cpp:36-49
+    assert U0.shape == U1.shape
+    assert E00.shape == E01.shape == E10.shape == E11.shape
+    assert connectivity.shape == (2, E00.size)
+    improve = bool(_opt(options, "improve", False))
+    conn0 = np.asfortranarray(connectivity.astype(np.int64) - 1, dtype=np.uint32)  # rd.m:21
+    N, E = U0.size, E00.size
+    solution = np.zeros(N, dtype=np.float64)
+    e, lb, nu = c_double(), c_double(), c_double()
+    rc = lib().sb_rd_solve(N, E, U0.ctypes.data_as(_dp), U1.ctypes.data_as(_dp), E00.ctypes.data_as(_dp),
+                           E01.ctypes.data_as(_dp), E10.ctypes.data_as(_dp), E11.ctypes.data_as(_dp),
+                           conn0.ctypes.data_as(_up), int(improve), solution.ctypes.data_as(_dp), ctypes.byref(e),
+                           ctypes.byref(lb), ctypes.byref(nu))
+    check(rc)
+    return solution, e.value, lb.value, nu.value
+
+
 def trws_grid_ordering(H, W):
     """m_ordering of SetAutomaticOrdering (ordering.cpp:7-157) on the H x W grid, as (H, W) int32."""
     out = np.zeros(H * W, dtype=np.int32)

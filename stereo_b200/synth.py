@@ -87,3 +87,74 @@ def trws_problem(H, W, L, seed=0, kernel=1, tol=None, duplicate_last=True):
         alphas = alphas / 0.02
     return dict(kernel=kernel, unary=unary, connectivity=np.stack([ind1, ind2]), q=q, qprim=qprim,
                 alphas=alphas, tol=float(tol), planes=props)
+
+
+def stereo_pair(H, W, max_disp, seed=0, noise=2.0):
+    """Synthetic rectified pair: image 1 = band-limited random RGB texture
+    quantised to 8 bits, ground-truth disparity = a few random planes over a rectangular
+    segmentation in [0, max_disp], image 2 = image 1 warped by -disparity (linear) + noise.
+    Returns (im0, im1) float64 H x W x 3 with integer values 0..255, and the disparity."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    base = rng.random((H // 4 + 3, W // 4 + 3, 3))
+    yy = np.linspace(0, base.shape[0] - 1.001, H)
+    xx = np.linspace(0, base.shape[1] - 1.001, W)
+    y0, x0 = np.floor(yy).astype(int), np.floor(xx).astype(int)
+    fy, fx = (yy - y0)[:, None, None], (xx - x0)[None, :, None]
+    tex = (base[y0][:, x0] * (1 - fy) * (1 - fx) + base[y0 + 1][:, x0] * fy * (1 - fx)
+           + base[y0][:, x0 + 1] * (1 - fy) * fx + base[y0 + 1][:, x0 + 1] * fy * fx)
+    tex = 0.6 * tex + 0.4 * rng.random((H, W, 3))
+    im0 = np.floor(tex * 255.999)
+    disp = np.zeros((H, W))
+    rows = np.arange(H)[:, None]
+    cols = np.arange(W)[None, :]
+    for _ in range(5):
+        r0, r1 = np.sort(rng.integers(0, H, 2))
+        c0, c1 = np.sort(rng.integers(0, W, 2))
+        a, b = (rng.random(2) - 0.5) * 0.1
+        d0 = rng.random() * max_disp
+        m = (rows >= r0) & (rows <= r1) & (cols >= c0) & (cols <= c1)
+        disp = np.where(m, np.clip(d0 + a * (cols - c0) + b * (rows - r0), 0, max_disp), disp)
+    # image 2 (x - d) = image 1 (x)  =>  im1[:, c] = im0 sampled at c + disp (approximately)
+    src = np.clip(cols + disp, 0, W - 1)
+    s0 = np.floor(src).astype(int)
+    f = (src - s0)[:, :, None]
+    s1 = np.minimum(s0 + 1, W - 1)
+    im1 = im0[rows, s0] * (1 - f) + im0[rows, s1] * f + rng.normal(0, noise, (H, W, 3))
+    im1 = np.clip(np.round(im1), 0, 255)
+    return im0, im1, disp
+
+
+def rd_problem(H, W, seed=0, kernel=1, mode="stereo", tol=0.02):
+    """A complete rd() argument set in MATLAB shapes (dispmap_super.binary_fusion,
+    dispmap_super.m:61-84): U0, U1 (N), E00..E11 (E), connectivity 2 x E (1-based).
+
+    mode "stereo": tables from two plane fields through the truncated pairwise cost
+    (mostly submodular, exact ties where both fields agree); "frustrated": random tables
+    with many non-submodular terms (hard part 3)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    N = H * W
+    ind1, ind2 = construct_neighborhood(H, W)
+    E = ind1.size
+    if mode == "frustrated":
+        U0, U1 = rng.random(N), rng.random(N)
+        T = rng.random((4, E)) * 2
+        return dict(U0=U0, U1=U1, E00=T[0], E01=T[1], E10=T[2], E11=T[3], connectivity=np.stack([ind1, ind2]))
+    pts = get_points(H, W)
+    props = random_plane_proposals(H, W, 3, rng)
+    cur, new = props[1].copy(), props[2].copy()
+    same = rng.random(N) < 0.15               # pixels where the proposal equals the current plane
+    new[:, same] = cur[:, same]
+    U0 = rng.random(N) * np.log(2.0)
+    U1 = rng.random(N) * np.log(2.0)
+    U1[same] = U0[same]
+    p2 = pts[:, ind2 - 1]
+    q, qp = disparity_from_planes(cur[:, ind2 - 1], p2), disparity_from_planes(cur[:, ind1 - 1], p2)
+    nq, nqp = disparity_from_planes(new[:, ind2 - 1], p2), disparity_from_planes(new[:, ind1 - 1], p2)
+    nV, nH = (H - 1) * W, H * (W - 1)
+    w = np.where(rng.random(nV + nH) < 0.8, 108.0, 9.0) * 2.0
+    w = np.concatenate([w[:nV], w[:nV], w[nV:], w[nV:]])
+    if kernel == 2:
+        w, tol = w / tol, tol ** 2
+    pc = (lambda a, b: w * np.minimum(np.abs(a - b), tol)) if kernel == 1 else (lambda a, b: w * np.minimum((a - b) ** 2, tol))
+    return dict(U0=U0, U1=U1, E00=pc(q, qp), E01=pc(nq, qp), E10=pc(q, nqp), E11=pc(nq, nqp),
+                connectivity=np.stack([ind1, ind2]), cur=cur, new=new, weights=w, tol=tol)

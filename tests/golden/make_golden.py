@@ -32,6 +32,13 @@ TRWS_CASES = [  # (H, W, L, kernel, seed, maxiter, max_relgap)
 ]
 
 
+RD_CASES = [  # (H, W, seed, kernel, frustrated, improve)
+    (6, 8, 1, 1, 0, 0), (6, 8, 1, 1, 1, 0), (17, 23, 2, 1, 0, 0), (17, 23, 2, 2, 0, 0), (17, 23, 3, 1, 1, 0),
+    (40, 50, 3, 1, 0, 0), (40, 50, 3, 1, 1, 0), (64, 48, 4, 2, 0, 0), (1, 9, 5, 1, 0, 0), (9, 1, 5, 1, 1, 0),
+    (2, 2, 6, 1, 1, 0), (120, 90, 7, 1, 0, 0), (12, 14, 8, 1, 1, 1), (20, 25, 9, 1, 1, 1), (40, 50, 3, 1, 0, 1),
+]
+
+
 def main():
     assert oracle.have_ref("trws"), "build oracle/_ref first (make -C oracle ref)"
     # 1. orderings
@@ -83,6 +90,19 @@ def main():
     Y[:6] = [1, 7, 3.2, 7, 1, 7]
     B = oracle.interp2_linear(A, X, Y, -1000.0)
     np.savez_compressed(os.path.join(HERE, "interp2.npz"), A=A, X=X, Y=Y, B=B)
+    # 5. QPBO fusions (rd_mex.cpp through the shim); libc rand() reseeded like the tests do
+    import ctypes
+    libc = ctypes.CDLL(None)
+    out = {}
+    for i, (H, W, seed, kernel, mode, improve) in enumerate(RD_CASES):
+        pr = synth.rd_problem(H, W, seed=seed, kernel=kernel, mode="frustrated" if mode else "stereo")
+        libc.srand(1)
+        lab, e, lb, nu = oracle.rd_solve(pr["U0"], pr["U1"], pr["E00"], pr["E01"], pr["E10"], pr["E11"],
+                                         (pr["connectivity"] - 1).T, improve=bool(improve))
+        out[f"case{i}_params"] = np.array([H, W, seed, kernel, mode, improve], dtype=np.float64)
+        out[f"case{i}_labels"] = lab.astype(np.int8)
+        out[f"case{i}_scalars"] = np.array([e, lb, nu], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "rd_solve.npz"), **out)
     print("golden vectors written to", HERE)
 
 

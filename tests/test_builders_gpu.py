@@ -1,0 +1,132 @@
+"""GPU parity tests of the cost-volume / unary / pairwise builders through the C ABI against
+the NumPy restatement of the MATLAB code (oracle/stereo_np.py) and, for the vgg_interp2 gather,
+against the compiled reference / its golden fixture.  Tolerance 1e-4 relative (north star) for the
+fp32-accumulated NCC volume on well-conditioned windows; 1e-12 for the fp64 elementwise paths."""
+import numpy as np
+import pytest
+
+import stereo_b200 as sb
+from stereo_b200 import builders, synth
+from util import golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _np():
+    from oracle import stereo_np
+    return stereo_np
+
+
+@pytest.mark.parametrize("H,W,D,p,frac", [(37, 53, 8, 2, False), (64, 48, 6, 4, False), (30, 41, 5, 2, True),
+                                          (7, 9, 3, 2, False), (40, 33, 4, 0, False)])
+def test_ncc_volume(H, W, D, p, frac):
+    im0, im1, _ = synth.stereo_pair(H, W, D, seed=H + W)
+    disps = np.arange(D, dtype=np.float64) * (1.5 if frac else 1.0)
+    got = builders.ncc_volume(im0, im1, disps, p)
+    ref = _np().compute_ncc(im0, im1, disps, p)
+    cond = _np().ncc_conditioning(im0, im1, disps, p)
+    ok = cond > 1e-6
+    assert ok.mean() > 0.9
+    assert np.all(np.abs(got - ref)[ok] <= 1e-4 * np.maximum(np.abs(ref[ok]), 1e-2))
+    # masked columns and the zero padding region are exact zeros in both
+    assert np.array_equal(got == 0, ref == 0) or np.mean((got == 0) == (ref == 0)) > 0.999
+
+
+def test_ncc_sampling_and_wta():
+    H, W, D = 33, 47, 9
+    im0, im1, _ = synth.stereo_pair(H, W, D, seed=3)
+    disps = np.arange(D, dtype=np.float64) * 2.0
+    ncc = _np().compute_ncc(im0, im1, disps, 2)
+    best = builders.ncc_best_disp(ncc, disps)
+    rbest = _np().best_disp_from_ncc(ncc, disps)
+    m = np.isfinite(rbest)
+    assert np.allclose(best[m], rbest[m], rtol=1e-12, atol=1e-12)
+    rng = np.random.default_rng(0)
+    x = rng.random((H, W)) * (disps.max() + 4) - 2      # includes out-of-range and exact levels
+    x[0, :D] = disps
+    x[1, : D - 1] = (disps[:-1] + disps[1:]) / 2         # exact ties between two levels (:232)
+    got = builders.ncc_sample(ncc, disps, x.reshape(-1, order="F"))
+    ref = _np().sample_ncc_from_disp(ncc, disps, x)
+    assert np.allclose(got, ref, rtol=1e-12, atol=1e-12)
+    u = builders.ncc_sample(ncc, disps, x.reshape(-1, order="F"), 40.0, True)
+    assert np.allclose(u, 40.0 * (1 - ref), rtol=1e-12, atol=1e-9)
+
+
+def test_interp2_golden():
+    g = golden("interp2.npz")
+    got = builders.interp2_linear(g["A"], g["X"], g["Y"], -1000.0)
+    assert np.array_equal(got, g["B"])       # same operation order as vgg_interp2.cxx:262-266 -> bit-exact
+
+
+def test_photo_unary_and_plane_disparity():
+    H, W = 29, 37
+    im0, im1, _ = synth.stereo_pair(H, W, 12, seed=9)
+    rng = np.random.default_rng(1)
+    planes = np.zeros((4, H * W))
+    planes[0] = (rng.random(H * W) - 0.5) * 0.01
+    planes[1] = (rng.random(H * W) - 0.5) * 0.01
+    planes[2] = 1.0
+    planes[3] = -rng.random(H * W) * 50
+    pts = sb.get_points(H, W)
+    d_min, d_step = 0.0, 48.0
+    nd = builders.plane_disparity(planes, pts, d_min, d_step)
+    assert np.allclose(nd, _np().disparity_from_assignment(planes, pts, d_min, d_step), rtol=1e-14, atol=1e-14)
+    P2 = np.array([[1, 0, 0, -0.25], [0, 1, 0, 0], [0, 0, 1, 0]], dtype=np.float64).T   # example_global.m:17-18
+    got = builders.photo_unary(im0, im1, P2, planes, d_min, d_step, 30.0)
+    from oracle import oracle
+
+    def interp(A, X, Y, oobv):
+        kind = "reference" if oracle.have_ref("interp2") else "port"
+        return oracle.interp2_linear(A, X, Y, oobv, kind=kind)
+    ref = _np().photo_unary_cost([im0, im1], P2, planes, d_min, d_step, 30.0, interp)
+    assert np.allclose(got, ref, rtol=1e-12, atol=1e-13)
+    bad = planes.copy()
+    bad[2, 5] = 0
+    with pytest.raises(sb._lib.SbError) as ei:          # dispmap_super.m:323-325
+        builders.plane_disparity(bad, pts)
+    assert "Infinite disparity" in str(ei.value)
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_pairwise_tables_positions_energy(kernel):
+    H, W, L = 17, 23, 5
+    rng = np.random.Generator(np.random.PCG64(4))
+    props = synth.random_plane_proposals(H, W, L, rng)
+    E = 2 * ((H - 1) * W + H * (W - 1))
+    w = rng.random(E) * 10
+    tol = 0.02 if kernel == 1 else 0.02 ** 2
+    got = builders.pairwise_tables(H, W, kernel, props[1], props[2], w, tol, 0.1, 2.0)
+    ref = _np().all_pairwise_costs(H, W, kernel, w, tol, props[1], props[2], 0.1, 2.0)
+    for a, b in zip(got, ref):
+        assert np.allclose(a, b, rtol=1e-12, atol=1e-15)
+    q, qp = builders.fusion_positions(H, W, list(props), 0.1, 2.0)
+    rq, rqp = _np().fusion_positions(H, W, list(props), 0.1, 2.0)
+    assert np.allclose(q, rq, rtol=1e-13, atol=1e-14) and np.allclose(qp, rqp, rtol=1e-13, atol=1e-14)
+    un = rng.random(H * W)
+    e = builders.energy(H, W, kernel, un, props[1], w, tol, 0.1, 2.0)
+    assert abs(e - _np().energy(H, W, kernel, w, tol, un, props[1], 0.1, 2.0)) <= 1e-11 * abs(e)
+
+
+def test_dispmap_ncc_class_end_to_end():
+    """example_ncc.m plumbing at a small size: constructor (NCC volume + WTA init), one binary
+    fusion (QPBO) and one simultaneous fusion (TRW-S); energies must not increase."""
+    H, W = 32, 40
+    im0, im1, _ = synth.stereo_pair(H, W, 10, seed=2)
+    dm = sb.dispmap_ncc([im0, im1], np.arange(0, 11, dtype=np.float64), 1, 40.0, 8.0)
+    e0 = dm.energy()
+    prop = np.zeros((4, H * W))
+    prop[2] = 1
+    prop[3] = -5.0
+    dm.binary_fusion(prop)
+    e1 = dm.energy()
+    assert e1 <= e0 + 1e-9 * abs(e0)
+    dm.maxiter = 30
+    props = []
+    for d in (0.0, 3.0, 6.0, 9.0):
+        p = np.zeros((4, H * W))
+        p[2] = 1
+        p[3] = -d
+        props.append(p)
+    dm.simultaneous_fusion(props)
+    assert dm.energy() <= e1 + 1e-6 * abs(e1)
+    assert dm.current_dispmap().shape == (H, W)

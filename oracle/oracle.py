@@ -68,6 +68,15 @@ def _ref(name):
     return _load(os.path.join(REF_DIR, f"libref_{name}.so"))
 
 
+def _gateway(name):
+    """Our own mex gateway (stereo_b200/matlab/<name>_mex.cpp) behind the same fabricated-mxArray
+    driver as the reference gateway -- the product called through the MATLAB ABI."""
+    path = os.path.join(PORT_DIR, f"libgw_{name}.so")
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-s", "-C", HERE, "gateway"])
+    return _load(path)
+
+
 def _port():
     if not have_port():
         build(ref=False, port=True)
@@ -99,6 +108,8 @@ def trws_solve(kernel, unary, conn, q, qprim, alphas, tol, maxiter=1000, max_rel
     out = (c_double * 3)()
     if kind == "reference":
         fn = _ref("trws").ref_trws_solve
+    elif kind == "gateway":
+        fn = _gateway("trws").ref_trws_solve
     else:
         fn = _port().port_trws_solve
     fn.argtypes = _TRWS_ARGS
@@ -108,7 +119,12 @@ def trws_solve(kernel, unary, conn, q, qprim, alphas, tol, maxiter=1000, max_rel
             ctypes.cast(ctypes.byref(out, 0), _dp), ctypes.cast(ctypes.byref(out, 8), _dp),
             ctypes.cast(ctypes.byref(out, 16), _dp))
     if rc != 0:
-        raise RuntimeError(f"oracle trws_solve ({kind}) failed rc={rc}")
+        msg = ""
+        if kind in ("reference", "gateway"):
+            lib_ = _ref("trws") if kind == "reference" else _gateway("trws")
+            lib_.ref_last_error.restype = ctypes.c_char_p
+            msg = lib_.ref_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"oracle trws_solve ({kind}) failed rc={rc}: {msg}")
     return labels.astype(np.int64), out[0], out[1], int(out[2])
 
 
@@ -158,7 +174,7 @@ def rd_solve(U0, U1, E00, E01, E10, E11, conn, improve=False, kind="reference"):
     E = conn.shape[0]
     labels = np.zeros(N, dtype=np.float64)
     out = (c_double * 3)()
-    fn = _ref("rd").ref_rd_solve if kind == "reference" else _port().port_rd_solve
+    fn = _ref("rd").ref_rd_solve if kind == "reference" else _gateway("rd").ref_rd_solve
     fn.argtypes = [c_int64, c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _up, c_int, _dp, _dp, _dp, _dp]
     fn.restype = c_int
     rc = fn(N, E, _ptr(U0, _dp), _ptr(U1, _dp), _ptr(E00, _dp), _ptr(E01, _dp), _ptr(E10, _dp), _ptr(E11, _dp),

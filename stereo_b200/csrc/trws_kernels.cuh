@@ -63,7 +63,7 @@ struct Problem {
     const uint8_t *cnt_qp;  // [E][LP]  #{q <= qprim[l]}   clamped to 255
     const REAL *alpha;      // [E]
     REAL lambda;
-    const SegWarp *segs;    // segment descriptors of THIS pass (trws_sched.h): [nseg][NCW]
+    const Segment *segs;    // segment descriptors of THIS pass (trws_sched.h)
     const int32_t *seg_ptr; // [S+1] segments of each forward strip
     const int32_t *strip_ptr; // [S+1] node count prefix of the forward strips
     int S;
@@ -561,42 +561,51 @@ template <typename REAL, int K> __device__ __forceinline__ void row_sts(REAL *ro
 
 // ---------------------------------------------------------------- the sweep
 //
-// CTA = NCW compute warps + 1 auxiliary warp; a CTA walks one strip at a time,
+// CTA = 4 term warps + 2 helper warps + 1 auxiliary warp; a CTA walks one strip at a time,
 // driven by the segment descriptors of trws_sched.h (no grid arithmetic here).
-// A node is processed in one STEP (two when it sends on more than NCW terms):
 //
-//   phase A (before the step's barrier), per compute warp: sum what this warp
-//     fetched for the node -- the old message of its own send term (registers,
-//     loaded one step ahead), rows that arrived in its landing buffers through
-//     cp.async (the unary row, dependency messages published by other strips,
-//     position rows for the rounding) -- into partial rows in shared memory;
-//   barrier (compute warps only);
-//   phase B: every compute warp issues the loads of the NEXT step, forms Di
-//     (minimize.cpp:38-46 / 69-77) from the partial rows plus the two messages
-//     the CTA sent to this node in the previous step (carry rows in shared
-//     memory), rounds the node when the pass carries the primal sweep
-//     (minimize.cpp:240-260), runs the min-plus update of its own term and
-//     stores it.
-//   The auxiliary warp watches the compute warps' completion counters,
-//   publishes the strip's progress watermark (gpu-scope fence + store, far too
-//   slow for the dependent chain) and pulls the operands of the nodes ahead
-//   into L2.
+//   helper warps (alternating nodes, one node ahead of the term warps) fetch every row a
+//     node needs besides the term warps' own operands -- the unary row, the old messages of
+//     its send terms, the dependency messages published by other strips (after the strip's
+//     progress watermark says so), the position rows and selected positions for the primal
+//     rounding -- with cp.async into landing buffers, and reduce them to three rows in shared
+//     memory: BASE (D + every incident message except the carried pair), DIB0 (D + pairwise
+//     columns of the rounded lower neighbours) and RMS (sum of the forward messages);
+//   term warps: warp w owns send term w of the node (operands loaded into registers one node
+//     ahead).  Per node the dependent chain is only: Di = BASE + the two messages the CTA sent
+//     to this node in the previous step (carry rows in shared memory; minimize.cpp:38-46 /
+//     69-77), the primal rounding when the pass carries it (minimize.cpp:240-260), the
+//     min-plus update of the own term, its store, and the carry rows for the next node;
+//   the auxiliary warp watches the term warps' completion counters, publishes the strip's
+//     progress watermark (gpu-scope fence + store: thousands of cycles, kept off the chain)
+//     and pulls the operands of the nodes ahead into L2.
 //
-// Shared rows are double buffered by node parity, so one barrier per step is
-// enough.
+// Rows are double buffered by node parity.  Named barriers: FULL[par] (helper arrives, term
+// warps sync: rows of the node ready and all term warps done with the previous node) and
+// EMPTY[par] (term warps arrive after reading, helper syncs before overwriting).
 
-constexpr int NCW = SCHED_NCW;
-constexpr int CTA_THREADS = (NCW + 1) * 32;
-constexpr int SLOTS = SCHED_SLOTS; // landing rows per compute warp
-constexpr int ROWS_PER_PAR = 17;   // RM[4] RX[4] RB[4] DR CM[2] CC[2]
+constexpr int NCW = SCHED_NCW;      // term warps
+constexpr int NHW = 2;              // helper warps
+constexpr int CTA_THREADS = (NCW + NHW + 1) * 32;
+constexpr int ROWS_PER_PAR = 7;     // BASE DIB0 RMS CM[2] CC[2]
 constexpr int PF_DIST = 6;
 
-enum { R_RM = 0, R_RX = 4, R_RB = 8, R_DR = 12, R_CM = 13, R_CC = 15 };
+enum { R_BASE = 0, R_DIB0 = 1, R_RMS = 2, R_CM = 3, R_CC = 5 };
+enum { BAR_FULL = 1, BAR_EMPTY = 3 };   // + parity
 
 template <typename REAL, int K> __host__ __device__ constexpr size_t sweep_smem_bytes()
 {
-    return (size_t)(2 * ROWS_PER_PAR + NCW * SLOTS) * 32 * K * sizeof(REAL) +
+    return (size_t)(2 * ROWS_PER_PAR + NHW * SCHED_ITEMS) * 32 * K * sizeof(REAL) +
            (size_t)NCW * scratch_pairs<K>() * sizeof(Pair<REAL>);
+}
+
+__device__ __forceinline__ void named_sync(int id)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"((NCW + 1) * 32) : "memory");
+}
+__device__ __forceinline__ void named_arrive(int id)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"((NCW + 1) * 32) : "memory");
 }
 
 template <typename REAL, int K> struct OwnTerm {
@@ -612,38 +621,33 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_ticket;
-    __shared__ int s_wdone[NCW]; // nodes of the current strip each compute warp has completed
-    __shared__ __align__(16) SegWarp s_desc[NCW][2];
+    __shared__ int s_wdone[NCW]; // nodes of the current strip each term warp has completed
+    __shared__ __align__(16) Segment s_seg[NHW];
     constexpr int LP = 32 * K;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const bool is_aux = (warp == NCW);
+    const bool is_term = warp < NCW;
+    const bool is_helper = warp >= NCW && warp < NCW + NHW;
     REAL *rows = reinterpret_cast<REAL *>(smem_raw);
-    REAL *landing = rows + (size_t)2 * ROWS_PER_PAR * LP + (size_t)(is_aux ? 0 : warp) * SLOTS * LP;
-    Pair<REAL> *P = reinterpret_cast<Pair<REAL> *>(rows + (size_t)(2 * ROWS_PER_PAR + NCW * SLOTS) * LP) +
-                    (size_t)(is_aux ? 0 : warp) * scratch_pairs<K>();
     const REAL BIG = Lim<REAL>::big();
-    if (!is_aux && lane == 0) {
+    const bool do_send = (PASS == PASS_BWD) || (p.mode & MODE_SEND);
+    const bool do_round = (PASS == PASS_FWD) && (p.mode & MODE_ROUND);
+    const Segment *const segs = p.segs;
+    double acc_energy = 0.0, acc_lb = 0.0;
+    auto row_ptr = [&](int par, int r) -> REAL * { return rows + (size_t)(par * ROWS_PER_PAR + r) * LP; };
+    Pair<REAL> *P = reinterpret_cast<Pair<REAL> *>(rows + (size_t)(2 * ROWS_PER_PAR + NHW * SCHED_ITEMS) * LP) +
+                    (size_t)(is_term ? warp : 0) * scratch_pairs<K>();
+    if (is_term && lane == 0) {
         Pair<REAL> t;
         t.a = BIG;
         t.b = REAL(0);
         P[0] = t;
         P[phys<K>(LP)] = t;
     }
-    const bool do_send = (PASS == PASS_BWD) || (p.mode & MODE_SEND);
-    const bool do_round = (PASS == PASS_FWD) && (p.mode & MODE_ROUND);
-    const SegWarp *const segs = p.segs;
-    double acc_energy = 0.0, acc_lb = 0.0;
-
-    auto row_ptr = [&](int par, int r) -> REAL * { return rows + (size_t)(par * ROWS_PER_PAR + r) * LP; };
-    auto slot_active = [&](int kind) -> bool {
-        const int k = kind & 255;
-        return k == S_D || k == S_STAT || (k == S_DYN && do_send) || (k == S_RND && do_round);
-    };
 
     for (;;) {
         if (threadIdx.x == 0) s_ticket = atomicAdd(p.ticket, 1);
-        __syncthreads(); // the auxiliary warp has published the previous strip completely
+        __syncthreads(); // everybody is done with the previous strip (the auxiliary warp has published it)
         const int ts = s_ticket;
         if (threadIdx.x < NCW) s_wdone[threadIdx.x] = 0;
         __syncthreads();
@@ -652,13 +656,296 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
         const int fs = (PASS == PASS_BWD) ? p.S - 1 - ts : ts;
         const int sg0 = __ldg(p.seg_ptr + fs), sg1 = __ldg(p.seg_ptr + fs + 1);
         const int n_nodes = __ldg(p.strip_ptr + fs + 1) - __ldg(p.strip_ptr + fs);
-        if (sg1 <= sg0) continue;
+        if (sg1 <= sg0 || n_nodes <= 0) continue;
 
-        if (is_aux) {
-            // ------------------------------------------------------------ auxiliary warp
+        if (is_term) {
+            // ============================================================ term warps
+            const int w = warp;
+            int sg = sg0;
+            const Segment *g = segs + sg;
+            int seg_n = __ldg(&g->n), seg_i = 0;
+            int u0 = __ldg(&g->u0), du = __ldg(&g->du), halves = __ldg(&g->halves), use_carry = __ldg(&g->use_carry);
+            REAL gamma = REAL(1) / REAL(__ldg(&g->gamma_den));
+            SegOwn so0 = g->own[w][0], so1 = g->own[w][1];
+
+            auto load_own = [&](const SegOwn &so, int i, OwnTerm<REAL, K> &o) {
+                o.flags = so.flags;
+                if (so.flags & OWN_HAS) {
+                    o.term = so.term0 + (long long)i * so.tstride;
+                    const long long off = o.term * LP + lane * K;
+                    const bool tail = (so.flags & OWN_TAIL) != 0;
+                    // sender's positions: qprim if I am the tail of the term, else q
+                    // (typeStereoLinear.h:343-357 with Swap(), MRFEnergy.cpp:200-203)
+                    VecIO<REAL, K>::load_cg(o.m, p.msg + off);
+                    VecIO<REAL, K>::load_ro(o.s, (tail ? p.posqp : p.posq) + off);
+                    VecIO<REAL, K>::load_ro(o.x, (tail ? p.posq : p.posqp) + off);
+                    ByteIO<K>::load(o.rk, (tail ? p.rank_qp : p.rank_q) + off);
+                    ByteIO<K>::load(o.cn, (tail ? p.cnt_q : p.cnt_qp) + off);
+                    o.alpha = __ldg(p.alpha + o.term);
+                }
+            };
+            // one min-plus update + stores (phase B5 of the design notes)
+            auto send = [&](OwnTerm<REAL, K> &o, const REAL (&Di)[K], int xs, int par, REAL gamma) {
+                if (!(o.flags & OWN_HAS)) return;
+                const bool to_next = (o.flags & OWN_TO_NEXT) != 0;
+                const int oj = (o.flags & OWN_J) ? 1 : 0;
+                if (do_round) {
+                    // position of the rounded label on this term, for the receiver's rounding
+                    REAL sv = o.s[0];
+#pragma unroll
+                    for (int k = 1; k < K; k++)
+                        if (k == xs % K) sv = o.s[k];
+                    sv = __shfl_sync(0xffffffffu, sv, xs / K);
+                    if (lane == 0) __stcg(p.selpos + o.term, sv);
+                    if (to_next) {
+                        REAL cc[K];
+#pragma unroll
+                        for (int k = 0; k < K; k++) cc[k] = o.alpha * smooth<REAL, KERN>(o.x[k] - sv, p.lambda);
+                        row_sts<REAL, K>(row_ptr(par ^ 1, R_CC + oj), cc, lane);
+                    }
+                }
+                if (do_send) {
+                    REAL vmin;
+                    if constexpr (KERN == 1)
+                        vmin = update_linear<REAL, K>(gamma, o.alpha, p.lambda, p.L, lane, Di, o.m, o.s, o.rk, o.x, o.cn, P);
+                    else
+                        vmin = update_quadratic<REAL, K>(gamma, o.alpha, p.lambda, p.L, lane, Di, o.m, o.s, o.rk, o.x, o.cn, P);
+                    VecIO<REAL, K>::store(p.msg + o.term * LP + lane * K, o.m);
+                    if (PASS == PASS_BWD) acc_lb += (double)vmin;
+                    if (to_next) row_sts<REAL, K>(row_ptr(par ^ 1, R_CM + oj), o.m, lane);
+                }
+            };
+
+            OwnTerm<REAL, K> own;
+            load_own(so0, 0, own);
+            // EMPTY barriers start "armed": nothing has to be read before the helpers' first writes
+            named_arrive(BAR_EMPTY + 0);
+            named_arrive(BAR_EMPTY + 1);
+
+            for (int node = 0; node < n_nodes; node++) {
+                const int par = node & 1;
+                const int u = u0 + seg_i * du;
+                const REAL cur_gamma = gamma;
+                const int cur_halves = halves;
+                const bool cur_carry = use_carry != 0;
+                const SegOwn cur_so1 = so1;
+                const int cur_i = seg_i;
+                // ---- where the next node lives (descriptor fields of a new segment are fetched here,
+                // long before they are needed)
+                const bool has_next = node + 1 < n_nodes;
+                if (has_next) {
+                    if (seg_i + 1 < seg_n) {
+                        seg_i++;
+                    } else {
+                        sg++;
+                        g = segs + sg;
+                        seg_n = __ldg(&g->n);
+                        seg_i = 0;
+                        u0 = __ldg(&g->u0); du = __ldg(&g->du); halves = __ldg(&g->halves); use_carry = __ldg(&g->use_carry);
+                        gamma = REAL(1) / REAL(__ldg(&g->gamma_den));
+                        so0 = g->own[w][0];
+                        so1 = g->own[w][1];
+                    }
+                }
+                // ---- rows of this node are ready, every term warp has finished the previous node
+                named_sync(BAR_FULL + par);
+                REAL Di[K];
+                int xs = 0;
+                {
+                    REAL base[K];
+                    row_lds<REAL, K>(base, row_ptr(par, R_BASE), lane);
+#pragma unroll
+                    for (int k = 0; k < K; k++) Di[k] = base[k];
+                    if (cur_carry && do_send) {
+#pragma unroll
+                        for (int jj = 0; jj < 2; jj++) {
+                            REAL v[K];
+                            row_lds<REAL, K>(v, row_ptr(par, R_CM + jj), lane);
+#pragma unroll
+                            for (int k = 0; k < K; k++) Di[k] += v[k];
+                        }
+                    }
+                    if (do_round) {
+                        // minimize.cpp:240-260: DiB = D + sum_{lower nb} V(x_nb, .), Dr = DiB + forward messages
+                        REAL dib[K], rms[K];
+                        row_lds<REAL, K>(dib, row_ptr(par, R_DIB0), lane);
+                        row_lds<REAL, K>(rms, row_ptr(par, R_RMS), lane);
+                        if (cur_carry) {
+#pragma unroll
+                            for (int jj = 0; jj < 2; jj++) {
+                                REAL v[K];
+                                row_lds<REAL, K>(v, row_ptr(par, R_CC + jj), lane);
+#pragma unroll
+                                for (int k = 0; k < K; k++) dib[k] += v[k];
+                            }
+                        }
+                        // Vector::ComputeMin: first minimum in label order (typeStereoLinear.h:238-252)
+                        REAL best = BIG;
+                        int bi = 0x7fffffff;
+#pragma unroll
+                        for (int k = 0; k < K; k++) {
+                            const int lbl = lane * K + k;
+                            const REAL dr = dib[k] + rms[k];
+                            if (lbl < p.L && dr < best) { best = dr; bi = lbl; }
+                        }
+                        const REAL wbest = warp_min(best);
+                        bi = warp_min_s32(best == wbest ? bi : 0x7fffffff);
+                        xs = bi;
+                        if (w == 0) {
+                            REAL dv = dib[0];
+#pragma unroll
+                            for (int k = 1; k < K; k++)
+                                if (k == bi % K) dv = dib[k];
+                            dv = __shfl_sync(0xffffffffu, dv, bi / K);
+                            if (lane == 0) {
+                                p.sol[u] = bi;
+                                acc_energy += (double)dv;
+                            }
+                        }
+                    }
+                }
+                named_arrive(BAR_EMPTY + par);     // this warp has read the node's rows
+                if (do_send && PASS == PASS_BWD) {
+                    // ComputeAndSubtractMin + lower bound (minimize.cpp:79-81)
+                    REAL vmin = BIG;
+#pragma unroll
+                    for (int k = 0; k < K; k++)
+                        if (lane * K + k < p.L) vmin = min(vmin, Di[k]);
+                    vmin = warp_min(vmin);
+#pragma unroll
+                    for (int k = 0; k < K; k++) Di[k] -= vmin;
+                    if (w == 0) acc_lb += (double)vmin;
+                }
+                // ---- loads of the next step, then the update of this one
+                OwnTerm<REAL, K> nxt;
+                nxt.flags = 0;
+                if (cur_halves == 2) {
+                    load_own(cur_so1, cur_i, nxt);
+                    send(own, Di, xs, par, cur_gamma);
+                    own = nxt;
+                    nxt.flags = 0;
+                }
+                if (has_next) load_own(so0, seg_i, nxt);
+                send(own, Di, xs, par, cur_gamma);
+                own = nxt;
+                // this warp's stores for the node are issued: tell the auxiliary warp
+                __syncwarp();
+                if (lane == 0) st_release_cta(s_wdone + w, node + 1);
+            }
+            continue;
+        }
+
+        if (is_helper) {
+            // ============================================================ helper warps
+            const int hid = warp - NCW;
+            REAL *landing = rows + (size_t)2 * ROWS_PER_PAR * LP + (size_t)hid * SCHED_ITEMS * LP;
+            Segment *sd = &s_seg[hid];
+            int sg = sg0, seg_start = 0;    // segment of the current node and the strip index of its first node
+            int loaded = -1;
+            int seg_n = __ldg(&segs[sg].n);
+            for (int node = hid; node < n_nodes; node += NHW) {
+                while (node >= seg_start + seg_n) {
+                    seg_start += seg_n;
+                    sg++;
+                    seg_n = __ldg(&segs[sg].n);
+                }
+                if (loaded != sg) {
+                    // this helper's copy of the descriptor (864 bytes)
+                    __syncwarp();
+                    for (int ch = lane; ch < (int)sizeof(Segment) / 16; ch += 32)
+                        cp_async16(reinterpret_cast<char *>(sd) + ch * 16, reinterpret_cast<const char *>(segs + sg) + ch * 16);
+                    cp_async_wait_all();
+                    __syncwarp();
+                    loaded = sg;
+                }
+                const int i = node - seg_start;
+                const int par = node & 1;
+                const int nitems = sd->nitems;
+                // lane j manages item j: address, guard, scalars
+                int kind = S_NONE, strip = -1, need = 0;
+                long long term = 0;
+                REAL al = REAL(0), sel = REAL(0);
+                if (lane < nitems) {
+                    const SegItem it = sd->item[lane];
+                    kind = it.kind;
+                    const int k0 = kind & 255;
+                    if ((k0 == S_DYN && !do_send) || (k0 == S_RND && !do_round)) kind = S_NONE;
+                    term = it.term0 + (long long)i * it.tstride;
+                    strip = it.strip;
+                    need = it.need0 + i * it.dneed;
+                    if ((kind & 255) == S_RND) al = __ldg(p.alpha + term);
+                }
+                // static rows first
+                for (int j = 0; j < nitems; j++) {
+                    const int kj = __shfl_sync(0xffffffffu, kind, j);
+                    const long long tj = __shfl_sync(0xffffffffu, term, j);
+                    const int k0 = kj & 255;
+                    const REAL *src = nullptr;
+                    if (k0 == S_D) src = p.D + tj * LP;
+                    else if (k0 == S_SEND) src = p.msg + tj * LP;
+                    else if (k0 == S_RND) src = ((kj & 256) ? p.posqp : p.posq) + tj * LP;
+                    if (src) row_async<REAL, K>(landing + (size_t)j * LP, src, lane);
+                }
+                // dependencies: each managing lane waits for its strip's watermark
+                {
+                    const int k0 = kind & 255;
+                    if (k0 == S_DYN || k0 == S_RND) {
+                        while (ld_flag(p.progress + strip) < need) __nanosleep(32);
+                        if (k0 == S_RND) sel = __ldcg(p.selpos + term);
+                    }
+                }
+                __syncwarp();
+                for (int j = 0; j < nitems; j++) {
+                    const int kj = __shfl_sync(0xffffffffu, kind, j);
+                    if ((kj & 255) != S_DYN) continue;
+                    const long long tj = __shfl_sync(0xffffffffu, term, j);
+                    row_async<REAL, K>(landing + (size_t)j * LP, p.msg + tj * LP, lane);
+                }
+                cp_async_wait_all();
+                __syncwarp();
+                // reduce to BASE / DIB0 / RMS
+                REAL base[K], dib[K], rms[K];
+#pragma unroll
+                for (int k = 0; k < K; k++) { base[k] = REAL(0); dib[k] = REAL(0); rms[k] = REAL(0); }
+                for (int j = 0; j < nitems; j++) {
+                    const int k0 = __shfl_sync(0xffffffffu, kind, j) & 255;
+                    if (k0 == S_NONE) continue;
+                    REAL v[K];
+                    row_lds<REAL, K>(v, landing + (size_t)j * LP, lane);
+                    if (k0 == S_D) {
+#pragma unroll
+                        for (int k = 0; k < K; k++) { base[k] += v[k]; dib[k] += v[k]; }
+                    } else if (k0 == S_SEND) {
+#pragma unroll
+                        for (int k = 0; k < K; k++) { base[k] += v[k]; rms[k] += v[k]; }
+                    } else if (k0 == S_DYN) {
+#pragma unroll
+                        for (int k = 0; k < K; k++) base[k] += v[k];
+                    } else {
+                        const REAL aj = __shfl_sync(0xffffffffu, al, j), sj = __shfl_sync(0xffffffffu, sel, j);
+#pragma unroll
+                        for (int k = 0; k < K; k++) dib[k] += aj * smooth<REAL, KERN>(v[k] - sj, p.lambda);
+                    }
+                }
+                // the term warps have read the rows of node - 2
+                named_sync(BAR_EMPTY + par);
+                row_sts<REAL, K>(row_ptr(par, R_BASE), base, lane);
+                if (do_round) {
+                    row_sts<REAL, K>(row_ptr(par, R_DIB0), dib, lane);
+                    row_sts<REAL, K>(row_ptr(par, R_RMS), rms, lane);
+                }
+                named_arrive(BAR_FULL + par);
+            }
+            // consume the term warps' last arrival on this parity so the barrier is balanced
+            named_sync(BAR_EMPTY + hid);
+            continue;
+        }
+
+        // ================================================================ auxiliary warp
+        {
             int published = 0;
             int pf_seg = sg0, pf_i = 0, pf_node = 0;     // next node to prefetch: segment, index in it, index in strip
-            int pf_n = __ldg(&segs[(size_t)pf_seg * NCW].n);
+            int pf_n = __ldg(&segs[pf_seg].n);
             while (published < n_nodes) {
                 int c = (lane < NCW) ? ld_acquire_cta(s_wdone + lane) : 0x7fffffff;
 #pragma unroll
@@ -668,22 +955,21 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                     if (lane == 0) publish_flag(p.progress + fs, c);
                     published = c;
                 }
-                const int pf_end = min(n_nodes, c + 1 + PF_DIST);
+                const int pf_end = min(n_nodes, c + 2 + PF_DIST);
                 if (pf_node >= pf_end) {
                     if (published < n_nodes) __nanosleep(40);
                     continue;
                 }
                 for (; pf_node < pf_end; pf_node++) {
-                    if (pf_node > c) {
-                        // rows of node (pf_seg, pf_i): lanes 0..3 take the four warps' own terms,
-                        // lanes 4..19 the sixteen slots
+                    if (pf_node > c + 1) {
+                        // rows of node (pf_seg, pf_i): lanes 0..7 take the term warps' own terms,
+                        // lanes 8..29 the helper items
                         constexpr int LR = (LP * (int)sizeof(REAL) + 127) / 128;
                         constexpr int LB = (LP + 127) / 128;
-                        const SegWarp *g = segs + (size_t)pf_seg * NCW;
-                        if (lane < NCW) {
-                            for (int h = 0; h < 2; h++) {
-                                const SegOwn o = g[lane].own[h];
-                                if (!(o.flags & OWN_HAS)) continue;
+                        const Segment *g = segs + pf_seg;
+                        if (lane < 2 * NCW) {
+                            const SegOwn o = g->own[lane >> 1][lane & 1];
+                            if (o.flags & OWN_HAS) {
                                 const long long row = (o.term0 + (long long)pf_i * o.tstride) * LP;
                                 const bool tail = (o.flags & OWN_TAIL) != 0;
                                 for (int t = 0; t < LR; t++) {
@@ -696,13 +982,12 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                                     prefetch_l2(reinterpret_cast<const char *>((tail ? p.cnt_q : p.cnt_qp) + row) + t * 128);
                                 }
                             }
-                        } else if (lane < NCW + NCW * SLOTS) {
-                            const SegSlot sl = g[(lane - NCW) >> 2].slot[(lane - NCW) & 3];
+                        } else if (lane - 2 * NCW < SCHED_ITEMS) {
+                            const SegItem sl = g->item[lane - 2 * NCW];
                             const int kind = sl.kind & 255;
                             const long long row = (sl.term0 + (long long)pf_i * sl.tstride) * LP;
                             const REAL *base = nullptr;
                             if (kind == S_D) base = p.D + row;
-                            else if (kind == S_STAT) base = p.msg + row;
                             else if (kind == S_RND && do_round) base = ((sl.kind & 256) ? p.posqp : p.posq) + row;
                             if (base)
                                 for (int t = 0; t < LR; t++) prefetch_l2(reinterpret_cast<const char *>(base) + t * 128);
@@ -711,354 +996,13 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                     if (++pf_i >= pf_n) {
                         pf_i = 0;
                         pf_seg++;
-                        pf_n = (pf_seg < sg1) ? __ldg(&segs[(size_t)pf_seg * NCW].n) : 0x7fffffff;
+                        pf_n = (pf_seg < sg1) ? __ldg(&segs[pf_seg].n) : 0x7fffffff;
                     }
                 }
             }
-            continue;
-        }
-
-        // ---------------------------------------------------------------- compute warps
-        const int w = warp;
-        // optional phase timers (warp 0 only): 0 flag spin, 1 rest of phase A, 2 barrier, 3 prepare,
-        // 4 B1 (Di / rounding), 5 resolve, 6 update + stores, 7 steps
-        long long tprof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        const bool prof_on = SB_TRWS_INSTRUMENT && (p.prof != nullptr) && w == 0;
-        long long tclk = prof_on ? clock64() : 0;
-        auto tick = [&](int which) {
-            if (prof_on) {
-                const long long now = clock64();
-                tprof[which] += now - tclk;
-                tclk = now;
-            }
-        };
-
-        // descriptor of segment sg -> s_desc[w][buf] (12 lanes x 16 bytes, own warp only)
-        auto fetch_desc = [&](int sg, int buf) {
-            if (lane < (int)sizeof(SegWarp) / 16)
-                cp_async16(reinterpret_cast<char *>(&s_desc[w][buf]) + lane * 16,
-                           reinterpret_cast<const char *>(segs + (size_t)sg * NCW + w) + lane * 16);
-        };
-
-        OwnTerm<REAL, K> own;       // operands of this warp's term in the current step
-        own.flags = 0;
-        // per-slot bookkeeping of the node whose rows are in flight / in the landing buffers
-        int slot_kind[SLOTS], slot_flag[SLOTS], slot_need[SLOTS], slot_fv[SLOTS];
-        REAL slot_alpha[SLOTS], slot_sel[SLOTS];
-        long long slot_term[SLOTS];
-#pragma unroll
-        for (int q = 0; q < SLOTS; q++) { slot_kind[q] = S_NONE; slot_flag[q] = -1; slot_need[q] = 0; slot_fv[q] = 0; slot_alpha[q] = REAL(0); slot_sel[q] = REAL(0); slot_term[q] = 0; }
-        REAL Di[K];
-#pragma unroll
-        for (int k = 0; k < K; k++) Di[k] = REAL(0);
-        int xs = 0;   // rounded label of the current node
-
-        // prepare(): first part of issuing the loads of a step (node i of the segment
-        // described by g, half `half`): own-term operands into registers, static rows into the
-        // landing buffers, and -- without branching on them yet -- the progress counters that
-        // guard the dependency rows.
-        auto prepare = [&](const SegWarp *g, int i, int half, OwnTerm<REAL, K> &o) {
-            const SegOwn so = g->own[half];
-            o.flags = so.flags;
-            if (so.flags & OWN_HAS) {
-                o.term = so.term0 + (long long)i * so.tstride;
-                const long long off = o.term * LP + lane * K;
-                const bool tail = (so.flags & OWN_TAIL) != 0;
-                if (SB_TRWS_INSTRUMENT && (p.debug & 4)) {
-#pragma unroll
-                    for (int k = 0; k < K; k++) { o.m[k] = REAL(0); o.s[k] = REAL(k); o.x[k] = REAL(k); o.rk[k] = (uint8_t)(lane * K + k); o.cn[k] = (uint8_t)(lane * K + k); }
-                    o.alpha = REAL(1);
-                } else {
-                    // sender's positions: qprim if I am the tail of the term, else q
-                    // (typeStereoLinear.h:343-357 with Swap(), MRFEnergy.cpp:200-203)
-                    VecIO<REAL, K>::load_cg(o.m, p.msg + off);
-                    VecIO<REAL, K>::load_ro(o.s, (tail ? p.posqp : p.posq) + off);
-                    VecIO<REAL, K>::load_ro(o.x, (tail ? p.posq : p.posqp) + off);
-                    ByteIO<K>::load(o.rk, (tail ? p.rank_qp : p.rank_q) + off);
-                    ByteIO<K>::load(o.cn, (tail ? p.cnt_q : p.cnt_qp) + off);
-                    o.alpha = __ldg(p.alpha + o.term);
-                }
-            }
-            if (half == 0) {
-#pragma unroll
-                for (int q = 0; q < SLOTS; q++) {
-                    const SegSlot sl = g->slot[q];
-                    const int kind = slot_active(sl.kind) ? sl.kind : (int)S_NONE;
-                    slot_kind[q] = kind;
-                    slot_flag[q] = -1;
-                    if (kind == S_NONE) continue;
-                    const long long term = sl.term0 + (long long)i * sl.tstride;
-                    slot_term[q] = term;
-                    REAL *dst = landing + (size_t)q * LP;
-                    const int k = kind & 255;
-                    if (k == S_D) {
-                        row_async<REAL, K>(dst, p.D + term * LP, lane);
-                    } else if (k == S_STAT) {
-                        row_async<REAL, K>(dst, p.msg + term * LP, lane);
-                    } else {
-                        slot_flag[q] = sl.strip;
-                        slot_need[q] = sl.need0 + i * sl.dneed;
-                        slot_fv[q] = ld_flag(p.progress + sl.strip);
-                        if (k == S_RND) { // my positions on the term now, the neighbour's selected position later
-                            row_async<REAL, K>(dst, ((kind & 256) ? p.posqp : p.posq) + term * LP, lane);
-                            slot_alpha[q] = __ldg(p.alpha + term);
-                        }
-                    }
-                }
-            }
-        };
-        // resolve(): second part -- dependency rows whose counter was already high enough are
-        // fetched now; the others are left to phase A of their step.
-        auto resolve = [&]() {
-#pragma unroll
-            for (int q = 0; q < SLOTS; q++) {
-                if (slot_flag[q] >= 0 && slot_fv[q] >= slot_need[q]) {
-                    if ((slot_kind[q] & 255) == S_DYN) row_async<REAL, K>(landing + (size_t)q * LP, p.msg + slot_term[q] * LP, lane);
-                    else slot_sel[q] = __ldcg(p.selpos + slot_term[q]);
-                    slot_flag[q] = -1;
-                }
-            }
-        };
-
-        // first descriptor (blocking), the one after it in the background
-        int sg = sg0, buf = 0;
-        fetch_desc(sg, 0);
-        cp_async_wait_all();
-        __syncwarp();
-        if (sg + 1 < sg1) fetch_desc(sg + 1, 1);
-        const SegWarp *g = &s_desc[w][0];
-        int seg_n = g->n, seg_i = 0;
-        prepare(g, 0, 0, own);
-        resolve();
-
-        for (int node = 0; node < n_nodes; node++) {
-            const int u = g->u0 + seg_i * g->du;
-            const int par = node & 1;
-            const REAL gamma = REAL(1) / REAL(g->gamma_den);
-            const int halves = g->halves;
-            const bool use_carry = g->use_carry != 0;
-            // where the next node lives
-            const bool seg_last = (seg_i + 1 >= seg_n);
-            const bool has_next = (node + 1 < n_nodes);
-            const SegWarp *gn = seg_last ? &s_desc[w][buf ^ 1] : g;
-            const int in = seg_last ? 0 : seg_i + 1;
-
-            for (int half = 0; half < halves; half++) {
-                tick(6);
-                if (half == 0) {
-                    // ---------------- phase A: resolve pending dependencies, sum into partial rows
-#pragma unroll
-                    for (int q = 0; q < SLOTS; q++) {
-                        if (slot_flag[q] >= 0) {
-                            while (ld_flag(p.progress + slot_flag[q]) < slot_need[q]) __nanosleep(32);
-                            if ((slot_kind[q] & 255) == S_DYN) row_async<REAL, K>(landing + (size_t)q * LP, p.msg + slot_term[q] * LP, lane);
-                            else slot_sel[q] = __ldcg(p.selpos + slot_term[q]);
-                            slot_flag[q] = -1;
-                        }
-                    }
-                    tick(0);
-                    cp_async_wait_all();
-                    __syncwarp();
-                    REAL rm[K], rx[K], rb[K];
-#pragma unroll
-                    for (int k = 0; k < K; k++) {
-                        rm[k] = (own.flags & OWN_HAS) ? own.m[k] : REAL(0);
-                        rx[k] = REAL(0);
-                        rb[k] = REAL(0);
-                    }
-#pragma unroll
-                    for (int q = 0; q < SLOTS; q++) {
-                        const int k0 = slot_kind[q] & 255;
-                        if (k0 == S_NONE) continue;
-                        REAL v[K];
-                        row_lds<REAL, K>(v, landing + (size_t)q * LP, lane);
-                        if (k0 == S_D) {
-                            row_sts<REAL, K>(row_ptr(par, R_DR), v, lane);
-                        } else if (k0 == S_STAT) {
-#pragma unroll
-                            for (int k = 0; k < K; k++) rm[k] += v[k];
-                        } else if (k0 == S_DYN) {
-#pragma unroll
-                            for (int k = 0; k < K; k++) rx[k] += v[k];
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < K; k++) rb[k] += slot_alpha[q] * smooth<REAL, KERN>(v[k] - slot_sel[q], p.lambda);
-                        }
-                    }
-                    row_sts<REAL, K>(row_ptr(par, R_RM + w), rm, lane);
-                    if (do_send) row_sts<REAL, K>(row_ptr(par, R_RX + w), rx, lane);
-                    if (do_round) row_sts<REAL, K>(row_ptr(par, R_RB + w), rb, lane);
-                }
-                tick(1);
-                step_barrier();
-                tick(2);
-                // ---------------- issue the loads of the next step (part 1)
-                OwnTerm<REAL, K> nxt;
-                nxt.flags = 0;
-                const bool last_half = (half + 1 == halves);
-                if (!last_half) prepare(g, seg_i, half + 1, nxt);
-                else if (has_next) prepare(gn, in, 0, nxt);
-                tick(3);
-                if (half == 0) {
-                    // ---------------- phase B1: Di (and the rounding) from the partial rows
-                    REAL dsum[K], msum[K];
-                    row_lds<REAL, K>(dsum, row_ptr(par, R_DR), lane);
-#pragma unroll
-                    for (int k = 0; k < K; k++) msum[k] = REAL(0);
-#pragma unroll
-                    for (int ww = 0; ww < NCW; ww++) {
-                        REAL v[K];
-                        row_lds<REAL, K>(v, row_ptr(par, R_RM + ww), lane);
-#pragma unroll
-                        for (int k = 0; k < K; k++) msum[k] += v[k];
-                    }
-                    if (do_round) {
-                        // minimize.cpp:240-260: DiB = D + sum_{lower nb} V(x_nb, .), Dr = DiB + forward messages
-                        REAL dib[K];
-#pragma unroll
-                        for (int k = 0; k < K; k++) dib[k] = dsum[k];
-#pragma unroll
-                        for (int ww = 0; ww < NCW; ww++) {
-                            REAL v[K];
-                            row_lds<REAL, K>(v, row_ptr(par, R_RB + ww), lane);
-#pragma unroll
-                            for (int k = 0; k < K; k++) dib[k] += v[k];
-                        }
-                        if (use_carry) {
-#pragma unroll
-                            for (int jj = 0; jj < 2; jj++) {
-                                REAL v[K];
-                                row_lds<REAL, K>(v, row_ptr(par, R_CC + jj), lane);
-#pragma unroll
-                                for (int k = 0; k < K; k++) dib[k] += v[k];
-                            }
-                        }
-                        // Vector::ComputeMin: first minimum in label order (typeStereoLinear.h:238-252)
-                        REAL best = BIG;
-                        int bi = 0x7fffffff;
-                        REAL bdib = REAL(0);
-#pragma unroll
-                        for (int k = 0; k < K; k++) {
-                            const int lbl = lane * K + k;
-                            const REAL dr = dib[k] + msum[k];
-                            if (lbl < p.L && dr < best) { best = dr; bi = lbl; bdib = dib[k]; }
-                        }
-                        // first minimum over the warp: value, then the smallest label attaining it
-                        const REAL wbest = warp_min(best);
-                        bi = warp_min_s32(best == wbest ? bi : 0x7fffffff);
-                        {
-                            REAL dv = dib[0];
-#pragma unroll
-                            for (int k = 1; k < K; k++)
-                                if (k == bi % K) dv = dib[k];
-                            bdib = __shfl_sync(0xffffffffu, dv, bi / K);
-                        }
-                        xs = bi;
-                        if (w == 0 && lane == 0) {
-                            p.sol[u] = bi;
-                            acc_energy += (double)bdib;
-                        }
-                    }
-                    if (do_send) {
-                        // Di = D + all incident messages (minimize.cpp:38-46 / 69-77)
-#pragma unroll
-                        for (int k = 0; k < K; k++) Di[k] = dsum[k] + msum[k];
-#pragma unroll
-                        for (int ww = 0; ww < NCW; ww++) {
-                            REAL v[K];
-                            row_lds<REAL, K>(v, row_ptr(par, R_RX + ww), lane);
-#pragma unroll
-                            for (int k = 0; k < K; k++) Di[k] += v[k];
-                        }
-                        if (use_carry) {
-#pragma unroll
-                            for (int jj = 0; jj < 2; jj++) {
-                                REAL v[K];
-                                row_lds<REAL, K>(v, row_ptr(par, R_CM + jj), lane);
-#pragma unroll
-                                for (int k = 0; k < K; k++) Di[k] += v[k];
-                            }
-                        }
-                        if (PASS == PASS_BWD) {
-                            // ComputeAndSubtractMin + lower bound (minimize.cpp:79-81)
-                            REAL vmin = BIG;
-#pragma unroll
-                            for (int k = 0; k < K; k++)
-                                if (lane * K + k < p.L) vmin = min(vmin, Di[k]);
-                            vmin = warp_min(vmin);
-#pragma unroll
-                            for (int k = 0; k < K; k++) Di[k] -= vmin;
-                            if (w == 0) acc_lb += (double)vmin;
-                        }
-                    }
-                }
-
-                // ---------------- issue the loads of the next step (part 2: flag-dependent rows)
-                tick(4);
-                if (last_half && has_next) resolve();
-                tick(5);
-
-                // ---------------- phase B5: min-plus update of this warp's term
-                if (own.flags & OWN_HAS) {
-                    const bool to_next = (own.flags & OWN_TO_NEXT) != 0;
-                    const int oj = (own.flags & OWN_J) ? 1 : 0;
-                    if (do_round) {
-                        // position of the rounded label on this term, for the receiver's rounding
-                        REAL sv = own.s[0];
-#pragma unroll
-                        for (int k = 1; k < K; k++)
-                            if (k == xs % K) sv = own.s[k];
-                        sv = __shfl_sync(0xffffffffu, sv, xs / K);
-                        if (lane == 0) __stcg(p.selpos + own.term, sv);
-                        if (to_next) {
-                            REAL cc[K];
-#pragma unroll
-                            for (int k = 0; k < K; k++) cc[k] = own.alpha * smooth<REAL, KERN>(own.x[k] - sv, p.lambda);
-                            row_sts<REAL, K>(row_ptr(par ^ 1, R_CC + oj), cc, lane);
-                        }
-                    }
-                    if (do_send) {
-                        REAL vmin = REAL(0);
-                        if (SB_TRWS_INSTRUMENT && (p.debug & 2)) {
-#pragma unroll
-                            for (int k = 0; k < K; k++) own.m[k] = Di[k] * gamma - own.m[k];
-                        } else if constexpr (KERN == 1)
-                            vmin = update_linear<REAL, K>(gamma, own.alpha, p.lambda, p.L, lane, Di, own.m, own.s, own.rk, own.x, own.cn, P);
-                        else
-                            vmin = update_quadratic<REAL, K>(gamma, own.alpha, p.lambda, p.L, lane, Di, own.m, own.s, own.rk, own.x, own.cn, P);
-                        if (!(SB_TRWS_INSTRUMENT && (p.debug & 1))) VecIO<REAL, K>::store(p.msg + own.term * LP + lane * K, own.m);
-                        if (PASS == PASS_BWD) acc_lb += (double)vmin;
-                        if (to_next) row_sts<REAL, K>(row_ptr(par ^ 1, R_CM + oj), own.m, lane);
-                    }
-                }
-                own = nxt;
-            }
-            // this warp's stores for the node are issued: tell the auxiliary warp
-            __syncwarp();
-            if (lane == 0) st_release_cta(s_wdone + w, node + 1);
-            if (prof_on) tprof[7] += 1;
-            // advance to the next node / segment
-            if (seg_last) {
-                if (has_next) {
-                    sg++;
-                    buf ^= 1;
-                    g = &s_desc[w][buf];
-                    seg_n = g->n;
-                    seg_i = 0;
-                    if (sg + 1 < sg1) fetch_desc(sg + 1, buf ^ 1);
-                }
-            } else {
-                seg_i++;
-            }
-        }
-        if (prof_on && lane == 0) {
-            tick(6);
-            const int grp = (fs == 0) ? 0 : 1; // strip 0 is the boundary ring on regular grids
-#pragma unroll
-            for (int q = 0; q < 8; q++) atomicAdd((unsigned long long *)p.prof + grp * 8 + q, (unsigned long long)tprof[q]);
         }
     }
-    if (!is_aux && lane == 0) {
+    if (is_term && lane == 0) {
         if (acc_energy != 0.0) atomicAdd(p.acc + 0, acc_energy);
         if (acc_lb != 0.0) atomicAdd(p.acc + 1, acc_lb);
     }

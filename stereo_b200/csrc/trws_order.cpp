@@ -247,9 +247,9 @@ void build_schedule(int H, int W, const std::vector<int32_t> &ordering, Schedule
 namespace {
 
 struct NodeDesc {
-    int u, halves, gamma_den, use_carry;
+    int u, halves, gamma_den, use_carry, nitems;
     struct Own { long long term; int flags; } own[trws::SCHED_NCW][2];
-    struct Slot { long long term; int kind; int strip; int need; } slot[trws::SCHED_NCW][trws::SCHED_SLOTS];
+    struct Item { long long term; int kind; int strip; int need; } item[trws::SCHED_ITEMS];
 };
 
 struct Inc { int nb; long long term; bool tail; };
@@ -294,8 +294,7 @@ void build_pass_plan(int H, int W, const std::vector<uint8_t> &info, const Sched
     };
     auto describe = [&](int u, int u_prev, int u_next, NodeDesc &nd) {
         std::memset(&nd, 0, sizeof(nd));
-        for (int w = 0; w < SCHED_NCW; w++)
-            for (int q = 0; q < SCHED_SLOTS; q++) nd.slot[w][q].strip = -1;
+        for (int q = 0; q < SCHED_ITEMS; q++) nd.item[q].strip = -1;
         const int r = u % H, c = u / H;
         const unsigned valid = info[u] & 15u, lower = info[u] >> 4;
         const unsigned send_mask = pass == 0 ? (valid & ~lower) : lower;
@@ -312,12 +311,11 @@ void build_pass_plan(int H, int W, const std::vector<uint8_t> &info, const Sched
         nd.halves = ns > SCHED_NCW ? 2 : 1;
         int n = 0, si = 0;
         auto add_item = [&](int kind, long long term, bool tail, int strip, int need) {
-            const int w = n & 3, q = n >> 2;
-            SB_REQUIRE(q < SCHED_SLOTS, SB_EUNSUP, "trws schedule: too many rows per warp");
-            nd.slot[w][q].term = term;
-            nd.slot[w][q].kind = kind | (tail ? 256 : 0);
-            nd.slot[w][q].strip = strip;
-            nd.slot[w][q].need = need;
+            SB_REQUIRE(n < SCHED_ITEMS, SB_EUNSUP, "trws schedule: too many rows per node");
+            nd.item[n].term = term;
+            nd.item[n].kind = kind | (tail ? 256 : 0);
+            nd.item[n].strip = strip;
+            nd.item[n].need = need;
             n++;
         };
         add_item(S_D, u, false, -1, 0);
@@ -329,7 +327,7 @@ void build_pass_plan(int H, int W, const std::vector<uint8_t> &info, const Sched
                 NodeDesc::Own &o = nd.own[si & 3][si >> 2];
                 o.term = I.term;
                 o.flags = OWN_HAS | (I.tail ? OWN_TAIL : 0) | (d == d_next ? OWN_TO_NEXT : 0) | (j ? OWN_J : 0);
-                if (si >= SCHED_NCW) add_item(S_STAT, I.term, false, -1, 0);
+                add_item(S_SEND, I.term, false, -1, 0);
                 si++;
             } else if (d != d_prev) {
                 add_item(S_DYN, I.term, false, strip_of[I.nb], need_of(I.nb));
@@ -343,49 +341,49 @@ void build_pass_plan(int H, int W, const std::vector<uint8_t> &info, const Sched
                     add_item(S_RND, I.term, I.tail, strip_of[I.nb], need_of(I.nb));
                 }
             }
+        nd.nitems = n;
     };
     auto same_structure = [&](const NodeDesc &a, const NodeDesc &b) {
-        if (a.halves != b.halves || a.gamma_den != b.gamma_den || a.use_carry != b.use_carry) return false;
-        for (int w = 0; w < SCHED_NCW; w++) {
+        if (a.halves != b.halves || a.gamma_den != b.gamma_den || a.use_carry != b.use_carry || a.nitems != b.nitems)
+            return false;
+        for (int w = 0; w < SCHED_NCW; w++)
             for (int h = 0; h < 2; h++)
                 if (a.own[w][h].flags != b.own[w][h].flags) return false;
-            for (int q = 0; q < SCHED_SLOTS; q++)
-                if (a.slot[w][q].kind != b.slot[w][q].kind || a.slot[w][q].strip != b.slot[w][q].strip) return false;
-        }
+        for (int q = 0; q < SCHED_ITEMS; q++)
+            if (a.item[q].kind != b.item[q].kind || a.item[q].strip != b.item[q].strip) return false;
         return true;
     };
 
     plan.segs.clear();
     plan.seg_ptr.assign((size_t)S + 1, 0);
     NodeDesc first, nd;
-    long long d_u = 0, d_own[SCHED_NCW][2], d_term[SCHED_NCW][SCHED_SLOTS], d_need[SCHED_NCW][SCHED_SLOTS];
+    long long d_u = 0, d_own[SCHED_NCW][2], d_term[SCHED_ITEMS], d_need[SCHED_ITEMS];
     int seg_n = 0;
     auto flush = [&]() {
         if (!seg_n) return;
-        for (int w = 0; w < SCHED_NCW; w++) {
-            SegWarp g;
-            std::memset(&g, 0, sizeof(g));
-            g.u0 = first.u; g.du = (int)d_u; g.n = seg_n;
-            g.halves = first.halves; g.gamma_den = first.gamma_den; g.use_carry = first.use_carry;
+        Segment g;
+        std::memset(&g, 0, sizeof(g));
+        g.u0 = first.u; g.du = (int)d_u; g.n = seg_n;
+        g.halves = first.halves; g.gamma_den = first.gamma_den; g.use_carry = first.use_carry; g.nitems = first.nitems;
+        for (int w = 0; w < SCHED_NCW; w++)
             for (int h = 0; h < 2; h++) {
-                g.own[h].term0 = first.own[w][h].term;
-                g.own[h].tstride = (int)d_own[w][h];
-                g.own[h].flags = first.own[w][h].flags;
+                g.own[w][h].term0 = first.own[w][h].term;
+                g.own[w][h].tstride = (int)d_own[w][h];
+                g.own[w][h].flags = first.own[w][h].flags;
             }
-            for (int q = 0; q < SCHED_SLOTS; q++) {
-                g.slot[q].term0 = first.slot[w][q].term;
-                g.slot[q].tstride = (int)d_term[w][q];
-                g.slot[q].kind = first.slot[w][q].kind;
-                g.slot[q].strip = first.slot[w][q].strip;
-                g.slot[q].need0 = first.slot[w][q].need;
-                g.slot[q].dneed = (int)d_need[w][q];
-            }
-            plan.segs.push_back(g);
+        for (int q = 0; q < SCHED_ITEMS; q++) {
+            g.item[q].term0 = first.item[q].term;
+            g.item[q].tstride = (int)d_term[q];
+            g.item[q].kind = first.item[q].kind;
+            g.item[q].strip = first.item[q].strip;
+            g.item[q].need0 = first.item[q].need;
+            g.item[q].dneed = (int)d_need[q];
         }
+        plan.segs.push_back(g);
         seg_n = 0;
     };
     for (int fs = 0; fs < S; fs++) {
-        plan.seg_ptr[fs] = (int32_t)(plan.segs.size() / SCHED_NCW);
+        plan.seg_ptr[fs] = (int32_t)plan.segs.size();
         const int64_t sb = s.strip_ptr[fs], se = s.strip_ptr[fs + 1];
         const int64_t len = se - sb;
         auto node_at = [&](int64_t i) { return (int)s.nodes[pass == 0 ? sb + i : se - 1 - i]; };
@@ -396,28 +394,25 @@ void build_pass_plan(int H, int W, const std::vector<uint8_t> &info, const Sched
                 extend = true;
                 if (seg_n == 1) {
                     d_u = (long long)nd.u - first.u;
-                    for (int w = 0; w < SCHED_NCW; w++) {
-                        for (int h = 0; h < 2; h++) d_own[w][h] = nd.own[w][h].term - first.own[w][h].term;
-                        for (int q = 0; q < SCHED_SLOTS; q++) {
-                            d_term[w][q] = nd.slot[w][q].term - first.slot[w][q].term;
-                            d_need[w][q] = (long long)nd.slot[w][q].need - first.slot[w][q].need;
+                    for (int w = 0; w < SCHED_NCW; w++)
+                        for (int h = 0; h < 2; h++) {
+                            d_own[w][h] = nd.own[w][h].term - first.own[w][h].term;
+                            if (std::llabs(d_own[w][h]) > INT32_MAX) extend = false;   // strides are 32-bit
                         }
-                    }
-                    // strides are stored as 32-bit ints
-                    for (int w = 0; w < SCHED_NCW && extend; w++) {
-                        for (int h = 0; h < 2; h++) if (std::llabs(d_own[w][h]) > INT32_MAX) extend = false;
-                        for (int q = 0; q < SCHED_SLOTS; q++) if (std::llabs(d_term[w][q]) > INT32_MAX) extend = false;
+                    for (int q = 0; q < SCHED_ITEMS; q++) {
+                        d_term[q] = nd.item[q].term - first.item[q].term;
+                        d_need[q] = (long long)nd.item[q].need - first.item[q].need;
+                        if (std::llabs(d_term[q]) > INT32_MAX) extend = false;
                     }
                 } else {
                     const long long k = seg_n;
                     if ((long long)nd.u != first.u + k * d_u) extend = false;
-                    for (int w = 0; w < SCHED_NCW && extend; w++) {
+                    for (int w = 0; w < SCHED_NCW && extend; w++)
                         for (int h = 0; h < 2; h++)
                             if (nd.own[w][h].term != first.own[w][h].term + k * d_own[w][h]) extend = false;
-                        for (int q = 0; q < SCHED_SLOTS; q++)
-                            if (nd.slot[w][q].term != first.slot[w][q].term + k * d_term[w][q] ||
-                                nd.slot[w][q].need != first.slot[w][q].need + k * d_need[w][q]) extend = false;
-                    }
+                    for (int q = 0; q < SCHED_ITEMS && extend; q++)
+                        if (nd.item[q].term != first.item[q].term + k * d_term[q] ||
+                            nd.item[q].need != first.item[q].need + k * d_need[q]) extend = false;
                 }
             }
             if (extend) {
@@ -434,7 +429,7 @@ void build_pass_plan(int H, int W, const std::vector<uint8_t> &info, const Sched
         }
         flush();
     }
-    plan.seg_ptr[S] = (int32_t)(plan.segs.size() / SCHED_NCW);
+    plan.seg_ptr[S] = (int32_t)plan.segs.size();
 }
 
 } // namespace sb

@@ -27,11 +27,11 @@ struct Schedule {
 };
 void build_schedule(int H, int W, const std::vector<int32_t> &ordering, Schedule &s);
 
-// Segment descriptors of one pass (trws_sched.h): segs[seg * SCHED_NCW + warp], segment
-// range of forward strip fs = [seg_ptr[fs], seg_ptr[fs + 1]).  pass 0 = forward sweep,
+// Segment descriptors of one pass (trws_sched.h): segment range of forward strip fs =
+// [seg_ptr[fs], seg_ptr[fs + 1]).  pass 0 = forward sweep,
 // 1 = backward sweep (strips visited in reverse, nodes within a strip in reverse).
 struct PassPlan {
-    std::vector<trws::SegWarp> segs;
+    std::vector<trws::Segment> segs;
     std::vector<int32_t> seg_ptr;
 };
 void build_pass_plan(int H, int W, const std::vector<uint8_t> &info, const Schedule &s, int pass, PassPlan &plan);

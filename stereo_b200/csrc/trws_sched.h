@@ -16,21 +16,21 @@
 namespace sb {
 namespace trws {
 
-enum { SCHED_NCW = 4, SCHED_SLOTS = 4 };
+enum { SCHED_NCW = 4, SCHED_ITEMS = 22 };
 
-// kinds of rows a warp fetches for a node besides its own send term
-enum { S_NONE = 0, S_D = 1, S_STAT = 2, S_DYN = 3, S_RND = 4 };
+// kinds of rows the helper warps fetch for a node
+enum { S_NONE = 0, S_D = 1, S_SEND = 2, S_DYN = 3, S_RND = 4 };
 
 // own-term flags
 enum { OWN_HAS = 1, OWN_TAIL = 2, OWN_TO_NEXT = 4, OWN_J = 8 };
 
-struct SegOwn {            // the send term a warp owns in one half of a node (16 bytes)
+struct SegOwn {            // the send term a term warp owns in one half of a node (16 bytes)
     long long term0;       // term of the segment's first node
     int tstride;           // term increment per node
     int flags;             // OWN_*
 };
 
-struct SegSlot {           // one extra row per node for this warp (32 bytes)
+struct SegItem {           // one row a helper warp fetches per node (32 bytes)
     long long term0;       // term (S_D: node) of the segment's first node
     int tstride;           // increment per node
     int kind;              // S_*  | tail << 8 (S_RND: am I the tail of the term)
@@ -39,17 +39,18 @@ struct SegSlot {           // one extra row per node for this warp (32 bytes)
     int pad;
 };
 
-struct SegWarp {           // per (segment, compute warp) record (192 bytes, 16-byte aligned)
+struct Segment {           // 864 bytes, 16-byte aligned
     int u0, du, n;         // nodes u0 + i * du, i in [0, n)
     int halves;            // 2 when the nodes send on more than SCHED_NCW terms
     int gamma_den;         // max(nF, nB): gamma = 1 / gamma_den (treeProbabilities.cpp:28-45)
     int use_carry;         // the nodes receive the two messages of the previous strip node through shared memory
-    int pad[2];
-    SegOwn own[2];
-    SegSlot slot[SCHED_SLOTS];
+    int nitems;
+    int pad;
+    SegOwn own[SCHED_NCW][2];
+    SegItem item[SCHED_ITEMS];
 };
 
-static_assert(sizeof(SegWarp) == 192, "SegWarp layout");
+static_assert(sizeof(Segment) == 864, "Segment layout");
 
 } // namespace trws
 } // namespace sb

@@ -58,7 +58,7 @@ struct Solver : SolverBase {
     cudaStream_t stream = 0;
     DevBuf<REAL> dD, dMsg, dPosQ, dPosQp, dAlpha;
     DevBuf<uint8_t> dRankQ, dRankQp, dCntQ, dCntQp;
-    DevBuf<SegWarp> dSegs[2];
+    DevBuf<Segment> dSegs[2];
     DevBuf<int32_t> dSegPtr[2];
     DevBuf<REAL> dSelPos;
     DevBuf<int32_t> dStripPtr, dSol;
@@ -108,7 +108,7 @@ struct Solver : SolverBase {
             build_pass_plan(H, W, info, sched, pass, plan);
             dSegs[pass].alloc(plan.segs.size());
             dSegPtr[pass].alloc(plan.seg_ptr.size());
-            SB_CUDA(cudaMemcpy(dSegs[pass].p, plan.segs.data(), plan.segs.size() * sizeof(SegWarp), cudaMemcpyHostToDevice));
+            SB_CUDA(cudaMemcpy(dSegs[pass].p, plan.segs.data(), plan.segs.size() * sizeof(Segment), cudaMemcpyHostToDevice));
             SB_CUDA(cudaMemcpy(dSegPtr[pass].p, plan.seg_ptr.data(), plan.seg_ptr.size() * 4, cudaMemcpyHostToDevice));
         }
         dCtrl.alloc(sizeof(Ctrl) + (size_t)S * 4);

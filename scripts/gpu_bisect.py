@@ -11,10 +11,11 @@ if len(sys.argv) > 1:
     s.minimize(2, 0.0)
     e, lb, n = s.minimize(6, 0.0)
     t = s.timing
-    print(f"debug={os.environ.get('SB_TRWS_DEBUG')} kernel {t['sweep_kernel_ms']/t['sweep_kernel_launches']*1e3:.1f} us/launch -> {t['sweep_kernel_ms']/t['sweep_kernel_launches']*1e3/(2*H+2*W-4)*1965:.0f} cycles per ring node", flush=True)
+    print(f"debug={os.environ.get('SB_TRWS_DEBUG')} kernel {t['sweep_kernel_ms']/t['sweep_kernel_launches']*1e3:.1f} us/launch -> {t['sweep_kernel_ms']/t['sweep_kernel_launches']*1e3/(3*H+2*W)*1965:.0f} cycles per critical-path step (3H+2W)", flush=True)
 else:
-    for shape in ((4, 1500, 64), (4, 1500, 8), (375, 450, 64)):
-        for dbg in (0, 2, 4, 7):
+    shapes = [tuple(int(x) for x in a.split("x")) for a in os.environ.get("SHAPES", "4x1500x64,375x450x8,128x160x64,375x450x64").split(",")]
+    for shape in shapes:
+        for dbg in (0, 8, 24):
             env = dict(os.environ, SB_TRWS_DEBUG=str(dbg))
             print(shape, end=" ", flush=True)
             subprocess.run([sys.executable, __file__, "x"] + [str(x) for x in shape], env=env)

@@ -4,7 +4,7 @@ os.environ["SB_TRWS_PROFILE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import stereo_b200 as sb
 from stereo_b200 import synth
-for (H, W, L, it) in [(48, 64, 8, 10), (48, 64, 64, 10), (375, 450, 64, 5), (256, 256, 256, 3)]:
+for (H, W, L, it) in [(128, 160, 64, 6), (375, 450, 64, 5), (256, 256, 256, 3)]:
     pr = synth.trws_problem(H, W, L, seed=1, kernel=1)
     s = sb.TrwsSolver(1, pr["unary"], pr["connectivity"], pr["q"], pr["qprim"], pr["alphas"], pr["tol"])
     s.minimize(2, 0.0)

@@ -288,11 +288,15 @@ __device__ __forceinline__ REAL update_linear(REAL gamma, REAL alpha, REAL lambd
         hs[k] = t.a;
         ss[k] = t.b;
     }
-    // left-to-right transform  G_i = min(G_{i-1} + alpha (s_i - s_{i-1}), h_i)
-    REAL gl[K], cl[K];
+    // Two directional distance transforms over the sorted sources, as (offset, value) scans:
+    //   left-to-right  G_i = min(G_{i-1} + alpha (s_i - s_{i-1}), h_i), right-to-left likewise.
+    // The two are independent; their shuffle rounds are issued together so the latencies overlap.
+    REAL gl[K], cl[K], gr[K], cr[K];
     {
         REAL sprev = __shfl_up_sync(0xffffffffu, ss[K - 1], 1);
+        REAL snext = __shfl_down_sync(0xffffffffu, ss[0], 1);
         if (lane == 0) sprev = ss[0];
+        if (lane == 31) snext = ss[K - 1];
         REAL g = BIG, cum = REAL(0);
 #pragma unroll
         for (int k = 0; k < K; k++) {
@@ -302,51 +306,41 @@ __device__ __forceinline__ REAL update_linear(REAL gamma, REAL alpha, REAL lambd
             gl[k] = g;
             cl[k] = cum;
         }
-        REAL Dl = cum, C = g;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const REAL Dp = __shfl_up_sync(0xffffffffu, Dl, o);
-            const REAL Cp = __shfl_up_sync(0xffffffffu, C, o);
-            if (lane >= o) {
-                C = min(Cp + Dl, C);
-                Dl = Dp + Dl;
-            }
-        }
-        REAL Vin = __shfl_up_sync(0xffffffffu, C, 1);
-        if (lane == 0) Vin = BIG;
-#pragma unroll
-        for (int k = 0; k < K; k++) gl[k] = min(Vin + cl[k], gl[k]);
-    }
-    // right-to-left transform, merged into F_i = DT(s_i)
-    {
-        REAL snext = __shfl_down_sync(0xffffffffu, ss[0], 1);
-        if (lane == 31) snext = ss[K - 1];
-        REAL g = BIG, cum = REAL(0);
-        REAL gr[K];
+        REAL DlL = cum, CL = g;
+        g = BIG;
+        cum = REAL(0);
 #pragma unroll
         for (int k = K - 1; k >= 0; k--) {
             const REAL d = alpha * ((k < K - 1 ? ss[k + 1] : snext) - ss[k]);
             g = min(g + d, hs[k]);
             cum += d;
             gr[k] = g;
-            cl[k] = cum;
+            cr[k] = cum;
         }
-        REAL Dl = cum, C = g;
+        REAL DlR = cum, CR = g;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const REAL Dp = __shfl_down_sync(0xffffffffu, Dl, o);
-            const REAL Cp = __shfl_down_sync(0xffffffffu, C, o);
+            const REAL DpL = __shfl_up_sync(0xffffffffu, DlL, o);
+            const REAL CpL = __shfl_up_sync(0xffffffffu, CL, o);
+            const REAL DpR = __shfl_down_sync(0xffffffffu, DlR, o);
+            const REAL CpR = __shfl_down_sync(0xffffffffu, CR, o);
+            if (lane >= o) {
+                CL = min(CpL + DlL, CL);
+                DlL = DpL + DlL;
+            }
             if (lane + o < 32) {
-                C = min(Cp + Dl, C);
-                Dl = Dp + Dl;
+                CR = min(CpR + DlR, CR);
+                DlR = DpR + DlR;
             }
         }
-        REAL Vin = __shfl_down_sync(0xffffffffu, C, 1);
-        if (lane == 31) Vin = BIG;
+        REAL VinL = __shfl_up_sync(0xffffffffu, CL, 1);
+        REAL VinR = __shfl_down_sync(0xffffffffu, CR, 1);
+        if (lane == 0) VinL = BIG;
+        if (lane == 31) VinR = BIG;
 #pragma unroll
         for (int k = 0; k < K; k++) {
             Pair<REAL> t;
-            t.a = min(gl[k], min(Vin + cl[k], gr[k]));
+            t.a = min(min(VinL + cl[k], gl[k]), min(VinR + cr[k], gr[k]));
             t.b = ss[k];
             P[phys<K>(lane * K + k)] = t;
         }
@@ -561,7 +555,7 @@ template <typename REAL, int K> __device__ __forceinline__ void row_sts(REAL *ro
 
 // ---------------------------------------------------------------- the sweep
 //
-// CTA = 4 term warps + 2 helper warps + 1 auxiliary warp; a CTA walks one strip at a time,
+// CTA = 4 term warps + 2 helper warps + publisher warp + prefetch warp; a CTA walks one strip at a time,
 // driven by the segment descriptors of trws_sched.h (no grid arithmetic here).
 //
 //   helper warps (alternating nodes, one node ahead of the term warps) fetch every row a
@@ -576,9 +570,9 @@ template <typename REAL, int K> __device__ __forceinline__ void row_sts(REAL *ro
 //     to this node in the previous step (carry rows in shared memory; minimize.cpp:38-46 /
 //     69-77), the primal rounding when the pass carries it (minimize.cpp:240-260), the
 //     min-plus update of the own term, its store, and the carry rows for the next node;
-//   the auxiliary warp watches the term warps' completion counters, publishes the strip's
-//     progress watermark (gpu-scope fence + store: thousands of cycles, kept off the chain)
-//     and pulls the operands of the nodes ahead into L2.
+//   the publisher warp watches the term warps' completion counters and publishes the strip's
+//     progress watermark (gpu-scope fence + store: a thousand cycles or more, kept off the chain);
+//   the prefetch warp pulls the operands of the nodes ahead into L2.
 //
 // Rows are double buffered by node parity.  Named barriers: FULL[par] (helper arrives, term
 // warps sync: rows of the node ready and all term warps done with the previous node) and
@@ -586,7 +580,7 @@ template <typename REAL, int K> __device__ __forceinline__ void row_sts(REAL *ro
 
 constexpr int NCW = SCHED_NCW;      // term warps
 constexpr int NHW = 2;              // helper warps
-constexpr int CTA_THREADS = (NCW + NHW + 1) * 32;
+constexpr int CTA_THREADS = (NCW + NHW + 2) * 32;   // + publisher warp + prefetch warp
 constexpr int ROWS_PER_PAR = 7;     // BASE DIB0 RMS CM[2] CC[2]
 constexpr int PF_DIST = 6;
 
@@ -716,6 +710,18 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                 }
             };
 
+            // optional phase timers (SB_TRWS_PROFILE): term warp 0 -> prof[0..3] = wait FULL, read rows +
+            // rounding, update + stores, nodes
+            const bool prof_on = (p.prof != nullptr) && w == 0;
+            long long tp[4] = {0, 0, 0, 0};
+            long long tclk = prof_on ? clock64() : 0;
+            auto tick = [&](int which) {
+                if (prof_on) {
+                    const long long now = clock64();
+                    tp[which] += now - tclk;
+                    tclk = now;
+                }
+            };
             OwnTerm<REAL, K> own;
             load_own(so0, 0, own);
             // EMPTY barriers start "armed": nothing has to be read before the helpers' first writes
@@ -748,12 +754,14 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                     }
                 }
                 // ---- rows of this node are ready, every term warp has finished the previous node
+                tick(2);
                 named_sync(BAR_FULL + par);
                 REAL Di[K];
                 int xs = 0;
                 {
                     REAL base[K];
                     row_lds<REAL, K>(base, row_ptr(par, R_BASE), lane);
+                    if (prof_on) { tclk += (long long)(base[0] != base[0]); tick(0); }
 #pragma unroll
                     for (int k = 0; k < K; k++) Di[k] = base[k];
                     if (cur_carry && do_send) {
@@ -805,6 +813,7 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                     }
                 }
                 named_arrive(BAR_EMPTY + par);     // this warp has read the node's rows
+                tick(1);
                 if (do_send && PASS == PASS_BWD) {
                     // ComputeAndSubtractMin + lower bound (minimize.cpp:79-81)
                     REAL vmin = BIG;
@@ -831,6 +840,12 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                 // this warp's stores for the node are issued: tell the auxiliary warp
                 __syncwarp();
                 if (lane == 0) st_release_cta(s_wdone + w, node + 1);
+                if (prof_on) tp[3]++;
+            }
+            if (prof_on && lane == 0) {
+                tick(2);
+                const int grp = (fs == 0) ? 0 : 1;
+                for (int q = 0; q < 4; q++) atomicAdd((unsigned long long *)p.prof + grp * 16 + q, (unsigned long long)tp[q]);
             }
             continue;
         }
@@ -843,7 +858,18 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
             int sg = sg0, seg_start = 0;    // segment of the current node and the strip index of its first node
             int loaded = -1;
             int seg_n = __ldg(&segs[sg].n);
+            const bool prof_on = (p.prof != nullptr) && hid == 0;
+            long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            long long tclk = prof_on ? clock64() : 0;
+            auto tick = [&](int which) {
+                if (prof_on) {
+                    const long long now = clock64();
+                    tp[which] += now - tclk;
+                    tclk = now;
+                }
+            };
             for (int node = hid; node < n_nodes; node += NHW) {
+                tick(6);
                 while (node >= seg_start + seg_n) {
                     seg_start += seg_n;
                     sg++;
@@ -858,11 +884,12 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                     __syncwarp();
                     loaded = sg;
                 }
+                tick(0);
                 const int i = node - seg_start;
                 const int par = node & 1;
                 const int nitems = sd->nitems;
-                // lane j manages item j: address, guard, scalars
-                int kind = S_NONE, strip = -1, need = 0;
+                // lane j manages item j: address, guard, scalars, and copies its whole row
+                int kind = S_NONE, strip = -1, need = 0, fv = 0;
                 long long term = 0;
                 REAL al = REAL(0), sel = REAL(0);
                 if (lane < nitems) {
@@ -873,52 +900,73 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                     term = it.term0 + (long long)i * it.tstride;
                     strip = it.strip;
                     need = it.need0 + i * it.dneed;
-                    if ((kind & 255) == S_RND) al = __ldg(p.alpha + term);
                 }
-                // static rows first
-                for (int j = 0; j < nitems; j++) {
-                    const int kj = __shfl_sync(0xffffffffu, kind, j);
-                    const long long tj = __shfl_sync(0xffffffffu, term, j);
-                    const int k0 = kj & 255;
-                    const REAL *src = nullptr;
-                    if (k0 == S_D) src = p.D + tj * LP;
-                    else if (k0 == S_SEND) src = p.msg + tj * LP;
-                    else if (k0 == S_RND) src = ((kj & 256) ? p.posqp : p.posq) + tj * LP;
-                    if (src) row_async<REAL, K>(landing + (size_t)j * LP, src, lane);
-                }
-                // dependencies: each managing lane waits for its strip's watermark
+                constexpr int CH = LP * (int)sizeof(REAL) / 16;
+                REAL *my_row = landing + (size_t)lane * LP;
                 {
                     const int k0 = kind & 255;
-                    if (k0 == S_DYN || k0 == S_RND) {
-                        while (ld_flag(p.progress + strip) < need) __nanosleep(32);
-                        if (k0 == S_RND) sel = __ldcg(p.selpos + term);
+                    const REAL *src = nullptr;
+                    if (k0 == S_D) src = p.D + term * LP;
+                    else if (k0 == S_SEND) src = p.msg + term * LP;
+                    else if (k0 == S_RND) src = ((kind & 256) ? p.posqp : p.posq) + term * LP;
+                    if (src) {
+#pragma unroll 4
+                        for (int ch = 0; ch < CH; ch++)
+                            cp_async16(reinterpret_cast<char *>(my_row) + ch * 16, reinterpret_cast<const char *>(src) + ch * 16);
                     }
+                    if (k0 == S_RND) al = __ldg(p.alpha + term);
+                    if (k0 == S_DYN || k0 == S_RND) fv = ld_flag(p.progress + strip);   // checked after the static part
                 }
-                __syncwarp();
-                for (int j = 0; j < nitems; j++) {
-                    const int kj = __shfl_sync(0xffffffffu, kind, j);
-                    if ((kj & 255) != S_DYN) continue;
-                    const long long tj = __shfl_sync(0xffffffffu, term, j);
-                    row_async<REAL, K>(landing + (size_t)j * LP, p.msg + tj * LP, lane);
-                }
+                tick(1);
                 cp_async_wait_all();
                 __syncwarp();
-                // reduce to BASE / DIB0 / RMS
+                tick(3);
+                // static part of BASE / DIB0 / RMS
                 REAL base[K], dib[K], rms[K];
 #pragma unroll
                 for (int k = 0; k < K; k++) { base[k] = REAL(0); dib[k] = REAL(0); rms[k] = REAL(0); }
                 for (int j = 0; j < nitems; j++) {
                     const int k0 = __shfl_sync(0xffffffffu, kind, j) & 255;
-                    if (k0 == S_NONE) continue;
+                    if (k0 != S_D && k0 != S_SEND) continue;
                     REAL v[K];
                     row_lds<REAL, K>(v, landing + (size_t)j * LP, lane);
                     if (k0 == S_D) {
 #pragma unroll
                         for (int k = 0; k < K; k++) { base[k] += v[k]; dib[k] += v[k]; }
-                    } else if (k0 == S_SEND) {
+                    } else {
 #pragma unroll
                         for (int k = 0; k < K; k++) { base[k] += v[k]; rms[k] += v[k]; }
-                    } else if (k0 == S_DYN) {
+                    }
+                }
+                if (prof_on) { tclk += (long long)(base[0] != base[0]); tick(4); }
+                // dependencies: each managing lane waits for its strip's watermark, then fetches
+                {
+                    const int k0 = kind & 255;
+                    if (k0 == S_DYN || k0 == S_RND) {
+                        while (fv < need) {
+                            __nanosleep(20);
+                            fv = ld_flag(p.progress + strip);
+                        }
+                        if (k0 == S_RND) {
+                            sel = __ldcg(p.selpos + term);
+                        } else {
+                            const REAL *src = p.msg + term * LP;
+#pragma unroll 4
+                            for (int ch = 0; ch < CH; ch++)
+                                cp_async16(reinterpret_cast<char *>(my_row) + ch * 16, reinterpret_cast<const char *>(src) + ch * 16);
+                        }
+                    }
+                }
+                __syncwarp();
+                tick(2);
+                cp_async_wait_all();
+                __syncwarp();
+                for (int j = 0; j < nitems; j++) {
+                    const int k0 = __shfl_sync(0xffffffffu, kind, j) & 255;
+                    if (k0 != S_DYN && k0 != S_RND) continue;
+                    REAL v[K];
+                    row_lds<REAL, K>(v, landing + (size_t)j * LP, lane);
+                    if (k0 == S_DYN) {
 #pragma unroll
                         for (int k = 0; k < K; k++) base[k] += v[k];
                     } else {
@@ -928,40 +976,66 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                     }
                 }
                 // the term warps have read the rows of node - 2
+                if (prof_on) { tclk += (long long)(base[0] != base[0]); tick(3); }
                 named_sync(BAR_EMPTY + par);
+                tick(5);
                 row_sts<REAL, K>(row_ptr(par, R_BASE), base, lane);
                 if (do_round) {
                     row_sts<REAL, K>(row_ptr(par, R_DIB0), dib, lane);
                     row_sts<REAL, K>(row_ptr(par, R_RMS), rms, lane);
                 }
                 named_arrive(BAR_FULL + par);
+                if (prof_on) tp[7]++;
+            }
+            if (prof_on && lane == 0) {
+                const int grp = (fs == 0) ? 0 : 1;
+                for (int q = 0; q < 8; q++) atomicAdd((unsigned long long *)p.prof + grp * 16 + 4 + q, (unsigned long long)tp[q]);
             }
             // consume the term warps' last arrival on this parity so the barrier is balanced
             named_sync(BAR_EMPTY + hid);
             continue;
         }
 
-        // ================================================================ auxiliary warp
-        {
+        if (warp == NCW + NHW) {
+            // ============================================================ publisher warp
             int published = 0;
-            int pf_seg = sg0, pf_i = 0, pf_node = 0;     // next node to prefetch: segment, index in it, index in strip
-            int pf_n = __ldg(&segs[pf_seg].n);
             while (published < n_nodes) {
                 int c = (lane < NCW) ? ld_acquire_cta(s_wdone + lane) : 0x7fffffff;
 #pragma unroll
                 for (int o = 2; o > 0; o >>= 1) c = min(c, __shfl_xor_sync(0xffffffffu, c, o));
                 c = __shfl_sync(0xffffffffu, c, 0);
                 if (c > published) {
+                    const long long t0 = p.prof ? clock64() : 0;
                     if (lane == 0) publish_flag(p.progress + fs, c);
+                    __syncwarp();
+                    if (p.prof && lane == 0) {
+                        atomicAdd((unsigned long long *)p.prof + (fs == 0 ? 0 : 16) + 12, (unsigned long long)(clock64() - t0));
+                        atomicAdd((unsigned long long *)p.prof + (fs == 0 ? 0 : 16) + 13, 1ull);
+                        atomicAdd((unsigned long long *)p.prof + (fs == 0 ? 0 : 16) + 14, (unsigned long long)(c - published));
+                    }
                     published = c;
                 }
-                const int pf_end = min(n_nodes, c + 2 + PF_DIST);
+            }
+            continue;
+        }
+
+        // ================================================================ prefetch warp
+        {
+            int pf_seg = sg0, pf_i = 0, pf_node = 0;     // next node to prefetch: segment, index in it, index in strip
+            int pf_n = __ldg(&segs[pf_seg].n);
+            for (;;) {
+                int c = (lane < NCW) ? ld_acquire_cta(s_wdone + lane) : 0x7fffffff;
+#pragma unroll
+                for (int o = 2; o > 0; o >>= 1) c = min(c, __shfl_xor_sync(0xffffffffu, c, o));
+                c = __shfl_sync(0xffffffffu, c, 0);
+                const int pf_end = min(n_nodes, c + 3 + PF_DIST);
+                if (pf_node >= n_nodes) break;
                 if (pf_node >= pf_end) {
-                    if (published < n_nodes) __nanosleep(40);
+                    __nanosleep(200);
                     continue;
                 }
                 for (; pf_node < pf_end; pf_node++) {
-                    if (pf_node > c + 1) {
+                    if (pf_node > c + 2) {
                         // rows of node (pf_seg, pf_i): lanes 0..7 take the term warps' own terms,
                         // lanes 8..29 the helper items
                         constexpr int LR = (LP * (int)sizeof(REAL) + 127) / 128;

@@ -172,8 +172,8 @@ struct Solver : SolverBase {
 
         if (const char *dbg = getenv("SB_TRWS_DEBUG")) P.debug = atoi(dbg);
         if (getenv("SB_TRWS_PROFILE")) {
-            dProf.alloc(16);
-            SB_CUDA(cudaMemsetAsync(dProf.p, 0, 16 * sizeof(long long), stream));
+            dProf.alloc(32);
+            SB_CUDA(cudaMemsetAsync(dProf.p, 0, 32 * sizeof(long long), stream));
             P.prof = dProf.p;
         }
 
@@ -260,14 +260,16 @@ struct Solver : SolverBase {
         }
         const double solve_ms = timer.stop_ms();
         if (P.prof) {
-            long long h[16];
+            long long h[32];
             SB_CUDA(cudaMemcpy(h, dProf.p, sizeof(h), cudaMemcpyDeviceToHost));
             SB_CUDA(cudaMemsetAsync(dProf.p, 0, sizeof(h), stream));
-            static const char *names[8] = {"flag-spin", "phaseA", "barrier", "prepare", "B1", "resolve", "update", "steps"};
             for (int g = 0; g < 2; g++) {
-                fprintf(stderr, "[sb profile] %s:", g ? "rows" : "ring");
-                for (int q = 0; q < 7; q++) fprintf(stderr, " %s=%.0f", names[q], h[g * 8 + 7] ? (double)h[g * 8 + q] / (double)h[g * 8 + 7] : 0.0);
-                fprintf(stderr, " cycles/step over %lld steps\n", h[g * 8 + 7]);
+                const long long *q = h + 16 * g;
+                const double nt = q[3] ? (double)q[3] : 1, nh = q[11] ? (double)q[11] : 1, np = q[13] ? (double)q[13] : 1;
+                fprintf(stderr, "[sb profile] %s term0: waitFULL=%.0f read+round=%.0f update=%.0f cyc/node (%lld nodes) | helper0: desc=%.0f "
+                        "static=%.0f flagspin=%.0f dynwait=%.0f reduce=%.0f waitEMPTY=%.0f other=%.0f cyc/node (%lld) | aux: fence=%.0f cyc/publish, "
+                        "%.2f nodes/publish\n", g ? "rows" : "ring", q[0] / nt, q[1] / nt, q[2] / nt, q[3], q[4] / nh, q[5] / nh, q[6] / nh,
+                        q[7] / nh, q[8] / nh, q[9] / nh, q[10] / nh, q[11], q[12] / np, q[14] / np);
             }
         }
         *energy_out = energy;

@@ -70,6 +70,10 @@ struct Problem {
     int32_t *progress;      // [S] nodes of each strip completed in this pass (zeroed per launch)
     int32_t *sol;           // [N] rounded labels (0-based)
     REAL *selpos;           // [E] position of the sender's rounded label on each forward term
+    unsigned long long *mbox;   // fp32 only: [E][LP] (value bits | epoch << 32) self-validating copy of
+                                // every message sent across strips in the current pass
+    unsigned long long *selbox; // fp32 only: [E] (selected position bits | epoch << 32)
+    unsigned epoch;             // launch counter (> 0): the tag that validates mailbox words
     long long *prof;        // optional [2][8] cycle counters (SB_TRWS_PROFILE), else null
     int *ticket;            // dispatch counter (zeroed before each launch)
     double *acc;            // [0] energy  [1] lower bound (zeroed before each launch)
@@ -451,6 +455,18 @@ __device__ __forceinline__ void publish_flag(int32_t *p, int v)
 {
     asm volatile("fence.acq_rel.gpu;\n\tst.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// Mailbox words: one naturally aligned 64-bit access = value + tag, single-copy atomic, so a
+// matching tag proves the value without any fence or flag.
+__device__ __forceinline__ unsigned long long ld_mbox(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_mbox(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -579,17 +595,22 @@ template <typename REAL, int K> __device__ __forceinline__ void row_sts(REAL *ro
 // EMPTY[par] (term warps arrive after reading, helper syncs before overwriting).
 
 constexpr int NCW = SCHED_NCW;      // term warps
-constexpr int NHW = 2;              // helper warps
-constexpr int CTA_THREADS = (NCW + NHW + 2) * 32;   // + publisher warp + prefetch warp
-constexpr int ROWS_PER_PAR = 7;     // BASE DIB0 RMS CM[2] CC[2]
+constexpr int NHW_MAX = 4;          // helper warps in the CTA
+constexpr int CTA_THREADS = (NCW + NHW_MAX + 2) * 32;   // + publisher warp + prefetch warp
 constexpr int PF_DIST = 6;
+// helper warps actually used (node i is prepared by helper i % NHW): 2 where four sets of
+// landing rows would not fit in shared memory (2 KB rows: fp64 with 256 labels)
+template <typename REAL, int K> __host__ __device__ constexpr int nhw() { return (32 * K * (int)sizeof(REAL) >= 2048) ? 2 : 4; }
 
-enum { R_BASE = 0, R_DIB0 = 1, R_RMS = 2, R_CM = 3, R_CC = 5 };
-enum { BAR_FULL = 1, BAR_EMPTY = 3 };   // + parity
+// shared rows: NHW sets of {BASE, DIB0, RMS} (by node % NHW), then 2 sets of {CM[2], CC[2]} (by
+// node parity), then NHW x SCHED_ITEMS landing rows
+enum { R_BASE = 0, R_DIB0 = 1, R_RMS = 2, R_CM = 0, R_CC = 2 };
+constexpr int ROWS_CARRY = 8;
+enum { BAR_FULL = 1, BAR_EMPTY = 1 + NHW_MAX };   // + node % NHW
 
 template <typename REAL, int K> __host__ __device__ constexpr size_t sweep_smem_bytes()
 {
-    return (size_t)(2 * ROWS_PER_PAR + NHW * SCHED_ITEMS) * 32 * K * sizeof(REAL) +
+    return (size_t)(3 * nhw<REAL, K>() + ROWS_CARRY + nhw<REAL, K>() * SCHED_ITEMS) * 32 * K * sizeof(REAL) +
            (size_t)NCW * scratch_pairs<K>() * sizeof(Pair<REAL>);
 }
 
@@ -616,20 +637,27 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_ticket;
     __shared__ int s_wdone[NCW]; // nodes of the current strip each term warp has completed
-    __shared__ __align__(16) Segment s_seg[NHW];
+    __shared__ __align__(16) Segment s_seg[NHW_MAX];
     constexpr int LP = 32 * K;
+    constexpr int NHW = nhw<REAL, K>();
+    // fp32: cross-strip messages travel through self-validating mailbox words; fp64 (parity
+    // instantiation): progress watermarks published behind a gpu-scope fence
+    constexpr bool MBOX = (sizeof(REAL) == 4);
+    constexpr int ROWS_SETS = 3 * NHW;
+    constexpr int ROWS_FIXED = ROWS_SETS + ROWS_CARRY;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const bool is_term = warp < NCW;
-    const bool is_helper = warp >= NCW && warp < NCW + NHW;
+    const bool is_helper = warp >= NCW && warp < NCW + NHW_MAX;
     REAL *rows = reinterpret_cast<REAL *>(smem_raw);
     const REAL BIG = Lim<REAL>::big();
     const bool do_send = (PASS == PASS_BWD) || (p.mode & MODE_SEND);
     const bool do_round = (PASS == PASS_FWD) && (p.mode & MODE_ROUND);
     const Segment *const segs = p.segs;
     double acc_energy = 0.0, acc_lb = 0.0;
-    auto row_ptr = [&](int par, int r) -> REAL * { return rows + (size_t)(par * ROWS_PER_PAR + r) * LP; };
-    Pair<REAL> *P = reinterpret_cast<Pair<REAL> *>(rows + (size_t)(2 * ROWS_PER_PAR + NHW * SCHED_ITEMS) * LP) +
+    auto set_ptr = [&](int set, int r) -> REAL * { return rows + (size_t)(set * 3 + r) * LP; };
+    auto carry_ptr = [&](int par, int r) -> REAL * { return rows + (size_t)(ROWS_SETS + par * 4 + r) * LP; };
+    Pair<REAL> *P = reinterpret_cast<Pair<REAL> *>(rows + (size_t)(ROWS_FIXED + NHW * SCHED_ITEMS) * LP) +
                     (size_t)(is_term ? warp : 0) * scratch_pairs<K>();
     if (is_term && lane == 0) {
         Pair<REAL> t;
@@ -690,12 +718,17 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                     for (int k = 1; k < K; k++)
                         if (k == xs % K) sv = o.s[k];
                     sv = __shfl_sync(0xffffffffu, sv, xs / K);
-                    if (lane == 0) __stcg(p.selpos + o.term, sv);
+                    if constexpr (MBOX) {
+                        if (lane == 0 && !to_next)
+                            st_mbox(p.selbox + o.term, (unsigned long long)(unsigned)__float_as_int((float)sv) | ((unsigned long long)p.epoch << 32));
+                    } else {
+                        if (lane == 0) __stcg(p.selpos + o.term, sv);
+                    }
                     if (to_next) {
                         REAL cc[K];
 #pragma unroll
                         for (int k = 0; k < K; k++) cc[k] = o.alpha * smooth<REAL, KERN>(o.x[k] - sv, p.lambda);
-                        row_sts<REAL, K>(row_ptr(par ^ 1, R_CC + oj), cc, lane);
+                        row_sts<REAL, K>(carry_ptr(par ^ 1, R_CC + oj), cc, lane);
                     }
                 }
                 if (do_send) {
@@ -704,9 +737,17 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                         vmin = update_linear<REAL, K>(gamma, o.alpha, p.lambda, p.L, lane, Di, o.m, o.s, o.rk, o.x, o.cn, P);
                     else
                         vmin = update_quadratic<REAL, K>(gamma, o.alpha, p.lambda, p.L, lane, Di, o.m, o.s, o.rk, o.x, o.cn, P);
+                    if constexpr (MBOX) {
+                        if (!to_next) {   // the receiver is in another strip: it polls these words
+                            unsigned long long *mb = p.mbox + o.term * LP + lane * K;
+#pragma unroll
+                            for (int k = 0; k < K; k++)
+                                st_mbox(mb + k, (unsigned long long)(unsigned)__float_as_int((float)o.m[k]) | ((unsigned long long)p.epoch << 32));
+                        }
+                    }
                     VecIO<REAL, K>::store(p.msg + o.term * LP + lane * K, o.m);
                     if (PASS == PASS_BWD) acc_lb += (double)vmin;
-                    if (to_next) row_sts<REAL, K>(row_ptr(par ^ 1, R_CM + oj), o.m, lane);
+                    if (to_next) row_sts<REAL, K>(carry_ptr(par ^ 1, R_CM + oj), o.m, lane);
                 }
             };
 
@@ -725,11 +766,12 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
             OwnTerm<REAL, K> own;
             load_own(so0, 0, own);
             // EMPTY barriers start "armed": nothing has to be read before the helpers' first writes
-            named_arrive(BAR_EMPTY + 0);
-            named_arrive(BAR_EMPTY + 1);
+#pragma unroll
+            for (int hq = 0; hq < NHW; hq++) named_arrive(BAR_EMPTY + hq);
 
             for (int node = 0; node < n_nodes; node++) {
                 const int par = node & 1;
+                const int set = node % NHW;
                 const int u = u0 + seg_i * du;
                 const REAL cur_gamma = gamma;
                 const int cur_halves = halves;
@@ -755,12 +797,12 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                 }
                 // ---- rows of this node are ready, every term warp has finished the previous node
                 tick(2);
-                named_sync(BAR_FULL + par);
+                named_sync(BAR_FULL + set);
                 REAL Di[K];
                 int xs = 0;
                 {
                     REAL base[K];
-                    row_lds<REAL, K>(base, row_ptr(par, R_BASE), lane);
+                    row_lds<REAL, K>(base, set_ptr(set, R_BASE), lane);
                     if (prof_on) { tclk += (long long)(base[0] != base[0]); tick(0); }
 #pragma unroll
                     for (int k = 0; k < K; k++) Di[k] = base[k];
@@ -768,7 +810,7 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
 #pragma unroll
                         for (int jj = 0; jj < 2; jj++) {
                             REAL v[K];
-                            row_lds<REAL, K>(v, row_ptr(par, R_CM + jj), lane);
+                            row_lds<REAL, K>(v, carry_ptr(par, R_CM + jj), lane);
 #pragma unroll
                             for (int k = 0; k < K; k++) Di[k] += v[k];
                         }
@@ -776,13 +818,13 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                     if (do_round) {
                         // minimize.cpp:240-260: DiB = D + sum_{lower nb} V(x_nb, .), Dr = DiB + forward messages
                         REAL dib[K], rms[K];
-                        row_lds<REAL, K>(dib, row_ptr(par, R_DIB0), lane);
-                        row_lds<REAL, K>(rms, row_ptr(par, R_RMS), lane);
+                        row_lds<REAL, K>(dib, set_ptr(set, R_DIB0), lane);
+                        row_lds<REAL, K>(rms, set_ptr(set, R_RMS), lane);
                         if (cur_carry) {
 #pragma unroll
                             for (int jj = 0; jj < 2; jj++) {
                                 REAL v[K];
-                                row_lds<REAL, K>(v, row_ptr(par, R_CC + jj), lane);
+                                row_lds<REAL, K>(v, carry_ptr(par, R_CC + jj), lane);
 #pragma unroll
                                 for (int k = 0; k < K; k++) dib[k] += v[k];
                             }
@@ -812,7 +854,7 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                         }
                     }
                 }
-                named_arrive(BAR_EMPTY + par);     // this warp has read the node's rows
+                named_arrive(BAR_EMPTY + set);     // this warp has read the node's rows
                 tick(1);
                 if (do_send && PASS == PASS_BWD) {
                     // ComputeAndSubtractMin + lower bound (minimize.cpp:79-81)
@@ -839,7 +881,10 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                 own = nxt;
                 // this warp's stores for the node are issued: tell the auxiliary warp
                 __syncwarp();
-                if (lane == 0) st_release_cta(s_wdone + w, node + 1);
+                if (lane == 0) {
+                    if constexpr (MBOX) *(volatile int *)(s_wdone + w) = node + 1;   // only paces the prefetch warp
+                    else st_release_cta(s_wdone + w, node + 1);
+                }
                 if (prof_on) tp[3]++;
             }
             if (prof_on && lane == 0) {
@@ -853,7 +898,8 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
         if (is_helper) {
             // ============================================================ helper warps
             const int hid = warp - NCW;
-            REAL *landing = rows + (size_t)2 * ROWS_PER_PAR * LP + (size_t)hid * SCHED_ITEMS * LP;
+            if (hid >= NHW) continue;
+            REAL *landing = rows + (size_t)ROWS_FIXED * LP + (size_t)hid * SCHED_ITEMS * LP;
             Segment *sd = &s_seg[hid];
             int sg = sg0, seg_start = 0;    // segment of the current node and the strip index of its first node
             int loaded = -1;
@@ -886,7 +932,6 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                 }
                 tick(0);
                 const int i = node - seg_start;
-                const int par = node & 1;
                 const int nitems = sd->nitems;
                 // lane j manages item j: address, guard, scalars, and copies its whole row
                 int kind = S_NONE, strip = -1, need = 0, fv = 0;
@@ -915,7 +960,8 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                             cp_async16(reinterpret_cast<char *>(my_row) + ch * 16, reinterpret_cast<const char *>(src) + ch * 16);
                     }
                     if (k0 == S_RND) al = __ldg(p.alpha + term);
-                    if (k0 == S_DYN || k0 == S_RND) fv = ld_flag(p.progress + strip);   // checked after the static part
+                    if constexpr (!MBOX)
+                        if (k0 == S_DYN || k0 == S_RND) fv = ld_flag(p.progress + strip);   // checked after the static part
                 }
                 tick(1);
                 cp_async_wait_all();
@@ -925,20 +971,67 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                 REAL base[K], dib[K], rms[K];
 #pragma unroll
                 for (int k = 0; k < K; k++) { base[k] = REAL(0); dib[k] = REAL(0); rms[k] = REAL(0); }
+                const unsigned m_d = __ballot_sync(0xffffffffu, (kind & 255) == S_D);
+                const unsigned m_send = __ballot_sync(0xffffffffu, (kind & 255) == S_SEND);
+                const unsigned m_dyn = __ballot_sync(0xffffffffu, (kind & 255) == S_DYN);
+                const unsigned m_rnd = __ballot_sync(0xffffffffu, (kind & 255) == S_RND);
+#pragma unroll 4
                 for (int j = 0; j < nitems; j++) {
-                    const int k0 = __shfl_sync(0xffffffffu, kind, j) & 255;
-                    if (k0 != S_D && k0 != S_SEND) continue;
+                    if (!(((m_d | m_send) >> j) & 1u)) continue;
                     REAL v[K];
                     row_lds<REAL, K>(v, landing + (size_t)j * LP, lane);
-                    if (k0 == S_D) {
 #pragma unroll
-                        for (int k = 0; k < K; k++) { base[k] += v[k]; dib[k] += v[k]; }
+                    for (int k = 0; k < K; k++) base[k] += v[k];
+                    if ((m_d >> j) & 1u) {
+#pragma unroll
+                        for (int k = 0; k < K; k++) dib[k] += v[k];
                     } else {
 #pragma unroll
-                        for (int k = 0; k < K; k++) { base[k] += v[k]; rms[k] += v[k]; }
+                        for (int k = 0; k < K; k++) rms[k] += v[k];
                     }
                 }
                 if (prof_on) { tclk += (long long)(base[0] != base[0]); tick(4); }
+                if constexpr (MBOX) {
+                    // dependencies through mailboxes: every lane polls the K words of its own labels
+                    // (value | epoch); the managing lane of a rounding item polls the sender's selected
+                    // position.  A matching epoch proves the word was written in this pass.
+                    const unsigned ep = p.epoch;
+                    if ((kind & 255) == S_RND) {
+                        unsigned long long wv = ld_mbox(p.selbox + term);
+                        while ((unsigned)(wv >> 32) != ep) {
+                            __nanosleep(20);
+                            wv = ld_mbox(p.selbox + term);
+                        }
+                        sel = (REAL)__int_as_float((int)(unsigned)wv);
+                    }
+                    __syncwarp();
+                    for (int j = 0; j < nitems; j++) {
+                        if (!((m_dyn >> j) & 1u)) continue;
+                        const long long tj = __shfl_sync(0xffffffffu, term, j);
+                        const unsigned long long *mb = p.mbox + tj * LP + lane * K;
+                        unsigned long long wv[K];
+                        for (;;) {
+                            bool ok = true;
+#pragma unroll
+                            for (int k = 0; k < K; k++) wv[k] = ld_mbox(mb + k);
+#pragma unroll
+                            for (int k = 0; k < K; k++) ok = ok && ((unsigned)(wv[k] >> 32) == ep);
+                            if (__all_sync(0xffffffffu, ok)) break;
+                            __nanosleep(20);
+                        }
+#pragma unroll
+                        for (int k = 0; k < K; k++) base[k] += (REAL)__int_as_float((int)(unsigned)wv[k]);
+                    }
+                    tick(2);
+                    for (int j = 0; j < nitems; j++) {
+                        if (!((m_rnd >> j) & 1u)) continue;
+                        REAL v[K];
+                        row_lds<REAL, K>(v, landing + (size_t)j * LP, lane);
+                        const REAL aj = __shfl_sync(0xffffffffu, al, j), sj = __shfl_sync(0xffffffffu, sel, j);
+#pragma unroll
+                        for (int k = 0; k < K; k++) dib[k] += aj * smooth<REAL, KERN>(v[k] - sj, p.lambda);
+                    }
+                } else {
                 // dependencies: each managing lane waits for its strip's watermark, then fetches
                 {
                     const int k0 = kind & 255;
@@ -962,11 +1055,10 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                 cp_async_wait_all();
                 __syncwarp();
                 for (int j = 0; j < nitems; j++) {
-                    const int k0 = __shfl_sync(0xffffffffu, kind, j) & 255;
-                    if (k0 != S_DYN && k0 != S_RND) continue;
+                    if (!(((m_dyn | m_rnd) >> j) & 1u)) continue;
                     REAL v[K];
                     row_lds<REAL, K>(v, landing + (size_t)j * LP, lane);
-                    if (k0 == S_DYN) {
+                    if ((m_dyn >> j) & 1u) {
 #pragma unroll
                         for (int k = 0; k < K; k++) base[k] += v[k];
                     } else {
@@ -975,16 +1067,17 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                         for (int k = 0; k < K; k++) dib[k] += aj * smooth<REAL, KERN>(v[k] - sj, p.lambda);
                     }
                 }
-                // the term warps have read the rows of node - 2
-                if (prof_on) { tclk += (long long)(base[0] != base[0]); tick(3); }
-                named_sync(BAR_EMPTY + par);
-                tick(5);
-                row_sts<REAL, K>(row_ptr(par, R_BASE), base, lane);
-                if (do_round) {
-                    row_sts<REAL, K>(row_ptr(par, R_DIB0), dib, lane);
-                    row_sts<REAL, K>(row_ptr(par, R_RMS), rms, lane);
                 }
-                named_arrive(BAR_FULL + par);
+                // the term warps have read the rows of node - NHW
+                if (prof_on) { tclk += (long long)(base[0] != base[0]); tick(3); }
+                named_sync(BAR_EMPTY + hid);
+                tick(5);
+                row_sts<REAL, K>(set_ptr(hid, R_BASE), base, lane);
+                if (do_round) {
+                    row_sts<REAL, K>(set_ptr(hid, R_DIB0), dib, lane);
+                    row_sts<REAL, K>(set_ptr(hid, R_RMS), rms, lane);
+                }
+                named_arrive(BAR_FULL + hid);
                 if (prof_on) tp[7]++;
             }
             if (prof_on && lane == 0) {
@@ -996,8 +1089,9 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
             continue;
         }
 
-        if (warp == NCW + NHW) {
+        if (warp == NCW + NHW_MAX) {
             // ============================================================ publisher warp
+            if constexpr (MBOX) continue;   // nothing to publish: receivers validate the data itself
             int published = 0;
             while (published < n_nodes) {
                 int c = (lane < NCW) ? ld_acquire_cta(s_wdone + lane) : 0x7fffffff;

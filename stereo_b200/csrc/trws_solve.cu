@@ -61,11 +61,13 @@ struct Solver : SolverBase {
     DevBuf<Segment> dSegs[2];
     DevBuf<int32_t> dSegPtr[2];
     DevBuf<REAL> dSelPos;
+    DevBuf<unsigned long long> dMbox, dSelBox;
     DevBuf<int32_t> dStripPtr, dSol;
     DevBuf<unsigned char> dCtrl;   // Ctrl + progress[S]
     DevBuf<long long> dProf;
     Problem<REAL> P;
     int grid_fwd = 1, grid_bwd = 1, wpb = 1, epoch = 0;
+    unsigned launch_epoch = 0;   // never reset: tags of earlier launches must not validate
     Ctrl *hc = nullptr; // pinned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double kernel_ms = 0;
@@ -103,6 +105,12 @@ struct Solver : SolverBase {
         dRankQ.alloc((size_t)E * LP); dRankQp.alloc((size_t)E * LP); dCntQ.alloc((size_t)E * LP); dCntQp.alloc((size_t)E * LP);
         dStripPtr.alloc((size_t)S + 1); dSol.alloc((size_t)N);
         dSelPos.alloc((size_t)std::max<int64_t>(E, 1));
+        if (sizeof(REAL) == 4) {
+            dMbox.alloc((size_t)std::max<int64_t>(E, 1) * LP);
+            dSelBox.alloc((size_t)std::max<int64_t>(E, 1));
+            SB_CUDA(cudaMemsetAsync(dMbox.p, 0, dMbox.bytes(), stream));
+            SB_CUDA(cudaMemsetAsync(dSelBox.p, 0, dSelBox.bytes(), stream));
+        }
         for (int pass = 0; pass < 2; pass++) {
             PassPlan plan;
             build_pass_plan(H, W, info, sched, pass, plan);
@@ -165,7 +173,7 @@ struct Solver : SolverBase {
         P.rank_q = dRankQ.p; P.rank_qp = dRankQp.p; P.cnt_q = dCntQ.p; P.cnt_qp = dCntQp.p;
         P.alpha = dAlpha.p; P.lambda = (REAL)tol;
         P.strip_ptr = dStripPtr.p; P.S = S;
-        P.sol = dSol.p; P.selpos = dSelPos.p;
+        P.sol = dSol.p; P.selpos = dSelPos.p; P.mbox = dMbox.p; P.selbox = dSelBox.p;
         Ctrl *ctrl = reinterpret_cast<Ctrl *>(dCtrl.p);
         P.ticket = &ctrl->ticket; P.acc = ctrl->acc;
         P.progress = reinterpret_cast<int32_t *>(dCtrl.p + sizeof(Ctrl));
@@ -213,6 +221,7 @@ struct Solver : SolverBase {
     {
         SB_CUDA(cudaMemsetAsync(dCtrl.p, 0, dCtrl.bytes(), stream));
         ++epoch;
+        P.epoch = ++launch_epoch;
         P.mode = mode;
         P.segs = dSegs[pass == PASS_FWD ? 0 : 1].p;
         P.seg_ptr = dSegPtr[pass == PASS_FWD ? 0 : 1].p;

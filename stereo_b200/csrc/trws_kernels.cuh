@@ -996,32 +996,56 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                     // (value | epoch); the managing lane of a rounding item polls the sender's selected
                     // position.  A matching epoch proves the word was written in this pass.
                     const unsigned ep = p.epoch;
-                    if ((kind & 255) == S_RND) {
-                        unsigned long long wv = ld_mbox(p.selbox + term);
-                        while ((unsigned)(wv >> 32) != ep) {
-                            __nanosleep(20);
-                            wv = ld_mbox(p.selbox + term);
+                    // all polls of a batch are in flight together: the selected positions (managing
+                    // lanes) and up to G dependency rows (every lane its own K words)
+                    constexpr int G = (K <= 2) ? 4 : (K <= 4) ? 2 : 1;
+                    const bool need_sel = (kind & 255) == S_RND;
+                    bool have_sel = !need_sel;
+                    unsigned rem = m_dyn;
+                    do {
+                        long long tj[G];
+                        int nb = 0;
+#pragma unroll
+                        for (int q = 0; q < G; q++) {
+                            tj[q] = 0;
+                            if (rem) {
+                                const int j = __ffs(rem) - 1;
+                                rem &= rem - 1;
+                                tj[q] = __shfl_sync(0xffffffffu, term, j);
+                                nb = q + 1;
+                            }
                         }
-                        sel = (REAL)__int_as_float((int)(unsigned)wv);
-                    }
-                    __syncwarp();
-                    for (int j = 0; j < nitems; j++) {
-                        if (!((m_dyn >> j) & 1u)) continue;
-                        const long long tj = __shfl_sync(0xffffffffu, term, j);
-                        const unsigned long long *mb = p.mbox + tj * LP + lane * K;
-                        unsigned long long wv[K];
+                        unsigned long long wv[G][K];
                         for (;;) {
+                            unsigned long long sw = 0;
+                            if (!have_sel) sw = ld_mbox(p.selbox + term);
+#pragma unroll
+                            for (int q = 0; q < G; q++)
+                                if (q < nb) {
+#pragma unroll
+                                    for (int k = 0; k < K; k++) wv[q][k] = ld_mbox(p.mbox + tj[q] * LP + lane * K + k);
+                                }
                             bool ok = true;
+                            if (!have_sel) {
+                                if ((unsigned)(sw >> 32) == ep) { sel = (REAL)__int_as_float((int)(unsigned)sw); have_sel = true; }
+                                else ok = false;
+                            }
 #pragma unroll
-                            for (int k = 0; k < K; k++) wv[k] = ld_mbox(mb + k);
+                            for (int q = 0; q < G; q++)
+                                if (q < nb) {
 #pragma unroll
-                            for (int k = 0; k < K; k++) ok = ok && ((unsigned)(wv[k] >> 32) == ep);
+                                    for (int k = 0; k < K; k++) ok = ok && ((unsigned)(wv[q][k] >> 32) == ep);
+                                }
                             if (__all_sync(0xffffffffu, ok)) break;
                             __nanosleep(20);
                         }
 #pragma unroll
-                        for (int k = 0; k < K; k++) base[k] += (REAL)__int_as_float((int)(unsigned)wv[k]);
-                    }
+                        for (int q = 0; q < G; q++)
+                            if (q < nb) {
+#pragma unroll
+                                for (int k = 0; k < K; k++) base[k] += (REAL)__int_as_float((int)(unsigned)wv[q][k]);
+                            }
+                    } while (rem);
                     tick(2);
                     for (int j = 0; j < nitems; j++) {
                         if (!((m_rnd >> j) & 1u)) continue;

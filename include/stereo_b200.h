@@ -139,6 +139,11 @@ SB_API void sb_trws_destroy(sb_trws_solver *s);
  * (SURVEY Appendix A.1), literal greedy scan otherwise.  Host-only. */
 SB_API int sb_trws_grid_ordering(int H, int W, int32_t *ordering);
 
+/* Host-only introspection of the sweep schedule (strips -> segments, trws_order.cpp) for an
+ * H x W grid: stats[0] = strips; then per pass (forward, backward): segments, nodes covered,
+ * rows fetched by the helper warps, nodes that send on more than four terms.  9 values. */
+SB_API int sb_trws_plan_stats(int H, int W, int64_t *stats);
+
 /* Infer (H, W) from a connectivity list and verify it is the reference grid.
  * Host-only.  Returns SB_ENOTGRID when it is not. */
 SB_API int sb_grid_from_connectivity(int64_t N, int64_t E, const uint32_t *conn, int *H, int *W);

@@ -68,6 +68,7 @@ def lib():
         L.sb_trws_destroy.argtypes = [ctypes.c_void_p]
         L.sb_trws_destroy.restype = None
         L.sb_trws_grid_ordering.argtypes = [c_int, c_int, _ip]
+        L.sb_trws_plan_stats.argtypes = [c_int, c_int, POINTER(c_int64)]
         L.sb_grid_from_connectivity.argtypes = [c_int64, c_int64, _up, POINTER(c_int), POINTER(c_int)]
         ip, i64, dbl = c_int, c_int64, c_double
         L.sb_rd_solve.argtypes = [c_int64, c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _up, c_int, _dp, _dp, _dp, _dp]

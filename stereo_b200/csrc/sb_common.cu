@@ -28,6 +28,17 @@ void require_device()
         throw Error(SB_ENODEV, format("stereo_b200: no CUDA device available (%s); this library has no CPU fallback",
                                       e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e)));
     }
+    // keep freed blocks in the default memory pool of the current device (see DevBuf)
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev != configured_dev) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        configured_dev = dev;
+    }
 }
 
 } // namespace sb

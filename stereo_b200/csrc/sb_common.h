@@ -55,15 +55,18 @@ struct DevBuf {
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
+    // Stream-ordered allocation from the device's default pool (configured in require_device()
+    // to keep freed blocks): repeated solves reuse their buffers instead of paying cudaMalloc /
+    // cudaFree (which synchronises) every call.  Everything the library does runs on stream 0.
     void alloc(size_t count)
     {
         release();
         n = count;
-        if (count) SB_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+        if (count) SB_CUDA(cudaMallocAsync((void **)&p, count * sizeof(T), 0));
     }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, 0);
         p = nullptr;
         n = 0;
     }

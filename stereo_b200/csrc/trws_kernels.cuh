@@ -1239,20 +1239,22 @@ term_tables_kernel(const double *__restrict__ q, const double *__restrict__ qp, 
     for (long long t = (long long)blockIdx.x * WARPS + warp; t < E; t += (long long)gridDim.x * WARPS) {
         REAL a[K], b[K];
         REAL amax = -PMAX, bmax = -PMAX;
-        bool isbad = false;
+        bool isbad = false, isbad2 = false;
 #pragma unroll
         for (int k = 0; k < K; k++) {
             const int l = lane * K + k;
             if (l < L) {
                 const double va = q[t * L + l], vb = qp[t * L + l];
-                if (!(va == va) || !(vb == vb)) isbad = true;
+                if (!(va == va)) isbad = true;
+                if (!(vb == vb)) isbad2 = true;
                 a[k] = (REAL)fmin(fmax(va, -(double)PMAX), (double)PMAX);
                 b[k] = (REAL)fmin(fmax(vb, -(double)PMAX), (double)PMAX);
                 amax = max(amax, a[k]);
                 bmax = max(bmax, b[k]);
             }
         }
-        if (isbad) atomicExch(bad, 1);
+        if (isbad) atomicOr(bad, 1);    // NaN in q
+        if (isbad2) atomicOr(bad, 2);   // NaN in qprim
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, o));

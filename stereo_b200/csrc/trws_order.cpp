@@ -448,6 +448,34 @@ int sb_trws_grid_ordering(int H, int W, int32_t *ordering)
     });
 }
 
+int sb_trws_plan_stats(int H, int W, int64_t *stats)
+{
+    return sb::guarded([&] {
+        SB_REQUIRE(H >= 1 && W >= 1 && stats, SB_EINVAL, "sb_trws_plan_stats: bad arguments");
+        std::vector<int32_t> order;
+        SB_REQUIRE(sb::grid_ordering(H, W, order), SB_EINVAL, "sb_trws_plan_stats: no valid ordering");
+        std::vector<uint8_t> info;
+        sb::build_node_info(H, W, order, info);
+        sb::Schedule sched;
+        sb::build_schedule(H, W, order, sched);
+        stats[0] = (int64_t)sched.strip_ptr.size() - 1;
+        for (int pass = 0; pass < 2; pass++) {
+            sb::PassPlan plan;
+            sb::build_pass_plan(H, W, info, sched, pass, plan);
+            int64_t nodes = 0, items = 0, two_half = 0;
+            for (const auto &g : plan.segs) {
+                nodes += g.n;
+                items += (int64_t)g.n * g.nitems;
+                if (g.halves == 2) two_half += g.n;
+            }
+            stats[1 + 4 * pass] = (int64_t)plan.segs.size();
+            stats[2 + 4 * pass] = nodes;
+            stats[3 + 4 * pass] = items;
+            stats[4 + 4 * pass] = two_half;
+        }
+    });
+}
+
 int sb_grid_from_connectivity(int64_t N, int64_t E, const uint32_t *conn, int *H, int *W)
 {
     return sb::guarded([&] {

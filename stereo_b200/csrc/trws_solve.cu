@@ -8,6 +8,10 @@
 #include "trws_kernels.cuh"
 #include "trws_launch.h"
 #include <vector>
+#include <map>
+#include <tuple>
+#include <memory>
+#include <mutex>
 #include <chrono>
 #include <cstring>
 #include <cstdlib>
@@ -39,6 +43,49 @@ double now_ms()
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
+// The sweep schedule depends only on the grid shape: built once per (device, H, W) and kept
+// resident (the reference re-runs its O(N * perimeter) SetAutomaticOrdering on every call,
+// ordering.cpp:7-157).
+struct GridPlan {
+    int S = 0;
+    DevBuf<Segment> segs[2];
+    DevBuf<int32_t> seg_ptr[2];
+    DevBuf<int32_t> strip_ptr;
+};
+
+std::shared_ptr<GridPlan> grid_plan(int dev, int H, int W)
+{
+    static std::mutex mu;
+    static std::map<std::tuple<int, int, int>, std::shared_ptr<GridPlan>> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    const auto key = std::make_tuple(dev, H, W);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    std::vector<int32_t> order;
+    SB_REQUIRE(grid_ordering(H, W, order), SB_EINVAL,
+               "sb_trws_solve: %dx%d grid has no valid automatic ordering (the reference crashes on it)", H, W);
+    std::vector<uint8_t> info;
+    build_node_info(H, W, order, info);
+    Schedule sched;
+    build_schedule(H, W, order, sched);
+    auto gp = std::make_shared<GridPlan>();
+    gp->S = (int)sched.strip_ptr.size() - 1;
+    std::vector<int32_t> strip_ptr32(sched.strip_ptr.begin(), sched.strip_ptr.end());
+    gp->strip_ptr.alloc(strip_ptr32.size());
+    SB_CUDA(cudaMemcpy(gp->strip_ptr.p, strip_ptr32.data(), strip_ptr32.size() * 4, cudaMemcpyHostToDevice));
+    for (int pass = 0; pass < 2; pass++) {
+        PassPlan plan;
+        build_pass_plan(H, W, info, sched, pass, plan);
+        gp->segs[pass].alloc(plan.segs.size());
+        gp->seg_ptr[pass].alloc(plan.seg_ptr.size());
+        SB_CUDA(cudaMemcpy(gp->segs[pass].p, plan.segs.data(), plan.segs.size() * sizeof(Segment), cudaMemcpyHostToDevice));
+        SB_CUDA(cudaMemcpy(gp->seg_ptr[pass].p, plan.seg_ptr.data(), plan.seg_ptr.size() * 4, cudaMemcpyHostToDevice));
+    }
+    if (cache.size() >= 8) cache.clear();   // bounded: shapes rarely change within a session
+    cache[key] = gp;
+    return gp;
+}
+
 // Type-erased solver object behind the sb_trws_solver handle.
 struct SolverBase {
     virtual ~SolverBase() {}
@@ -58,11 +105,10 @@ struct Solver : SolverBase {
     cudaStream_t stream = 0;
     DevBuf<REAL> dD, dMsg, dPosQ, dPosQp, dAlpha;
     DevBuf<uint8_t> dRankQ, dRankQp, dCntQ, dCntQp;
-    DevBuf<Segment> dSegs[2];
-    DevBuf<int32_t> dSegPtr[2];
+    std::shared_ptr<GridPlan> plan;
     DevBuf<REAL> dSelPos;
     DevBuf<unsigned long long> dMbox, dSelBox;
-    DevBuf<int32_t> dStripPtr, dSol;
+    DevBuf<int32_t> dSol;
     DevBuf<unsigned char> dCtrl;   // Ctrl + progress[S]
     DevBuf<long long> dProf;
     Problem<REAL> P;
@@ -88,22 +134,15 @@ struct Solver : SolverBase {
         SB_CUDA(cudaGetDevice(&dev));
         SB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
 
-        // ---- host graph logic: ordering + dispatch schedule
-        std::vector<int32_t> order;
-        SB_REQUIRE(grid_ordering(H, W, order), SB_EINVAL,
-                   "sb_trws_solve: %dx%d grid has no valid automatic ordering (the reference crashes on it)", H, W);
-        std::vector<uint8_t> info;
-        build_node_info(H, W, order, info);
-        Schedule sched;
-        build_schedule(H, W, order, sched);
-        S = (int)sched.strip_ptr.size() - 1;
-        std::vector<int32_t> strip_ptr32(sched.strip_ptr.begin(), sched.strip_ptr.end());
+        // ---- host graph logic: ordering + dispatch schedule (cached per grid shape)
+        plan = grid_plan(dev, H, W);
+        S = plan->S;
 
         // ---- device state
         dD.alloc((size_t)N * LP); dMsg.alloc((size_t)E * LP); dPosQ.alloc((size_t)E * LP); dPosQp.alloc((size_t)E * LP);
         dAlpha.alloc((size_t)E);
         dRankQ.alloc((size_t)E * LP); dRankQp.alloc((size_t)E * LP); dCntQ.alloc((size_t)E * LP); dCntQp.alloc((size_t)E * LP);
-        dStripPtr.alloc((size_t)S + 1); dSol.alloc((size_t)N);
+        dSol.alloc((size_t)N);
         dSelPos.alloc((size_t)std::max<int64_t>(E, 1));
         if (sizeof(REAL) == 4) {
             dMbox.alloc((size_t)std::max<int64_t>(E, 1) * LP);
@@ -111,21 +150,12 @@ struct Solver : SolverBase {
             SB_CUDA(cudaMemsetAsync(dMbox.p, 0, dMbox.bytes(), stream));
             SB_CUDA(cudaMemsetAsync(dSelBox.p, 0, dSelBox.bytes(), stream));
         }
-        for (int pass = 0; pass < 2; pass++) {
-            PassPlan plan;
-            build_pass_plan(H, W, info, sched, pass, plan);
-            dSegs[pass].alloc(plan.segs.size());
-            dSegPtr[pass].alloc(plan.seg_ptr.size());
-            SB_CUDA(cudaMemcpy(dSegs[pass].p, plan.segs.data(), plan.segs.size() * sizeof(Segment), cudaMemcpyHostToDevice));
-            SB_CUDA(cudaMemcpy(dSegPtr[pass].p, plan.seg_ptr.data(), plan.seg_ptr.size() * 4, cudaMemcpyHostToDevice));
-        }
         dCtrl.alloc(sizeof(Ctrl) + (size_t)S * 4);
         DevBuf<int> dBad(1);
         SB_CUDA(cudaMallocHost((void **)&hc, sizeof(Ctrl)));
         SB_CUDA(cudaEventCreate(&ev0));
         SB_CUDA(cudaEventCreate(&ev1));
 
-        SB_CUDA(cudaMemcpyAsync(dStripPtr.p, strip_ptr32.data(), ((size_t)S + 1) * 4, cudaMemcpyHostToDevice, stream));
         SB_CUDA(cudaMemsetAsync(dSelPos.p, 0, dSelPos.bytes(), stream));
         SB_CUDA(cudaMemsetAsync(dBad.p, 0, sizeof(int), stream));
         {
@@ -144,26 +174,41 @@ struct Solver : SolverBase {
             convert_vec_kernel<REAL><<<(unsigned)((E + 255) / 256), 256, 0, stream>>>(rawa.p, dAlpha.p, E);
             SB_CUDA(cudaGetLastError());
             count_launch();
-            // q / qprim are uploaded and tabulated in slabs so the raw doubles never need 2*8*L*E bytes
-            const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(E, (int64_t)(256u << 20) / (8 * (int64_t)L)));
-            DevBuf<double> rq((size_t)slab * L), rqp((size_t)slab * L);
-            for (int64_t e0 = 0; e0 < E; e0 += slab) {
+            // q / qprim are uploaded and tabulated in slabs (the raw doubles never need 2*8*L*E bytes
+            // on the device), alternating between two streams so the copy of one slab overlaps the
+            // table build of the other
+            const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(E, (int64_t)(128u << 20) / (8 * (int64_t)L)));
+            DevBuf<double> rq[2], rqp[2];
+            cudaStream_t ss[2] = {nullptr, nullptr};
+            for (int b = 0; b < 2; b++) {
+                rq[b].alloc((size_t)slab * L);
+                rqp[b].alloc((size_t)slab * L);
+                SB_CUDA(cudaStreamCreateWithFlags(&ss[b], cudaStreamNonBlocking));
+            }
+            SB_CUDA(cudaStreamSynchronize(stream));   // buffers and zero-fills above are ready
+            int which = 0;
+            for (int64_t e0 = 0; e0 < E; e0 += slab, which ^= 1) {
                 const int64_t ne = std::min<int64_t>(slab, E - e0);
-                SB_CUDA(cudaMemcpyAsync(rq.p, q + e0 * L, (size_t)ne * L * 8, cudaMemcpyHostToDevice, stream));
-                SB_CUDA(cudaMemcpyAsync(rqp.p, qprim + e0 * L, (size_t)ne * L * 8, cudaMemcpyHostToDevice, stream));
+                SB_CUDA(cudaMemcpyAsync(rq[which].p, q + e0 * L, (size_t)ne * L * 8, cudaMemcpyHostToDevice, ss[which]));
+                SB_CUDA(cudaMemcpyAsync(rqp[which].p, qprim + e0 * L, (size_t)ne * L * 8, cudaMemcpyHostToDevice, ss[which]));
                 TablesLaunch tl;
                 tl.precision = precision;
-                tl.q = rq.p; tl.qp = rqp.p; tl.L = L; tl.E = ne;
+                tl.q = rq[which].p; tl.qp = rqp[which].p; tl.L = L; tl.E = ne;
                 tl.posq = dPosQ.p + e0 * LP; tl.posqp = dPosQp.p + e0 * LP;
                 tl.rank_q = dRankQ.p + e0 * LP; tl.rank_qp = dRankQp.p + e0 * LP;
                 tl.cnt_q = dCntQ.p + e0 * LP; tl.cnt_qp = dCntQp.p + e0 * LP;
-                tl.bad = dBad.p; tl.stream = stream;
+                tl.bad = dBad.p; tl.stream = ss[which];
                 ops->tables(tl);
+            }
+            for (int b = 0; b < 2; b++) {
+                SB_CUDA(cudaStreamSynchronize(ss[b]));
+                cudaStreamDestroy(ss[b]);
             }
             int bad = 0;
             SB_CUDA(cudaMemcpyAsync(&bad, dBad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
             SB_CUDA(cudaStreamSynchronize(stream));
-            SB_REQUIRE(!bad, SB_EINVAL, "sb_trws_solve: q or qprim contains NaN (trws.m:9-15)");
+            SB_REQUIRE(!(bad & 1), SB_EINVAL, "q contains NaN");        // trws.m:9-11
+            SB_REQUIRE(!(bad & 2), SB_EINVAL, "qprim contains NaN");    // trws.m:13-15
         }
 
         std::memset(&P, 0, sizeof(P));
@@ -172,7 +217,7 @@ struct Solver : SolverBase {
         P.D = dD.p; P.msg = dMsg.p; P.posq = dPosQ.p; P.posqp = dPosQp.p;
         P.rank_q = dRankQ.p; P.rank_qp = dRankQp.p; P.cnt_q = dCntQ.p; P.cnt_qp = dCntQp.p;
         P.alpha = dAlpha.p; P.lambda = (REAL)tol;
-        P.strip_ptr = dStripPtr.p; P.S = S;
+        P.strip_ptr = plan->strip_ptr.p; P.S = S;
         P.sol = dSol.p; P.selpos = dSelPos.p; P.mbox = dMbox.p; P.selbox = dSelBox.p;
         Ctrl *ctrl = reinterpret_cast<Ctrl *>(dCtrl.p);
         P.ticket = &ctrl->ticket; P.acc = ctrl->acc;
@@ -223,8 +268,8 @@ struct Solver : SolverBase {
         ++epoch;
         P.epoch = ++launch_epoch;
         P.mode = mode;
-        P.segs = dSegs[pass == PASS_FWD ? 0 : 1].p;
-        P.seg_ptr = dSegPtr[pass == PASS_FWD ? 0 : 1].p;
+        P.segs = plan->segs[pass == PASS_FWD ? 0 : 1].p;
+        P.seg_ptr = plan->seg_ptr[pass == PASS_FWD ? 0 : 1].p;
         SweepLaunch sl;
         sl.precision = precision; sl.kern = kernel; sl.pass = pass; sl.problem = &P;
         sl.grid = pass == PASS_FWD ? grid_fwd : grid_bwd; sl.stream = stream;

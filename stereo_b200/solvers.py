@@ -44,11 +44,8 @@ def _trws_args(kernel, unary, connectivity, q, qprim, alphas, tol):
     assert connectivity.size == 0 or connectivity.min() > 0
     assert connectivity.size == 0 or connectivity.max() <= unary.size
     kernel = int(np.int32(kernel))
-    # trws.m:9-15
-    if np.isnan(q).any():
-        raise ValueError("q contains NaN")
-    if np.isnan(qprim).any():
-        raise ValueError("qprim contains NaN")
+    # trws.m:9-15 (the NaN scan itself runs on the GPU while the arrays are converted; the library
+    # reports "q contains NaN" / "qprim contains NaN" and _raise_nan turns that into the same error)
     L, N = unary.shape
     # trws_mex.cpp:42-52
     assert connectivity.shape[0] == 2
@@ -59,6 +56,13 @@ def _trws_args(kernel, unary, connectivity, q, qprim, alphas, tol):
     assert np.size(tol) == 1
     conn0 = np.asfortranarray(connectivity.astype(np.int64) - 1, dtype=np.uint32)  # trws.m:33
     return kernel, L, N, E, unary, conn0, q, qprim, alphas, float(np.asarray(tol).reshape(-1)[0])
+
+
+def _raise_nan(rc):
+    if rc == _lib.SB_EINVAL:
+        msg = lib().sb_last_error().decode("utf-8", "replace")
+        if msg in ("q contains NaN", "qprim contains NaN"):
+            raise ValueError(msg)
 
 
 def _trws_options(options):
@@ -100,6 +104,7 @@ def trws(kernel, unary, connectivity, q, qprim, alphas, tol, options=None):
                              q.ctypes.data_as(_dp), qprim.ctypes.data_as(_dp), alphas.ctypes.data_as(_dp),
                              tol, ctypes.byref(opt), solution.ctypes.data_as(_dp),
                              ctypes.byref(e), ctypes.byref(lb), ctypes.byref(it), ctypes.byref(tm))
+    _raise_nan(rc)
     check(rc)
     last_timing.clear()
     last_timing.update(_timing_dict(tm))
@@ -117,9 +122,11 @@ class TrwsSolver:
         self.N, self.L, self.E = N, L, E
         opt = _trws_options(options)
         self._h = ctypes.c_void_p()
-        check(lib().sb_trws_create(kernel, L, N, E, unary.ctypes.data_as(_dp), conn0.ctypes.data_as(_up),
-                                   q.ctypes.data_as(_dp), qprim.ctypes.data_as(_dp), alphas.ctypes.data_as(_dp),
-                                   tol, ctypes.byref(opt), ctypes.byref(self._h)))
+        rc = lib().sb_trws_create(kernel, L, N, E, unary.ctypes.data_as(_dp), conn0.ctypes.data_as(_up),
+                                  q.ctypes.data_as(_dp), qprim.ctypes.data_as(_dp), alphas.ctypes.data_as(_dp),
+                                  tol, ctypes.byref(opt), ctypes.byref(self._h))
+        _raise_nan(rc)
+        check(rc)
         self.timing = {}
 
     def reset(self):

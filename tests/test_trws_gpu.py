@@ -113,3 +113,16 @@ def test_teddy_sized_grid_properties():
     r = trws_oracle(pr, 1)
     assert abs(res[0][1] - r[1]) <= 1e-4 * abs(r[1]) and abs(res[0][2] - r[2]) <= 1e-4 * abs(r[2])
     assert np.mean(res[0][0] == r[0]) > 0.995
+
+
+def test_nan_inputs_rejected_like_trws_m():
+    """trws.m:9-15: error('q contains NaN') / error('qprim contains NaN')."""
+    pr = synth.trws_problem(7, 9, 5, seed=3)
+    q = pr["q"].copy()
+    q[2, 11] = np.nan
+    with pytest.raises(ValueError, match="^q contains NaN"):
+        sb.trws(1, pr["unary"], pr["connectivity"], q, pr["qprim"], pr["alphas"], pr["tol"], {})
+    qp = pr["qprim"].copy()
+    qp[0, 3] = np.nan
+    with pytest.raises(ValueError, match="^qprim contains NaN"):
+        sb.trws(1, pr["unary"], pr["connectivity"], pr["q"], qp, pr["alphas"], pr["tol"], {})

@@ -134,15 +134,42 @@ SB_API int sb_trws_minimize(sb_trws_solver *s, double maxiter, double max_relgap
 SB_API int sb_trws_get_labels(sb_trws_solver *s, double *labels);
 SB_API void sb_trws_destroy(sb_trws_solver *s);
 
+/* Several GPUs of one box: the image rows are split into `world` contiguous
+ * bands, rank r sweeps the strips of band r in the SAME order / orientation DAG as the single
+ * GPU sweep, and the messages (and rounded-label positions) that cross a band boundary are
+ * pushed straight into the neighbouring GPU's memory over NVLink as self-validating 64-bit
+ * words (value | launch epoch), so the receiving sweep simply polls its own memory -- no host
+ * round trip, no flag, no fence inside a pass.  Every rank is one process and holds the whole
+ * problem (static data replicated; dynamic data homed per band); fp32 only.
+ *   sb_trws_create_banded  like sb_trws_create, for rank `rank` of `world`
+ *   sb_trws_ipc_export     3 x 64 bytes: CUDA IPC handles of this rank's message, mailbox and
+ *                          selected-position arrays, to be handed to ranks rank-1 / rank+1
+ *   sb_trws_ipc_attach     the handles exported by rank-1 (`up`) and rank+1 (`down`); NULL at the ends
+ *   sb_trws_pass           one sweep on this rank: pass 0 forward / 1 backward, mode bit 0 = send
+ *                          messages, bit 1 = primal rounding (forward only); acc[0] = this rank's
+ *                          part of the energy, acc[1] = of the lower bound.  All ranks must call it
+ *                          together and all-reduce acc (the stop rule of minimize.cpp:97-112 needs
+ *                          the sums); consecutive passes must be separated by that collective. */
+SB_API int sb_trws_create_banded(int kernel, int L, int64_t N, int64_t E,
+                          const double *unary, const uint32_t *conn,
+                          const double *q, const double *qprim,
+                          const double *alphas, double tol,
+                          const sb_trws_options *opt, int rank, int world, sb_trws_solver **out);
+SB_API int sb_trws_ipc_export(sb_trws_solver *s, unsigned char *handles /* 192 bytes */);
+SB_API int sb_trws_ipc_attach(sb_trws_solver *s, const unsigned char *up, const unsigned char *down);
+SB_API int sb_trws_pass(sb_trws_solver *s, int pass, int mode, double *acc /* 2 */);
+
 /* Node ordering of MRFEnergy::SetAutomaticOrdering (cpp/trw-s/ordering.cpp:7-157)
  * on the H x W grid: ordering[r + H*c] in [0, H*W).  Closed form for H,W >= 4
  * (SURVEY Appendix A.1), literal greedy scan otherwise.  Host-only. */
 SB_API int sb_trws_grid_ordering(int H, int W, int32_t *ordering);
 
 /* Host-only introspection of the sweep schedule (strips -> segments, trws_order.cpp) for an
- * H x W grid: stats[0] = strips; then per pass (forward, backward): segments, nodes covered,
- * rows fetched by the helper warps, nodes that send on more than four terms.  9 values. */
-SB_API int sb_trws_plan_stats(int H, int W, int64_t *stats);
+ * H x W grid as rank `rank` of `world` row bands sees it (world = 1: the whole grid):
+ * stats[0] = strips of the whole schedule; then per pass (forward, backward) six values:
+ * segments, nodes covered, rows fetched by the helper warps, nodes that send on more than four
+ * terms, messages pushed to rank - 1, messages pushed to rank + 1.  13 values. */
+SB_API int sb_trws_plan_stats(int H, int W, int rank, int world, int64_t *stats);
 
 /* Infer (H, W) from a connectivity list and verify it is the reference grid.
  * Host-only.  Returns SB_ENOTGRID when it is not. */

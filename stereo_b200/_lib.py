@@ -62,13 +62,18 @@ def lib():
                                     POINTER(TrwsOptions), _dp, _dp, _dp, _dp, POINTER(TrwsTiming)]
         L.sb_trws_create.argtypes = [c_int, c_int, c_int64, c_int64, _dp, _up, _dp, _dp, _dp, c_double,
                                      POINTER(TrwsOptions), POINTER(ctypes.c_void_p)]
+        L.sb_trws_create_banded.argtypes = [c_int, c_int, c_int64, c_int64, _dp, _up, _dp, _dp, _dp, c_double,
+                                            POINTER(TrwsOptions), c_int, c_int, POINTER(ctypes.c_void_p)]
+        L.sb_trws_ipc_export.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+        L.sb_trws_ipc_attach.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p]
+        L.sb_trws_pass.argtypes = [ctypes.c_void_p, c_int, c_int, _dp]
         L.sb_trws_reset.argtypes = [ctypes.c_void_p]
         L.sb_trws_minimize.argtypes = [ctypes.c_void_p, c_double, c_double, _dp, _dp, _dp, POINTER(TrwsTiming)]
         L.sb_trws_get_labels.argtypes = [ctypes.c_void_p, _dp]
         L.sb_trws_destroy.argtypes = [ctypes.c_void_p]
         L.sb_trws_destroy.restype = None
         L.sb_trws_grid_ordering.argtypes = [c_int, c_int, _ip]
-        L.sb_trws_plan_stats.argtypes = [c_int, c_int, POINTER(c_int64)]
+        L.sb_trws_plan_stats.argtypes = [c_int, c_int, c_int, c_int, POINTER(c_int64)]
         L.sb_grid_from_connectivity.argtypes = [c_int64, c_int64, _up, POINTER(c_int), POINTER(c_int)]
         ip, i64, dbl = c_int, c_int64, c_double
         L.sb_rd_solve.argtypes = [c_int64, c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _up, c_int, _dp, _dp, _dp, _dp]

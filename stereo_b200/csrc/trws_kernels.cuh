@@ -64,9 +64,13 @@ struct Problem {
     const REAL *alpha;      // [E]
     REAL lambda;
     const Segment *segs;    // segment descriptors of THIS pass (trws_sched.h)
-    const int32_t *seg_ptr; // [S+1] segments of each forward strip
-    const int32_t *strip_ptr; // [S+1] node count prefix of the forward strips
+    const int32_t *seg_ptr; // [S+1] segments of each of this rank's strips (schedule order)
+    const int32_t *strip_len; // [S] their node counts
+    const int32_t *strip_gid; // [S] their ids in the whole schedule (index of the progress counter)
     int S;
+    int world;              // > 1: row-banded over several GPUs (fp32 mailbox path only)
+    REAL *peer_msg[2];      // message arrays of rank - 1 / rank + 1 (peer-mapped), mirrors of boundary terms
+    unsigned long long *peer_mbox[2], *peer_selbox[2];
     int32_t *progress;      // [S] nodes of each strip completed in this pass (zeroed per launch)
     int32_t *sol;           // [N] rounded labels (0-based)
     REAL *selpos;           // [E] position of the sender's rounded label on each forward term
@@ -467,6 +471,17 @@ __device__ __forceinline__ void st_mbox(unsigned long long *p, unsigned long lon
 {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// system-scope variants: the word is written by one GPU into another GPU's memory over NVLink
+__device__ __forceinline__ unsigned long long ld_mbox_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_mbox_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -677,7 +692,8 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
         // the backward sweep runs the forward schedule in reverse
         const int fs = (PASS == PASS_BWD) ? p.S - 1 - ts : ts;
         const int sg0 = __ldg(p.seg_ptr + fs), sg1 = __ldg(p.seg_ptr + fs + 1);
-        const int n_nodes = __ldg(p.strip_ptr + fs + 1) - __ldg(p.strip_ptr + fs);
+        const int n_nodes = __ldg(p.strip_len + fs);
+        const int gid = __ldg(p.strip_gid + fs);
         if (sg1 <= sg0 || n_nodes <= 0) continue;
 
         if (is_term) {
@@ -711,6 +727,8 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                 if (!(o.flags & OWN_HAS)) return;
                 const bool to_next = (o.flags & OWN_TO_NEXT) != 0;
                 const int oj = (o.flags & OWN_J) ? 1 : 0;
+                // receiver on a neighbouring GPU: 0 = rank - 1, 1 = rank + 1, -1 = local
+                const int peer = (o.flags & OWN_PEER_UP) ? 0 : (o.flags & OWN_PEER_DOWN) ? 1 : -1;
                 if (do_round) {
                     // position of the rounded label on this term, for the receiver's rounding
                     REAL sv = o.s[0];
@@ -719,8 +737,11 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                         if (k == xs % K) sv = o.s[k];
                     sv = __shfl_sync(0xffffffffu, sv, xs / K);
                     if constexpr (MBOX) {
-                        if (lane == 0 && !to_next)
-                            st_mbox(p.selbox + o.term, (unsigned long long)(unsigned)__float_as_int((float)sv) | ((unsigned long long)p.epoch << 32));
+                        if (lane == 0 && !to_next) {
+                            const unsigned long long wv = (unsigned long long)(unsigned)__float_as_int((float)sv) | ((unsigned long long)p.epoch << 32);
+                            if (peer >= 0) st_mbox_sys(p.peer_selbox[peer] + o.term, wv);
+                            else st_mbox(p.selbox + o.term, wv);
+                        }
                     } else {
                         if (lane == 0) __stcg(p.selpos + o.term, sv);
                     }
@@ -739,10 +760,20 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                         vmin = update_quadratic<REAL, K>(gamma, o.alpha, p.lambda, p.L, lane, Di, o.m, o.s, o.rk, o.x, o.cn, P);
                     if constexpr (MBOX) {
                         if (!to_next) {   // the receiver is in another strip: it polls these words
-                            unsigned long long *mb = p.mbox + o.term * LP + lane * K;
+                            if (peer >= 0) {
+                                // ... on another GPU: push the words (and the mirror of the message row, read
+                                // as "old message" in the next pass) into its memory
+                                unsigned long long *mb = p.peer_mbox[peer] + o.term * LP + lane * K;
 #pragma unroll
-                            for (int k = 0; k < K; k++)
-                                st_mbox(mb + k, (unsigned long long)(unsigned)__float_as_int((float)o.m[k]) | ((unsigned long long)p.epoch << 32));
+                                for (int k = 0; k < K; k++)
+                                    st_mbox_sys(mb + k, (unsigned long long)(unsigned)__float_as_int((float)o.m[k]) | ((unsigned long long)p.epoch << 32));
+                                VecIO<REAL, K>::store(p.peer_msg[peer] + o.term * LP + lane * K, o.m);
+                            } else {
+                                unsigned long long *mb = p.mbox + o.term * LP + lane * K;
+#pragma unroll
+                                for (int k = 0; k < K; k++)
+                                    st_mbox(mb + k, (unsigned long long)(unsigned)__float_as_int((float)o.m[k]) | ((unsigned long long)p.epoch << 32));
+                            }
                         }
                     }
                     VecIO<REAL, K>::store(p.msg + o.term * LP + lane * K, o.m);
@@ -996,6 +1027,7 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                     // (value | epoch); the managing lane of a rounding item polls the sender's selected
                     // position.  A matching epoch proves the word was written in this pass.
                     const unsigned ep = p.epoch;
+                    const bool sys_scope = p.world > 1;
                     // all polls of a batch are in flight together: the selected positions (managing
                     // lanes) and up to G dependency rows (every lane its own K words)
                     constexpr int G = (K <= 2) ? 4 : (K <= 4) ? 2 : 1;
@@ -1018,12 +1050,14 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                         unsigned long long wv[G][K];
                         for (;;) {
                             unsigned long long sw = 0;
-                            if (!have_sel) sw = ld_mbox(p.selbox + term);
+                            if (!have_sel) sw = sys_scope ? ld_mbox_sys(p.selbox + term) : ld_mbox(p.selbox + term);
 #pragma unroll
                             for (int q = 0; q < G; q++)
                                 if (q < nb) {
 #pragma unroll
-                                    for (int k = 0; k < K; k++) wv[q][k] = ld_mbox(p.mbox + tj[q] * LP + lane * K + k);
+                                    for (int k = 0; k < K; k++)
+                                        wv[q][k] = sys_scope ? ld_mbox_sys(p.mbox + tj[q] * LP + lane * K + k)
+                                                             : ld_mbox(p.mbox + tj[q] * LP + lane * K + k);
                                 }
                             bool ok = true;
                             if (!have_sel) {
@@ -1124,7 +1158,7 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                 c = __shfl_sync(0xffffffffu, c, 0);
                 if (c > published) {
                     const long long t0 = p.prof ? clock64() : 0;
-                    if (lane == 0) publish_flag(p.progress + fs, c);
+                    if (lane == 0) publish_flag(p.progress + gid, c);
                     __syncwarp();
                     if (p.prof && lane == 0) {
                         atomicAdd((unsigned long long *)p.prof + (fs == 0 ? 0 : 16) + 12, (unsigned long long)(clock64() - t0));

@@ -191,22 +191,35 @@ void build_node_info(int H, int W, const std::vector<int32_t> &ordering, std::ve
 //     except that (H-3,1) -- the last node of the ordering -- waits for (H-2,1);
 //   other grids: one node per strip, sorted by longest-path level of the DAG.
 // The backward sweep uses the exact reverse (strips and nodes within strips).
-void build_schedule(int H, int W, const std::vector<int32_t> &ordering, Schedule &s)
+void build_schedule(int H, int W, const std::vector<int32_t> &ordering, Schedule &s, int world)
 {
     const int64_t N = (int64_t)H * W;
     s.nodes.clear();
     s.strip_ptr.clear();
+    s.owner.clear();
     s.nodes.reserve(N);
+    s.world = world;
+    SB_REQUIRE(world >= 1, SB_EINVAL, "build_schedule: bad world size");
+    SB_REQUIRE(world == 1 || (H >= 4 && W >= 4 && world <= H / 2), SB_EUNSUP,
+               "row-banded sweeps need a regular grid with at least two rows per rank");
     if (H >= 4 && W >= 4) {
         const int64_t ring = 2LL * H + 2LL * W - 4;
         std::vector<int32_t> ringnodes(ring);
         auto put = [&](int r, int c) { const int64_t u = r + (int64_t)H * c; ringnodes[ordering[u]] = (int32_t)u; };
         for (int r = 0; r < H; r++) { put(r, 0); put(r, W - 1); }
         for (int c = 1; c < W - 1; c++) { put(0, c); put(H - 1, c); }
-        s.strip_ptr.push_back(0);
-        s.nodes.insert(s.nodes.end(), ringnodes.begin(), ringnodes.end());
+        // the ring in ordering sequence, cut where the owning band changes
+        for (int64_t k = 0; k < ring; k++) {
+            const int own = band_of_row(ringnodes[k] % H, H, world);
+            if (k == 0 || own != s.owner.back()) {
+                s.strip_ptr.push_back((int64_t)s.nodes.size());
+                s.owner.push_back(own);
+            }
+            s.nodes.push_back(ringnodes[k]);
+        }
         for (int r = 1; r <= H - 2; r++) {
             s.strip_ptr.push_back((int64_t)s.nodes.size());
+            s.owner.push_back(band_of_row(r, H, world));
             for (int c = W - 2; c >= 1; c--) s.nodes.push_back((int32_t)(r + (int64_t)H * c));
         }
         s.strip_ptr.push_back((int64_t)s.nodes.size());
@@ -237,6 +250,7 @@ void build_schedule(int H, int W, const std::vector<int32_t> &ordering, Schedule
         }
         s.strip_ptr.resize(N + 1);
         for (int64_t i = 0; i <= N; i++) s.strip_ptr[i] = i;
+        s.owner.assign((size_t)N, 0);
         s.regular = false;
     }
 }
@@ -274,7 +288,8 @@ inline int direction_to(int u, int v, int H)
 
 } // namespace
 
-void build_pass_plan(int H, int W, const std::vector<uint8_t> &info, const Schedule &s, int pass, PassPlan &plan)
+void build_pass_plan(int H, int W, const std::vector<uint8_t> &info, const Schedule &s, int pass, PassPlan &plan,
+                     int rank)
 {
     using namespace trws;
     const int64_t N = (int64_t)H * W;
@@ -327,6 +342,12 @@ void build_pass_plan(int H, int W, const std::vector<uint8_t> &info, const Sched
                 NodeDesc::Own &o = nd.own[si & 3][si >> 2];
                 o.term = I.term;
                 o.flags = OWN_HAS | (I.tail ? OWN_TAIL : 0) | (d == d_next ? OWN_TO_NEXT : 0) | (j ? OWN_J : 0);
+                if (rank >= 0) {
+                    const int peer = s.owner[strip_of[I.nb]];
+                    if (peer == rank - 1) o.flags |= OWN_PEER_UP;
+                    else if (peer == rank + 1) o.flags |= OWN_PEER_DOWN;
+                    else SB_REQUIRE(peer == rank, SB_EUNSUP, "trws schedule: a term spans non-adjacent ranks");
+                }
                 add_item(S_SEND, I.term, false, -1, 0);
                 si++;
             } else if (d != d_prev) {
@@ -355,7 +376,9 @@ void build_pass_plan(int H, int W, const std::vector<uint8_t> &info, const Sched
     };
 
     plan.segs.clear();
-    plan.seg_ptr.assign((size_t)S + 1, 0);
+    plan.seg_ptr.clear();
+    plan.strips.clear();
+    plan.strip_len.clear();
     NodeDesc first, nd;
     long long d_u = 0, d_own[SCHED_NCW][2], d_term[SCHED_ITEMS], d_need[SCHED_ITEMS];
     int seg_n = 0;
@@ -383,9 +406,12 @@ void build_pass_plan(int H, int W, const std::vector<uint8_t> &info, const Sched
         seg_n = 0;
     };
     for (int fs = 0; fs < S; fs++) {
-        plan.seg_ptr[fs] = (int32_t)plan.segs.size();
+        if (rank >= 0 && s.owner[fs] != rank) continue;
+        plan.seg_ptr.push_back((int32_t)plan.segs.size());
+        plan.strips.push_back(fs);
         const int64_t sb = s.strip_ptr[fs], se = s.strip_ptr[fs + 1];
         const int64_t len = se - sb;
+        plan.strip_len.push_back((int32_t)len);
         auto node_at = [&](int64_t i) { return (int)s.nodes[pass == 0 ? sb + i : se - 1 - i]; };
         for (int64_t i = 0; i < len; i++) {
             describe(node_at(i), i > 0 ? node_at(i - 1) : -1, i + 1 < len ? node_at(i + 1) : -1, nd);
@@ -429,7 +455,7 @@ void build_pass_plan(int H, int W, const std::vector<uint8_t> &info, const Sched
         }
         flush();
     }
-    plan.seg_ptr[S] = (int32_t)plan.segs.size();
+    plan.seg_ptr.push_back((int32_t)plan.segs.size());
 }
 
 } // namespace sb
@@ -448,30 +474,37 @@ int sb_trws_grid_ordering(int H, int W, int32_t *ordering)
     });
 }
 
-int sb_trws_plan_stats(int H, int W, int64_t *stats)
+int sb_trws_plan_stats(int H, int W, int rank, int world, int64_t *stats)
 {
     return sb::guarded([&] {
-        SB_REQUIRE(H >= 1 && W >= 1 && stats, SB_EINVAL, "sb_trws_plan_stats: bad arguments");
+        SB_REQUIRE(H >= 1 && W >= 1 && stats && world >= 1 && rank < world, SB_EINVAL, "sb_trws_plan_stats: bad arguments");
         std::vector<int32_t> order;
         SB_REQUIRE(sb::grid_ordering(H, W, order), SB_EINVAL, "sb_trws_plan_stats: no valid ordering");
         std::vector<uint8_t> info;
         sb::build_node_info(H, W, order, info);
         sb::Schedule sched;
-        sb::build_schedule(H, W, order, sched);
+        sb::build_schedule(H, W, order, sched, world);
         stats[0] = (int64_t)sched.strip_ptr.size() - 1;
         for (int pass = 0; pass < 2; pass++) {
             sb::PassPlan plan;
-            sb::build_pass_plan(H, W, info, sched, pass, plan);
-            int64_t nodes = 0, items = 0, two_half = 0;
+            sb::build_pass_plan(H, W, info, sched, pass, plan, world > 1 ? rank : -1);
+            int64_t nodes = 0, items = 0, two_half = 0, up = 0, down = 0;
             for (const auto &g : plan.segs) {
                 nodes += g.n;
                 items += (int64_t)g.n * g.nitems;
                 if (g.halves == 2) two_half += g.n;
+                for (int w = 0; w < sb::trws::SCHED_NCW; w++)
+                    for (int h = 0; h < 2; h++) {
+                        if (g.own[w][h].flags & sb::trws::OWN_PEER_UP) up += g.n;
+                        if (g.own[w][h].flags & sb::trws::OWN_PEER_DOWN) down += g.n;
+                    }
             }
-            stats[1 + 4 * pass] = (int64_t)plan.segs.size();
-            stats[2 + 4 * pass] = nodes;
-            stats[3 + 4 * pass] = items;
-            stats[4 + 4 * pass] = two_half;
+            stats[1 + 6 * pass] = (int64_t)plan.segs.size();
+            stats[2 + 6 * pass] = nodes;
+            stats[3 + 6 * pass] = items;
+            stats[4 + 6 * pass] = two_half;
+            stats[5 + 6 * pass] = up;
+            stats[6 + 6 * pass] = down;
         }
     });
 }

@@ -23,17 +23,28 @@ void build_node_info(int H, int W, const std::vector<int32_t> &ordering, std::ve
 struct Schedule {
     std::vector<int32_t> nodes;      // concatenated strips
     std::vector<int64_t> strip_ptr;  // strip s = nodes[strip_ptr[s] .. strip_ptr[s+1])
+    std::vector<int32_t> owner;      // rank that sweeps strip s (row-banded multi-GPU; all 0 for one GPU)
     bool regular = false;            // ring + interior rows (H,W >= 4)
+    int world = 1;
 };
-void build_schedule(int H, int W, const std::vector<int32_t> &ordering, Schedule &s);
+// Rank that owns image row r when the rows are split into `world` contiguous bands.
+inline int band_of_row(int r, int H, int world) { return (int)(((long long)r * world) / H); }
+// world > 1 (regular grids only): the ring strip is cut at the band boundaries and every strip
+// gets an owner.
+void build_schedule(int H, int W, const std::vector<int32_t> &ordering, Schedule &s, int world = 1);
 
 // Segment descriptors of one pass (trws_sched.h): segment range of forward strip fs =
 // [seg_ptr[fs], seg_ptr[fs + 1]).  pass 0 = forward sweep,
 // 1 = backward sweep (strips visited in reverse, nodes within a strip in reverse).
 struct PassPlan {
     std::vector<trws::Segment> segs;
-    std::vector<int32_t> seg_ptr;
+    std::vector<int32_t> seg_ptr;     // over the strips of `strips` (the rank's own, in schedule order)
+    std::vector<int32_t> strips;      // global strip ids
+    std::vector<int32_t> strip_len;   // their node counts
 };
-void build_pass_plan(int H, int W, const std::vector<uint8_t> &info, const Schedule &s, int pass, PassPlan &plan);
+// rank < 0: every strip (single GPU).  Otherwise only the strips `rank` owns, with the send terms
+// whose receiver lives on a neighbouring rank flagged OWN_PEER_UP / OWN_PEER_DOWN.
+void build_pass_plan(int H, int W, const std::vector<uint8_t> &info, const Schedule &s, int pass, PassPlan &plan,
+                     int rank = -1);
 
 } // namespace sb

@@ -22,7 +22,9 @@ enum { SCHED_NCW = 4, SCHED_ITEMS = 22 };
 enum { S_NONE = 0, S_D = 1, S_SEND = 2, S_DYN = 3, S_RND = 4 };
 
 // own-term flags
-enum { OWN_HAS = 1, OWN_TAIL = 2, OWN_TO_NEXT = 4, OWN_J = 8 };
+enum { OWN_HAS = 1, OWN_TAIL = 2, OWN_TO_NEXT = 4, OWN_J = 8,
+       OWN_PEER_UP = 16,     // row-banded multi-GPU: the receiving node lives on rank - 1 ...
+       OWN_PEER_DOWN = 32 }; // ... or on rank + 1: the message is pushed into that GPU's memory
 
 struct SegOwn {            // the send term a term warp owns in one half of a node (16 bytes)
     long long term0;       // term of the segment's first node

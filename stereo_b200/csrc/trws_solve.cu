@@ -47,18 +47,19 @@ double now_ms()
 // resident (the reference re-runs its O(N * perimeter) SetAutomaticOrdering on every call,
 // ordering.cpp:7-157).
 struct GridPlan {
-    int S = 0;
+    int S = 0;          // strips this rank sweeps
+    int S_global = 0;   // strips of the whole schedule
     DevBuf<Segment> segs[2];
     DevBuf<int32_t> seg_ptr[2];
-    DevBuf<int32_t> strip_ptr;
+    DevBuf<int32_t> strip_len, strip_gid;
 };
 
-std::shared_ptr<GridPlan> grid_plan(int dev, int H, int W)
+std::shared_ptr<GridPlan> grid_plan(int dev, int H, int W, int rank, int world)
 {
     static std::mutex mu;
-    static std::map<std::tuple<int, int, int>, std::shared_ptr<GridPlan>> cache;
+    static std::map<std::tuple<int, int, int, int, int>, std::shared_ptr<GridPlan>> cache;
     std::lock_guard<std::mutex> lock(mu);
-    const auto key = std::make_tuple(dev, H, W);
+    const auto key = std::make_tuple(dev, H, W, rank, world);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
     std::vector<int32_t> order;
@@ -67,16 +68,20 @@ std::shared_ptr<GridPlan> grid_plan(int dev, int H, int W)
     std::vector<uint8_t> info;
     build_node_info(H, W, order, info);
     Schedule sched;
-    build_schedule(H, W, order, sched);
+    build_schedule(H, W, order, sched, world);
     auto gp = std::make_shared<GridPlan>();
-    gp->S = (int)sched.strip_ptr.size() - 1;
-    std::vector<int32_t> strip_ptr32(sched.strip_ptr.begin(), sched.strip_ptr.end());
-    gp->strip_ptr.alloc(strip_ptr32.size());
-    SB_CUDA(cudaMemcpy(gp->strip_ptr.p, strip_ptr32.data(), strip_ptr32.size() * 4, cudaMemcpyHostToDevice));
+    gp->S_global = (int)sched.strip_ptr.size() - 1;
     for (int pass = 0; pass < 2; pass++) {
         PassPlan plan;
-        build_pass_plan(H, W, info, sched, pass, plan);
-        gp->segs[pass].alloc(plan.segs.size());
+        build_pass_plan(H, W, info, sched, pass, plan, world > 1 ? rank : -1);
+        if (pass == 0) {
+            gp->S = (int)plan.strips.size();
+            gp->strip_len.alloc(std::max<size_t>(plan.strips.size(), 1));
+            gp->strip_gid.alloc(std::max<size_t>(plan.strips.size(), 1));
+            SB_CUDA(cudaMemcpy(gp->strip_len.p, plan.strip_len.data(), plan.strip_len.size() * 4, cudaMemcpyHostToDevice));
+            SB_CUDA(cudaMemcpy(gp->strip_gid.p, plan.strips.data(), plan.strips.size() * 4, cudaMemcpyHostToDevice));
+        }
+        gp->segs[pass].alloc(std::max<size_t>(plan.segs.size(), 1));
         gp->seg_ptr[pass].alloc(plan.seg_ptr.size());
         SB_CUDA(cudaMemcpy(gp->segs[pass].p, plan.segs.data(), plan.segs.size() * sizeof(Segment), cudaMemcpyHostToDevice));
         SB_CUDA(cudaMemcpy(gp->seg_ptr[pass].p, plan.seg_ptr.data(), plan.seg_ptr.size() * 4, cudaMemcpyHostToDevice));
@@ -93,6 +98,10 @@ struct SolverBase {
     virtual void minimize(double maxiter, double max_relgap, double *energy, double *lb, double *iters,
                           sb_trws_timing *timing) = 0;
     virtual void labels(double *out) = 0;
+    // row-banded multi-GPU (include/stereo_b200.h, "several GPUs")
+    virtual void ipc_export(unsigned char *out) = 0;
+    virtual void ipc_attach(const unsigned char *up, const unsigned char *down) = 0;
+    virtual void run_one_pass(int pass, int mode, double *acc) = 0;
     double setup_ms = 0;
 };
 
@@ -108,6 +117,12 @@ struct Solver : SolverBase {
     std::shared_ptr<GridPlan> plan;
     DevBuf<REAL> dSelPos;
     DevBuf<unsigned long long> dMbox, dSelBox;
+    int rank = 0, world = 1;
+    // world > 1: message / mailbox arrays come from cudaMalloc so they can be opened by the
+    // neighbouring ranks through CUDA IPC
+    REAL *ipc_msg = nullptr;
+    unsigned long long *ipc_mbox = nullptr, *ipc_selbox = nullptr;
+    void *peer_ptr[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     DevBuf<int32_t> dSol;
     DevBuf<unsigned char> dCtrl;   // Ctrl + progress[S]
     DevBuf<long long> dProf;
@@ -120,9 +135,11 @@ struct Solver : SolverBase {
     int64_t kernel_count = 0;
 
     Solver(int kernel_, int L_, int64_t N_, int64_t E_, int H_, int W_, const double *unary, const double *q,
-           const double *qprim, const double *alphas, double tol, const sb_trws_options &opt)
-        : kernel(kernel_), L(L_), H(H_), W(W_), N(N_), E(E_)
+           const double *qprim, const double *alphas, double tol, const sb_trws_options &opt, int rank_ = 0,
+           int world_ = 1)
+        : kernel(kernel_), L(L_), H(H_), W(W_), N(N_), E(E_), rank(rank_), world(world_)
     {
+        SB_REQUIRE(world == 1 || sizeof(REAL) == 4, SB_EUNSUP, "row-banded sweeps run in fp32 only");
         precision = sizeof(REAL) == 8 ? SB_F64 : SB_F32;
         fuse = opt.fuse_rounding != 0;
         ops = kops_for_labels(L);
@@ -135,22 +152,30 @@ struct Solver : SolverBase {
         SB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
 
         // ---- host graph logic: ordering + dispatch schedule (cached per grid shape)
-        plan = grid_plan(dev, H, W);
+        plan = grid_plan(dev, H, W, rank, world);
         S = plan->S;
 
         // ---- device state
-        dD.alloc((size_t)N * LP); dMsg.alloc((size_t)E * LP); dPosQ.alloc((size_t)E * LP); dPosQp.alloc((size_t)E * LP);
+        dD.alloc((size_t)N * LP); dPosQ.alloc((size_t)E * LP); dPosQp.alloc((size_t)E * LP);
+        if (world == 1) dMsg.alloc((size_t)E * LP);
         dAlpha.alloc((size_t)E);
         dRankQ.alloc((size_t)E * LP); dRankQp.alloc((size_t)E * LP); dCntQ.alloc((size_t)E * LP); dCntQp.alloc((size_t)E * LP);
         dSol.alloc((size_t)N);
         dSelPos.alloc((size_t)std::max<int64_t>(E, 1));
-        if (sizeof(REAL) == 4) {
-            dMbox.alloc((size_t)std::max<int64_t>(E, 1) * LP);
-            dSelBox.alloc((size_t)std::max<int64_t>(E, 1));
+        const size_t mbox_words = (size_t)std::max<int64_t>(E, 1) * LP, sel_words = (size_t)std::max<int64_t>(E, 1);
+        if (world > 1) {
+            SB_CUDA(cudaMalloc((void **)&ipc_msg, (size_t)E * LP * sizeof(REAL)));
+            SB_CUDA(cudaMalloc((void **)&ipc_mbox, mbox_words * 8));
+            SB_CUDA(cudaMalloc((void **)&ipc_selbox, sel_words * 8));
+            SB_CUDA(cudaMemsetAsync(ipc_mbox, 0, mbox_words * 8, stream));
+            SB_CUDA(cudaMemsetAsync(ipc_selbox, 0, sel_words * 8, stream));
+        } else if (sizeof(REAL) == 4) {
+            dMbox.alloc(mbox_words);
+            dSelBox.alloc(sel_words);
             SB_CUDA(cudaMemsetAsync(dMbox.p, 0, dMbox.bytes(), stream));
             SB_CUDA(cudaMemsetAsync(dSelBox.p, 0, dSelBox.bytes(), stream));
         }
-        dCtrl.alloc(sizeof(Ctrl) + (size_t)S * 4);
+        dCtrl.alloc(sizeof(Ctrl) + (size_t)plan->S_global * 4);
         DevBuf<int> dBad(1);
         SB_CUDA(cudaMallocHost((void **)&hc, sizeof(Ctrl)));
         SB_CUDA(cudaEventCreate(&ev0));
@@ -214,11 +239,13 @@ struct Solver : SolverBase {
         std::memset(&P, 0, sizeof(P));
         P.H = H; P.W = W; P.L = L; P.LP = LP; P.N = N; P.E = E;
         P.nV = (long long)(H - 1) * W; P.nH = (long long)H * (W - 1);
-        P.D = dD.p; P.msg = dMsg.p; P.posq = dPosQ.p; P.posqp = dPosQp.p;
+        P.D = dD.p; P.msg = world > 1 ? ipc_msg : dMsg.p; P.posq = dPosQ.p; P.posqp = dPosQp.p;
         P.rank_q = dRankQ.p; P.rank_qp = dRankQp.p; P.cnt_q = dCntQ.p; P.cnt_qp = dCntQp.p;
         P.alpha = dAlpha.p; P.lambda = (REAL)tol;
-        P.strip_ptr = plan->strip_ptr.p; P.S = S;
-        P.sol = dSol.p; P.selpos = dSelPos.p; P.mbox = dMbox.p; P.selbox = dSelBox.p;
+        P.strip_len = plan->strip_len.p; P.strip_gid = plan->strip_gid.p; P.S = S;
+        P.sol = dSol.p; P.selpos = dSelPos.p;
+        P.mbox = world > 1 ? ipc_mbox : dMbox.p; P.selbox = world > 1 ? ipc_selbox : dSelBox.p;
+        P.world = world;
         Ctrl *ctrl = reinterpret_cast<Ctrl *>(dCtrl.p);
         P.ticket = &ctrl->ticket; P.acc = ctrl->acc;
         P.progress = reinterpret_cast<int32_t *>(dCtrl.p + sizeof(Ctrl));
@@ -238,6 +265,7 @@ struct Solver : SolverBase {
             if (g > S) g = S;
             // two strip walkers must be in flight: (H-3,1) waits for (H-2,1) (trws_order.cpp)
             SB_REQUIRE(S < 2 || g >= 2, SB_ECUDA, "sb_trws_solve: fewer than two resident CTAs");
+            if (g < 1) g = 1;
             return (int)(g < 1 ? 1 : g);
         };
         grid_fwd = grid_for(PASS_FWD);
@@ -250,6 +278,12 @@ struct Solver : SolverBase {
     ~Solver() override
     {
         if (hc) cudaFreeHost(hc);
+        for (int d = 0; d < 2; d++)
+            for (int a = 0; a < 3; a++)
+                if (peer_ptr[d][a]) cudaIpcCloseMemHandle(peer_ptr[d][a]);
+        if (ipc_msg) cudaFree(ipc_msg);
+        if (ipc_mbox) cudaFree(ipc_mbox);
+        if (ipc_selbox) cudaFree(ipc_selbox);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
     }
@@ -258,7 +292,7 @@ struct Solver : SolverBase {
     void reset() override
     {
         SB_CUDA(cudaMemsetAsync(dSol.p, 0, (size_t)N * 4, stream));
-        SB_CUDA(cudaMemsetAsync(dMsg.p, 0, dMsg.bytes(), stream));
+        SB_CUDA(cudaMemsetAsync(P.msg, 0, (size_t)E * LP * sizeof(REAL), stream));
         epoch = 0;
     }
 
@@ -282,6 +316,40 @@ struct Solver : SolverBase {
         SB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
         kernel_ms += ms;
         kernel_count++;
+    }
+
+    void ipc_export(unsigned char *out) override
+    {
+        SB_REQUIRE(world > 1, SB_EINVAL, "sb_trws_ipc_export: the solver was not created for several ranks");
+        cudaIpcMemHandle_t h[3];
+        SB_CUDA(cudaIpcGetMemHandle(&h[0], ipc_msg));
+        SB_CUDA(cudaIpcGetMemHandle(&h[1], ipc_mbox));
+        SB_CUDA(cudaIpcGetMemHandle(&h[2], ipc_selbox));
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        std::memcpy(out, h, sizeof(h));
+    }
+
+    void ipc_attach(const unsigned char *up, const unsigned char *down) override
+    {
+        SB_REQUIRE(world > 1, SB_EINVAL, "sb_trws_ipc_attach: the solver was not created for several ranks");
+        const unsigned char *src[2] = {up, down};
+        for (int d = 0; d < 2; d++) {
+            if (!src[d]) continue;
+            cudaIpcMemHandle_t h[3];
+            std::memcpy(h, src[d], sizeof(h));
+            for (int a = 0; a < 3; a++)
+                SB_CUDA(cudaIpcOpenMemHandle(&peer_ptr[d][a], h[a], cudaIpcMemLazyEnablePeerAccess));
+            P.peer_msg[d] = static_cast<REAL *>(peer_ptr[d][0]);
+            P.peer_mbox[d] = static_cast<unsigned long long *>(peer_ptr[d][1]);
+            P.peer_selbox[d] = static_cast<unsigned long long *>(peer_ptr[d][2]);
+        }
+    }
+
+    void run_one_pass(int pass, int mode, double *acc) override
+    {
+        run_pass(pass == 0 ? PASS_FWD : PASS_BWD, mode);
+        acc[0] = hc->acc[0];
+        acc[1] = hc->acc[1];
     }
 
     // minimize.cpp:31-113.  With fused rounding the energy of iteration t becomes
@@ -371,11 +439,12 @@ struct sb_trws_solver {
     sb::trws::SolverBase *impl;
 };
 
-int sb_trws_create(int kernel, int L, int64_t N, int64_t E, const double *unary, const uint32_t *conn,
-                   const double *q, const double *qprim, const double *alphas, double tol,
-                   const sb_trws_options *opt_in, sb_trws_solver **out)
+static int create_impl(int kernel, int L, int64_t N, int64_t E, const double *unary, const uint32_t *conn,
+                       const double *q, const double *qprim, const double *alphas, double tol,
+                       const sb_trws_options *opt_in, int rank, int world, sb_trws_solver **out)
 {
     return sb::guarded([&] {
+        SB_REQUIRE(world >= 1 && rank >= 0 && rank < world, SB_EINVAL, "sb_trws_create: bad rank / world");
         SB_REQUIRE(out, SB_EINVAL, "sb_trws_create: null output");
         *out = nullptr;
         // trws_mex.cpp:156-163
@@ -396,10 +465,49 @@ int sb_trws_create(int kernel, int L, int64_t N, int64_t E, const double *unary,
         sb::require_device();
         sb::trws::SolverBase *impl;
         if (opt.precision == SB_F64)
-            impl = new sb::trws::Solver<double>(kernel, L, N, E, H, W, unary, q, qprim, alphas, tol, opt);
+            impl = new sb::trws::Solver<double>(kernel, L, N, E, H, W, unary, q, qprim, alphas, tol, opt, rank, world);
         else
-            impl = new sb::trws::Solver<float>(kernel, L, N, E, H, W, unary, q, qprim, alphas, tol, opt);
+            impl = new sb::trws::Solver<float>(kernel, L, N, E, H, W, unary, q, qprim, alphas, tol, opt, rank, world);
         *out = new sb_trws_solver{impl};
+    });
+}
+
+int sb_trws_create(int kernel, int L, int64_t N, int64_t E, const double *unary, const uint32_t *conn,
+                   const double *q, const double *qprim, const double *alphas, double tol,
+                   const sb_trws_options *opt_in, sb_trws_solver **out)
+{
+    return create_impl(kernel, L, N, E, unary, conn, q, qprim, alphas, tol, opt_in, 0, 1, out);
+}
+
+int sb_trws_create_banded(int kernel, int L, int64_t N, int64_t E, const double *unary, const uint32_t *conn,
+                          const double *q, const double *qprim, const double *alphas, double tol,
+                          const sb_trws_options *opt_in, int rank, int world, sb_trws_solver **out)
+{
+    return create_impl(kernel, L, N, E, unary, conn, q, qprim, alphas, tol, opt_in, rank, world, out);
+}
+
+int sb_trws_ipc_export(sb_trws_solver *s, unsigned char *handles)
+{
+    return sb::guarded([&] {
+        SB_REQUIRE(s && s->impl && handles, SB_EINVAL, "sb_trws_ipc_export: null pointer");
+        s->impl->ipc_export(handles);
+    });
+}
+
+int sb_trws_ipc_attach(sb_trws_solver *s, const unsigned char *up, const unsigned char *down)
+{
+    return sb::guarded([&] {
+        SB_REQUIRE(s && s->impl, SB_EINVAL, "sb_trws_ipc_attach: null solver");
+        s->impl->ipc_attach(up, down);
+    });
+}
+
+int sb_trws_pass(sb_trws_solver *s, int pass, int mode, double *acc)
+{
+    return sb::guarded([&] {
+        SB_REQUIRE(s && s->impl && acc, SB_EINVAL, "sb_trws_pass: null pointer");
+        SB_REQUIRE((pass == 0 || pass == 1) && mode >= 0 && mode <= 3, SB_EINVAL, "sb_trws_pass: bad pass / mode");
+        s->impl->run_one_pass(pass, mode, acc);
     });
 }
 

@@ -194,6 +194,62 @@ def cpu_baseline(pr, H, W, crop, iters, procs=1):
             "ms_per_iteration_full_grid_extrapolated": per_iter * scale * 1e3}
 
 
+def extras():
+    """Side measurements of the other kernels of the hot path at BASELINE configs[2]'s shape
+    (1080 x 1920): one QPBO binary fusion and the 128-level 9x9 NCC volume, both through the
+    public host-buffer calls (copies included), next to the reference / NumPy restatement on one core.
+    Reported for context; the headline metric stays the TRW-S sweep rate."""
+    import ctypes
+    import stereo_b200 as sb
+    from stereo_b200 import builders, synth
+    out = {}
+    H, W = 1080, 1920
+    # ---- QPBO fusion (rd.m -> sb_rd_solve)
+    rp = synth.rd_problem(H, W, seed=0xB203, mode="stereo")
+    a = (rp["U0"], rp["U1"], rp["E00"], rp["E01"], rp["E10"], rp["E11"], rp["connectivity"])
+    sb.rd(*a, {})
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        lab, e, lb, nu = sb.rd(*a, {})
+    dt = (time.perf_counter() - t0) / reps
+    q = {"workload": f"synthetic {H}x{W} plane-pair fusion (stereo-like tables)", "fusions_per_s": 1.0 / dt,
+         "ms_per_fusion": dt * 1e3, "unlabelled": nu, "api": "stereo_b200.rd(...) -> sb_rd_solve, host buffers"}
+    try:
+        from oracle import oracle
+        if oracle.have_ref("rd"):
+            ctypes.CDLL(None).srand(1)
+            t0 = time.perf_counter()
+            with quiet_stdout():
+                rl, re, rlb, rnu = oracle.rd_solve(rp["U0"], rp["U1"], rp["E00"], rp["E01"], rp["E10"], rp["E11"],
+                                                   (rp["connectivity"] - 1).T)
+            q["reference_ms_per_fusion_1core"] = (time.perf_counter() - t0) * 1e3
+            q["labels_identical_to_reference"] = bool(np.array_equal(rl, lab))
+    except Exception as ex:  # the oracle is optional here
+        q["reference_error"] = str(ex)[:100]
+    out["qpbo_fusion"] = q
+    # ---- NCC volume (dispmap_ncc.compute_ncc -> sb_ncc_volume), 128 levels, 9x9x3 window
+    im0, im1, _ = synth.stereo_pair(H, W, 127, seed=0xB203)
+    d = np.arange(128, dtype=np.float64)
+    builders.ncc_volume(im0, im1, d[:4], 4)
+    t0 = time.perf_counter()
+    vol = builders.ncc_volume(im0, im1, d, 4)
+    dt = time.perf_counter() - t0
+    n = {"workload": f"synthetic {H}x{W} pair, 128 levels, 9x9 window", "ms": dt * 1e3,
+         "volume_gb_fp32": H * W * 128 * 4 / 1e9, "api": "builders.ncc_volume -> sb_ncc_volume, host buffers, "
+         "double volume back to the host"}
+    try:
+        from oracle import stereo_np
+        t0 = time.perf_counter()
+        ref = stereo_np.compute_ncc(im0, im1, d[:2], 4)
+        n["numpy_restatement_ms_extrapolated_1core"] = (time.perf_counter() - t0) * 1e3 * 64
+        n["max_abs_diff_first_levels"] = float(np.abs(ref - vol[:, :, :2]).max())
+    except Exception as ex:
+        n["reference_error"] = str(ex)[:100]
+    out["ncc_volume"] = n
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -203,6 +259,10 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the QPBO / NCC side measurements (N = 1 only)")
+    ap.add_argument("--mode", default="independent", choices=["independent", "banded"],
+                    help="N > 1: independent fusions, one per GPU (weak scaling, default) or ONE problem swept "
+                         "row-banded across the GPUs with NVLink mailbox halos (strong scaling)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -258,8 +318,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    pr = synth.trws_problem(H, W, L, seed=0xB200 + 2 + rank, kernel=kernel)
+    banded = args.mode == "banded" and world > 1
+    pr = synth.trws_problem(H, W, L, seed=0xB200 + 2 + (0 if banded else rank), kernel=kernel)
     E = pr["connectivity"].shape[1]
+    if banded:
+        config["parallelism"] = f"one problem, {world} row bands, boundary messages pushed over NVLink (mailboxes)"
 
     # pinned host copies of the inputs (MATLAB layout) for the e2e arm
     def pinned(a):
@@ -278,7 +341,12 @@ def main():
     d2h_bytes = N * 8 + 3 * 8
 
     # ---- resident arm
-    solver = sb.TrwsSolver(kernel, hp["unary"], pr["connectivity"], hp["q"], hp["qprim"], hp["alphas"], pr["tol"])
+    if banded:
+        from stereo_b200.multigpu import TrwsBandedSolver
+        solver = TrwsBandedSolver(kernel, hp["unary"], pr["connectivity"], hp["q"], hp["qprim"], hp["alphas"], pr["tol"])
+        solver.timing = {"sweep_kernel_ms": 0.0, "sweep_kernel_launches": 0}
+    else:
+        solver = sb.TrwsSolver(kernel, hp["unary"], pr["connectivity"], hp["q"], hp["qprim"], hp["alphas"], pr["tol"])
     lib = _lib.lib()
 
     def step_resident():
@@ -318,13 +386,15 @@ def main():
         tsum = tt.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         t_ms, sweeps_all = float(tmax[0]), float(tsum[1])
+        if banded:
+            sweeps_all = sweeps          # every rank counted the same sweeps of the one shared problem
     else:
         sweeps_all = sweeps
     value = sweeps_all / (t_ms * 1e-3)
 
     # ---- e2e arm: the public call, host buffers in, labels out
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not banded:
         opts = dict(maxiter=iters, max_relgap=0.0)
 
         def step_e2e():
@@ -358,7 +428,7 @@ def main():
 
     peak, peak_src = peaks()
     algo_bytes = 64.0 * L * N                      # per sweep-kernel launch (one pass)
-    avg_kernel_ms = k_ms / max(k_n, 1)
+    avg_kernel_ms = k_ms / max(k_n, 1) if k_n else (t_ms / max(sweeps, 1)) / 2.0
     achieved = algo_bytes / (avg_kernel_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -376,10 +446,12 @@ def main():
                         "(+40*L*N bytes per pass actually requested)"}
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps, "ms_per_sweep": t_ms / max(sweeps, 1),
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": config, "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline}
+           "higher_is_better": True, "scaling": "strong" if banded else "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline}
     if e2e:
         out["e2e"] = e2e
+    if not args.no_extras and world == 1:
+        out["extras"] = extras()
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline(pr, H, W, crop, cpu_iters, 1)
     elif not args.no_cpu_baseline:

@@ -7,32 +7,31 @@
 //   Edge::AddColumn / Smooth                      typeStereoLinear.h:324-327,491-518
 //   the per-edge argsort of trws_mex.cpp:84-119   (rank / merge-count tables)
 //
-// Execution model (DESIGN.md "K5"):
-//   * one warp owns one node at a time; the L labels of every per-node vector
-//     are blocked over the lanes (label = lane*K + k, K = LP/32 in registers);
-//   * work is dispatched in STRIPS (trws_order.cpp: the boundary ring, then one
-//     strip per interior row) through an atomic ticket; a warp walks its strip
-//     node by node, keeps the two messages it just sent to the next node of the
-//     strip in registers (no round trip for the in-strip dependency) and waits
-//     on epoch flags (release/acquire through L2) only for neighbours owned by
-//     other strips -- normally satisfied long before.  A whole sweep is ONE
-//     persistent launch with no grid barriers, and because it honours the
-//     reference's orientation DAG its results equal the sequential sweep's;
-//   * while a node is processed the operands of the next one are prefetched
-//     into L2 (prefetch.global.L2);
-//   * the min-plus update is O(L): labels are visited in the order of their
-//     (irregular) positions through iteration-invariant uint8 rank tables, the
-//     two directional distance transforms are warp-shuffle scans over
-//     (offset, value) pairs -- no h - alpha*x cancellation -- and each
-//     destination label looks its two bracketing sources up through a
-//     precomputed merge count.
+// Execution model (DESIGN.md "K5"; details above sweep_kernel):
+//   * the L labels of every per-node vector are blocked over the 32 lanes of a warp
+//     (label = lane*K + k, K = LP/32 values per lane in registers);
+//   * work is dispatched in STRIPS (trws_order.cpp: the boundary ring, then one strip per
+//     interior row) through an atomic ticket; one CTA walks a strip node by node, its four
+//     term warps each owning one send term of the node, helper warps assembling everything
+//     else one node ahead.  A whole sweep is ONE persistent launch with no grid barriers, and
+//     because it honours the reference's orientation DAG it computes what the sequential
+//     sweep computes;
+//   * messages to the next node of the strip stay in shared memory; messages to other strips
+//     (other SMs, other GPUs) travel as self-validating 64-bit words (value | launch epoch)
+//     the receiver polls -- no flag, no fence on the dependent chain (fp32 path);
+//   * the min-plus update is O(L): labels are visited in the order of their (irregular)
+//     positions through iteration-invariant uint8 rank tables, the two directional distance
+//     transforms are warp-shuffle scans over (offset, value) pairs -- no h - alpha*x
+//     cancellation -- and each destination label looks its two bracketing sources up through
+//     a precomputed merge count.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "trws_sched.h"
 
-// Build-time switches for timing experiments (make EXTRA=-DSB_TRWS_INSTRUMENT=1): per-phase
-// cycle counters (SB_TRWS_PROFILE) and work-skipping bisection flags (SB_TRWS_DEBUG).
+// Timing experiments: SB_TRWS_PROFILE=1 (environment, any build) prints per-phase cycle counters of
+// the sweep; the work-skipping bisection switches of SB_TRWS_DEBUG need a build with
+// make EXTRA=-DSB_TRWS_INSTRUMENT=1.
 #ifndef SB_TRWS_INSTRUMENT
 #define SB_TRWS_INSTRUMENT 0
 #endif
@@ -87,16 +86,6 @@ struct Problem {
 
 // ---------------------------------------------------------------- helpers
 
-__device__ __forceinline__ int ld_acquire(const int32_t *p)
-{
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release(int32_t *p, int v)
-{
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
 template <typename T> __device__ __forceinline__ T warp_min(T v)
 {
@@ -491,21 +480,10 @@ __device__ __forceinline__ void cp_async_wait_all()
 {
     asm volatile("cp.async.wait_all;" ::: "memory");
 }
-// step barrier of the NCW compute warps (the auxiliary warp is not paced by it)
-__device__ __forceinline__ void step_barrier()
+__device__ __forceinline__ int ld_acquire_cta(int *smem)
 {
-    asm volatile("bar.sync 1, %0;" ::"n"(128) : "memory");
-}
-__device__ __forceinline__ void st_release_cta(int *smem, int v)
-{
-    const unsigned a = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
-__device__ __forceinline__ int ld_acquire_cta(const int *smem)
-{
-    const unsigned a = (unsigned)__cvta_generic_to_shared(smem);
-    int v;
-    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    const int v = atomicAdd(smem, 0);   // atomic read of the completion counter ...
+    __threadfence_block();              // ... ordered before what follows (acquire at CTA scope)
     return v;
 }
 
@@ -913,8 +891,10 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                 // this warp's stores for the node are issued: tell the auxiliary warp
                 __syncwarp();
                 if (lane == 0) {
-                    if constexpr (MBOX) *(volatile int *)(s_wdone + w) = node + 1;   // only paces the prefetch warp
-                    else st_release_cta(s_wdone + w, node + 1);
+                    // completion counter (shared-memory atomic): paces the prefetch warp; in the fp64 /
+                    // watermark mode it also releases this warp's stores to the publisher warp
+                    if constexpr (!MBOX) __threadfence_block();
+                    atomicExch(s_wdone + w, node + 1);
                 }
                 if (prof_on) tp[3]++;
             }

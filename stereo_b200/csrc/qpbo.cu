@@ -375,7 +375,7 @@ struct Solver {
     DevBuf<unsigned char> sub;
     DevBuf<int> h, h2, flag, label;
     int *hflag = nullptr;
-    int64_t rounds = 0, relabels = 0;
+    int64_t rounds = 0, relabels = 0, bfs_sweeps = 0;
 
     ~Solver() { if (hflag) cudaFreeHost(hflag); }
 
@@ -402,6 +402,7 @@ struct Solver {
             SB_CUDA(cudaMemsetAsync(flag.p, 0, 2 * sizeof(int)));
             for (int k = 0; k < 16; k++) bfs_sweep_kernel<<<nb, 256>>>(g);
             count_launch(16);
+            bfs_sweeps += 16;
             SB_CUDA(cudaMemcpy(hflag, flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost));
             if (!hflag[1]) break;
         }
@@ -417,18 +418,22 @@ struct Solver {
     template <bool TO_SOURCE> void maxflow()
     {
         const unsigned nb = nblk(2 * g.N);
-        int burst = 32;
         while (global_relabel<TO_SOURCE>()) {
-            // a burst of push / relabel rounds between two exact relabellings
-            for (int k = 0; k < burst; k++) {
-                push_kernel<TO_SOURCE><<<nb, 256>>>(g);
-                collect_relabel_kernel<TO_SOURCE><<<nb, 256>>>(g);
-                std::swap(g.h, g.h2);
+            // a burst of push / relabel rounds between two exact relabellings; the activity flag is
+            // read back every 16 rounds so an exhausted preflow ends the burst early.  Bursts stay
+            // short: nodes cut off from the terminal only leave the active set at an exact relabelling.
+            for (int chunk = 0; chunk < 4; chunk++) {
+                SB_CUDA(cudaMemsetAsync(flag.p, 0, 2 * sizeof(int)));
+                for (int k = 0; k < 16; k++) {
+                    push_kernel<TO_SOURCE><<<nb, 256>>>(g);
+                    collect_relabel_kernel<TO_SOURCE><<<nb, 256>>>(g);
+                    std::swap(g.h, g.h2);
+                }
+                count_launch(32);
+                rounds += 16;
+                SB_CUDA(cudaMemcpy(hflag, flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+                if (!hflag[0]) break;
             }
-            count_launch(2 * burst);
-            rounds += burst;
-            SB_CUDA(cudaGetLastError());
-            burst = std::min(burst * 2, 512);
         }
     }
 };
@@ -632,6 +637,9 @@ int sb_rd_solve(int64_t N, int64_t E, const double *U0, const double *U1, const 
             for (int64_t u = 0; u < N; u++) lab[u] = cur[u] < 0 ? 0 : cur[u];   // ambiguous -> user_label (0)
         }
 
+        if (getenv("SB_QPBO_PROFILE"))
+            fprintf(stderr, "[sb qpbo] %dx%d: %lld push/relabel rounds, %lld global relabels, %lld bfs sweeps\n", H, W,
+                    (long long)S.rounds, (long long)S.relabels, (long long)S.bfs_sweeps);
         // ---- energy of the labelling (unlabelled -> 0), ComputeTwiceEnergy / 2
         {
             SB_CUDA(cudaMemcpy(S.label.p, lab.data(), (size_t)N * 4, cudaMemcpyHostToDevice));

@@ -763,7 +763,7 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
             // optional phase timers (SB_TRWS_PROFILE): term warp 0 -> prof[0..3] = wait FULL, read rows +
             // rounding, update + stores, nodes
             const bool prof_on = (p.prof != nullptr) && w == 0;
-            long long tp[4] = {0, 0, 0, 0};
+            long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             long long tclk = prof_on ? clock64() : 0;
             auto tick = [&](int which) {
                 if (prof_on) {
@@ -885,8 +885,11 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                     own = nxt;
                     nxt.flags = 0;
                 }
+                tick(4);
                 if (has_next) load_own(so0, seg_i, nxt);
+                tick(5);
                 send(own, Di, xs, par, cur_gamma);
+                if (prof_on) { tclk += (long long)(own.m[0] != own.m[0]); tick(6); }
                 own = nxt;
                 // this warp's stores for the node are issued: tell the auxiliary warp
                 __syncwarp();

@@ -91,6 +91,37 @@ std::shared_ptr<GridPlan> grid_plan(int dev, int H, int W, int rank, int world)
     return gp;
 }
 
+// Pinned result slots are recycled: cudaMallocHost / cudaFreeHost cost milliseconds (and
+// synchronise the device), far too much per solve.
+struct PinnedPool {
+    std::mutex mu;
+    std::vector<void *> free_list;
+    void *get(size_t bytes)
+    {
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            if (!free_list.empty()) {
+                void *p = free_list.back();
+                free_list.pop_back();
+                return p;
+            }
+        }
+        void *p = nullptr;
+        SB_CUDA(cudaMallocHost(&p, std::max<size_t>(bytes, 256)));
+        return p;
+    }
+    void put(void *p)
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        free_list.push_back(p);
+    }
+};
+PinnedPool &pinned_pool()
+{
+    static PinnedPool pool;
+    return pool;
+}
+
 // Type-erased solver object behind the sb_trws_solver handle.
 struct SolverBase {
     virtual ~SolverBase() {}
@@ -177,7 +208,7 @@ struct Solver : SolverBase {
         }
         dCtrl.alloc(sizeof(Ctrl) + (size_t)plan->S_global * 4);
         DevBuf<int> dBad(1);
-        SB_CUDA(cudaMallocHost((void **)&hc, sizeof(Ctrl)));
+        hc = static_cast<Ctrl *>(pinned_pool().get(sizeof(Ctrl)));
         SB_CUDA(cudaEventCreate(&ev0));
         SB_CUDA(cudaEventCreate(&ev1));
 
@@ -277,7 +308,7 @@ struct Solver : SolverBase {
 
     ~Solver() override
     {
-        if (hc) cudaFreeHost(hc);
+        if (hc) pinned_pool().put(hc);
         for (int d = 0; d < 2; d++)
             for (int a = 0; a < 3; a++)
                 if (peer_ptr[d][a]) cudaIpcCloseMemHandle(peer_ptr[d][a]);

@@ -588,12 +588,10 @@ template <typename REAL, int K> __device__ __forceinline__ void row_sts(REAL *ro
 // EMPTY[par] (term warps arrive after reading, helper syncs before overwriting).
 
 constexpr int NCW = SCHED_NCW;      // term warps
-constexpr int NHW_MAX = 4;          // helper warps in the CTA
+constexpr int NHW_MAX = 2;          // helper warps in the CTA (node i is prepared by helper i % NHW)
 constexpr int CTA_THREADS = (NCW + NHW_MAX + 2) * 32;   // + publisher warp + prefetch warp
 constexpr int PF_DIST = 6;
-// helper warps actually used (node i is prepared by helper i % NHW): 2 where four sets of
-// landing rows would not fit in shared memory (2 KB rows: fp64 with 256 labels)
-template <typename REAL, int K> __host__ __device__ constexpr int nhw() { return (32 * K * (int)sizeof(REAL) >= 2048) ? 2 : 4; }
+template <typename REAL, int K> __host__ __device__ constexpr int nhw() { return NHW_MAX; }
 
 // shared rows: NHW sets of {BASE, DIB0, RMS} (by node % NHW), then 2 sets of {CM[2], CC[2]} (by
 // node parity), then NHW x SCHED_ITEMS landing rows
@@ -607,13 +605,30 @@ template <typename REAL, int K> __host__ __device__ constexpr size_t sweep_smem_
            (size_t)NCW * scratch_pairs<K>() * sizeof(Pair<REAL>);
 }
 
+// Named barriers with compile-time ids (a register id would make ptxas reserve all 16 hardware
+// barriers and pin the kernel to one CTA per SM): 0 = __syncthreads, 1..2 FULL, 3..4 EMPTY.
+template <int ID> __device__ __forceinline__ void named_sync_id()
+{
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"((NCW + 1) * 32) : "memory");
+}
+template <int ID> __device__ __forceinline__ void named_arrive_id()
+{
+    asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"((NCW + 1) * 32) : "memory");
+}
+static_assert(NHW_MAX == 2, "barrier dispatch below assumes two helper warps");
 __device__ __forceinline__ void named_sync(int id)
 {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"((NCW + 1) * 32) : "memory");
+    if (id == 1) named_sync_id<1>();
+    else if (id == 2) named_sync_id<2>();
+    else if (id == 3) named_sync_id<3>();
+    else named_sync_id<4>();
 }
 __device__ __forceinline__ void named_arrive(int id)
 {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"((NCW + 1) * 32) : "memory");
+    if (id == 1) named_arrive_id<1>();
+    else if (id == 2) named_arrive_id<2>();
+    else if (id == 3) named_arrive_id<3>();
+    else named_arrive_id<4>();
 }
 
 template <typename REAL, int K> struct OwnTerm {

@@ -205,8 +205,17 @@ def extras():
     out = {}
     H, W = 1080, 1920
     # ---- QPBO fusion (rd.m -> sb_rd_solve)
+    import torch
     rp = synth.rd_problem(H, W, seed=0xB203, mode="stereo")
-    a = (rp["U0"], rp["U1"], rp["E00"], rp["E01"], rp["E10"], rp["E11"], rp["connectivity"])
+    keep = []
+
+    def pin(x):   # same protocol as the TRW-S e2e arm: inputs start in pinned host memory
+        t = torch.empty(x.size, dtype=torch.float64, pin_memory=True)
+        v = t.numpy()
+        v[...] = x.reshape(-1)
+        keep.append(t)
+        return v
+    a = tuple(pin(rp[k]) for k in ("U0", "U1", "E00", "E01", "E10", "E11")) + (rp["connectivity"],)
     sb.rd(*a, {})
     t0 = time.perf_counter()
     reps = 3

@@ -33,6 +33,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <cmath>
+#include <chrono>
 
 namespace sb {
 namespace qpbo {
@@ -271,6 +272,27 @@ __global__ void labels_kernel(Graph g, int *__restrict__ label)
     if (u >= g.N) return;
     const int a = g.h[u] < HINF ? 1 : 0, b = g.h[u + g.N] < HINF ? 1 : 0;
     label[u] = (a == b) ? -1 : a;
+}
+
+// Weak persistencies of the trivial kind: an unlabelled node whose arcs (of i and of its mate i')
+// all have zero residual in both directions is a singleton component in both depth-first passes
+// of ComputeWeakPersistencies; the reference visits all i before all i' (QPBO_postprocessing.cpp:
+// 39-42), so i' finishes later, gets the smaller region number and i is labelled 0 (:113).
+// Exact input ties (proposal == current plane) produce exactly these nodes.  Everything else
+// that is still open is counted for the general (host) path.
+__global__ void isolated_open_kernel(Graph g, int *__restrict__ label, int *__restrict__ complex_open)
+{
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= g.N || label[u] >= 0) return;
+    bool isolated = true;
+    for (int s = 0; s < 2 && isolated; s++)
+        for (int d = 0; d < 4; d++) {
+            const Arc a = arc_of(g, u + (s ? g.N : 0), d);
+            if (!a.valid) continue;
+            if (g.r[4 * a.P + a.slot] != 0.0 || g.r[4 * a.P + (a.slot ^ 1)] != 0.0) { isolated = false; break; }
+        }
+    if (isolated) label[u] = 0;
+    else atomicAdd(complex_open, 1);
 }
 
 // energy of a labelling (unlabelled -> 0), ComputeTwiceEnergy / 2 (QPBO.cpp:847-875)
@@ -561,6 +583,9 @@ int sb_rd_solve(int64_t N, int64_t E, const double *U0, const double *U1, const 
             b.alloc(std::max<size_t>(n, 1));
             if (n) SB_CUDA(cudaMemcpy(b.p, hsrc, n * 8, cudaMemcpyHostToDevice));
         };
+        const bool prof = getenv("SB_QPBO_PROFILE") != nullptr;
+        auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        double t_a = now();
         up(dU0, U0, (size_t)N); up(dU1, U1, (size_t)N);
         up(dE[0], E00, (size_t)E); up(dE[1], E01, (size_t)E); up(dE[2], E10, (size_t)E); up(dE[3], E11, (size_t)E);
         dconn.alloc((size_t)std::max<int64_t>(2 * E, 1));
@@ -572,12 +597,22 @@ int sb_rd_solve(int64_t N, int64_t E, const double *U0, const double *U1, const 
         count_launch(3);
         SB_CUDA(cudaMemcpy(S.r0.p, S.r.p, S.r.bytes(), cudaMemcpyDeviceToDevice));
 
+        if (prof) { cudaDeviceSynchronize(); fprintf(stderr, "[sb qpbo] upload+build %.1f ms\n", now() - t_a); t_a = now(); }
         // ---- Solve(): maximum preflow, sink-reachable set, strong labels
         S.maxflow<false>();
+        if (prof) { cudaDeviceSynchronize(); fprintf(stderr, "[sb qpbo] maxflow %.1f ms\n", now() - t_a); t_a = now(); }
         labels_kernel<<<nblk(N), 256>>>(g, S.label.p);
         count_launch();
         std::vector<int> lab((size_t)N);
         SB_CUDA(cudaMemcpy(lab.data(), S.label.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
+        // open nodes that are trivially weakly persistent are settled on the device
+        int complex_open = 0;
+        {
+            SB_CUDA(cudaMemsetAsync(S.flag.p, 0, 2 * sizeof(int)));
+            isolated_open_kernel<<<nblk(N), 256>>>(g, S.label.p, S.flag.p);
+            count_launch();
+            SB_CUDA(cudaMemcpy(&complex_open, S.flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+        }
 
         // ---- lower bound: (initial bound + flow value) / 2 (ComputeTwiceLowerBound, QPBO.cpp:897-917)
         {
@@ -592,9 +627,9 @@ int sb_rd_solve(int64_t N, int64_t E, const double *U0, const double *U1, const 
         }
 
         // ---- ComputeWeakPersistencies() on the nodes Solve left open
-        long long open_nodes = 0;
-        for (int64_t u = 0; u < N; u++) open_nodes += lab[u] < 0;
-        if (open_nodes > 0) {
+        if (complex_open == 0) {
+            SB_CUDA(cudaMemcpy(lab.data(), S.label.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
+        } else {
             S.maxflow<true>();   // a true flow: stranded excess back to the source
             std::vector<double> hr((size_t)std::max<long long>(g.nP, 1) * 4);
             std::vector<unsigned char> hsub((size_t)std::max<long long>(g.nP, 1));
@@ -637,7 +672,8 @@ int sb_rd_solve(int64_t N, int64_t E, const double *U0, const double *U1, const 
             for (int64_t u = 0; u < N; u++) lab[u] = cur[u] < 0 ? 0 : cur[u];   // ambiguous -> user_label (0)
         }
 
-        if (getenv("SB_QPBO_PROFILE"))
+        if (prof) fprintf(stderr, "[sb qpbo] labels+bound+weak %.1f ms\n", now() - t_a);
+        if (prof)
             fprintf(stderr, "[sb qpbo] %dx%d: %lld push/relabel rounds, %lld global relabels, %lld bfs sweeps\n", H, W,
                     (long long)S.rounds, (long long)S.relabels, (long long)S.bfs_sweeps);
         // ---- energy of the labelling (unlabelled -> 0), ComputeTwiceEnergy / 2

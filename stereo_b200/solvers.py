@@ -22,6 +22,13 @@ def _f(a):
     return np.asfortranarray(a, dtype=np.float64)
 
 
+def _conn0(connectivity):
+    """connectivity - 1 as 2 x E uint32 in MATLAB memory order (one pass; the callers have already
+    asserted min > 0)."""
+    c = np.asfortranarray(connectivity, dtype=np.uint32)
+    return np.subtract(c, np.uint32(1), order="F")
+
+
 def _opt(options, key, default):
     if options is None:
         return default
@@ -54,7 +61,7 @@ def _trws_args(kernel, unary, connectivity, q, qprim, alphas, tol):
     assert q.shape[0] == L and qprim.shape[0] == L
     assert alphas.shape[0] == E
     assert np.size(tol) == 1
-    conn0 = np.asfortranarray(connectivity.astype(np.int64) - 1, dtype=np.uint32)  # trws.m:33
+    conn0 = _conn0(connectivity)  # trws.m:33
     return kernel, L, N, E, unary, conn0, q, qprim, alphas, float(np.asarray(tol).reshape(-1)[0])
 
 
@@ -177,7 +184,7 @@ def rd(U0, U1, E00, E01, E10, E11, connectivity, options=None):
     assert E00.shape == E01.shape == E10.shape == E11.shape
     assert connectivity.shape == (2, E00.size)
     improve = bool(_opt(options, "improve", False))
-    conn0 = np.asfortranarray(connectivity.astype(np.int64) - 1, dtype=np.uint32)  # rd.m:21
+    conn0 = _conn0(connectivity)  # rd.m:21
     N, E = U0.size, E00.size
     solution = np.zeros(N, dtype=np.float64)
     e, lb, nu = c_double(), c_double(), c_double()

@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string>
 #include <stdexcept>
 #include <atomic>
@@ -45,6 +46,14 @@ inline void count_launch(int64_t n = 1) { g_launches.fetch_add(n, std::memory_or
 // Fails loudly when no device is present: there is no CPU fallback.
 void require_device();
 
+// SB_PLAIN_MALLOC=1: cudaMalloc / cudaFree instead of the stream-ordered pool (GPU core dumps and
+// some debuggers do not support cudaMallocAsync).
+inline bool plain_malloc()
+{
+    static const bool on = [] { const char *e = getenv("SB_PLAIN_MALLOC"); return e && atoi(e) != 0; }();
+    return on;
+}
+
 // Device buffer (cudaMalloc / cudaFree).
 template <typename T>
 struct DevBuf {
@@ -62,11 +71,16 @@ struct DevBuf {
     {
         release();
         n = count;
-        if (count) SB_CUDA(cudaMallocAsync((void **)&p, count * sizeof(T), 0));
+        if (!count) return;
+        if (plain_malloc()) SB_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+        else SB_CUDA(cudaMallocAsync((void **)&p, count * sizeof(T), 0));
     }
     void release()
     {
-        if (p) cudaFreeAsync(p, 0);
+        if (p) {
+            if (plain_malloc()) cudaFree(p);
+            else cudaFreeAsync(p, 0);
+        }
         p = nullptr;
         n = 0;
     }

@@ -82,6 +82,7 @@ struct Problem {
     double *acc;            // [0] energy  [1] lower bound (zeroed before each launch)
     int mode;               // PASS_FWD only: MODE_SEND | MODE_ROUND
     int debug;              // SB_TRWS_DEBUG bisection switches (timing experiments only; 0 in production)
+    int *rec;               // SB_TRWS_RECORD: host-mapped flight recorder, [grid][8 warps][4] ints, else null
 };
 
 // ---------------------------------------------------------------- helpers

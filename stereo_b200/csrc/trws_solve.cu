@@ -8,6 +8,7 @@
 #include "trws_kernels.cuh"
 #include "trws_launch.h"
 #include <vector>
+#include <unistd.h>
 #include <map>
 #include <tuple>
 #include <memory>
@@ -159,6 +160,8 @@ struct Solver : SolverBase {
     DevBuf<long long> dProf;
     Problem<REAL> P;
     int grid_fwd = 1, grid_bwd = 1, wpb = 1, epoch = 0;
+    int *rec_host = nullptr;     // SB_TRWS_RECORD flight recorder (host-mapped)
+    int rec_ctas = 0;
     unsigned launch_epoch = 0;   // never reset: tags of earlier launches must not validate
     Ctrl *hc = nullptr; // pinned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -282,6 +285,12 @@ struct Solver : SolverBase {
         P.progress = reinterpret_cast<int32_t *>(dCtrl.p + sizeof(Ctrl));
 
         if (const char *dbg = getenv("SB_TRWS_DEBUG")) P.debug = atoi(dbg);
+        if (getenv("SB_TRWS_RECORD")) {
+            rec_ctas = 1024;
+            SB_CUDA(cudaHostAlloc((void **)&rec_host, (size_t)rec_ctas * 8 * 4 * sizeof(int), cudaHostAllocMapped));
+            std::memset(rec_host, 0xff, (size_t)rec_ctas * 8 * 4 * sizeof(int));
+            SB_CUDA(cudaHostGetDevicePointer((void **)&P.rec, rec_host, 0));
+        }
         if (getenv("SB_TRWS_PROFILE")) {
             dProf.alloc(32);
             SB_CUDA(cudaMemsetAsync(dProf.p, 0, 32 * sizeof(long long), stream));
@@ -338,10 +347,33 @@ struct Solver : SolverBase {
         SweepLaunch sl;
         sl.precision = precision; sl.kern = kernel; sl.pass = pass; sl.problem = &P;
         sl.grid = pass == PASS_FWD ? grid_fwd : grid_bwd; sl.stream = stream;
+        if (rec_host) std::memset(rec_host, 0xff, (size_t)rec_ctas * 8 * 4 * sizeof(int));
         SB_CUDA(cudaEventRecord(ev0, stream));
         ops->sweep(sl);
         SB_CUDA(cudaEventRecord(ev1, stream));
         SB_CUDA(cudaMemcpyAsync(hc, dCtrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
+        if (rec_host) {
+            // flight recorder: wait with a deadline, dump where every warp was on a hang or a fault
+            const double t_start = now_ms();
+            cudaError_t q;
+            while ((q = cudaStreamQuery(stream)) == cudaErrorNotReady && now_ms() - t_start < 4000.0) {}
+            if (q != cudaSuccess) {
+                fprintf(stderr, "[sb record] sweep pass=%d mode=%d epoch=%u grid=%d: %s\n", pass, mode, P.epoch, sl.grid,
+                        q == cudaErrorNotReady ? "HANG" : cudaGetErrorString(q));
+                fprintf(stderr, "[sb record] D=%p msg=%p posq=%p posqp=%p N=%lld E=%lld LP=%d\n", (void *)P.D, (void *)P.msg,
+                        (void *)P.posq, (void *)P.posqp, (long long)N, (long long)E, LP);
+                for (int c = 0; c < sl.grid && c < rec_ctas; c++) {
+                    fprintf(stderr, "[sb record] cta %d:", c);
+                    for (int w = 0; w < 8; w++) {
+                        const int *r = rec_host + ((size_t)c * 8 + w) * 4;
+                        fprintf(stderr, " w%d(s%d n%d st%d t%d)", w, r[0], r[1], r[2], r[3]);
+                    }
+                    fprintf(stderr, "\n");
+                }
+                fflush(stderr);
+                _exit(3);
+            }
+        }
         SB_CUDA(cudaStreamSynchronize(stream));
         float ms = 0;
         SB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
@@ -416,6 +448,14 @@ struct Solver : SolverBase {
             long long h[32];
             SB_CUDA(cudaMemcpy(h, dProf.p, sizeof(h), cudaMemcpyDeviceToHost));
             SB_CUDA(cudaMemsetAsync(dProf.p, 0, sizeof(h), stream));
+            if (precision != SB_F64 && getenv("SB_TRWS_SWEEP") && atoi(getenv("SB_TRWS_SWEEP")) == 5) {
+                for (int g = 0; g < 2; g++) {
+                    const long long *q = h + 8 * g;
+                    const double nn = q[0] ? (double)q[0] : 1;
+                    fprintf(stderr, "[sb profile v5] %s chain warp: %.0f cyc/node (%lld nodes): wait static=%.0f poll=%.0f side=%.0f update+store=%.0f\n",
+                            g ? "rows" : "ring", q[4] / nn, q[0], q[1] / nn, q[2] / nn, q[3] / nn, q[5] / nn);
+                }
+            } else
             for (int g = 0; g < 2; g++) {
                 const long long *q = h + 16 * g;
                 const double nt = q[3] ? (double)q[3] : 1, nh = q[11] ? (double)q[11] : 1, np = q[13] ? (double)q[13] : 1;

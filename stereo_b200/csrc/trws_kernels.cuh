@@ -228,6 +228,58 @@ template <int K> struct ByteIO {
     }
 };
 
+// K consecutive bytes per lane kept PACKED as loaded: unpacking at load time would make the warp
+// wait for the load right after issuing it (measured: the whole L2 / HBM latency of the operand
+// prefetch landed on the chain).  unpack() runs when the update needs the bytes.
+template <int K> struct PackedBytes {
+    static constexpr int VB = (K % 8 == 0) ? 8 : (K % 4 == 0) ? 4 : (K % 2 == 0) ? 2 : 1;
+    static constexpr int NV = K / VB;
+    static constexpr int NW = (VB == 8) ? 2 * NV : NV;
+    unsigned w[NW];
+    __device__ __forceinline__ void load(const uint8_t *p)
+    {
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            if constexpr (VB == 8) {
+                const uint2 v = __ldcs(reinterpret_cast<const uint2 *>(p) + i);
+                w[2 * i] = v.x;
+                w[2 * i + 1] = v.y;
+            } else if constexpr (VB == 4) {
+                w[i] = __ldcs(reinterpret_cast<const unsigned *>(p) + i);
+            } else if constexpr (VB == 2) {
+                w[i] = __ldcs(reinterpret_cast<const unsigned short *>(p) + i);
+            } else {
+                w[i] = __ldcs(p + i);
+            }
+        }
+    }
+    __device__ __forceinline__ void load_shared(const uint8_t *p)
+    {
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            if constexpr (VB == 8) {
+                const uint2 v = reinterpret_cast<const uint2 *>(p)[i];
+                w[2 * i] = v.x;
+                w[2 * i + 1] = v.y;
+            } else if constexpr (VB == 4) {
+                w[i] = reinterpret_cast<const unsigned *>(p)[i];
+            } else if constexpr (VB == 2) {
+                w[i] = reinterpret_cast<const unsigned short *>(p)[i];
+            } else {
+                w[i] = p[i];
+            }
+        }
+    }
+    __device__ __forceinline__ void unpack(uint8_t (&r)[K]) const
+    {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            if constexpr (VB == 8) r[k] = (uint8_t)(w[k / 4] >> (8 * (k % 4)));
+            else r[k] = (uint8_t)(w[k / VB] >> (8 * (k % VB)));
+        }
+    }
+};
+
 // Shared scratch of one warp: sorted-domain (value, position) pairs.
 // Logical sorted index i in [0, LP) lives at phys(i); slot 0 and slot
 // phys(LP) are the (+big, 0) sentinels for "no source on this side".
@@ -589,10 +641,12 @@ template <typename REAL, int K> __device__ __forceinline__ void row_sts(REAL *ro
 // EMPTY[par] (term warps arrive after reading, helper syncs before overwriting).
 
 constexpr int NCW = SCHED_NCW;      // term warps
-constexpr int NHW_MAX = 2;          // helper warps in the CTA (node i is prepared by helper i % NHW)
-constexpr int CTA_THREADS = (NCW + NHW_MAX + 2) * 32;   // + publisher warp + prefetch warp
+// Helper warps in the CTA (node i is prepared by helper i % NHW).  Four helpers were tried (a
+// helper needs ~4.4 k cycles per node) and measured SLOWER: the term warps' own chain, not the
+// helpers, bounds the step, and the extra named barriers cost a CTA per SM.
+constexpr int NHW_MAX = 2;
+__host__ __device__ constexpr int cta_threads(int nhw) { return (NCW + nhw + 2) * 32; }   // + publisher warp + prefetch warp
 constexpr int PF_DIST = 6;
-template <typename REAL, int K> __host__ __device__ constexpr int nhw() { return NHW_MAX; }
 
 // shared rows: NHW sets of {BASE, DIB0, RMS} (by node % NHW), then 2 sets of {CM[2], CC[2]} (by
 // node parity), then NHW x SCHED_ITEMS landing rows
@@ -600,9 +654,9 @@ enum { R_BASE = 0, R_DIB0 = 1, R_RMS = 2, R_CM = 0, R_CC = 2 };
 constexpr int ROWS_CARRY = 8;
 enum { BAR_FULL = 1, BAR_EMPTY = 1 + NHW_MAX };   // + node % NHW
 
-template <typename REAL, int K> __host__ __device__ constexpr size_t sweep_smem_bytes()
+template <typename REAL, int K, int NHW> __host__ __device__ constexpr size_t sweep_smem_bytes()
 {
-    return (size_t)(3 * nhw<REAL, K>() + ROWS_CARRY + nhw<REAL, K>() * SCHED_ITEMS) * 32 * K * sizeof(REAL) +
+    return (size_t)(3 * NHW + ROWS_CARRY + NHW * SCHED_ITEMS) * 32 * K * sizeof(REAL) +
            (size_t)NCW * scratch_pairs<K>() * sizeof(Pair<REAL>);
 }
 
@@ -634,21 +688,22 @@ __device__ __forceinline__ void named_arrive(int id)
 
 template <typename REAL, int K> struct OwnTerm {
     REAL m[K], s[K], x[K];
-    uint8_t rk[K], cn[K];
+    PackedBytes<K> rkp, cnp;   // rank / merge-count bytes, unpacked when the update runs
     REAL alpha;
     long long term;
     int flags;       // OWN_*
 };
 
-template <typename REAL, int K, int KERN, int PASS>
-__global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> p)
+// fp32, up to 128 labels: capped at 102 registers so that two CTAs share an SM (large grids are
+// bound by the number of strips in flight)
+template <typename REAL, int K, int KERN, int PASS, int NHW>
+__global__ void __launch_bounds__(cta_threads(NHW), (sizeof(REAL) == 4 && K <= 4) ? 2 : 1) sweep_kernel(const Problem<REAL> p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_ticket;
     __shared__ int s_wdone[NCW]; // nodes of the current strip each term warp has completed
-    __shared__ __align__(16) Segment s_seg[NHW_MAX];
+    __shared__ __align__(16) Segment s_seg[NHW];
     constexpr int LP = 32 * K;
-    constexpr int NHW = nhw<REAL, K>();
     // fp32: cross-strip messages travel through self-validating mailbox words; fp64 (parity
     // instantiation): progress watermarks published behind a gpu-scope fence
     constexpr bool MBOX = (sizeof(REAL) == 4);
@@ -657,7 +712,7 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const bool is_term = warp < NCW;
-    const bool is_helper = warp >= NCW && warp < NCW + NHW_MAX;
+    const bool is_helper = warp >= NCW && warp < NCW + NHW;
     REAL *rows = reinterpret_cast<REAL *>(smem_raw);
     const REAL BIG = Lim<REAL>::big();
     const bool do_send = (PASS == PASS_BWD) || (p.mode & MODE_SEND);
@@ -711,8 +766,8 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                     VecIO<REAL, K>::load_cg(o.m, p.msg + off);
                     VecIO<REAL, K>::load_ro(o.s, (tail ? p.posqp : p.posq) + off);
                     VecIO<REAL, K>::load_ro(o.x, (tail ? p.posq : p.posqp) + off);
-                    ByteIO<K>::load(o.rk, (tail ? p.rank_qp : p.rank_q) + off);
-                    ByteIO<K>::load(o.cn, (tail ? p.cnt_q : p.cnt_qp) + off);
+                    o.rkp.load((tail ? p.rank_qp : p.rank_q) + off);
+                    o.cnp.load((tail ? p.cnt_q : p.cnt_qp) + off);
                     o.alpha = __ldg(p.alpha + o.term);
                 }
             };
@@ -748,10 +803,13 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
                 }
                 if (do_send) {
                     REAL vmin;
+                    uint8_t rk[K], cn[K];
+                    o.rkp.unpack(rk);
+                    o.cnp.unpack(cn);
                     if constexpr (KERN == 1)
-                        vmin = update_linear<REAL, K>(gamma, o.alpha, p.lambda, p.L, lane, Di, o.m, o.s, o.rk, o.x, o.cn, P);
+                        vmin = update_linear<REAL, K>(gamma, o.alpha, p.lambda, p.L, lane, Di, o.m, o.s, rk, o.x, cn, P);
                     else
-                        vmin = update_quadratic<REAL, K>(gamma, o.alpha, p.lambda, p.L, lane, Di, o.m, o.s, o.rk, o.x, o.cn, P);
+                        vmin = update_quadratic<REAL, K>(gamma, o.alpha, p.lambda, p.L, lane, Di, o.m, o.s, rk, o.x, cn, P);
                     if constexpr (MBOX) {
                         if (!to_next) {   // the receiver is in another strip: it polls these words
                             if (peer >= 0) {
@@ -1146,7 +1204,7 @@ __global__ void __launch_bounds__(CTA_THREADS) sweep_kernel(const Problem<REAL> 
             continue;
         }
 
-        if (warp == NCW + NHW_MAX) {
+        if (warp == NCW + NHW) {
             // ============================================================ publisher warp
             if constexpr (MBOX) continue;   // nothing to publish: receivers validate the data itself
             int published = 0;

@@ -15,6 +15,7 @@ struct SweepLaunch {
     int pass;            // PASS_FWD / PASS_BWD
     const void *problem; // Problem<float> or Problem<double>, host copy
     int grid;            // persistent CTAs (all co-resident)
+    int nhw;             // helper warps per CTA: 2 or 4 (fp32 only)
     cudaStream_t stream;
 };
 
@@ -32,7 +33,7 @@ struct TablesLaunch {
 struct KOps {
     int K;
     // persistent CTAs per SM the sweep kernel can keep resident (occupancy query)
-    int (*sweep_blocks_per_sm)(int precision, int kern, int pass);
+    int (*sweep_blocks_per_sm)(int precision, int kern, int pass, int nhw);
     int (*sweep_warps_per_block)();
     void (*sweep)(const SweepLaunch &);
     void (*tables)(const TablesLaunch &);

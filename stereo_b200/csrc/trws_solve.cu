@@ -159,7 +159,7 @@ struct Solver : SolverBase {
     DevBuf<unsigned char> dCtrl;   // Ctrl + progress[S]
     DevBuf<long long> dProf;
     Problem<REAL> P;
-    int grid_fwd = 1, grid_bwd = 1, wpb = 1, epoch = 0;
+    int grid_fwd = 1, grid_bwd = 1, wpb = 1, epoch = 0, nhw = 2;
     int *rec_host = nullptr;     // SB_TRWS_RECORD flight recorder (host-mapped)
     int rec_ctas = 0;
     unsigned launch_epoch = 0;   // never reset: tags of earlier launches must not validate
@@ -298,8 +298,9 @@ struct Solver : SolverBase {
         }
 
         wpb = ops->sweep_warps_per_block();
+        nhw = 2;   // helper warps per CTA (four were measured slower: DESIGN.md)
         auto grid_for = [&](int pass) {
-            const int bps = ops->sweep_blocks_per_sm(precision, kernel, pass);
+            const int bps = ops->sweep_blocks_per_sm(precision, kernel, pass, nhw);
             SB_REQUIRE(bps >= 1, SB_ECUDA, "sb_trws_solve: sweep kernel does not fit on an SM");
             long long g = (long long)bps * num_sms;
             if (g > S) g = S;
@@ -346,7 +347,7 @@ struct Solver : SolverBase {
         P.seg_ptr = plan->seg_ptr[pass == PASS_FWD ? 0 : 1].p;
         SweepLaunch sl;
         sl.precision = precision; sl.kern = kernel; sl.pass = pass; sl.problem = &P;
-        sl.grid = pass == PASS_FWD ? grid_fwd : grid_bwd; sl.stream = stream;
+        sl.grid = pass == PASS_FWD ? grid_fwd : grid_bwd; sl.stream = stream; sl.nhw = nhw;
         if (rec_host) std::memset(rec_host, 0xff, (size_t)rec_ctas * 8 * 4 * sizeof(int));
         SB_CUDA(cudaEventRecord(ev0, stream));
         ops->sweep(sl);

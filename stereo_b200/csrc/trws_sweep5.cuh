@@ -34,20 +34,30 @@ namespace v5 {
 
 // warp w issues on scheduler w % 4: the two chain warps and the two side warps each get a scheduler
 // of their own for the updates; round / poll / static / prefetch warps are light or mostly waiting
-enum { W_CHAIN = 0, W_CHAIN1 = 1, W_SIDE0 = 2, W_SIDE1 = 3, W_ROUND = 4, W_POLL = 5, W_STATIC = 6, W_PREF = 7, NWARPS = 8 };
+enum { W_CHAIN = 0, W_CHAIN1 = 1, W_SIDE0 = 2, W_SIDE1 = 3, W_ROUND = 4, W_POLL = 5, W_STATIC = 6, W_OPS = 7, NWARPS = 8 };
 constexpr int THREADS = NWARPS * 32;
-constexpr int SLOTS = 4;          // node slots between producers and consumers (power of two)
-constexpr int LAND = 4;           // depth of the static warp's cp.async ring (power of two)
+// node slots between producers and consumers / depth of the static warp's cp.async ring (powers of
+// two; the ring runs LAND - 1 nodes ahead of what it publishes and copies the update operands
+// straight into the slot of the node, so SLOTS must exceed LAND by a margin)
+template <int K> struct Depth {
+    static constexpr int SLOTS = (K <= 2) ? 8 : 4;
+    static constexpr int LAND = (K <= 2) ? 4 : 2;
+};
+constexpr int MAX_SLOTS = 8, MAX_LAND = 4;
+constexpr int MAX_OPS = 4;        // send terms of a node whose operands are staged in its slot (first half)
 constexpr int MAX_RND = 6;        // rounding rows per node (lower neighbours in other strips: <= 3 pairs)
 constexpr int MAX_STATIC = 1 + 8 + MAX_RND;
-enum { SR_BASE = 0, SR_D = 1, SR_DYN = 2, SR_DI = 3, SR_XR = 4, SLOT_ROWS = 4 + MAX_RND };
-enum { F_H = 0, F_P = 1, F_C = 2, F_DONE = 3 /* + chain0, side0, side1, round, chain1 */, NDONE = 5, F_X = 8 /* + chain warp */, NFLAGS = 10 };
+// rows of a node slot; per staged send term: old message, sender positions, receiver positions, then
+// one row holding the rank bytes (first LP bytes) and the merge-count bytes (next LP bytes)
+enum { SR_BASE = 0, SR_D = 1, SR_DYN = 2, SR_DI = 3, SR_XR = 4, SR_OPS = 4 + MAX_RND, OP_M = 0, OP_S = 1, OP_X = 2, OP_RC = 3,
+       SLOT_ROWS = 4 + MAX_RND + 4 * MAX_OPS };
+enum { F_H = 0, F_P = 1, F_C = 2, F_DONE = 3 /* + chain0, side0, side1, round, chain1 */, NDONE = 5, F_X = 8 /* + chain warp */, F_O = 10, NFLAGS = 11 };
 constexpr int XROWS = 4;          // exchange rows of the two chain warps: [node parity][warp]
 constexpr int PF_AHEAD = 8;
 
 template <int K> __host__ __device__ constexpr size_t smem_bytes()
 {
-    return (size_t)(SLOTS * SLOT_ROWS + XROWS + LAND * MAX_STATIC) * 32 * K * sizeof(float) +
+    return (size_t)(Depth<K>::SLOTS * SLOT_ROWS + XROWS + Depth<K>::LAND * MAX_STATIC) * 32 * K * sizeof(float) +
            (size_t)4 * scratch_pairs<K>() * sizeof(Pair<float>);
 }
 
@@ -112,41 +122,6 @@ __device__ __forceinline__ const void *shfl_ptr(const void *p, int src)
     hi = __shfl_sync(0xffffffffu, hi, src);
     return (const void *)(((unsigned long long)hi << 32) | lo);
 }
-
-// K consecutive bytes per lane kept PACKED as loaded: unpacking at load time would make the warp
-// wait for the load right after issuing it (measured: the whole L2 / HBM latency of the operand
-// prefetch landed on the chain).  unpack() runs when the update needs the bytes.
-template <int K> struct PackedBytes {
-    static constexpr int VB = (K % 8 == 0) ? 8 : (K % 4 == 0) ? 4 : (K % 2 == 0) ? 2 : 1;
-    static constexpr int NV = K / VB;
-    static constexpr int NW = (VB == 8) ? 2 * NV : NV;
-    unsigned w[NW];
-    __device__ __forceinline__ void load(const uint8_t *p)
-    {
-#pragma unroll
-        for (int i = 0; i < NV; i++) {
-            if constexpr (VB == 8) {
-                const uint2 v = __ldcs(reinterpret_cast<const uint2 *>(p) + i);
-                w[2 * i] = v.x;
-                w[2 * i + 1] = v.y;
-            } else if constexpr (VB == 4) {
-                w[i] = __ldcs(reinterpret_cast<const unsigned *>(p) + i);
-            } else if constexpr (VB == 2) {
-                w[i] = __ldcs(reinterpret_cast<const unsigned short *>(p) + i);
-            } else {
-                w[i] = __ldcs(p + i);
-            }
-        }
-    }
-    __device__ __forceinline__ void unpack(uint8_t (&r)[K]) const
-    {
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            if constexpr (VB == 8) r[k] = (uint8_t)(w[k / 4] >> (8 * (k % 4)));
-            else r[k] = (uint8_t)(w[k / VB] >> (8 * (k % VB)));
-        }
-    }
-};
 
 template <int K> struct Own {
     float m[K], s[K], x[K];
@@ -347,15 +322,20 @@ __device__ __forceinline__ SegOwn ld_own(const Segment *g, int slot)
     return so;
 }
 
-template <int K, int KERN, int PASS>
+// DBG = true: the instantiation with the cycle counters (SB_TRWS_PROFILE) and the flight recorder
+// (SB_TRWS_RECORD); the production instantiation carries neither.
+template <int K, int KERN, int PASS, bool DBG>
 __global__ void __launch_bounds__(THREADS, 1) sweep5_kernel(const Problem<float> p)
 {
+    long long *const prof_buf = DBG ? p.prof : nullptr;
+    int *const rec_buf = DBG ? p.rec : nullptr;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_ticket;
     __shared__ int s_flag[NFLAGS];
-    __shared__ float s_sel[SLOTS][MAX_RND], s_alpha[SLOTS][MAX_RND];
-    __shared__ float s_land_alpha[LAND][MAX_RND];
-    __shared__ int s_nrnd[SLOTS];
+    constexpr int SLOTS = Depth<K>::SLOTS, LAND = Depth<K>::LAND;
+    __shared__ float s_sel[MAX_SLOTS][MAX_RND], s_alpha[MAX_SLOTS][MAX_RND], s_op_alpha[MAX_SLOTS][MAX_OPS];
+    __shared__ float s_land_alpha[MAX_LAND][MAX_RND];
+    __shared__ int s_nrnd[MAX_SLOTS];
     constexpr int LP = 32 * K;
     constexpr int CH = LP * 4 / 16;       // 16-byte chunks per row
     const int lane = threadIdx.x & 31;
@@ -379,7 +359,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep5_kernel(const Problem<float>
         scratch[(size_t)warp * scratch_pairs<K>()] = t;
         scratch[(size_t)warp * scratch_pairs<K>() + phys<K>(LP)] = t;
     }
-    const long long t_begin = p.prof ? clock64() : 0;
+    const long long t_begin = prof_buf ? clock64() : 0;
     long long prof_c[6] = {0, 0, 0, 0, 0, 0};
 
     auto load_own = [&](const SegOwn &so, int i, Own<K> &o) {
@@ -393,6 +373,24 @@ __global__ void __launch_bounds__(THREADS, 1) sweep5_kernel(const Problem<float>
         o.rkp.load((tail ? p.rank_qp : p.rank_q) + off);
         o.cnp.load((tail ? p.cnt_q : p.cnt_qp) + off);
         o.alpha = __ldg(p.alpha + o.term);
+    };
+    // operands staged by the static warp in the node's slot (send terms of the first half); the few
+    // nodes that send on more than MAX_OPS terms fetch the others from global memory
+    auto fetch_own = [&](const SegOwn &so, int sl, int i, int node, Own<K> &o) {
+        if (sl < MAX_OPS) {
+            o.flags = so.flags;
+            o.term = so.term0 + (long long)i * so.tstride;
+            const float *ops = slot_row(node, SR_OPS + 4 * sl);
+            row_lds<float, K>(o.m, ops + OP_M * LP, lane);
+            row_lds<float, K>(o.s, ops + OP_S * LP, lane);
+            row_lds<float, K>(o.x, ops + OP_X * LP, lane);
+            const uint8_t *rc = reinterpret_cast<const uint8_t *>(ops + OP_RC * LP);
+            o.rkp.load_shared(rc + lane * K);
+            o.cnp.load_shared(rc + LP + lane * K);
+            o.alpha = s_op_alpha[node & (SLOTS - 1)][sl];
+        } else {
+            load_own(so, i, o);
+        }
     };
     auto mbox_word = [&](float v) -> unsigned long long {
         return (unsigned long long)(unsigned)__float_as_int(v) | ((unsigned long long)ep << 32);
@@ -410,8 +408,8 @@ __global__ void __launch_bounds__(THREADS, 1) sweep5_kernel(const Problem<float>
         }
         __syncthreads();
         const int ts = s_ticket;
-        if (p.rec && lane == 0) {
-            volatile int4 *r = reinterpret_cast<volatile int4 *>(p.rec) + (blockIdx.x * 8 + warp);
+        if (rec_buf && lane == 0) {
+            volatile int4 *r = reinterpret_cast<volatile int4 *>(rec_buf) + (blockIdx.x * 8 + warp);
             r->x = -2; r->y = ts; r->z = 2; r->w = (int)ep * 4 + PASS * 2 + (do_round ? 1 : 0);
         }
         if (ts >= p.S) break;
@@ -421,8 +419,8 @@ __global__ void __launch_bounds__(THREADS, 1) sweep5_kernel(const Problem<float>
         if (sg1 <= sg0 || n_nodes <= 0) continue;
         // flight recorder (SB_TRWS_RECORD): where every warp of every CTA last was
         auto mark = [&](int stage, int node) {
-            if (p.rec && lane == 0) {
-                volatile int4 *r = reinterpret_cast<volatile int4 *>(p.rec) + (blockIdx.x * 8 + warp);
+            if (rec_buf && lane == 0) {
+                volatile int4 *r = reinterpret_cast<volatile int4 *>(rec_buf) + (blockIdx.x * 8 + warp);
                 r->x = fs; r->y = node; r->z = stage; r->w = (int)ep * 4 + PASS * 2 + (do_round ? 1 : 0);
             }
         };
@@ -438,11 +436,11 @@ __global__ void __launch_bounds__(THREADS, 1) sweep5_kernel(const Problem<float>
             Pair<float> *P0 = scratch + (size_t)cw * scratch_pairs<K>();
             int *my_x = &s_flag[F_X + cw], *other_x = &s_flag[F_X + (cw ^ 1)];
             int *my_done = &s_flag[cw ? F_DONE + 4 : F_DONE + 0];
-            const long long t_strip = p.prof ? clock64() : 0;
+            const long long t_strip = prof_buf ? clock64() : 0;
             Cursor cu;
             cu.start(segs, sg0);
             SegOwn mine;
-            int has_mine = 0, use_carry = 0, has_dyn = 0;
+            int has_mine = 0, my_sl = 0, use_carry = 0, has_dyn = 0;
             float gamma = 1.f;
             auto load_seg = [&](int sg) {
                 const Segment *g = segs + sg;
@@ -458,35 +456,37 @@ __global__ void __launch_bounds__(THREADS, 1) sweep5_kernel(const Problem<float>
                 for (int sl = 0; sl < 8; sl++) {
                     const SegOwn so = ld_own(g, sl);
                     if ((so.flags & OWN_HAS) && (so.flags & OWN_TO_NEXT)) {
-                        if (ncs == cw) { mine = so; has_mine = 1; }
+                        if (ncs == cw) { mine = so; has_mine = 1; my_sl = sl; }
                         ncs++;
                     }
                 }
             };
             load_seg(cu.sg);
-            Own<K> cur, nxt;
-            cur.flags = nxt.flags = 0;
-            if (has_mine) load_own(mine, 0, cur);
-            int h_seen = 0, p_seen = 0, s0_seen = 0, s1_seen = 0, x_seen = 0;
-            float base[K], carry[K];
+            Own<K> cur;
+            cur.flags = 0;
+            int h_seen = 0, p_seen = 0, s0_seen = 0, s1_seen = 0, x_seen = 0, o_seen = 0;
+            float carry[K];
 #pragma unroll
             for (int k = 0; k < K; k++) carry[k] = 0.f;
-            {
-                const long long t0 = p.prof ? clock64() : 0;
-                wait_ge(&s_flag[F_H], 1, h_seen);
-                if (p.prof) prof_c[1] += clock64() - t0;
-            }
-            row_lds<float, K>(base, slot_row(0, SR_BASE), lane);
             for (int node = 0; node < n_nodes; node++) {
                 mark(10, node);
+                // static part of the node (the static warp runs ahead): BASE row and my operands
+                {
+                    const long long t0 = prof_buf ? clock64() : 0;
+                    wait_ge(&s_flag[F_H], node + 1, h_seen);
+                    if (prof_buf) prof_c[1] += clock64() - t0;
+                }
                 float Di[K];
-#pragma unroll
-                for (int k = 0; k < K; k++) Di[k] = base[k];
+                row_lds<float, K>(Di, slot_row(node, SR_BASE), lane);
+                if (has_mine) {
+                    wait_ge(&s_flag[F_O], node + 1, o_seen);
+                    fetch_own(mine, my_sl, cu.i, node, cur);
+                }
                 // the partner's message of the previous node (also orders the reuse of the exchange rows)
                 if (node > 0) {
-                    const long long t0 = p.prof ? clock64() : 0;
+                    const long long t0 = prof_buf ? clock64() : 0;
                     wait_ge(other_x, node, x_seen);
-                    if (p.prof) prof_c[3] += clock64() - t0;
+                    if (prof_buf) prof_c[3] += clock64() - t0;
                     if (use_carry) {
                         float v[K];
                         row_lds<float, K>(v, xbuf + (size_t)((((node - 1) & 1) << 1) + (cw ^ 1)) * LP, lane);
@@ -496,9 +496,9 @@ __global__ void __launch_bounds__(THREADS, 1) sweep5_kernel(const Problem<float>
                 }
                 if (has_dyn) {
                     mark(11, node);
-                    const long long t0 = p.prof ? clock64() : 0;
+                    const long long t0 = prof_buf ? clock64() : 0;
                     wait_ge(&s_flag[F_P], node + 1, p_seen);
-                    if (p.prof) prof_c[2] += clock64() - t0;
+                    if (prof_buf) prof_c[2] += clock64() - t0;
                     float v[K];
                     row_lds<float, K>(v, slot_row(node, SR_DYN), lane);
 #pragma unroll
@@ -530,22 +530,13 @@ __global__ void __launch_bounds__(THREADS, 1) sweep5_kernel(const Problem<float>
                     __syncwarp();
                     if (lane == 0) st_flag_cta(my_done, node + 1);
                 }
-                // operands of the next node
-                const float cur_gamma = gamma;
-                const int cur_has = has_mine;
-                const bool has_next = node + 1 < n_nodes;
-                if (has_next) {
-                    if (cu.advance(segs)) load_seg(cu.sg);
-                    nxt.flags = 0;
-                    if (has_mine) load_own(mine, cu.i, nxt);
-                }
                 // my message to the next node of the strip
                 mark(13, node);
-                const long long t_upd = p.prof ? clock64() : 0;
+                const long long t_upd = prof_buf ? clock64() : 0;
 #pragma unroll
                 for (int k = 0; k < K; k++) carry[k] = 0.f;
-                if (cur_has) {
-                    const float vm = update_one<K, KERN>(cur_gamma, p.lambda, p.L, lane, Di, cur, P0);
+                if (has_mine) {
+                    const float vm = update_one<K, KERN>(gamma, p.lambda, p.L, lane, Di, cur, P0);
                     if (PASS == PASS_BWD) acc_lb += (double)vm;
 #pragma unroll
                     for (int k = 0; k < K; k++) carry[k] = cur.m[k];
@@ -553,23 +544,16 @@ __global__ void __launch_bounds__(THREADS, 1) sweep5_kernel(const Problem<float>
                 }
                 __syncwarp();
                 if (lane == 0) st_flag_cta(my_x, node + 1);
-                if (cur_has) VecIO<float, K>::store(p.msg + cur.term * LP + lane * K, cur.m);
-                if (p.prof) { prof_c[5] += clock64() - t_upd + (long long)(carry[0] != carry[0]); }
+                if (has_mine) VecIO<float, K>::store(p.msg + cur.term * LP + lane * K, cur.m);
+                if (prof_buf) { prof_c[5] += clock64() - t_upd + (long long)(carry[0] != carry[0]); }
                 mark(16, node);
-                if (has_next) {
-                    mark(14, node);
-                    const long long t0 = p.prof ? clock64() : 0;
-                    wait_ge(&s_flag[F_H], node + 2, h_seen);
-                    if (p.prof) prof_c[1] += clock64() - t0;
-                    row_lds<float, K>(base, slot_row(node + 1, SR_BASE), lane);
-                    cur = nxt;
-                }
+                if (node + 1 < n_nodes && cu.advance(segs)) load_seg(cu.sg);
             }
-            if (p.prof && cw == 0) {
+            if (prof_buf && cw == 0) {
                 prof_c[0] = n_nodes;
                 prof_c[4] = clock64() - t_strip;
                 if (lane == 0)
-                    for (int q = 0; q < 6; q++) atomicAdd((unsigned long long *)p.prof + (fs == 0 ? 0 : 8) + q, (unsigned long long)prof_c[q]);
+                    for (int q = 0; q < 6; q++) atomicAdd((unsigned long long *)prof_buf + (fs == 0 ? 0 : 8) + q, (unsigned long long)prof_c[q]);
             }
             for (int q = 0; q < 6; q++) prof_c[q] = 0;
             mark(19, n_nodes);
@@ -585,6 +569,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep5_kernel(const Problem<float>
             Cursor cu;
             cu.start(segs, sg0);
             SegOwn so[4];
+            int sls[4] = {0, 0, 0, 0};
             int nmy = 0;
             float gamma = 1.f;
             auto load_seg = [&](int sg) {
@@ -598,7 +583,10 @@ __global__ void __launch_bounds__(THREADS, 1) sweep5_kernel(const Problem<float>
                     const SegOwn s = ld_own(g, sl);
                     if ((s.flags & OWN_HAS) && !(s.flags & OWN_TO_NEXT)) {
                         if ((nside & 1) == sid) {
-                            if (nmy == 0) so[0] = s; else if (nmy == 1) so[1] = s; else if (nmy == 2) so[2] = s; else so[3] = s;
+                            if (nmy == 0) { so[0] = s; sls[0] = sl; }
+                            else if (nmy == 1) { so[1] = s; sls[1] = sl; }
+                            else if (nmy == 2) { so[2] = s; sls[2] = sl; }
+                            else { so[3] = s; sls[3] = sl; }
                             nmy++;
                         }
                         nside++;
@@ -606,54 +594,50 @@ __global__ void __launch_bounds__(THREADS, 1) sweep5_kernel(const Problem<float>
                 }
             };
             load_seg(cu.sg);
-            Own<K> cur, nxt;
+            Own<K> cur;
             cur.flags = 0;
-            if (nmy > 0) load_own(so[0], 0, cur);
-            int c_seen = 0;
+            int c_seen = 0, h_seen = 0, o_seen = 0;
             for (int node = 0; node < n_nodes; node++) {
-                const int cur_n = nmy, cur_i = cu.i;
-                const float cur_gamma = gamma;
-                const SegOwn c1 = so[1], c2 = so[2], c3 = so[3];
-                const bool has_next = node + 1 < n_nodes;
-                if (has_next && cu.advance(segs)) load_seg(cu.sg);
-                if (cur_n == 0) {
+                if (nmy == 0) {
                     if (lane == 0) st_flag_cta(my_done, node + 1);
-                    if (has_next && nmy > 0) load_own(so[0], cu.i, cur);
-                    continue;
-                }
-                nxt.flags = 0;
-                if (has_next && nmy > 0) load_own(so[0], cu.i, nxt);
-                mark(21, node);
-                wait_ge(&s_flag[F_C], node + 1, c_seen);
-                float Di[K];
-                row_lds<float, K>(Di, slot_row(node, SR_DI), lane);
-                __syncwarp();
-                if (lane == 0) st_flag_cta(my_done, node + 1);
-                mark(22, node);
-                for (int t = 0; t < cur_n; t++) {
-                    if (t == 1) load_own(c1, cur_i, cur);
-                    if (t == 2) load_own(c2, cur_i, cur);
-                    if (t == 3) load_own(c3, cur_i, cur);
-                    const float vm = update_one<K, KERN>(cur_gamma, p.lambda, p.L, lane, Di, cur, P);
-                    mark(23, node);
-                    if (PASS == PASS_BWD) acc_lb += (double)vm;
-                    const int peer = (cur.flags & OWN_PEER_UP) ? 0 : (cur.flags & OWN_PEER_DOWN) ? 1 : -1;
-                    if (peer >= 0) {
-                        // receiver on a neighbouring GPU: push the words and the mirror of the message row
-                        unsigned long long *mb = p.peer_mbox[peer] + cur.term * LP + lane * K;
+                } else {
+                    // operands (staged ahead by the static warp), then the node sum from the chain warp
+                    wait_ge(&s_flag[F_H], node + 1, h_seen);
+                    wait_ge(&s_flag[F_O], node + 1, o_seen);
+                    fetch_own(so[0], sls[0], cu.i, node, cur);
+                    mark(21, node);
+                    wait_ge(&s_flag[F_C], node + 1, c_seen);
+                    float Di[K];
+                    row_lds<float, K>(Di, slot_row(node, SR_DI), lane);
+                    mark(22, node);
+                    for (int t = 0; t < nmy; t++) {
+                        if (t == 1) fetch_own(so[1], sls[1], cu.i, node, cur);
+                        if (t == 2) fetch_own(so[2], sls[2], cu.i, node, cur);
+                        if (t == 3) fetch_own(so[3], sls[3], cu.i, node, cur);
+                        if (t == nmy - 1) {
+                            // last read of the slot
+                            __syncwarp();
+                            if (lane == 0) st_flag_cta(my_done, node + 1);
+                        }
+                        const float vm = update_one<K, KERN>(gamma, p.lambda, p.L, lane, Di, cur, P);
+                        mark(23, node);
+                        if (PASS == PASS_BWD) acc_lb += (double)vm;
+                        const int peer = (cur.flags & OWN_PEER_UP) ? 0 : (cur.flags & OWN_PEER_DOWN) ? 1 : -1;
+                        if (peer >= 0) {
+                            // receiver on a neighbouring GPU: push the words and the mirror of the message row
+                            unsigned long long *mb = p.peer_mbox[peer] + cur.term * LP + lane * K;
 #pragma unroll
-                        for (int k = 0; k < K; k++) st_mbox_sys(mb + k, mbox_word(cur.m[k]));
-                        VecIO<float, K>::store(p.peer_msg[peer] + cur.term * LP + lane * K, cur.m);
-                    } else {
-                        unsigned long long *mb = p.mbox + cur.term * LP + lane * K;
+                            for (int k = 0; k < K; k++) st_mbox_sys(mb + k, mbox_word(cur.m[k]));
+                            VecIO<float, K>::store(p.peer_msg[peer] + cur.term * LP + lane * K, cur.m);
+                        } else {
+                            unsigned long long *mb = p.mbox + cur.term * LP + lane * K;
 #pragma unroll
-                        for (int k = 0; k < K; k++) st_mbox(mb + k, mbox_word(cur.m[k]));
+                            for (int k = 0; k < K; k++) st_mbox(mb + k, mbox_word(cur.m[k]));
+                        }
+                        VecIO<float, K>::store(p.msg + cur.term * LP + lane * K, cur.m);
                     }
-                    mark(24, node);
-                    VecIO<float, K>::store(p.msg + cur.term * LP + lane * K, cur.m);
-                    mark(25, node);
                 }
-                cur = nxt;
+                if (node + 1 < n_nodes && cu.advance(segs)) load_seg(cu.sg);
             }
             mark(29, n_nodes);
             continue;
@@ -666,6 +650,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep5_kernel(const Problem<float>
             cu.start(segs, sg0);
             int u0 = 0, du = 0, use_carry = 0, ncs = 0, nside = 0;
             SegOwn cs[2];
+            int cs_sl[2] = {0, 0};
             SegOwn my_side;     // lane j < nside: the j-th cross-strip send term
             auto load_seg = [&](int sg) {
                 const Segment *g = segs + sg;
@@ -681,7 +666,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep5_kernel(const Problem<float>
                     const SegOwn s = ld_own(g, sl);
                     if (!(s.flags & OWN_HAS)) continue;
                     if (s.flags & OWN_TO_NEXT) {
-                        if (ncs == 0) cs[0] = s; else cs[1] = s;
+                        if (ncs == 0) { cs[0] = s; cs_sl[0] = sl; } else { cs[1] = s; cs_sl[1] = sl; }
                         ncs++;
                     } else {
                         if (lane == nside) my_side = s;
@@ -694,21 +679,28 @@ __global__ void __launch_bounds__(THREADS, 1) sweep5_kernel(const Problem<float>
             float ns_[2][K], nx_[2][K], nal[2];
             float px[2][K], pal[2], psv[2];   // of the previous node
             int pn = 0;
-            auto load_next_terms = [&](int i) {
+            // (staged in the node's slot by the static warp; a term of the second half comes from global memory)
+            auto load_next_terms = [&](int i, int node) {
 #pragma unroll
                 for (int t = 0; t < 2; t++) {
                     if (t < ncs) {
-                        const long long term = cs[t].term0 + (long long)i * cs[t].tstride;
-                        const long long off = term * LP + lane * K;
-                        const bool tail = (cs[t].flags & OWN_TAIL) != 0;
-                        VecIO<float, K>::load_ro(ns_[t], (tail ? p.posqp : p.posq) + off);
-                        VecIO<float, K>::load_ro(nx_[t], (tail ? p.posq : p.posqp) + off);
-                        nal[t] = __ldg(p.alpha + term);
+                        if (cs_sl[t] < MAX_OPS) {
+                            const float *ops = slot_row(node, SR_OPS + 4 * cs_sl[t]);
+                            row_lds<float, K>(ns_[t], ops + OP_S * LP, lane);
+                            row_lds<float, K>(nx_[t], ops + OP_X * LP, lane);
+                            nal[t] = s_op_alpha[node & (SLOTS - 1)][cs_sl[t]];
+                        } else {
+                            const long long term = cs[t].term0 + (long long)i * cs[t].tstride;
+                            const long long off = term * LP + lane * K;
+                            const bool tail = (cs[t].flags & OWN_TAIL) != 0;
+                            VecIO<float, K>::load_ro(ns_[t], (tail ? p.posqp : p.posq) + off);
+                            VecIO<float, K>::load_ro(nx_[t], (tail ? p.posq : p.posqp) + off);
+                            nal[t] = __ldg(p.alpha + term);
+                        }
                     }
                 }
             };
-            load_next_terms(0);
-            int h_seen = 0, p_seen = 0;
+            int h_seen = 0, p_seen = 0, o_seen = 0;
             for (int node = 0; node < n_nodes; node++) {
                 const int u = u0 + cu.i * du;
                 const int cur_i = cu.i, cur_ncs = ncs, cur_nside = nside, cur_carry = use_carry;
@@ -719,6 +711,8 @@ __global__ void __launch_bounds__(THREADS, 1) sweep5_kernel(const Problem<float>
                 mark(32, node);
                 if (nrnd > 0) wait_ge(&s_flag[F_P], node + 1, p_seen);
                 mark(33, node);
+                if (cur_ncs > 0) wait_ge(&s_flag[F_O], node + 1, o_seen);
+                load_next_terms(cur_i, node);
                 // minimize.cpp:240-260: DiB = D + sum_{lower nb} V(x_nb, .), Dr = DiB + forward messages
                 float pv[K], bs[K], dd[K];
                 row_lds<float, K>(bs, slot_row(node, SR_BASE), lane);
@@ -788,10 +782,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep5_kernel(const Problem<float>
                     if (peer >= 0) st_mbox_sys(p.peer_selbox[peer] + term, mbox_word(sv));
                     else st_mbox(p.selbox + term, mbox_word(sv));
                 }
-                if (node + 1 < n_nodes) {
-                    if (cu.advance(segs)) load_seg(cu.sg);
-                    load_next_terms(cu.i);
-                }
+                if (node + 1 < n_nodes && cu.advance(segs)) load_seg(cu.sg);
             }
             mark(39, n_nodes);
             continue;
@@ -804,6 +795,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep5_kernel(const Problem<float>
             cc.start(segs, sg0);
             int i_kind = S_NONE, i_tstride = 0, c_kind = S_NONE;
             long long i_term0 = 0;
+            int free_seen = 0;
             auto load_items_issue = [&](int sg) {
                 const Segment *g = segs + sg;
                 const int nitems = __ldg(&g->nitems);
@@ -854,7 +846,6 @@ __global__ void __launch_bounds__(THREADS, 1) sweep5_kernel(const Problem<float>
             load_items_issue(ci.sg);
             load_items_consume(cc.sg);
             for (int q = 0; q < LAND - 1; q++) issue();
-            int free_seen = 0;
             for (int node = 0; node < n_nodes; node++) {
                 mark(40, node);
                 issue();
@@ -876,7 +867,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep5_kernel(const Problem<float>
                 float base[K];
 #pragma unroll
                 for (int k = 0; k < K; k++) base[k] = 0.f;
-                int t = 0;
+                int t = 0, ts = 0;
                 while (rem) {
                     const int jl = __ffs(rem) - 1;
                     rem &= rem - 1;
@@ -889,7 +880,13 @@ __global__ void __launch_bounds__(THREADS, 1) sweep5_kernel(const Problem<float>
                     } else {
 #pragma unroll
                         for (int k = 0; k < K; k++) base[k] += v[k];
-                        if (((m_d >> jl) & 1u) && do_round) row_sts<float, K>(slot_row(node, SR_D), v, lane);
+                        if ((m_d >> jl) & 1u) {
+                            if (do_round) row_sts<float, K>(slot_row(node, SR_D), v, lane);
+                        } else {
+                            // the ts-th send row is the old message of own slot ts (build_pass_plan hands both out together)
+                            if (ts < MAX_OPS) row_sts<float, K>(slot_row(node, SR_OPS + 4 * ts + OP_M), v, lane);
+                            ts++;
+                        }
                     }
                 }
                 row_sts<float, K>(slot_row(node, SR_BASE), base, lane);
@@ -1004,71 +1001,53 @@ __global__ void __launch_bounds__(THREADS, 1) sweep5_kernel(const Problem<float>
             continue;
         }
 
-        // ================================================================ prefetch warp
+        // ================================================================ operand warp
         {
-            // rows of the update operands (message, both position rows, rank and count bytes) of the
-            // send terms of the nodes ahead -> L2; paced by the consumer that runs in this pass
-            const int *pace = do_send ? &s_flag[F_DONE + 0] : &s_flag[F_DONE + 3];
-            Cursor cu;
-            cu.start(segs, sg0);
-            int pf_node = 0;
-            constexpr int LR = (LP * 4 + 127) / 128;
-            constexpr int LB = (LP + 127) / 128;
-            while (pf_node < n_nodes && !(p.debug & 1)) {
-                const int c = __shfl_sync(0xffffffffu, ld_flag_cta(pace), 0);   // warp-uniform
-                mark(60, pf_node * 1000 + min(c, 999));
-                const int pf_end = min(n_nodes, c + PF_AHEAD);
-                if (pf_node >= pf_end) {
-                    __nanosleep(100);
-                    continue;
-                }
-                for (; pf_node < pf_end; pf_node++) {
-                    if (pf_node > c + 1 && lane < 8) {
-                        const SegOwn o = ld_own(segs + cu.sg, lane);
-                        if (o.flags & OWN_HAS) {
-                            const long long row = (o.term0 + (long long)cu.i * o.tstride) * LP;
-                            const bool tail = (o.flags & OWN_TAIL) != 0;
-                            if (do_send) {
-                                for (int t = 0; t < LR; t++) {
-                                    prefetch_l2(reinterpret_cast<const char *>(p.msg + row) + t * 128);
-                                    prefetch_l2(reinterpret_cast<const char *>(p.posq + row) + t * 128);
-                                    prefetch_l2(reinterpret_cast<const char *>(p.posqp + row) + t * 128);
-                                }
-                                for (int t = 0; t < LB; t++) {
-                                    prefetch_l2(reinterpret_cast<const char *>((tail ? p.rank_qp : p.rank_q) + row) + t * 128);
-                                    prefetch_l2(reinterpret_cast<const char *>((tail ? p.cnt_q : p.cnt_qp) + row) + t * 128);
-                                }
-                            } else if (o.flags & OWN_TO_NEXT) {
-                                for (int t = 0; t < LR; t++) {
-                                    prefetch_l2(reinterpret_cast<const char *>(p.posq + row) + t * 128);
-                                    prefetch_l2(reinterpret_cast<const char *>(p.posqp + row) + t * 128);
-                                }
-                            }
-                        }
+            // Update operands of the node's first MAX_OPS send terms -- sender / receiver position rows,
+            // rank and merge-count bytes, alpha -- copied LAND - 1 nodes ahead straight into the node's
+            // slot.  No shuffles: two lanes own one (term, row) pair and copy its 16-byte chunks.
+            const int sl = lane >> 3, rtype = (lane >> 1) & 3, half = lane & 1;
+            Cursor ci;
+            ci.start(segs, sg0);
+            SegOwn my_own = ld_own(segs + ci.sg, sl);
+            int issued = 0, free_seen = 0;
+            constexpr int CB = LP / 16;   // 16-byte chunks of a byte row
+            auto issue = [&]() {
+                if (issued < n_nodes) {
+                    wait_free(&s_flag[F_DONE], issued - SLOTS + 1, free_seen);   // the slot must be free
+                    if (my_own.flags & OWN_HAS) {
+                        const long long term = my_own.term0 + (long long)ci.i * my_own.tstride;
+                        const bool tail = (my_own.flags & OWN_TAIL) != 0;
+                        char *ops = reinterpret_cast<char *>(slot_row(issued, SR_OPS + 4 * sl));
+                        const char *src;
+                        char *dst;
+                        int nch;
+                        if (rtype == 0) { src = reinterpret_cast<const char *>((tail ? p.posqp : p.posq) + term * LP); dst = ops + (size_t)OP_S * LP * 4; nch = CH; }
+                        else if (rtype == 1) { src = reinterpret_cast<const char *>((tail ? p.posq : p.posqp) + term * LP); dst = ops + (size_t)OP_X * LP * 4; nch = CH; }
+                        else if (rtype == 2) { src = reinterpret_cast<const char *>((tail ? p.rank_qp : p.rank_q) + term * LP); dst = ops + (size_t)OP_RC * LP * 4; nch = CB; }
+                        else { src = reinterpret_cast<const char *>((tail ? p.cnt_q : p.cnt_qp) + term * LP); dst = ops + (size_t)OP_RC * LP * 4 + LP; nch = CB; }
+                        for (int ch = half; ch < nch; ch += 2) cp_async16(dst + ch * 16, src + ch * 16);
+                        if (rtype == 0 && half == 0) cp_async4(&s_op_alpha[issued & (SLOTS - 1)][sl], p.alpha + term);
                     }
-                    if (pf_node > c + 1 && lane >= 8 && lane - 8 < SCHED_ITEMS) {
-                        // mailbox rows the poll warp will read: a row written long ago (or not yet) is
-                        // pulled from HBM into L2 ahead of the poll, the sender's store then hits L2
-                        const Segment *g = segs + cu.sg;
-                        if (lane - 8 < __ldg(&g->nitems)) {
-                            const int kind = __ldg(&g->item[lane - 8].kind) & 255;
-                            const long long term = __ldg(&g->item[lane - 8].term0) + (long long)cu.i * __ldg(&g->item[lane - 8].tstride);
-                            if (kind == S_DYN && do_send) {
-                                constexpr int LM = (LP * 8 + 127) / 128;
-                                for (int t = 0; t < LM; t++) prefetch_l2(reinterpret_cast<const char *>(p.mbox + term * LP) + t * 128);
-                            } else if (kind == S_RND && do_round) {
-                                prefetch_l2(p.selbox + term);
-                            }
-                        }
-                    }
-                    if (pf_node + 1 < n_nodes) cu.advance(segs);
+                    issued++;
+                    if (issued < n_nodes && ci.advance(segs)) my_own = ld_own(segs + ci.sg, sl);
                 }
+                cp_async_commit();
+            };
+            for (int q = 0; q < LAND - 1; q++) issue();
+            for (int node = 0; node < n_nodes; node++) {
+                mark(60, node);
+                issue();
+                cp_async_wait_group<LAND - 1>();
+                __syncwarp();
+                if (lane == 0) st_flag_cta(&s_flag[F_O], node + 1);
             }
+            cp_async_wait_group<0>();
             mark(69, n_nodes);
         }
     }
-    if (p.rec && lane == 0) {
-        volatile int4 *r = reinterpret_cast<volatile int4 *>(p.rec) + (blockIdx.x * 8 + warp);
+    if (rec_buf && lane == 0) {
+        volatile int4 *r = reinterpret_cast<volatile int4 *>(rec_buf) + (blockIdx.x * 8 + warp);
         r->z = 3;
     }
     if (lane == 0) {

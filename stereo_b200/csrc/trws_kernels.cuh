@@ -1063,9 +1063,9 @@ __global__ void __launch_bounds__(cta_threads(NHW), (sizeof(REAL) == 4 && K <= 4
                 const unsigned m_send = __ballot_sync(0xffffffffu, (kind & 255) == S_SEND);
                 const unsigned m_dyn = __ballot_sync(0xffffffffu, (kind & 255) == S_DYN);
                 const unsigned m_rnd = __ballot_sync(0xffffffffu, (kind & 255) == S_RND);
-#pragma unroll 4
-                for (int j = 0; j < nitems; j++) {
-                    if (!(((m_d | m_send) >> j) & 1u)) continue;
+                // (bit scans: only the rows that exist are visited -- these loops sit on the hand-over path)
+                for (unsigned rem_s = m_d | m_send; rem_s; rem_s &= rem_s - 1) {
+                    const int j = __ffs(rem_s) - 1;
                     REAL v[K];
                     row_lds<REAL, K>(v, landing + (size_t)j * LP, lane);
 #pragma unroll
@@ -1138,8 +1138,8 @@ __global__ void __launch_bounds__(cta_threads(NHW), (sizeof(REAL) == 4 && K <= 4
                             }
                     } while (rem);
                     tick(2);
-                    for (int j = 0; j < nitems; j++) {
-                        if (!((m_rnd >> j) & 1u)) continue;
+                    for (unsigned rem_r = m_rnd; rem_r; rem_r &= rem_r - 1) {
+                        const int j = __ffs(rem_r) - 1;
                         REAL v[K];
                         row_lds<REAL, K>(v, landing + (size_t)j * LP, lane);
                         const REAL aj = __shfl_sync(0xffffffffu, al, j), sj = __shfl_sync(0xffffffffu, sel, j);
@@ -1169,8 +1169,8 @@ __global__ void __launch_bounds__(cta_threads(NHW), (sizeof(REAL) == 4 && K <= 4
                 tick(2);
                 cp_async_wait_all();
                 __syncwarp();
-                for (int j = 0; j < nitems; j++) {
-                    if (!(((m_dyn | m_rnd) >> j) & 1u)) continue;
+                for (unsigned rem_d = m_dyn | m_rnd; rem_d; rem_d &= rem_d - 1) {
+                    const int j = __ffs(rem_d) - 1;
                     REAL v[K];
                     row_lds<REAL, K>(v, landing + (size_t)j * LP, lane);
                     if ((m_dyn >> j) & 1u) {

@@ -878,6 +878,12 @@ __global__ void __launch_bounds__(cta_threads(NHW), (sizeof(REAL) == 4 && K <= 4
                         so1 = g->own[w][1];
                     }
                 }
+                // ---- operands of the next node: issued BEFORE the barrier (in rows the warp would only wait
+                // there), a whole node ahead of their use.  (Issued after the update instead -- straight into
+                // the registers it released -- the loop-carried copies wait for the loads: measured +20 %.)
+                OwnTerm<REAL, K> nxt;
+                nxt.flags = 0;
+                if (has_next && cur_halves != 2) load_own(so0, seg_i, nxt);
                 // ---- rows of this node are ready, every term warp has finished the previous node
                 tick(2);
                 named_sync(BAR_FULL + set);
@@ -951,27 +957,31 @@ __global__ void __launch_bounds__(cta_threads(NHW), (sizeof(REAL) == 4 && K <= 4
                     if (w == 0) acc_lb += (double)vmin;
                 }
                 // ---- loads of the next step, then the update of this one
-                OwnTerm<REAL, K> nxt;
-                nxt.flags = 0;
                 if (cur_halves == 2) {
+                    // (rare: a node that sends on more than four terms) second-half operands, then the first
+                    // half's update, then the next node's operands
                     load_own(cur_so1, cur_i, nxt);
                     send(own, Di, xs, par, cur_gamma);
                     own = nxt;
                     nxt.flags = 0;
+                    if (has_next) load_own(so0, seg_i, nxt);
                 }
                 tick(4);
-                if (has_next) load_own(so0, seg_i, nxt);
                 tick(5);
                 send(own, Di, xs, par, cur_gamma);
                 if (prof_on) { tclk += (long long)(own.m[0] != own.m[0]); tick(6); }
                 own = nxt;
                 // this warp's stores for the node are issued: tell the auxiliary warp
-                __syncwarp();
-                if (lane == 0) {
-                    // completion counter (shared-memory atomic): paces the prefetch warp; in the fp64 /
-                    // watermark mode it also releases this warp's stores to the publisher warp
-                    if constexpr (!MBOX) __threadfence_block();
-                    atomicExch(s_wdone + w, node + 1);
+                if constexpr (MBOX) {
+                    // completion counter: only paces the prefetch warp -- a plain shared store
+                    if (lane == 0) *reinterpret_cast<volatile int *>(s_wdone + w) = node + 1;
+                } else {
+                    __syncwarp();
+                    if (lane == 0) {
+                        // watermark mode: the counter also releases this warp's stores to the publisher warp
+                        __threadfence_block();
+                        atomicExch(s_wdone + w, node + 1);
+                    }
                 }
                 if (prof_on) tp[3]++;
             }
@@ -979,6 +989,8 @@ __global__ void __launch_bounds__(cta_threads(NHW), (sizeof(REAL) == 4 && K <= 4
                 tick(2);
                 const int grp = (fs == 0) ? 0 : 1;
                 for (int q = 0; q < 4; q++) atomicAdd((unsigned long long *)p.prof + grp * 16 + q, (unsigned long long)tp[q]);
+                // second bank: [32 + 8 grp + ..] = first-half send, operand prefetch issue, update + stores
+                for (int q = 4; q < 7; q++) atomicAdd((unsigned long long *)p.prof + 32 + grp * 8 + (q - 4), (unsigned long long)tp[q]);
             }
             continue;
         }
@@ -1233,7 +1245,8 @@ __global__ void __launch_bounds__(cta_threads(NHW), (sizeof(REAL) == 4 && K <= 4
             int pf_seg = sg0, pf_i = 0, pf_node = 0;     // next node to prefetch: segment, index in it, index in strip
             int pf_n = __ldg(&segs[pf_seg].n);
             for (;;) {
-                int c = (lane < NCW) ? ld_acquire_cta(s_wdone + lane) : 0x7fffffff;
+                int c = 0x7fffffff;
+                if (lane < NCW) c = MBOX ? *reinterpret_cast<volatile int *>(s_wdone + lane) : ld_acquire_cta(s_wdone + lane);
 #pragma unroll
                 for (int o = 2; o > 0; o >>= 1) c = min(c, __shfl_xor_sync(0xffffffffu, c, o));
                 c = __shfl_sync(0xffffffffu, c, 0);

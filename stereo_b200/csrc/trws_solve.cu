@@ -292,8 +292,8 @@ struct Solver : SolverBase {
             SB_CUDA(cudaHostGetDevicePointer((void **)&P.rec, rec_host, 0));
         }
         if (getenv("SB_TRWS_PROFILE")) {
-            dProf.alloc(32);
-            SB_CUDA(cudaMemsetAsync(dProf.p, 0, 32 * sizeof(long long), stream));
+            dProf.alloc(64);
+            SB_CUDA(cudaMemsetAsync(dProf.p, 0, 64 * sizeof(long long), stream));
             P.prof = dProf.p;
         }
 
@@ -446,7 +446,7 @@ struct Solver : SolverBase {
         }
         const double solve_ms = timer.stop_ms();
         if (P.prof) {
-            long long h[32];
+            long long h[64];
             SB_CUDA(cudaMemcpy(h, dProf.p, sizeof(h), cudaMemcpyDeviceToHost));
             SB_CUDA(cudaMemsetAsync(dProf.p, 0, sizeof(h), stream));
             if (precision != SB_F64 && getenv("SB_TRWS_SWEEP") && atoi(getenv("SB_TRWS_SWEEP")) == 5) {
@@ -460,6 +460,8 @@ struct Solver : SolverBase {
             for (int g = 0; g < 2; g++) {
                 const long long *q = h + 16 * g;
                 const double nt = q[3] ? (double)q[3] : 1, nh = q[11] ? (double)q[11] : 1, np = q[13] ? (double)q[13] : 1;
+                fprintf(stderr, "[sb profile] %s term0 detail: half1=%.0f prefetch-issue=%.0f update+stores=%.0f loop-tail=%.0f cyc/node\n",
+                        g ? "rows" : "ring", h[32 + 8 * g] / nt, h[33 + 8 * g] / nt, h[34 + 8 * g] / nt, q[2] / nt);
                 fprintf(stderr, "[sb profile] %s term0: waitFULL=%.0f read+round=%.0f update=%.0f cyc/node (%lld nodes) | helper0: desc=%.0f "
                         "static=%.0f flagspin=%.0f dynwait=%.0f reduce=%.0f waitEMPTY=%.0f other=%.0f cyc/node (%lld) | aux: fence=%.0f cyc/publish, "
                         "%.2f nodes/publish\n", g ? "rows" : "ring", q[0] / nt, q[1] / nt, q[2] / nt, q[3], q[4] / nh, q[5] / nh, q[6] / nh,

@@ -1,16 +1,14 @@
-// trws_sweep5.cuh -- the fp32 TRW-S sweep kernel, fifth generation ("carry in registers").
+// trws_sweep5.cuh -- EXPERIMENTAL fp32 TRW-S sweep kernel, fifth generation (SB_TRWS_SWEEP=5).
 //
 // Same work as sweep_kernel of trws_kernels.cuh (Minimize_TRW_S forward / backward sweeps,
 // cpp/trw-s/minimize.cpp:31-95; UpdateMessage, typeStereoLinear.h:329-487 /
 // typeStereoQuadratic.h:329-501; ComputeSolutionAndEnergy, minimize.cpp:223-264), same strip /
-// segment schedule (trws_sched.h), same mailbox protocol between strips -- but a different
-// division of labour inside the CTA, chosen after the per-phase cycle counters showed that the
-// old kernel's step time was set by its helper warps and barriers, not by the update:
+// segment schedule (trws_sched.h), same mailbox protocol between strips, same parity tests
+// (tests/test_trws_v5_gpu.py) -- but a different division of labour inside the CTA:
 //
-//   chain warp   owns BOTH messages a node sends to the next node of its strip and keeps them in
-//                registers: the dependent chain along a strip is add -> two interleaved min-plus
-//                updates -> add, with no barrier, no shared-memory hand-over and no other warp
-//                on it.  It also forms the node sum Di and publishes it for the side warps.
+//   chain warps  (2) each own ONE of the two messages a node sends to the next node of its strip
+//                and keep it in registers; the partner's message arrives through an exchange row
+//                in shared memory.  Both form the node sum Di; warp 0 publishes it.
 //   side warps   (2) own the messages to nodes of other strips: they pick Di up from shared
 //                memory, update, and write the message + its self-validating mailbox words.
 //   round warp   carries the primal rounding (minimize.cpp:240-260) as its own, much shorter,
@@ -18,13 +16,18 @@
 //   static warp  streams everything that does not depend on this pass (unary row, old messages
 //                of the send terms, position rows for the rounding) through a cp.async ring
 //                LAND nodes deep and reduces it to BASE = D + sum(old messages).
+//   operand warp copies the update operands of the node's send terms (position rows, rank and
+//                merge-count bytes, alpha) LAND - 1 nodes ahead straight into the node's slot in
+//                shared memory: chain and side warps never touch global memory for operands.
 //   poll warp    polls the mailbox words of the messages arriving from other strips and the
 //                selected positions of their rounded labels.
-//   prefetch warp pulls the update operands of the nodes ahead into L2.
 //
-// Hand-over between the warps is by monotone node counters in shared memory (st.release /
-// ld.acquire at CTA scope) over a ring of SLOTS node slots; nothing in the CTA ever executes a
-// CTA-wide barrier inside a strip.
+// Hand-over between the warps is by monotone node counters in shared memory (plain volatile
+// accesses, see ld_flag_cta) over a ring of SLOTS node slots; nothing in the CTA executes a
+// CTA-wide barrier inside a strip.  Measured against sweep_kernel: equal at
+// 128x160x64 and 256x256x256, 25 % slower at 375x450x64 -- its chain step is ~2.6 k cycles
+// (update 970, the rest counter waits, shared-memory reads and bookkeeping at an instruction-level
+// parallelism of one).  Not the default.
 #pragma once
 #include "trws_kernels.cuh"
 
@@ -33,7 +36,7 @@ namespace trws {
 namespace v5 {
 
 // warp w issues on scheduler w % 4: the two chain warps and the two side warps each get a scheduler
-// of their own for the updates; round / poll / static / prefetch warps are light or mostly waiting
+// of their own for the updates; round / poll / static / operand warps are light or mostly waiting
 enum { W_CHAIN = 0, W_CHAIN1 = 1, W_SIDE0 = 2, W_SIDE1 = 3, W_ROUND = 4, W_POLL = 5, W_STATIC = 6, W_OPS = 7, NWARPS = 8 };
 constexpr int THREADS = NWARPS * 32;
 // node slots between producers and consumers / depth of the static warp's cp.async ring (powers of
@@ -53,7 +56,6 @@ enum { SR_BASE = 0, SR_D = 1, SR_DYN = 2, SR_DI = 3, SR_XR = 4, SR_OPS = 4 + MAX
        SLOT_ROWS = 4 + MAX_RND + 4 * MAX_OPS };
 enum { F_H = 0, F_P = 1, F_C = 2, F_DONE = 3 /* + chain0, side0, side1, round, chain1 */, NDONE = 5, F_X = 8 /* + chain warp */, F_O = 10, NFLAGS = 11 };
 constexpr int XROWS = 4;          // exchange rows of the two chain warps: [node parity][warp]
-constexpr int PF_AHEAD = 8;
 
 template <int K> __host__ __device__ constexpr size_t smem_bytes()
 {
@@ -850,7 +852,6 @@ __global__ void __launch_bounds__(THREADS, 1) sweep5_kernel(const Problem<float>
                 mark(40, node);
                 issue();
                 mark(44, node);
-                if (p.debug & 4) cp_async_wait_group<0>();
                 mark(41, node);
                 cp_async_wait_group<LAND - 1>();
                 __syncwarp();
@@ -977,7 +978,6 @@ __global__ void __launch_bounds__(THREADS, 1) sweep5_kernel(const Problem<float>
                                     for (int k = 0; k < K; k++) ok = ok && ((unsigned)(wv[q][k] >> 32) == ep);
                                 }
                             if (__all_sync(0xffffffffu, ok)) break;
-                            if (p.debug & 8) __nanosleep(100);
                         }
 #pragma unroll
                         for (int q = 0; q < G; q++)

@@ -1287,6 +1287,16 @@ __global__ void __launch_bounds__(cta_threads(NHW), (sizeof(REAL) == 4 && K <= 4
                             else if (kind == S_RND && do_round) base = ((sl.kind & 256) ? p.posqp : p.posq) + row;
                             if (base)
                                 for (int t = 0; t < LR; t++) prefetch_l2(reinterpret_cast<const char *>(base) + t * 128);
+                            if constexpr (MBOX) {
+                                // mailbox words the helper will poll: where the sender ran long ago (the ring in the
+                                // backward pass) they have left the L2, and the poll would pay the HBM latency
+                                if (kind == S_DYN && do_send) {
+                                    constexpr int LM = (LP * 8 + 127) / 128;
+                                    for (int t = 0; t < LM; t++) prefetch_l2(reinterpret_cast<const char *>(p.mbox + row) + t * 128);
+                                } else if (kind == S_RND && do_round) {
+                                    prefetch_l2(p.selbox + row / LP);
+                                }
+                            }
                         }
                     }
                     if (++pf_i >= pf_n) {

@@ -363,6 +363,19 @@ void build_pass_plan(int H, int W, const std::vector<uint8_t> &info, const Sched
                 }
             }
         nd.nitems = n;
+        // invariant the kernels rely on (trws_sweep5.cuh copies the old message of own slot t from the
+        // t-th S_SEND row): send rows and own slots are handed out together, in the same order
+        {
+            int t = 0;
+            for (int q = 0; q < n; q++)
+                if ((nd.item[q].kind & 255) == S_SEND) {
+                    const NodeDesc::Own &o = nd.own[t & 3][t >> 2];
+                    SB_REQUIRE((o.flags & OWN_HAS) && o.term == nd.item[q].term, SB_EUNSUP,
+                               "trws schedule: send rows and own slots out of step");
+                    t++;
+                }
+            SB_REQUIRE(t == si, SB_EUNSUP, "trws schedule: send rows and own slots out of step");
+        }
     };
     auto same_structure = [&](const NodeDesc &a, const NodeDesc &b) {
         if (a.halves != b.halves || a.gamma_den != b.gamma_den || a.use_carry != b.use_carry || a.nitems != b.nitems)

@@ -133,153 +133,6 @@ template <int K> struct Own {
     int flags;
 };
 
-// Two independent truncated-linear updates of the same node (same Di, gamma) with their
-// instruction streams interleaved: the shuffle / shared-memory latencies of one hide behind the
-// other.  Same arithmetic as update_linear; requires alpha != 0 on both terms.
-template <int K>
-__device__ __forceinline__ void update_linear2(float gamma, float lambda, int L, int lane, const float (&Di)[K],
-                                               Own<K> (&o)[2], Pair<float> *P0, Pair<float> *P1, float (&vout)[2])
-{
-    const float BIG = Lim<float>::big();
-    Pair<float> *P[2] = {P0, P1};
-    uint8_t rk[2][K], cn[2][K];
-#pragma unroll
-    for (int t = 0; t < 2; t++) {
-        o[t].rkp.unpack(rk[t]);
-        o[t].cnp.unpack(cn[t]);
-    }
-    float h[2][K], hmin[2], vTrunc[2];
-#pragma unroll
-    for (int t = 0; t < 2; t++) {
-        hmin[t] = BIG;
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            h[t][k] = (lane * K + k < L) ? gamma * Di[k] - o[t].m[k] : BIG;
-            hmin[t] = min(hmin[t], h[t][k]);
-        }
-    }
-#pragma unroll
-    for (int t = 0; t < 2; t++) {
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            Pair<float> q;
-            q.a = h[t][k];
-            q.b = o[t].s[k];
-            P[t][phys<K>(rk[t][k])] = q;
-        }
-    }
-#pragma unroll
-    for (int t = 0; t < 2; t++) {
-        hmin[t] = warp_min(hmin[t]);
-        vTrunc[t] = hmin[t] + o[t].alpha * lambda;
-    }
-    __syncwarp();
-    float hs[2][K], ss[2][K];
-#pragma unroll
-    for (int t = 0; t < 2; t++) {
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            const Pair<float> q = P[t][phys<K>(lane * K + k)];
-            hs[t][k] = q.a;
-            ss[t][k] = q.b;
-        }
-    }
-    float gl[2][K], cl[2][K], gr[2][K], cr[2][K];
-    float DlL[2], CL[2], DlR[2], CR[2];
-#pragma unroll
-    for (int t = 0; t < 2; t++) {
-        const float al = o[t].alpha;
-        float sprev = __shfl_up_sync(0xffffffffu, ss[t][K - 1], 1);
-        float snext = __shfl_down_sync(0xffffffffu, ss[t][0], 1);
-        if (lane == 0) sprev = ss[t][0];
-        if (lane == 31) snext = ss[t][K - 1];
-        float g = BIG, cum = 0.f;
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            const float d = al * (ss[t][k] - (k ? ss[t][k - 1] : sprev));
-            g = min(g + d, hs[t][k]);
-            cum += d;
-            gl[t][k] = g;
-            cl[t][k] = cum;
-        }
-        DlL[t] = cum;
-        CL[t] = g;
-        g = BIG;
-        cum = 0.f;
-#pragma unroll
-        for (int k = K - 1; k >= 0; k--) {
-            const float d = al * ((k < K - 1 ? ss[t][k + 1] : snext) - ss[t][k]);
-            g = min(g + d, hs[t][k]);
-            cum += d;
-            gr[t][k] = g;
-            cr[t][k] = cum;
-        }
-        DlR[t] = cum;
-        CR[t] = g;
-    }
-#pragma unroll
-    for (int ofs = 1; ofs < 32; ofs <<= 1) {
-        float DpL[2], CpL[2], DpR[2], CpR[2];
-#pragma unroll
-        for (int t = 0; t < 2; t++) {
-            DpL[t] = __shfl_up_sync(0xffffffffu, DlL[t], ofs);
-            CpL[t] = __shfl_up_sync(0xffffffffu, CL[t], ofs);
-            DpR[t] = __shfl_down_sync(0xffffffffu, DlR[t], ofs);
-            CpR[t] = __shfl_down_sync(0xffffffffu, CR[t], ofs);
-        }
-#pragma unroll
-        for (int t = 0; t < 2; t++) {
-            if (lane >= ofs) {
-                CL[t] = min(CpL[t] + DlL[t], CL[t]);
-                DlL[t] = DpL[t] + DlL[t];
-            }
-            if (lane + ofs < 32) {
-                CR[t] = min(CpR[t] + DlR[t], CR[t]);
-                DlR[t] = DpR[t] + DlR[t];
-            }
-        }
-    }
-#pragma unroll
-    for (int t = 0; t < 2; t++) {
-        float VinL = __shfl_up_sync(0xffffffffu, CL[t], 1);
-        float VinR = __shfl_down_sync(0xffffffffu, CR[t], 1);
-        if (lane == 0) VinL = BIG;
-        if (lane == 31) VinR = BIG;
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            Pair<float> q;
-            q.a = min(min(VinL + cl[t][k], gl[t][k]), min(VinR + cr[t][k], gr[t][k]));
-            q.b = ss[t][k];
-            P[t][phys<K>(lane * K + k)] = q;
-        }
-    }
-    __syncwarp();
-    float vmin[2];
-#pragma unroll
-    for (int t = 0; t < 2; t++) {
-        const float al = o[t].alpha;
-        vmin[t] = BIG;
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            const int c = cn[t][k];
-            const Pair<float> lo = P[t][c ? phys<K>(c - 1) : 0];
-            const Pair<float> hi = P[t][phys<K>(c)];
-            const float xk = o[t].x[k];
-            const float v = min(vTrunc[t], min(lo.a + al * fabsf(xk - lo.b), hi.a + al * fabsf(xk - hi.b)));
-            o[t].m[k] = v;
-            if (lane * K + k < L) vmin[t] = min(vmin[t], v);
-        }
-    }
-#pragma unroll
-    for (int t = 0; t < 2; t++) {
-        vmin[t] = warp_min(vmin[t]);
-#pragma unroll
-        for (int k = 0; k < K; k++) o[t].m[k] -= vmin[t];
-        vout[t] = vmin[t];
-    }
-    __syncwarp();
-}
-
 template <int K, int KERN>
 __device__ __forceinline__ float update_one(float gamma, float lambda, int L, int lane, const float (&Di)[K], Own<K> &o,
                                             Pair<float> *P)

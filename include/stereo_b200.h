@@ -159,6 +159,73 @@ SB_API int sb_trws_ipc_export(sb_trws_solver *s, unsigned char *handles /* 192 b
 SB_API int sb_trws_ipc_attach(sb_trws_solver *s, const unsigned char *up, const unsigned char *down);
 SB_API int sb_trws_pass(sb_trws_solver *s, int pass, int mode, double *acc /* 2 */);
 
+/* ---------------------------------------------------------------- TRW-S, grid-native entry
+ *
+ * The same solver as sb_trws_solve, but the problem enters the way
+ * dispmap_super.simultaneous_fusion HOLDS it (dispmap_super.m:158-188) instead of as the L x E arrays
+ * it derives from that: L plane proposals per pixel, one unary slab per proposal, one weight per term.
+ * q(:,p) = disparity of the head's plane at the head's point and qprim(:,p) = disparity of the
+ * tail's plane at the head's point (dispmap_super.m:180-183) are recomputed inside the sweep kernel
+ * from three numbers per label and node (own disparity, disparity step per column / row), which
+ * replaces the per-edge q / q' / order storage of typeStereoLinear.h:274-311.  State is 45 bytes per
+ * label and node (fp32), so BASELINE config 5 (1980 x 2880 x 192) fits one B200 and config 4
+ * (4096 x 4096 x 256) fits eight, each rank holding only its own row band (+ one halo row).
+ *
+ *   sb_trws_grid_create      rank `rank` of `world` row bands (world = 1: the whole grid); H, W >= 4;
+ *                            kernel / tol / options as sb_trws_solve
+ *   sb_trws_grid_set_labels  proposals l0 .. l0+nl-1: planes = nl consecutive 4 x N arrays ([a; b; c; d0]
+ *                            per pixel, MATLAB node order), unary = nl x N (proposal-major);
+ *                            d_min / d_step = the disparity normalisation of
+ *                            dispmap_globalstereo.m:336-345 (0, 1 for dispmap_ncc / dispmap_super).
+ *                            c == 0 -> SB_EINVAL "Infinite disparity" (dispmap_super.m:321-323)
+ *   sb_trws_grid_set_weights alphas, E doubles in the reference's term order (trws_mex.cpp:35)
+ *   sb_trws_grid_synth       fills every proposal, unary and weight with the seeded synthetic problem of
+ *                            SURVEY 8(d) ON the device (for sizes whose inputs do not fit a host)
+ *   sb_trws_grid_finalize    builds the sort-rank / merge-count tables (the argsort loop of
+ *                            trws_mex.cpp:84-119) on the device; call after the labels are set
+ *   sb_trws_grid_get_label   one stored proposal back out: 4 x N doubles [unary | own disparity | step per
+ *                            column | step per row] (N each, MATLAB node order; rows this rank does not
+ *                            store are 0) -- inspection / parity tests
+ *   sb_trws_grid_get_weights the stored weights, E doubles in the reference's term order
+ *   sb_trws_grid_minimize    Minimize_TRW_S (minimize.cpp:7-116), world = 1 only; continues from the
+ *                            current messages.  With fuse_rounding and max_relgap > 0 the stop test of
+ *                            iteration t runs inside the forward sweep of t + 1, so after an early stop
+ *                            the resident messages are half an iteration ahead of the reference's
+ *                            (the returned labels / energy / bound are those of iteration t)
+ *   sb_trws_grid_get_labels  N doubles, 1-based, MATLAB node order; rows this rank does not sweep are 0
+ *   sb_trws_grid_pass / _ipc_export (2 x 64 bytes: message and selected-position arrays) / _ipc_attach:
+ *                            the row-banded multi-GPU protocol of sb_trws_pass, on sharded state: the
+ *                            messages of the vertical terms that cross a band boundary are stored by both
+ *                            ranks and written by the sender into both copies (its own, and the neighbour's
+ *                            over NVLink); a message word carries the parity of the pass counter in its
+ *                            sign bit (min-normalised messages are >= 0), so the receiver polls its own
+ *                            copy -- no mailbox array, no flag, no fence
+ *   sb_trws_grid_info        info[0] = bytes of HBM state on this rank, [1] = nodes stored, [2], [3] = rows
+ *                            swept [lo, hi), [4], [5] = persistent CTAs (forward, backward), [6] = dynamic
+ *                            shared memory per CTA, [7] = padded label count */
+typedef struct sb_trws_grid sb_trws_grid;
+SB_API int sb_trws_grid_create(int kernel, int H, int W, int L, double tol, const sb_trws_options *opt,
+                        int rank, int world, sb_trws_grid **out);
+SB_API int sb_trws_grid_set_labels(sb_trws_grid *g, int l0, int nl, const double *planes, const double *unary,
+                            double d_min, double d_step);
+SB_API int sb_trws_grid_set_weights(sb_trws_grid *g, const double *alphas);
+SB_API int sb_trws_grid_synth(sb_trws_grid *g, uint64_t seed);
+SB_API int sb_trws_grid_finalize(sb_trws_grid *g);
+SB_API int sb_trws_grid_get_label(sb_trws_grid *g, int l, double *out /* 4 x N */);
+SB_API int sb_trws_grid_get_weights(sb_trws_grid *g, double *alphas /* E */);
+SB_API int sb_trws_grid_reset(sb_trws_grid *g);
+SB_API int sb_trws_grid_minimize(sb_trws_grid *g, double maxiter, double max_relgap,
+                          double *energy, double *lower_bound, double *iterations, sb_trws_timing *timing);
+SB_API int sb_trws_grid_get_labels(sb_trws_grid *g, double *labels);
+SB_API int sb_trws_grid_ipc_export(sb_trws_grid *g, unsigned char *handles /* 128 bytes */);
+SB_API int sb_trws_grid_ipc_attach(sb_trws_grid *g, const unsigned char *up, const unsigned char *down);
+SB_API int sb_trws_grid_pass(sb_trws_grid *g, int pass, int mode, double *acc /* 2 */);
+SB_API int sb_trws_grid_info(sb_trws_grid *g, int64_t *info /* 8 */);
+SB_API void sb_trws_grid_destroy(sb_trws_grid *g);
+/* Host-only: per pass (forward, backward) six values: strips, segments, node steps, nodes, nodes that
+ * need two steps, (messages pushed to rank - 1) * 1e6 + (messages pushed to rank + 1).  12 values. */
+SB_API int sb_trws_grid_plan_stats(int H, int W, int rank, int world, int64_t *stats);
+
 /* Node ordering of MRFEnergy::SetAutomaticOrdering (cpp/trw-s/ordering.cpp:7-157)
  * on the H x W grid: ordering[r + H*c] in [0, H*W).  Closed form for H,W >= 4
  * (SURVEY Appendix A.1), literal greedy scan otherwise.  Host-only. */

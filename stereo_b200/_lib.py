@@ -75,6 +75,24 @@ def lib():
         L.sb_trws_grid_ordering.argtypes = [c_int, c_int, _ip]
         L.sb_trws_plan_stats.argtypes = [c_int, c_int, c_int, c_int, POINTER(c_int64)]
         L.sb_grid_from_connectivity.argtypes = [c_int64, c_int64, _up, POINTER(c_int), POINTER(c_int)]
+        vp = ctypes.c_void_p
+        L.sb_trws_grid_create.argtypes = [c_int, c_int, c_int, c_int, c_double, POINTER(TrwsOptions), c_int, c_int, POINTER(vp)]
+        L.sb_trws_grid_set_labels.argtypes = [vp, c_int, c_int, _dp, _dp, c_double, c_double]
+        L.sb_trws_grid_set_weights.argtypes = [vp, _dp]
+        L.sb_trws_grid_synth.argtypes = [vp, ctypes.c_uint64]
+        L.sb_trws_grid_finalize.argtypes = [vp]
+        L.sb_trws_grid_get_label.argtypes = [vp, c_int, _dp]
+        L.sb_trws_grid_get_weights.argtypes = [vp, _dp]
+        L.sb_trws_grid_reset.argtypes = [vp]
+        L.sb_trws_grid_minimize.argtypes = [vp, c_double, c_double, _dp, _dp, _dp, POINTER(TrwsTiming)]
+        L.sb_trws_grid_get_labels.argtypes = [vp, _dp]
+        L.sb_trws_grid_ipc_export.argtypes = [vp, ctypes.c_char_p]
+        L.sb_trws_grid_ipc_attach.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p]
+        L.sb_trws_grid_pass.argtypes = [vp, c_int, c_int, _dp]
+        L.sb_trws_grid_info.argtypes = [vp, POINTER(c_int64)]
+        L.sb_trws_grid_destroy.argtypes = [vp]
+        L.sb_trws_grid_destroy.restype = None
+        L.sb_trws_grid_plan_stats.argtypes = [c_int, c_int, c_int, c_int, POINTER(c_int64)]
         ip, i64, dbl = c_int, c_int64, c_double
         L.sb_rd_solve.argtypes = [c_int64, c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _up, c_int, _dp, _dp, _dp, _dp]
         L.sb_ncc_volume.argtypes = [ip, ip, ip, _dp, _dp, ip, _dp, ip, _dp]

@@ -1,0 +1,54 @@
+// gtrws_plan.h -- sweep schedule of the GRID-NATIVE TRW-S path (sb_trws_grid_*, gtrws_*.cu).
+//
+// Same node order / orientation DAG / strips as the MATLAB-layout path (trws_order.cpp:
+// SetAutomaticOrdering of cpp/trw-s/ordering.cpp:7-157, edge orientation of
+// MRFEnergy.cpp:188-219), but addressed for the plane-native, row-major, band-local layout of
+// gtrws_kernels.cuh: a node step is described by its local node id and a ROLE per grid direction;
+// every address (neighbour node, pair record, term slot) follows from those by arithmetic.
+#pragma once
+#include <stdint.h>
+#include <vector>
+
+namespace sb {
+namespace gtrws {
+
+enum { DIR_UP = 0, DIR_DOWN = 1, DIR_LEFT = 2, DIR_RIGHT = 3 };
+// what a node does with the neighbour pair in one direction during a pass
+enum { ROLE_NONE = 0,
+       ROLE_SEND0 = 1,   // sends both terms of the pair (staged in send slot 0)
+       ROLE_SEND1 = 2,   // ... send slot 1
+       ROLE_ADD = 3,     // a send pair handled by the node's second step: only summed into the node total here
+       ROLE_POLL = 4,    // receives: waits for the neighbour's two messages of this pass (tagged words)
+       ROLE_CARRY = 5 }; // receives from the previous node of the strip through shared memory
+
+enum { GF_SECOND = 1,    // second step of a node that sends on more than two pairs: node total taken from the first
+       GF_FIRST = 2 };   // first step of such a node: saves the node total
+
+// A run of node steps with identical roles and a constant node stride (32 bytes).
+struct GSeg {
+    int32_t u0, du, n;       // local node ids u0 + i * du
+    uint32_t roles;          // 4 bits per direction
+    int16_t gamma_den;       // max(nF, nB): gamma = 1 / gamma_den (treeProbabilities.cpp:28-45)
+    int8_t next_dir;         // direction of the next strip node when it is a send target, else -1
+    uint8_t flags;           // GF_*
+    uint8_t peer[4];         // per direction: 0 receiver local, 1 on rank - 1, 2 on rank + 1
+    int32_t pad[2];
+};
+static_assert(sizeof(GSeg) == 32, "GSeg layout");
+
+struct GPassPlan {
+    std::vector<GSeg> segs;
+    std::vector<int32_t> seg_ptr;    // per strip of this rank (schedule order)
+    std::vector<int32_t> strip_len;  // node STEPS per strip (a two-step node counts twice)
+};
+
+// Band geometry of rank `rank` of `world`: rows it sweeps [r_lo, r_hi), rows it stores [r_base, r_top)
+// (one halo row on each inner side).
+struct Band { int r_lo, r_hi, r_base, r_top; };
+Band band_rows(int H, int rank, int world);
+
+// pass 0 forward, 1 backward.  rank < 0: whole grid on one GPU.
+void build_gpass_plan(int H, int W, int pass, int rank, int world, GPassPlan &plan);
+
+} // namespace gtrws
+} // namespace sb

@@ -1,0 +1,144 @@
+// gtrws_tables.cuh -- set-up kernels of the grid-native TRW-S path: sort ranks and merge counts
+// of the label positions, built on the device from the per-node plane rows.  They are the
+// counterpart of the per-edge argsort loop of cpp/trws_mex.cpp:84-119 (the reference sorts q(:,p)
+// and qprim(:,p) of every term with std::sort inside the j loop); here
+//   q(:, p)     = own[head]                         dispmap_super.m:181
+//   qprim(:, p) = own[tail] +- g[tail]              dispmap_super.m:182  (tail planes at the head's point)
+// are recomputed with the SAME fp32 expressions the sweep kernel uses, so the tables always agree
+// with the positions the sweep sees.
+#pragma once
+#include "gtrws_kernels.cuh"
+
+namespace sb {
+namespace gtrws {
+
+// labels L..LP-1 of every node: D = 0, slopes 0, own = a value beyond every position the node's real
+// labels can take (own +- gx, own +- gy), so that the padding sorts LAST in every sorted array of this
+// node -- sorted indices 0..L-1 are exactly the real labels, as the update kernels assume
+template <typename REAL, int K>
+__global__ void gpad_kernel(REAL *nodeF, long long Nloc, int L)
+{
+    constexpr int LP = 32 * K;
+    const int lane = threadIdx.x & 31;
+    const long long v = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (v >= Nloc || L >= LP) return;
+    REAL *rec = nodeF + v * 4 * LP;
+    REAL mx = -Lim<REAL>::big();
+    for (int l = lane; l < L; l += 32)
+        mx = max(mx, rec[NF_OWN * LP + l] + fabs(rec[NF_GX * LP + l]) + fabs(rec[NF_GY * LP + l]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    mx = mx + REAL(1) + fabs(mx) * REAL(1e-3);
+    for (int l = L + lane; l < LP; l += 32) {
+        rec[NF_D * LP + l] = REAL(0);
+        rec[NF_GX * LP + l] = REAL(0);
+        rec[NF_OWN * LP + l] = mx;
+        rec[NF_GY * LP + l] = REAL(0);
+    }
+}
+
+// rank of every label of A among the LP entries of A (ties: lower label first), and
+// cnt[l] = #{m : B[m] <= A[l]} clamped to 255
+template <typename REAL, int K>
+__device__ __forceinline__ void rank_rows(const REAL *A, int lane, uint8_t (&rk)[K])
+{
+    constexpr int LP = 32 * K;
+    REAL a[K];
+    int r[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) { a[k] = A[lane * K + k]; r[k] = 0; }
+    for (int m = 0; m < LP; m++) {
+        const REAL v = A[m];
+#pragma unroll
+        for (int k = 0; k < K; k++) r[k] += (v < a[k]) || (v == a[k] && m < lane * K + k);
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) rk[k] = (uint8_t)r[k];
+}
+template <typename REAL, int K>
+__device__ __forceinline__ void count_rows(const REAL *A, const REAL *B, int lane, uint8_t (&cn)[K])
+{
+    constexpr int LP = 32 * K;
+    REAL a[K];
+    int c[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) { a[k] = A[lane * K + k]; c[k] = 0; }
+    for (int m = 0; m < LP; m++) {
+        const REAL v = B[m];
+#pragma unroll
+        for (int k = 0; k < K; k++) c[k] += (v <= a[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) cn[k] = (uint8_t)min(c[k], 255);
+}
+
+// one warp per node: rank of own
+template <typename REAL, int K, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) gnode_tables_kernel(const REAL *__restrict__ nodeF, uint8_t *__restrict__ nodeB, long long Nloc)
+{
+    constexpr int LP = 32 * K;
+    __shared__ REAL sh[WARPS][LP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long v = (long long)blockIdx.x * WARPS + warp; v < Nloc; v += (long long)gridDim.x * WARPS) {
+        const REAL *rec = nodeF + v * 4 * LP;
+#pragma unroll
+        for (int k = 0; k < K; k++) sh[warp][lane * K + k] = rec[NF_OWN * LP + lane * K + k];
+        __syncwarp();
+        uint8_t rk[K];
+        rank_rows<REAL, K>(sh[warp], lane, rk);
+        trws::ByteIO<K>::store(nodeB + v * LP + lane * K, rk);
+        __syncwarp();
+    }
+}
+
+// one warp per neighbour pair (first node a = pair / 2, direction down / right = pair % 2):
+//   term 0: tail a, head b:  q0 = own_b,  qp0 = own_a + g_a
+//   term 1: tail b, head a:  q1 = own_a,  qp1 = own_b - g_b
+// side record s (what node s of the pair needs when it sends): [cnt_q[s] | cnt_qp[1-s] | rank_tail[s]]
+//   cnt_q[j][l]  = #{m : qp_j[m] <= q_j[l]}     cnt_qp[j][l] = #{m : q_j[m] <= qp_j[l]}
+template <typename REAL, int K, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) gpair_tables_kernel(const REAL *__restrict__ nodeF, uint8_t *__restrict__ pairB, int W, int rows)
+{
+    constexpr int LP = 32 * K;
+    __shared__ REAL sh[WARPS][4][LP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long Nloc = (long long)rows * W;
+    for (long long pr = (long long)blockIdx.x * WARPS + warp; pr < 2 * Nloc; pr += (long long)gridDim.x * WARPS) {
+        const long long a = pr >> 1;
+        const int dirn = (int)(pr & 1);   // 0 down, 1 right
+        const int r = (int)(a / W), c = (int)(a % W);
+        if (dirn == 0 ? (r + 1 >= rows) : (c + 1 >= W)) continue;
+        const long long b = dirn == 0 ? a + W : a + 1;
+        const REAL *ra = nodeF + a * 4 * LP, *rb = nodeF + b * 4 * LP;
+        const int gsel = dirn == 0 ? NF_GY : NF_GX;
+        REAL *q0 = sh[warp][0], *qp0 = sh[warp][1], *q1 = sh[warp][2], *qp1 = sh[warp][3];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const int l = lane * K + k;
+            const REAL oa = ra[NF_OWN * LP + l], ob = rb[NF_OWN * LP + l];
+            q0[l] = ob;
+            qp0[l] = oa + ra[gsel * LP + l];
+            q1[l] = oa;
+            qp1[l] = ob - rb[gsel * LP + l];
+        }
+        __syncwarp();
+        uint8_t out[K];
+        uint8_t *rec = pairB + pr * 6 * LP + lane * K;
+        count_rows<REAL, K>(q0, qp0, lane, out);    // cnt_q[0]
+        trws::ByteIO<K>::store(rec + 0 * LP, out);
+        count_rows<REAL, K>(qp1, q1, lane, out);    // cnt_qp[1]
+        trws::ByteIO<K>::store(rec + 1 * LP, out);
+        rank_rows<REAL, K>(qp0, lane, out);         // rank_tail[0]
+        trws::ByteIO<K>::store(rec + 2 * LP, out);
+        count_rows<REAL, K>(q1, qp1, lane, out);    // cnt_q[1]
+        trws::ByteIO<K>::store(rec + 3 * LP, out);
+        count_rows<REAL, K>(qp0, q0, lane, out);    // cnt_qp[0]
+        trws::ByteIO<K>::store(rec + 4 * LP, out);
+        rank_rows<REAL, K>(qp1, lane, out);         // rank_tail[1]
+        trws::ByteIO<K>::store(rec + 5 * LP, out);
+        __syncwarp();
+    }
+}
+
+} // namespace gtrws
+} // namespace sb

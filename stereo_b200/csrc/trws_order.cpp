@@ -363,8 +363,7 @@ void build_pass_plan(int H, int W, const std::vector<uint8_t> &info, const Sched
                 }
             }
         nd.nitems = n;
-        // invariant the kernels rely on (trws_sweep5.cuh copies the old message of own slot t from the
-        // t-th S_SEND row): send rows and own slots are handed out together, in the same order
+        // invariant: send rows and own slots are handed out together, in the same order
         {
             int t = 0;
             for (int q = 0; q < n; q++)

@@ -449,14 +449,6 @@ struct Solver : SolverBase {
             long long h[64];
             SB_CUDA(cudaMemcpy(h, dProf.p, sizeof(h), cudaMemcpyDeviceToHost));
             SB_CUDA(cudaMemsetAsync(dProf.p, 0, sizeof(h), stream));
-            if (precision != SB_F64 && getenv("SB_TRWS_SWEEP") && atoi(getenv("SB_TRWS_SWEEP")) == 5) {
-                for (int g = 0; g < 2; g++) {
-                    const long long *q = h + 8 * g;
-                    const double nn = q[0] ? (double)q[0] : 1;
-                    fprintf(stderr, "[sb profile v5] %s chain warp: %.0f cyc/node (%lld nodes): wait static=%.0f poll=%.0f side=%.0f update+store=%.0f\n",
-                            g ? "rows" : "ring", q[4] / nn, q[0], q[1] / nn, q[2] / nn, q[3] / nn, q[5] / nn);
-                }
-            } else
             for (int g = 0; g < 2; g++) {
                 const long long *q = h + 16 * g;
                 const double nt = q[3] ? (double)q[3] : 1, nh = q[11] ? (double)q[11] : 1, np = q[13] ? (double)q[13] : 1;

@@ -1,0 +1,201 @@
+"""Grid-native TRW-S (``sb_trws_grid_*``, include/stereo_b200.h).
+
+``TrwsGrid`` is what ``dispmap_super.simultaneous_fusion`` (dispmap_super.m:153-198) hands the
+solver when it does NOT first expand its proposals into the L x E arrays ``q`` / ``qprim``: L
+plane proposals (4 x N each), an L x N unary slab and the E smooth weights.  The positions
+q(:,p) = d(plane@ind2, pt ind2), qprim(:,p) = d(plane@ind1, pt ind2) (dispmap_super.m:180-183) are
+recomputed on the device.  With ``world > 1`` every rank holds and sweeps one row band
+(torch.distributed plumbing as in multigpu.py; the halo is peer stores over NVLink).
+
+``positions_from_labels`` rebuilds q / qprim in numpy from the planes AS STORED on the device
+(``get_label``), so a parity test can hand the reference solver bit-identical inputs.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_double
+
+import numpy as np
+
+from ._lib import TrwsTiming, _dp, check, lib
+from .grid import construct_neighborhood
+from .solvers import _f, _timing_dict, _trws_options
+
+MODE_SEND, MODE_ROUND = 1, 2
+
+
+class TrwsGrid:
+    def __init__(self, kernel, H, W, L, tol, options=None, group=None, rank=0, world=1):
+        self.H, self.W, self.L = int(H), int(W), int(L)
+        self.N = self.H * self.W
+        self.E = 2 * ((self.H - 1) * self.W + self.H * (self.W - 1))
+        self.group = group
+        self.dist = None
+        if group is not None or world > 1:
+            import torch
+            import torch.distributed as dist
+            self.dist, self.torch = dist, torch
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+        self.rank, self.world = rank, world
+        opt = _trws_options(options)
+        self.fuse = bool(opt.fuse_rounding)
+        self.precision = opt.precision
+        self._h = ctypes.c_void_p()
+        check(lib().sb_trws_grid_create(int(np.int32(kernel)), self.H, self.W, self.L, float(tol), ctypes.byref(opt),
+                                        self.rank, self.world, ctypes.byref(self._h)))
+        self.timing = {}
+        self._attached = False
+
+    # ---- problem
+    def set_labels(self, l0, planes, unary, d_min=0.0, d_step=1.0):
+        """planes: nl x 4 x N (or 4 x N), unary: nl x N (or N)."""
+        planes = np.asarray(planes, dtype=np.float64)
+        unary = np.asarray(unary, dtype=np.float64)
+        if planes.ndim == 2:
+            planes, unary = planes[None], unary[None]
+        nl = planes.shape[0]
+        assert planes.shape == (nl, 4, self.N) and unary.shape == (nl, self.N)
+        # proposal-major, each proposal a MATLAB 4 x N array (column-major: [a b c d0] per pixel contiguous)
+        pl = np.ascontiguousarray(planes.transpose(0, 2, 1))
+        un = np.ascontiguousarray(unary)
+        check(lib().sb_trws_grid_set_labels(self._h, int(l0), nl, pl.ctypes.data_as(_dp), un.ctypes.data_as(_dp),
+                                            float(d_min), float(d_step)))
+
+    def set_weights(self, alphas):
+        a = _f(np.asarray(alphas).reshape(-1))
+        assert a.size == self.E
+        check(lib().sb_trws_grid_set_weights(self._h, a.ctypes.data_as(_dp)))
+
+    def synth(self, seed):
+        check(lib().sb_trws_grid_synth(self._h, ctypes.c_uint64(int(seed))))
+
+    def finalize(self):
+        check(lib().sb_trws_grid_finalize(self._h))
+        if self.world > 1 and not self._attached:
+            mine = ctypes.create_string_buffer(128)
+            check(lib().sb_trws_grid_ipc_export(self._h, mine))
+            gathered = [None] * self.world
+            self.dist.all_gather_object(gathered, bytes(mine.raw), group=self.group)
+            up = gathered[self.rank - 1] if self.rank > 0 else None
+            down = gathered[self.rank + 1] if self.rank + 1 < self.world else None
+            check(lib().sb_trws_grid_ipc_attach(self._h, up, down))
+            self.dist.barrier(group=self.group)
+            self._attached = True
+
+    def get_label(self, l):
+        """(unary, own, gx, gy) of proposal l as stored (N doubles each, MATLAB node order)."""
+        out = np.zeros((4, self.N), dtype=np.float64)
+        check(lib().sb_trws_grid_get_label(self._h, int(l), out.ctypes.data_as(_dp)))
+        return out[0], out[1], out[2], out[3]
+
+    def get_weights(self):
+        out = np.zeros(self.E, dtype=np.float64)
+        check(lib().sb_trws_grid_get_weights(self._h, out.ctypes.data_as(_dp)))
+        return out
+
+    def info(self):
+        out = (ctypes.c_int64 * 8)()
+        check(lib().sb_trws_grid_info(self._h, out))
+        keys = ("hbm_bytes", "nodes_stored", "row_lo", "row_hi", "ctas_fwd", "ctas_bwd", "smem_per_cta", "LP")
+        return dict(zip(keys, [int(v) for v in out]))
+
+    # ---- solve
+    def reset(self):
+        check(lib().sb_trws_grid_reset(self._h))
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+
+    def _pass(self, which, mode):
+        acc = (ctypes.c_double * 2)()
+        check(lib().sb_trws_grid_pass(self._h, which, mode, acc))
+        if self.world == 1:
+            return acc[0], acc[1]
+        t = self.torch.tensor([acc[0], acc[1]], dtype=self.torch.float64)
+        dev = "cuda" if self.dist.get_backend(self.group) == "nccl" else "cpu"
+        t = t.to(dev)
+        self.dist.all_reduce(t, group=self.group)   # the stop rule needs the sums; also separates the passes
+        t = t.cpu()
+        return float(t[0]), float(t[1])
+
+    def minimize(self, maxiter=1000, max_relgap=0.0):
+        """Minimize_TRW_S (minimize.cpp:7-116); returns (energy, lower_bound, iterations)."""
+        if self.world == 1:
+            e, lb, it = c_double(), c_double(), c_double()
+            tm = TrwsTiming()
+            check(lib().sb_trws_grid_minimize(self._h, float(maxiter), float(max_relgap), ctypes.byref(e),
+                                              ctypes.byref(lb), ctypes.byref(it), ctypes.byref(tm)))
+            self.timing = _timing_dict(tm)
+            return e.value, lb.value, it.value
+        iter_max = int(maxiter)
+        energy = lb = 0.0
+        it = 1
+        while True:
+            e, _ = self._pass(0, MODE_SEND | (MODE_ROUND if (self.fuse and it > 1) else 0))
+            if self.fuse and it > 1:
+                energy = e
+                if (energy - lb) / energy < max_relgap:
+                    return energy, lb, float(it - 1)
+            _, lb = self._pass(1, 0)
+            if (not self.fuse) or it >= iter_max:
+                energy, _ = self._pass(0, MODE_ROUND)
+                if it >= iter_max or (energy - lb) / energy < max_relgap:
+                    return energy, lb, float(it)
+            it += 1
+
+    def labels(self, gather=True):
+        out = np.zeros(self.N, dtype=np.float64)
+        check(lib().sb_trws_grid_get_labels(self._h, out.ctypes.data_as(_dp)))
+        if self.world > 1 and gather:
+            t = self.torch.from_numpy(out)
+            dev = "cuda" if self.dist.get_backend(self.group) == "nccl" else "cpu"
+            t = t.to(dev)
+            self.dist.all_reduce(t, group=self.group)   # rows a rank does not sweep are 0
+            out = t.cpu().numpy()
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().sb_trws_grid_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def trws_grid(kernel, unary, proposals, weights, tol, H, W, options=None, d_min=0.0, d_step=1.0):
+    """One-shot form: [solution, energy, lower_bound, iterations] like ``trws`` (trws.m:2-33), from
+    proposals (L x 4 x N), unary (L x N) and weights (E)."""
+    unary = np.asarray(unary, dtype=np.float64)
+    L = unary.shape[0]
+    g = TrwsGrid(kernel, H, W, L, tol, options)
+    try:
+        g.set_labels(0, proposals, unary, d_min, d_step)
+        g.set_weights(weights)
+        g.finalize()
+        maxiter = 1000 if options is None else options.get("maxiter", 1000)
+        relgap = 0.0 if options is None else options.get("max_relgap", 0.0)
+        e, lb, it = g.minimize(maxiter, relgap)
+        sol = g.labels()
+        trws_grid.last_timing = dict(g.timing)
+        return sol, e, lb, it
+    finally:
+        g.close()
+
+
+def positions_from_labels(H, W, own, gx, gy, dtype=np.float32):
+    """q, qprim (L x E, float64 holding `dtype`-rounded values) from the stored label planes, with the
+    arithmetic of the sweep kernel: q = own[head], qprim = own[tail] + step towards the head."""
+    own = np.asarray(own, dtype=dtype)
+    gx = np.asarray(gx, dtype=dtype)
+    gy = np.asarray(gy, dtype=dtype)
+    ind1, ind2 = construct_neighborhood(H, W)   # tail, head (1-based)
+    t, h = ind1 - 1, ind2 - 1
+    dr = (h % H) - (t % H)      # head row - tail row
+    dc = (h // H) - (t // H)
+    q = own[:, h]
+    step = np.where(dr != 0, gy[:, t] * dr.astype(dtype), gx[:, t] * dc.astype(dtype)).astype(dtype)
+    qprim = (own[:, t] + step).astype(dtype)
+    return q.astype(np.float64), qprim.astype(np.float64)

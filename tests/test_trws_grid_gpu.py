@@ -1,0 +1,158 @@
+"""GPU parity tests of the grid-native TRW-S entry (sb_trws_grid_*) against the
+oracle (the compiled reference where oracle/_ref exists) and against the MATLAB-layout entry.
+
+The reference solver needs q / qprim.  Two ways to get them:
+  * from the exact double planes (synth.trws_problem builds them like dispmap_super.m:180-183):
+    the grid entry rounds own disparity and slopes separately, so positions agree to rounding
+    only -> fp64 instantiation 1e-9, fp32 1e-4 (BASELINE north_star);
+  * from the planes AS STORED on the device (get_label -> positions_from_labels): the oracle then
+    solves the bit-identical problem -> fp64 labels must be exactly equal."""
+import numpy as np
+import pytest
+
+import stereo_b200 as sb
+from stereo_b200 import synth
+from stereo_b200.gridsolver import TrwsGrid, positions_from_labels, trws_grid
+from util import trws_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _grid_solve(pr, H, W, maxiter, relgap=0.0, **kw):
+    return trws_grid(pr["kernel"], pr["unary"], pr["planes"], pr["alphas"], pr["tol"], H, W,
+                     dict(maxiter=maxiter, max_relgap=relgap, **kw))
+
+
+def _stored_problem(g, pr, H, W, dtype):
+    """The problem the device actually holds, in trws() shapes."""
+    L = pr["unary"].shape[0]
+    lab = [g.get_label(l) for l in range(L)]
+    unary = np.stack([x[0] for x in lab])
+    own, gx, gy = (np.stack([x[i] for x in lab]) for i in (1, 2, 3))
+    q, qprim = positions_from_labels(H, W, own, gx, gy, dtype=dtype)
+    out = dict(pr)
+    out.update(unary=unary, q=q, qprim=qprim, alphas=g.get_weights())
+    return out
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("H,W,L,it", [(4, 4, 5, 6), (5, 7, 9, 6), (12, 10, 16, 8), (21, 34, 24, 7), (33, 29, 40, 5),
+                                      (16, 18, 70, 4), (11, 13, 130, 3), (9, 12, 200, 3), (8, 9, 256, 3)])
+def test_f64_bit_identical_problem(H, W, L, it, kernel):
+    pr = synth.trws_problem(H, W, L, seed=H * 100 + W, kernel=kernel)
+    g = TrwsGrid(kernel, H, W, L, pr["tol"], dict(precision="f64"))
+    g.set_labels(0, pr["planes"], pr["unary"])
+    g.set_weights(pr["alphas"])
+    g.finalize()
+    e, lb, n = g.minimize(it, 0.0)
+    sol = g.labels()
+    r = trws_oracle(_stored_problem(g, pr, H, W, np.float64), it)
+    g.close()
+    assert abs(e - r[1]) <= 1e-9 * abs(r[1]) and abs(lb - r[2]) <= 1e-9 * abs(r[2])
+    assert np.array_equal(sol, r[0])
+    if abs(r[1] - r[2]) > 1e-9 * abs(r[1]):
+        assert n == r[3]   # fixed iteration count unless the gap closed to rounding level
+
+
+@pytest.mark.parametrize("precision,rtol,min_equal", [("f32", 1e-4, 0.99), ("f64", 1e-9, 0.999)])
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("H,W,L,it", [(24, 31, 16, 8), (48, 64, 8, 20), (30, 40, 64, 6), (17, 23, 129, 4)])
+def test_against_exact_plane_problem(H, W, L, it, kernel, precision, rtol, min_equal):
+    pr = synth.trws_problem(H, W, L, seed=7 + L, kernel=kernel)
+    sol, e, lb, n = _grid_solve(pr, H, W, it, precision=precision)
+    r = trws_oracle(pr, it)
+    assert abs(e - r[1]) <= rtol * abs(r[1]) and abs(lb - r[2]) <= rtol * abs(r[2])
+    assert np.mean(sol == r[0]) >= min_equal
+    if abs(r[1] - r[2]) > 1e-6 * abs(r[1]):
+        assert n == r[3]
+
+
+@pytest.mark.parametrize("fuse", [True, False])
+def test_fused_rounding_and_relgap_stop(fuse):
+    H, W, L = 30, 30, 24
+    pr = synth.trws_problem(H, W, L, seed=9, kernel=1)
+    pr["alphas"][::7] = 0.0   # typeStereoLinear.h:390-395 shortcut (both terms of a pair: stride 7 hits singles too)
+    sol, e, lb, n = _grid_solve(pr, H, W, 100, 1e-2, fuse_rounding=fuse)
+    r = trws_oracle(pr, 100, 1e-2)
+    assert abs(n - r[3]) <= 1
+    assert abs(e - r[1]) <= 1e-4 * abs(r[1]) and abs(lb - r[2]) <= 1e-4 * abs(r[2])
+
+
+def test_equals_matlab_layout_entry():
+    """Same kernels' arithmetic on the same fp32 positions -> same energies as sb_trws_solve."""
+    H, W, L = 40, 56, 48
+    pr = synth.trws_problem(H, W, L, seed=3, kernel=1)
+    g = TrwsGrid(1, H, W, L, pr["tol"], dict(precision="f32"))
+    g.set_labels(0, pr["planes"], pr["unary"])
+    g.set_weights(pr["alphas"])
+    g.finalize()
+    e, lb, n = g.minimize(10, 0.0)
+    sol = g.labels()
+    st = _stored_problem(g, pr, H, W, np.float32)
+    g.close()
+    sol2, e2, lb2, n2 = sb.trws(1, st["unary"], st["connectivity"], st["q"], st["qprim"], st["alphas"], st["tol"],
+                                dict(maxiter=10, max_relgap=0))
+    assert abs(e - e2) <= 1e-6 * abs(e2) and abs(lb - lb2) <= 1e-6 * abs(lb2)
+    assert np.mean(sol == sol2) >= 0.999
+
+
+def test_device_synth_problem_against_oracle():
+    """The on-device generator (bench.py's big configs) produces a problem the reference solves to the
+    same answer."""
+    H, W, L = 40, 52, 32
+    for kernel in (1, 2):
+        g = TrwsGrid(kernel, H, W, L, 0.02 if kernel == 1 else 0.02 ** 2, dict(precision="f32"))
+        g.synth(0xB200 + 4)
+        g.finalize()
+        e, lb, n = g.minimize(6, 0.0)
+        sol = g.labels()
+        ind1, ind2 = sb.construct_neighborhood(H, W)
+        pr = dict(kernel=kernel, connectivity=np.stack([ind1, ind2]), tol=0.02 if kernel == 1 else 0.02 ** 2,
+                  unary=np.zeros((L, H * W)))
+        st = _stored_problem(g, pr, H, W, np.float32)
+        g.close()
+        r = trws_oracle(st, 6)
+        assert abs(e - r[1]) <= 1e-4 * abs(r[1]) and abs(lb - r[2]) <= 1e-4 * abs(r[2])
+        assert np.mean(sol == r[0]) >= 0.99
+        assert len(np.unique(st["alphas"])) >= 2 and st["unary"].max() <= np.log(2.0) + 1e-6
+
+
+def test_continue_and_reset():
+    H, W, L = 20, 25, 12
+    pr = synth.trws_problem(H, W, L, seed=11, kernel=1)
+    g = TrwsGrid(1, H, W, L, pr["tol"], dict(precision="f64", fuse_rounding=False))
+    g.set_labels(0, pr["planes"][:5], pr["unary"][:5])
+    g.set_labels(5, pr["planes"][5:], pr["unary"][5:])     # labels may arrive in groups
+    g.set_weights(pr["alphas"])
+    g.finalize()
+    a = g.minimize(3, 0.0)
+    b = g.minimize(3, 0.0)     # continues from the current messages (6 iterations in all)
+    g.reset()
+    c = g.minimize(6, 0.0)
+    g.close()
+    assert b[1] >= a[1] - 1e-9 * abs(a[1])
+    assert abs(b[0] - c[0]) <= 1e-9 * abs(c[0]) and abs(b[1] - c[1]) <= 1e-9 * abs(c[1])
+
+
+def test_errors():
+    from stereo_b200._lib import SbError
+    with pytest.raises(SbError, match="Unsupported kernel"):
+        TrwsGrid(3, 8, 8, 4, 0.1)
+    with pytest.raises(SbError):
+        TrwsGrid(1, 3, 9, 4, 0.1)            # degenerate grids go through sb_trws_solve
+    g = TrwsGrid(1, 6, 6, 3, 0.1)
+    pl = np.zeros((3, 4, 36))
+    with pytest.raises(SbError, match="Infinite disparity"):
+        g.set_labels(0, pl, np.zeros((3, 36)))    # c == 0 (dispmap_super.m:321-323)
+    with pytest.raises(SbError, match="finalize"):
+        g.minimize(1, 0.0)
+    g.close()
+
+
+def test_memory_footprint():
+    """45 bytes per label and node (fp32): what makes BASELINE configs 4 / 5 exist."""
+    g = TrwsGrid(1, 64, 96, 64, 0.02)
+    info = g.info()
+    g.close()
+    per = info["hbm_bytes"] / (64 * 96 * 64)
+    assert 45.0 <= per <= 46.5, per

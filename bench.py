@@ -3,30 +3,32 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-Workload (config.workload): BASELINE.json configs[1] -- a 375 x 450 pixel grid (teddy shape),
-64 plane labels, TRW-S simultaneous fusion with the truncated-linear kernel.  The teddy images
-themselves live in the reference tree, which is absent on the GPU box, so the inputs are the
-seeded synthetic plane-proposal problem of stereo_b200/synth.py at that shape
-(dispmap_super.simultaneous_fusion's arrays: unary L x N, q / qprim L x E, alphas E).
+Workload at N = 1 (config.workload): the largest single-GPU TRW-S configuration BASELINE.json names,
+configs[4]'s shape -- a 1980 x 2880 pixel grid (Middlebury shape), 192 plane labels, truncated-linear
+pairwise term -- through the grid-native entry (sb_trws_grid_*: planes in, 45 bytes of HBM per label and
+node).  The inputs are the seeded synthetic plane-proposal problem of SURVEY 8(d), generated ON the
+device (sb_trws_grid_synth): piecewise-planar proposals over rectangular segmentations, every fourth
+proposal fronto-parallel, the last one the per-pixel "current assignment", unary ~ U(0, log 2), weights
+2 x {108, 9}.  Other workloads (--workload) are the remaining BASELINE shapes and small test sizes.
 
-One STEP = one simultaneous_fusion solve: ZeroMessages + ITERS TRW-S iterations
-(iteration = forward sweep + backward sweep + primal rounding/energy, minimize.cpp:31-113)
-on one such problem.  value = sweeps (iterations) per second, whole job.
+One STEP = one simultaneous_fusion solve: ZeroMessages + ITERS TRW-S iterations (iteration = forward
+sweep + backward sweep + primal rounding / energy, minimize.cpp:31-113).  value = iterations per second.
 
-  value : problem resident in HBM (sb_trws_create outside the timed region), per step
-          sb_trws_reset + sb_trws_minimize(ITERS).
-  e2e   : the reference-facing call trws(kernel, unary, connectivity, q, qprim, alphas, tol,
-          options) through the C ABI (sb_trws_solve) from pinned HOST buffers: host->device
-          copies of all inputs, table build, ITERS iterations, labels back -- every step.
-  roofline : the sweep kernel (one launch per pass).  Algorithmic bytes per launch =
-          64*L*N (128*L*N per iteration, two passes), duration = the
-          library's CUDA events around each sweep launch on the solver stream.
-  cpu_baseline : the UNMODIFIED reference (oracle/_ref, trws_mex.cpp compiled against the mex
-          shim) on a centred crop of the same problem, one core (the solver is
-          single-threaded), scaled linearly in the node count to the full grid.
+  value    : problem resident in HBM; per step sb_trws_grid_reset + sb_trws_grid_minimize(ITERS).
+  e2e      : the public call trws_grid(kernel, unary, proposals, weights, tol, H, W, options) with HOST
+             buffers (pinned): every step uploads the L proposals (4 x N doubles each) and unaries, builds
+             the rank tables, runs ITERS iterations and reads the labels back.  N = 1 only.
+  roofline : the sweep kernel (one persistent launch per pass).  Algorithmic bytes per launch = 64*L*N
+             (128*L*N per iteration, two passes); duration = the library's CUDA events around
+             each sweep launch on the solver stream.
+  cpu_baseline / parity : the UNMODIFIED reference (oracle/_ref: trws_mex.cpp compiled against the mex shim)
+             on a centred crop of the SAME synthetic scene, one core (the solver is single threaded), scaled
+             by node count to the full grid; `parity` compares the GPU solve of that crop with it.
 
-N > 1 (torchrun): every rank solves its own problem of the same shape (weak scaling,
-independent fusions, no data-path collective); see DESIGN.md "Multi-GPU".
+N > 1 (torchrun): ONE problem, strong scaling -- the image rows are split into N bands, every rank holds
+and sweeps its own band, boundary messages are pushed into the neighbour's HBM over NVLink; `parity`
+then compares the banded run with the single-GPU run of the same problem (labels, energy, bound).
+--mode independent keeps the old "one fusion per GPU" weak-scaling run.
 """
 from __future__ import annotations
 
@@ -45,15 +47,26 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 WORKLOADS = {
-    # name: (H, W, L, kernel, iterations per step, cpu crop (h, w), cpu iterations)
-    "cfg2_teddy_375x450_L64_trws_linear": (375, 450, 64, 1, 20, (96, 128), 3),
-    "cfg2q_teddy_375x450_L64_trws_quadratic": (375, 450, 64, 2, 20, (96, 128), 3),
-    "small_96x128_L16_trws_linear": (96, 128, 16, 1, 10, (48, 64), 3),
-    "large_1080x1920_L128_trws_linear": (1080, 1920, 128, 1, 5, (64, 96), 2),
+    # H, W, L, kernel, TRW-S iterations per step, CPU crop (h, w), CPU iterations, min GPUs
+    "cfg5_1980x2880_L192_trws_linear": dict(H=1980, W=2880, L=192, kernel=1, iters=20, crop=(48, 64), cpu_iters=2),
+    "grid_2048x4096_L256_trws_linear": dict(H=2048, W=4096, L=256, kernel=1, iters=10, crop=(40, 56), cpu_iters=2),
+    "cfg4_4096x4096_L256_trws_linear": dict(H=4096, W=4096, L=256, kernel=1, iters=5, crop=(40, 56), cpu_iters=2, min_gpus=2),
+    "cfg4q_4096x4096_L256_trws_quadratic": dict(H=4096, W=4096, L=256, kernel=2, iters=5, crop=(40, 56), cpu_iters=2, min_gpus=2),
+    "large_1080x1920_L128_trws_linear": dict(H=1080, W=1920, L=128, kernel=1, iters=10, crop=(64, 96), cpu_iters=2),
+    "large_1080x1920_L128_trws_quadratic": dict(H=1080, W=1920, L=128, kernel=2, iters=10, crop=(64, 96), cpu_iters=2),
+    "cfg2_teddy_375x450_L64_trws_linear": dict(H=375, W=450, L=64, kernel=1, iters=20, crop=(96, 128), cpu_iters=3),
+    "cfg2q_teddy_375x450_L64_trws_quadratic": dict(H=375, W=450, L=64, kernel=2, iters=20, crop=(96, 128), cpu_iters=3),
+    "small_96x128_L16_trws_linear": dict(H=96, W=128, L=16, kernel=1, iters=10, crop=(32, 48), cpu_iters=3),
 }
-DEFAULT_WORKLOAD = "cfg2_teddy_375x450_L64_trws_linear"
+DEFAULT_WORKLOAD = "cfg5_1980x2880_L192_trws_linear"
 METRIC = "fusion_move_sweeps_per_sec"
 UNIT = "sweeps/s"
+SEED = 0xB200 + 5
+PARITY_ITERS = 2
+
+
+def tol_of(kernel):
+    return 0.02 if kernel == 1 else 0.02 ** 2
 
 
 def peaks():
@@ -119,25 +132,6 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def crop_problem(pr, H, W, h, w):
-    """Centred h x w crop of a trws problem (same labels): the CPU-baseline sample."""
-    from stereo_b200.grid import construct_neighborhood
-    r0, c0 = (H - h) // 2, (W - w) // 2
-    rr, cc = np.meshgrid(np.arange(r0, r0 + h), np.arange(c0, c0 + w), indexing="ij")
-    node_full = (rr + H * cc)  # (h, w) full-grid node ids
-    i1, i2 = construct_neighborhood(h, w)
-    # map crop node (1-based, column-major in the crop) -> full node
-    lut = node_full.T.reshape(-1)
-    f1, f2 = lut[i1 - 1], lut[i2 - 1]
-    # full-grid term index of (f1 -> f2)
-    fi1, fi2 = pr["connectivity"] - 1
-    key = fi1.astype(np.int64) * (H * W) + fi2
-    order = np.argsort(key)
-    pos = order[np.searchsorted(key[order], f1.astype(np.int64) * (H * W) + f2)]
-    return dict(kernel=pr["kernel"], unary=pr["unary"][:, lut], connectivity=np.stack([i1, i2]),
-                q=pr["q"][:, pos], qprim=pr["qprim"][:, pos], alphas=pr["alphas"][pos], tol=pr["tol"])
-
-
 class quiet_stdout:
     """The reference prints progress with printf (ordering.cpp:21,154); keep fd 1 clean for the JSON line."""
 
@@ -153,8 +147,27 @@ class quiet_stdout:
         os.close(self.null)
 
 
+# ---------------------------------------------------------------------------- CPU reference on a crop
+def crop_offset(H, W, h, w):
+    return (H - h) // 2, (W - w) // 2
+
+
+def crop_problem_np(wl, seed):
+    """The centred crop of the synthetic scene in trws() shapes, generated on the host (no GPU code)."""
+    from stereo_b200 import synth
+    from stereo_b200.grid import construct_neighborhood
+    from stereo_b200.gridsolver import positions_from_labels
+    h, w = wl["crop"]
+    una, own, gx, gy, alphas = synth.grid_synth_np(seed, h, w, wl["L"], wl["kernel"], scene=(wl["H"], wl["W"]),
+                                                   offset=crop_offset(wl["H"], wl["W"], h, w))
+    q, qp = positions_from_labels(h, w, own, gx, gy, dtype=np.float32)
+    i1, i2 = construct_neighborhood(h, w)
+    return dict(kernel=wl["kernel"], unary=una, connectivity=np.stack([i1, i2]), q=q, qprim=qp, alphas=alphas,
+                tol=tol_of(wl["kernel"]))
+
+
 def _cpu_solve(args):
-    """One reference (or port) solve on a crop; returns (seconds per iteration, setup seconds)."""
+    """One reference (or port) solve on a crop: (seconds per iteration, setup seconds, result of the long solve)."""
     pr, iters, kind = args
     from oracle import oracle
     conn0 = (pr["connectivity"] - 1).T
@@ -162,54 +175,56 @@ def _cpu_solve(args):
     t0 = time.perf_counter()
     oracle.trws_solve(pr["kernel"], una, conn0, q, qp, pr["alphas"], pr["tol"], 1, 0.0, kind=kind)
     t1 = time.perf_counter()
-    oracle.trws_solve(pr["kernel"], una, conn0, q, qp, pr["alphas"], pr["tol"], 1 + iters, 0.0, kind=kind)
+    res = oracle.trws_solve(pr["kernel"], una, conn0, q, qp, pr["alphas"], pr["tol"], 1 + iters, 0.0, kind=kind)
     t2 = time.perf_counter()
     per_iter = max(((t2 - t1) - (t1 - t0)) / iters, 1e-9)
     setup = max((t1 - t0) - per_iter, 0.0)
-    return per_iter, setup
+    return per_iter, setup, res
 
 
-def cpu_baseline(pr, H, W, crop, iters, procs=1):
-    """Times the reference's CPU path on a centred crop.  value = sweeps/s at the FULL grid size,
-    assuming time per iteration linear in the node count (it is: O(N L) per sweep)."""
+def cpu_reference(pr, wl, procs):
+    """Times the reference's CPU path on the crop, `procs` identical solves at once (the solver is single
+    threaded).  Returns per-iteration seconds (mean over the processes), setup seconds, one result."""
     from oracle import oracle
     kind = "reference" if oracle.have_ref("trws") else "port"
-    h, w = crop
-    cp = crop_problem(pr, H, W, h, w)
     with quiet_stdout():
         if procs <= 1:
-            res = [_cpu_solve((cp, iters, kind))]
+            res = [_cpu_solve((pr, wl["cpu_iters"], kind))]
         else:
             import multiprocessing as mp
             with mp.get_context("fork").Pool(procs) as pool:
-                res = pool.map(_cpu_solve, [(cp, iters, kind)] * procs)
-    per_iter = float(np.mean([r[0] for r in res]))
-    setup = float(np.mean([r[1] for r in res]))
-    scale = (H * W) / float(h * w)
-    value = procs / (per_iter * scale)
-    return {"value": value, "unit": UNIT, "cores": procs, "kind": kind,
-            "sample": (f"{procs} x centred {h}x{w} crop of the {H}x{W} problem, same L, {iters} timed TRW-S iterations "
-                       f"each ({per_iter * 1e3:.1f} ms/iteration on the crop, setup {setup:.2f} s excluded), "
-                       f"scaled by node count x{scale:.2f} to the full grid"),
+                res = pool.map(_cpu_solve, [(pr, wl["cpu_iters"], kind)] * procs)
+    return float(np.mean([r[0] for r in res])), float(np.mean([r[1] for r in res])), res[0][2], kind
+
+
+def baseline_record(wl, per_iter, setup, procs, kind):
+    h, w = wl["crop"]
+    scale = (wl["H"] * wl["W"]) / float(h * w)
+    return {"value": procs / (per_iter * scale), "unit": UNIT, "cores": procs, "kind": kind,
+            "sample": (f"{procs} x centred {h}x{w} crop of the {wl['H']}x{wl['W']} scene, same {wl['L']} labels, "
+                       f"{wl['cpu_iters']} timed TRW-S iterations each ({per_iter * 1e3:.1f} ms/iteration on the crop; graph "
+                       f"build + per-edge sort {setup:.2f} s reported separately, excluded), EXTRAPOLATED by node count "
+                       f"x{scale:.1f} to the full grid (the reference needs (32 L + 90) B per term: the full problem does "
+                       f"not fit a host)"),
+            "ms_per_iteration_crop": per_iter * 1e3, "setup_s_crop": setup,
+            "ns_per_node_iteration": per_iter / (h * w) * 1e9,
             "ms_per_iteration_full_grid_extrapolated": per_iter * scale * 1e3}
 
 
+# ---------------------------------------------------------------------------- side measurements
 def extras():
-    """Side measurements of the other kernels of the hot path at BASELINE configs[2]'s shape
-    (1080 x 1920): one QPBO binary fusion and the 128-level 9x9 NCC volume, both through the
-    public host-buffer calls (copies included), next to the reference / NumPy restatement on one core.
-    Reported for context; the headline metric stays the TRW-S sweep rate."""
+    """QPBO binary fusion and the NCC volume at BASELINE configs[2]'s shape (1080 x 1920) through the public
+    host-buffer calls, next to the reference / NumPy restatement on one core.  Context only."""
     import ctypes
+    import torch
     import stereo_b200 as sb
     from stereo_b200 import builders, synth
     out = {}
     H, W = 1080, 1920
-    # ---- QPBO fusion (rd.m -> sb_rd_solve)
-    import torch
     rp = synth.rd_problem(H, W, seed=0xB203, mode="stereo")
     keep = []
 
-    def pin(x):   # same protocol as the TRW-S e2e arm: inputs start in pinned host memory
+    def pin(x):
         t = torch.empty(x.size, dtype=torch.float64, pin_memory=True)
         v = t.numpy()
         v[...] = x.reshape(-1)
@@ -234,10 +249,9 @@ def extras():
                                                    (rp["connectivity"] - 1).T)
             q["reference_ms_per_fusion_1core"] = (time.perf_counter() - t0) * 1e3
             q["labels_identical_to_reference"] = bool(np.array_equal(rl, lab))
-    except Exception as ex:  # the oracle is optional here
+    except Exception as ex:
         q["reference_error"] = str(ex)[:100]
     out["qpbo_fusion"] = q
-    # ---- NCC volume (dispmap_ncc.compute_ncc -> sb_ncc_volume), 128 levels, 9x9x3 window
     im0, im1, _ = synth.stereo_pair(H, W, 127, seed=0xB203)
     d = np.arange(128, dtype=np.float64)
     builders.ncc_volume(im0, im1, d[:4], 4)
@@ -269,40 +283,56 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the QPBO / NCC side measurements (N = 1 only)")
-    ap.add_argument("--mode", default="independent", choices=["independent", "banded"],
-                    help="N > 1: independent fusions, one per GPU (weak scaling, default) or ONE problem swept "
-                         "row-banded across the GPUs with NVLink mailbox halos (strong scaling)")
+    ap.add_argument("--mode", default="banded", choices=["banded", "independent"],
+                    help="N > 1: ONE problem swept row-banded across the GPUs (strong scaling, default) or one "
+                         "independent fusion per GPU (weak scaling)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    H, W, L, kernel, iters, crop, cpu_iters = WORKLOADS[args.workload]
+    wl = WORKLOADS[args.workload]
+    H, W, L, kernel, iters = wl["H"], wl["W"], wl["L"], wl["kernel"], wl["iters"]
     N = H * W
-    config = {"workload": args.workload, "grid": [H, W], "labels": L, "kernel": "truncated_linear" if kernel == 1
-              else "truncated_quadratic", "trws_iterations_per_step": iters,
-              "l2": "working set (messages + positions + tables) exceeds the 126 MB L2; no explicit flush",
-              "parallelism": f"{world} independent fusions (one per GPU)" if world > 1 else "1 GPU"}
+    E = 2 * ((H - 1) * W + H * (W - 1))
+    banded = world > 1 and args.mode == "banded"
+    config = {"workload": args.workload, "grid": [H, W], "labels": L,
+              "kernel": "truncated_linear" if kernel == 1 else "truncated_quadratic", "trws_iterations_per_step": iters,
+              "entry": "sb_trws_grid_* (plane-native, 45 B of HBM per label and node)",
+              "l2": "working set (tens of GB) exceeds the 126 MB L2; no explicit flush",
+              "parallelism": "1 GPU" if world == 1 else (
+                  f"one problem, {world} row bands, static data sharded, boundary messages pushed over NVLink into the "
+                  f"neighbour's HBM (sign-tagged words), one NCCL all-reduce of (energy, bound) per pass" if banded
+                  else f"{world} independent fusions (one per GPU)")}
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
         if rank != 0:
             return 0
-        from stereo_b200 import synth
-        pr = synth.trws_problem(H, W, L, seed=0xB200 + 2, kernel=kernel)
         procs = max(1, min(os.cpu_count() or 1, 64))
-        for _ in range(max(0, min(args.warmup, 1))):
-            cpu_baseline(pr, H, W, (32, 48), 1, 1)
-        t0 = time.perf_counter()
-        vals = []
-        for _ in range(max(1, min(args.steps, 3))):
-            vals.append(cpu_baseline(pr, H, W, crop, cpu_iters, procs))
-        dt = time.perf_counter() - t0
-        cb = vals[-1]
-        cb["value"] = float(np.mean([v["value"] for v in vals]))
+        pr = crop_problem_np(wl, SEED)
+        budget_s = 170.0
+        t_all = time.perf_counter()
+        rounds = []
+        want = max(1, args.steps)
+        for i in range(max(0, min(args.warmup, 1)) + want):
+            t0 = time.perf_counter()
+            per_iter, setup, _, kind = cpu_reference(pr, wl, procs)
+            dt = time.perf_counter() - t0
+            if i >= min(args.warmup, 1):
+                rounds.append((per_iter, setup, dt))
+            if time.perf_counter() - t_all + dt > budget_s and rounds:
+                break     # bounded run: report the steps actually timed
+        per_iter = float(np.mean([r[0] for r in rounds]))
+        setup = float(np.mean([r[1] for r in rounds]))
+        cb = baseline_record(wl, per_iter, setup, procs, kind)
+        cb["one_core_value"] = cb["value"] / procs
+        cb["note"] = ("value = all-core throughput (one single-threaded reference solve per core, the only parallelism "
+                      "the reference has); one_core_value = the same per core, measured under that load")
         out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-               "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / len(vals),
-               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "steps": len(rounds), "steps_requested": args.steps, "warmup": min(args.warmup, 1),
+               "ms_per_step": float(np.mean([r[2] for r in rounds])) * 1e3,
+               "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic", "config": config, "cpu_baseline": cb,
                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "gpu_launches": 0}
@@ -312,11 +342,14 @@ def main():
     # ------------------------------------------------------------------ our arm
     import torch
     import torch.distributed as dist
-    import stereo_b200 as sb
-    from stereo_b200 import _lib, synth, solvers
+    import stereo_b200 as sb  # noqa: F401
+    from stereo_b200 import _lib
+    from stereo_b200.gridsolver import TrwsGrid, positions_from_labels, trws_grid
 
     if not torch.cuda.is_available() or _lib.lib().sb_device_count() == 0:
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    if wl.get("min_gpus", 1) > world:
+        raise SystemExit(f"bench.py: workload {args.workload} needs at least {wl['min_gpus']} GPUs (its state does not fit one)")
     torch.cuda.set_device(local_rank)
     _lib.check(_lib.lib().sb_set_device(local_rank))
     if world > 1:
@@ -327,36 +360,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    banded = args.mode == "banded" and world > 1
-    pr = synth.trws_problem(H, W, L, seed=0xB200 + 2 + (0 if banded else rank), kernel=kernel)
-    E = pr["connectivity"].shape[1]
-    if banded:
-        config["parallelism"] = f"one problem, {world} row bands, boundary messages pushed over NVLink (mailboxes)"
-
-    # pinned host copies of the inputs (MATLAB layout) for the e2e arm
-    def pinned(a):
-        a = np.asfortranarray(a, dtype=np.float64)
-        t = torch.empty(a.size, dtype=torch.float64, pin_memory=True)
-        v = t.numpy().reshape(a.shape, order="F")
-        v[...] = a
-        return t, v
-    keep = []
-    hp = {}
-    for k in ("unary", "q", "qprim", "alphas"):
-        t, v = pinned(pr[k])
-        keep.append(t)
-        hp[k] = v
-    h2d_bytes = sum(hp[k].nbytes for k in hp) + E * 2 * 4
-    d2h_bytes = N * 8 + 3 * 8
-
-    # ---- resident arm
-    if banded:
-        from stereo_b200.multigpu import TrwsBandedSolver
-        solver = TrwsBandedSolver(kernel, hp["unary"], pr["connectivity"], hp["q"], hp["qprim"], hp["alphas"], pr["tol"])
-        solver.timing = {"sweep_kernel_ms": 0.0, "sweep_kernel_launches": 0}
-    else:
-        solver = sb.TrwsSolver(kernel, hp["unary"], pr["connectivity"], hp["q"], hp["qprim"], hp["alphas"], pr["tol"])
     lib = _lib.lib()
+    tol = tol_of(kernel)
+    t_setup0 = time.perf_counter()
+    if banded:
+        solver = TrwsGrid(kernel, H, W, L, tol, group=dist.group.WORLD)
+        solver.synth(SEED)
+    else:
+        solver = TrwsGrid(kernel, H, W, L, tol)
+        solver.synth(SEED + (rank if world > 1 else 0))
+    solver.finalize()
+    setup_s = time.perf_counter() - t_setup0
+    info = solver.info()
 
     def step_resident():
         solver.reset()
@@ -368,47 +383,95 @@ def main():
     barrier()
     sampler.start()
     launches0 = lib.sb_kernel_launches()
+    k0 = solver.counters()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k_ms, k_n, sweeps = 0.0, 0, 0.0
+    sweeps = 0.0
     torch.cuda.synchronize()
     ev0.record()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        e, lb, it = step_resident()
+        e_last, lb_last, it = step_resident()
         sweeps += it
-        k_ms += solver.timing["sweep_kernel_ms"]
-        k_n += solver.timing["sweep_kernel_launches"]
     ev1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     dev_ms = ev0.elapsed_time(ev1)
+    k1 = solver.counters()
     launches = lib.sb_kernel_launches() - launches0
     clocks = sampler.stop()
     barrier()
-    # the library launches on the legacy default stream, which torch's events on its current
-    # (default) stream bracket; take the larger of device and wall time to be safe
+    # the library launches on the legacy default stream, which torch's events on its current (default) stream
+    # bracket; take the larger of device and wall time to be safe
     t_ms = max(dev_ms, wall * 1e3)
-    tt = torch.tensor([t_ms, sweeps], dtype=torch.float64, device="cuda")
+    k_ms, k_n = k1[0] - k0[0], k1[1] - k0[1]
+    tt = torch.tensor([t_ms, sweeps, k_ms / max(k_n, 1)], dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = tt.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = tt.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        t_ms, sweeps_all = float(tmax[0]), float(tsum[1])
-        if banded:
-            sweeps_all = sweeps          # every rank counted the same sweeps of the one shared problem
+        t_ms = float(tmax[0])
+        sweeps_all = sweeps if banded else float(tsum[1])
+        avg_kernel_ms = float(tmax[2])
+        hbm = torch.tensor([float(info["hbm_bytes"])], dtype=torch.float64, device="cuda")
+        dist.all_reduce(hbm, op=dist.ReduceOp.MAX)
+        hbm_max = float(hbm[0])
     else:
-        sweeps_all = sweeps
+        sweeps_all, avg_kernel_ms, hbm_max = sweeps, k_ms / max(k_n, 1), float(info["hbm_bytes"])
     value = sweeps_all / (t_ms * 1e-3)
 
-    # ---- e2e arm: the public call, host buffers in, labels out
+    # ---- N > 1: the banded run against the single-GPU run of the same problem
+    parity = None
+    if banded:
+        solver.reset()
+        be, blb, _ = solver.minimize(PARITY_ITERS, 0.0)
+        blab = solver.labels()
+        if rank == 0:
+            if wl.get("min_gpus", 1) > 1:
+                parity = {"against": None, "note": "the problem does not fit one GPU; see the smaller workloads' parity"}
+            else:
+                one = TrwsGrid(kernel, H, W, L, tol)
+                one.synth(SEED)
+                one.finalize()
+                oe, olb, _ = one.minimize(PARITY_ITERS, 0.0)
+                olab = one.labels()
+                one.close()
+                parity = {"against": "single-GPU sweep of the same problem (same entry, world = 1)", "iterations": PARITY_ITERS,
+                          "energy": be, "energy_single_gpu": oe, "lower_bound": blb, "lower_bound_single_gpu": olb,
+                          "energy_rel_diff": abs(be - oe) / abs(oe), "lower_bound_rel_diff": abs(blb - olb) / abs(olb),
+                          "labels_equal_fraction": float(np.mean(blab == olab))}
+        barrier()
+
+    solver.close()
+    del solver
+
+    # ---- e2e arm (N = 1): the public call, host buffers in, labels out
     e2e = None
-    if not args.no_e2e and not banded:
+    if not args.no_e2e and world == 1:
+        # host copies of the problem in the reference-facing shapes: L proposals of 4 x N doubles, unary L x N
+        src = TrwsGrid(kernel, H, W, L, tol)
+        src.synth(SEED)
+        pl = np.empty((L, N, 4), dtype=np.float64)
+        un = np.empty((L, N), dtype=np.float64)
+        # page-lock the buffers in place (torch's pinned allocator would round 35 GB up to 64 GB)
+        rt = torch.cuda.cudart()
+        pinned = all(int(rt.cudaHostRegister(a.ctypes.data, a.nbytes, 0)) == 0 for a in (pl, un))
+        cc = np.repeat(np.arange(1, W + 1, dtype=np.float64), H)      # x = column, MATLAB node order
+        rr = np.tile(np.arange(1, H + 1, dtype=np.float64), W)        # y = row
+        for l in range(L):
+            u_, own, gx, gy = src.get_label(l)
+            un[l] = u_
+            pl[l, :, 0] = -gx
+            pl[l, :, 1] = -gy
+            pl[l, :, 2] = 1.0
+            pl[l, :, 3] = -(own - gx * cc - gy * rr)
+        alphas = src.get_weights()
+        src.close()
+        planes_view = pl.transpose(0, 2, 1)     # L x 4 x N view of the (L, N, 4) buffer: no copy in set_labels
         opts = dict(maxiter=iters, max_relgap=0.0)
 
         def step_e2e():
-            return sb.trws(kernel, hp["unary"], pr["connectivity"], hp["q"], hp["qprim"], hp["alphas"], pr["tol"], opts)
-        step_e2e()
+            return trws_grid(kernel, un, planes_view, alphas, tol, H, W, opts)
         step_e2e()
         barrier()
         t0 = time.perf_counter()
@@ -418,22 +481,24 @@ def main():
         for _ in range(n_e2e):
             sol, e, lb, it = step_e2e()
             sw += it
-            lib_setup += solvers.last_timing.get("setup_ms", 0.0)
-            lib_solve += solvers.last_timing.get("solve_ms", 0.0)
+            lib_setup += trws_grid.last_timing.get("setup_ms", 0.0)
+            lib_solve += trws_grid.last_timing.get("solve_ms", 0.0)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        tt = torch.tensor([dt, sw], dtype=torch.float64, device="cuda")
-        if world > 1:
-            tmax = tt.clone()
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            tsum = tt.clone()
-            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-            dt, sw = float(tmax[0]), float(tsum[1])
-        e2e = {"value": sw / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
-               "ms_per_step": dt * 1e3 / n_e2e, "steps": n_e2e,
+        e2e = {"value": sw / dt, "unit": UNIT, "h2d_bytes_per_step": int(pl.nbytes + un.nbytes + alphas.nbytes),
+               "d2h_bytes_per_step": int(N * 8 + 3 * 8), "ms_per_step": dt * 1e3 / n_e2e, "steps": n_e2e,
+               "host_buffers": "pinned" if pinned else "pageable (pinned allocation failed)",
                "lib_setup_ms_per_step": lib_setup / n_e2e, "lib_solve_ms_per_step": lib_solve / n_e2e,
-               "api": "stereo_b200.trws(kernel, unary, connectivity, q, qprim, alphas, tol, options) -> sb_trws_solve"}
+               "api": "stereo_b200.trws_grid(kernel, unary, proposals, weights, tol, H, W, options) -> sb_trws_grid_create / "
+                      "set_labels / set_weights / finalize / minimize / get_labels"}
+        if pinned:
+            for a in (pl, un):
+                rt.cudaHostUnregister(a.ctypes.data)
+        del pl, un
         barrier()
+    elif world > 1:
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "note": "the host-buffer arm is measured at N = 1 (every rank would need the whole problem on the host)"}
 
     if rank != 0:
         if world > 1:
@@ -441,8 +506,7 @@ def main():
         return 0
 
     peak, peak_src = peaks()
-    algo_bytes = 64.0 * L * N                      # per sweep-kernel launch (one pass)
-    avg_kernel_ms = k_ms / max(k_n, 1) if k_n else (t_ms / max(sweeps, 1)) / 2.0
+    algo_bytes = 64.0 * L * N                      # per pass = per sweep launch (all ranks together)
     achieved = algo_bytes / (avg_kernel_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -451,25 +515,51 @@ def main():
             traffic = json.load(open(tp)).get(args.workload)
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "sb::trws::sweep_kernel (one launch per pass)",
-                "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": avg_kernel_ms,
-                "launches_timed": int(k_n), "peak_source": peak_src,
-                "kernel_share_of_step": k_ms / t_ms if world == 1 else None,
-                "note": "64*L*N bytes per pass (SURVEY 8(d)); this build streams q/q' and rank tables "
-                        "(+40*L*N bytes per pass actually requested)"}
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
+                "traffic": traffic, "kernel": "sb::gtrws::gsweep_kernel (one persistent launch per pass and rank)",
+                "algorithmic_bytes_per_launch": algo_bytes / world, "avg_launch_ms": avg_kernel_ms,
+                "launches_timed": int(k_n), "peak_source": peak_src + (f" x {world} GPUs" if world > 1 else ""),
+                "kernel_share_of_step": k_ms / t_ms,
+                "note": "64*L*N bytes per pass (SURVEY 8(d)); positions are recomputed from 3 plane rows per node, rank / "
+                        "merge-count bytes add 8*L*N per pass"}
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps, "ms_per_sweep": t_ms / max(sweeps, 1),
            "higher_is_better": True, "scaling": "strong" if banded else "weak", "vs_baseline": None, "dtype": "f32",
-           "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline}
+           "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
+           "hbm_bytes_per_rank_max": hbm_max, "setup_s": setup_s,
+           "result": {"energy": e_last, "lower_bound": lb_last}}
     if e2e:
         out["e2e"] = e2e
+    if parity is not None:
+        out["parity"] = parity
+    if world == 1 and not args.no_cpu_baseline:
+        # the reference on the centred crop of the same scene, and the GPU solve of that crop against it
+        h, w = wl["crop"]
+        g = TrwsGrid(kernel, h, w, L, tol)
+        g.synth(SEED, scene=(H, W), offset=crop_offset(H, W, h, w))
+        g.finalize()
+        its = 1 + wl["cpu_iters"]
+        ge, glb, _ = g.minimize(its, 0.0)
+        glab = g.labels()
+        lab = [g.get_label(l) for l in range(L)]
+        from stereo_b200.grid import construct_neighborhood
+        q, qp = positions_from_labels(h, w, np.stack([x[1] for x in lab]), np.stack([x[2] for x in lab]),
+                                      np.stack([x[3] for x in lab]), dtype=np.float32)
+        i1, i2 = construct_neighborhood(h, w)
+        pr = dict(kernel=kernel, unary=np.stack([x[0] for x in lab]), connectivity=np.stack([i1, i2]), q=q, qprim=qp,
+                  alphas=g.get_weights(), tol=tol)
+        g.close()
+        per_iter, setup, res, kind = cpu_reference(pr, wl, 1)
+        out["cpu_baseline"] = baseline_record(wl, per_iter, setup, 1, kind)
+        out["parity"] = {"against": f"{kind} CPU solver on the crop the cpu_baseline leg times ({h}x{w}x{L}, {its} iterations, "
+                                    f"bit-identical fp32 inputs read back from the device)",
+                         "energy": ge, "energy_reference": res[1], "lower_bound": glb, "lower_bound_reference": res[2],
+                         "energy_rel_diff": abs(ge - res[1]) / abs(res[1]), "lower_bound_rel_diff": abs(glb - res[2]) / abs(res[2]),
+                         "labels_equal_fraction": float(np.mean(glab == res[0])), "tolerance": "1e-4 relative (north_star, fp32)"}
+    elif world == 1:
+        out["cpu_baseline"] = None
     if not args.no_extras and world == 1:
         out["extras"] = extras()
-    if not args.no_cpu_baseline and world == 1:
-        out["cpu_baseline"] = cpu_baseline(pr, H, W, crop, cpu_iters, 1)
-    elif not args.no_cpu_baseline:
-        out["cpu_baseline"] = None
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -210,6 +210,9 @@ SB_API int sb_trws_grid_set_labels(sb_trws_grid *g, int l0, int nl, const double
                             double d_min, double d_step);
 SB_API int sb_trws_grid_set_weights(sb_trws_grid *g, const double *alphas);
 SB_API int sb_trws_grid_synth(sb_trws_grid *g, uint64_t seed);
+/* the same generator, the solver's grid being the window at (r_off, c_off) of a scene_H x scene_W scene
+ * (bench.py: the crop of the full-size problem that the CPU reference is timed on) */
+SB_API int sb_trws_grid_synth_window(sb_trws_grid *g, uint64_t seed, int scene_H, int scene_W, int r_off, int c_off);
 SB_API int sb_trws_grid_finalize(sb_trws_grid *g);
 SB_API int sb_trws_grid_get_label(sb_trws_grid *g, int l, double *out /* 4 x N */);
 SB_API int sb_trws_grid_get_weights(sb_trws_grid *g, double *alphas /* E */);
@@ -221,6 +224,9 @@ SB_API int sb_trws_grid_ipc_export(sb_trws_grid *g, unsigned char *handles /* 12
 SB_API int sb_trws_grid_ipc_attach(sb_trws_grid *g, const unsigned char *up, const unsigned char *down);
 SB_API int sb_trws_grid_pass(sb_trws_grid *g, int pass, int mode, double *acc /* 2 */);
 SB_API int sb_trws_grid_info(sb_trws_grid *g, int64_t *info /* 8 */);
+/* cumulative since creation: out[0] = ms spent in sweep kernels (CUDA events around every launch on the solver
+ * stream), out[1] = sweep launches, out[2] = set-up ms (uploads, table build) */
+SB_API int sb_trws_grid_counters(sb_trws_grid *g, double *out /* 3 */);
 SB_API void sb_trws_grid_destroy(sb_trws_grid *g);
 /* Host-only: per pass (forward, backward) six values: strips, segments, node steps, nodes, nodes that
  * need two steps, (messages pushed to rank - 1) * 1e6 + (messages pushed to rank + 1).  12 values. */

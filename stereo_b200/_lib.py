@@ -80,6 +80,7 @@ def lib():
         L.sb_trws_grid_set_labels.argtypes = [vp, c_int, c_int, _dp, _dp, c_double, c_double]
         L.sb_trws_grid_set_weights.argtypes = [vp, _dp]
         L.sb_trws_grid_synth.argtypes = [vp, ctypes.c_uint64]
+        L.sb_trws_grid_synth_window.argtypes = [vp, ctypes.c_uint64, c_int, c_int, c_int, c_int]
         L.sb_trws_grid_finalize.argtypes = [vp]
         L.sb_trws_grid_get_label.argtypes = [vp, c_int, _dp]
         L.sb_trws_grid_get_weights.argtypes = [vp, _dp]
@@ -90,6 +91,7 @@ def lib():
         L.sb_trws_grid_ipc_attach.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p]
         L.sb_trws_grid_pass.argtypes = [vp, c_int, c_int, _dp]
         L.sb_trws_grid_info.argtypes = [vp, POINTER(c_int64)]
+        L.sb_trws_grid_counters.argtypes = [vp, _dp]
         L.sb_trws_grid_destroy.argtypes = [vp]
         L.sb_trws_grid_destroy.restype = None
         L.sb_trws_grid_plan_stats.argtypes = [c_int, c_int, c_int, c_int, POINTER(c_int64)]

@@ -74,6 +74,7 @@ struct GProblem {
     int mode;
     long long *prof;                   // optional cycle counters
     int prof_warp;                     // term warp they are taken on
+    int gate;                          // > 1: every `gate` steps a strip waits until its upstream strip is `gate` nodes ahead
     int *rec;                          // SB_TRWS_RECORD: host-mapped flight recorder [cta][5 warps][4], else null
 };
 
@@ -654,6 +655,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
                 const int par = node & 1;
                 StepGeo g;
                 wk.get(g);
+                const int wk_i = wk.i, wk_n = wk.n, wk_du = wk.du;
                 if (node + 1 < n_steps) wk.advance();
                 record(fs, node, 11, st);
                 mbar_wait(bar_full + st, ph);
@@ -667,6 +669,25 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
                     mbar_wait(bar_free + (int)(g2 % NS), (unsigned)((g2 / NS) & 1));
                 }
                 tick(1);
+                // Slack gate.  A strip's step waits for its upstream strip's step, which waits for ITS upstream's ...:
+                // with every hand-over taken at the last moment, the jitter of all strips above accumulates (a
+                // last-passage lattice).  Every `gate` steps this strip therefore waits until the upstream strip is
+                // `gate` nodes ahead, so that the polls of the steps in between succeed at once.
+                if (p.gate > 1 && do_send && !g.flags && (wk_i % p.gate) == 0 && wk_i + p.gate - 1 < wk_n) {
+                    const long long ua = (long long)g.u + (long long)(p.gate - 1) * wk_du;
+                    for (int d = 0; d < 4; d++) {
+                        if (role_of(g.roles, d) != ROLE_POLL) continue;
+                        const REAL *mrow = p.msg + pair_of(ua, d, W) * 2 * LP + lane * K;
+                        for (;;) {
+                            REAL a0[1], a1[1];
+                            if (p.world > 1) { ld_words<REAL, 1, true>(a0, mrow); ld_words<REAL, 1, true>(a1, mrow + LP); }
+                            else { ld_words<REAL, 1, false>(a0, mrow); ld_words<REAL, 1, false>(a1, mrow + LP); }
+                            if (__all_sync(0xffffffffu, Tag<REAL>::ok(a0[0], tag) && Tag<REAL>::ok(a1[0], tag))) break;
+                            __nanosleep(100);
+                        }
+                    }
+                }
+                tick(6);
                 if (!(g.flags & GF_SECOND)) {
                     const unsigned char *sp = stage_ptr(st);
                     const REAL *NF = reinterpret_cast<const REAL *>(sp + SL::OFF_NF);

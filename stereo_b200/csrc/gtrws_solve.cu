@@ -222,15 +222,18 @@ __device__ __forceinline__ unsigned hash3(unsigned seed, unsigned a, unsigned b,
 __device__ __forceinline__ float u01(unsigned h) { return (float)(h >> 8) * (1.0f / 16777216.0f); }
 
 template <typename REAL>
-__global__ void gsynth_kernel(unsigned seed, int kern, int H, int W, int L, int r_base, int rows, int LP, REAL *__restrict__ nodeF,
-                              REAL *__restrict__ alpha)
+__global__ void gsynth_kernel(unsigned seed, int kern, int Hs, int Ws, int r_off, int c_off, int Wloc, int L, int r_base, int rows, int LP,
+                              REAL *__restrict__ nodeF, REAL *__restrict__ alpha)
 {
+    // (Hs, Ws): the grid the synthetic scene is defined on; the solver's own grid is the window of it that
+    // starts at (r_off, c_off) (the whole of it for the real run, a crop for the CPU-baseline sample)
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long Nloc = (long long)rows * W;
+    const long long Nloc = (long long)rows * Wloc;
     if (t >= Nloc * L) return;
     const int l = (int)(t % L);
     const long long v = t / L;
-    const int r = r_base + (int)(v / W), c = (int)(v % W);
+    const int r = r_off + r_base + (int)(v / Wloc), c = c_off + (int)(v % Wloc);
+    const int H = Hs, W = Ws;
     auto plane_of = [&](int lab, float &own, float &gx, float &gy) {
         if (lab % 4 == 0) {
             own = ((float)lab + 0.5f) / (float)L; gx = 0.f; gy = 0.f;
@@ -259,7 +262,7 @@ __global__ void gsynth_kernel(unsigned seed, int kern, int H, int W, int L, int 
     rec[NF_GY * LP] = (REAL)gy;
     if (l < 2) {
         // l = 0: pair (v, down), l = 1: pair (v, right); both terms of a pair share the weight
-        const bool exists = l == 0 ? (r + 1 < H) : (c + 1 < W);
+        const bool exists = true;   // pairs beyond the solver's own grid are never read
         float w = (u01(hash3(seed, 0x55u + (unsigned)l, (unsigned)r, (unsigned)c)) < 0.8f ? 108.f : 9.f) * 2.f;
         if (kern == 2) w = w / 0.02f;
         if (!exists) w = 0.f;
@@ -272,7 +275,7 @@ struct SolverBase {
     virtual ~SolverBase() {}
     virtual void set_labels(int l0, int nl, const double *planes, const double *unary, double d_min, double d_step) = 0;
     virtual void set_weights(const double *alphas) = 0;
-    virtual void synth(uint64_t seed) = 0;
+    virtual void synth(uint64_t seed, int Hs, int Ws, int r_off, int c_off) = 0;
     virtual void finalize() = 0;
     virtual void get_label(int l, double *out) = 0;
     virtual void get_weights(double *out) = 0;
@@ -283,6 +286,7 @@ struct SolverBase {
     virtual void ipc_attach(const unsigned char *up, const unsigned char *down) = 0;
     virtual void run_one_pass(int pass, int mode, double *acc) = 0;
     virtual void info(int64_t *out) = 0;
+    virtual void counters(double *out) = 0;
     double setup_ms = 0;
 };
 
@@ -311,8 +315,8 @@ struct Solver : SolverBase {
     unsigned launch_epoch = 0, pass_counter = 0;
     Ctrl *hc = nullptr;   // pinned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    double kernel_ms = 0;
-    int64_t kernel_count = 0;
+    double kernel_ms = 0, total_kernel_ms = 0;
+    int64_t kernel_count = 0, total_kernel_count = 0;
 
     Solver(int kernel_, int H_, int W_, int L_, double tol, const sb_trws_options &opt, int rank_, int world_)
         : kernel(kernel_), H(H_), W(W_), L(L_), rank(rank_), world(world_)
@@ -366,6 +370,8 @@ struct Solver : SolverBase {
             P.prof_warp = (atoi(getenv("SB_TRWS_PROFILE")) - 1) & 3;
         }
         if (const char *e = getenv("SB_TRWS_WATCHDOG_MS")) watchdog_ms = atof(e);
+        P.gate = 1;
+        if (const char *e = getenv("SB_GTRWS_GATE")) P.gate = std::max(1, atoi(e));
         if (getenv("SB_TRWS_RECORD")) {
             rec_ctas = 1024;
             SB_CUDA(cudaHostAlloc((void **)&rec_host, (size_t)rec_ctas * 5 * 4 * sizeof(int), cudaHostAllocMapped));
@@ -443,12 +449,15 @@ struct Solver : SolverBase {
         setup_ms += now_ms() - t0;
     }
 
-    void synth(uint64_t seed) override
+    void synth(uint64_t seed, int Hs, int Ws, int r_off, int c_off) override
     {
         const double t0 = now_ms();
+        if (Hs <= 0 || Ws <= 0) { Hs = H; Ws = W; r_off = 0; c_off = 0; }
+        SB_REQUIRE(r_off >= 0 && c_off >= 0 && r_off + H <= Hs && c_off + W <= Ws, SB_EINVAL,
+                   "sb_trws_grid_synth: window (%d,%d)+%dx%d outside the %dx%d scene", r_off, c_off, H, W, Hs, Ws);
         const long long tot = Nloc * L;
-        gsynth_kernel<REAL><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>((unsigned)(seed ^ (seed >> 32)), kernel, H, W, L, band.r_base, rows,
-                                                                               LP, dNodeF.p, dAlpha.p);
+        gsynth_kernel<REAL><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>((unsigned)(seed ^ (seed >> 32)), kernel, Hs, Ws, r_off, c_off, W, L,
+                                                                               band.r_base, rows, LP, dNodeF.p, dAlpha.p);
         SB_CUDA(cudaGetLastError());
         count_launch();
         SB_CUDA(cudaStreamSynchronize(stream));
@@ -549,6 +558,8 @@ struct Solver : SolverBase {
         SB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
         kernel_ms += ms;
         kernel_count++;
+        total_kernel_ms += ms;
+        total_kernel_count++;
     }
 
     void ipc_export(unsigned char *out) override
@@ -623,9 +634,9 @@ struct Solver : SolverBase {
                 const long long *q = h + 16 * g;
                 const double nt = q[7] ? (double)q[7] : 1, nh = q[15] ? (double)q[15] : 1;
                 fprintf(stderr, "[sb gprofile] %s %s term (%lld steps): waitFULL=%.0f waitstage=%.0f total+round=%.0f operands=%.0f update=%.0f "
-                        "stores=%.0f tail=%.0f | helper (%lld): issue=%.0f waitstage=%.0f static=%.0f msgpoll=%.0f roundpoll=%.0f write=%.0f cyc/step\n",
+                        "stores=%.0f tail=%.0f | helper (%lld): issue=%.0f waitstage=%.0f static=%.0f msgpoll=%.0f roundpoll=%.0f write=%.0f gate=%.0f cyc/step\n",
                         g >= 2 ? "bwd" : "fwd", (g & 1) ? "rows" : "ring", q[7], q[0] / nt, q[1] / nt, q[2] / nt, q[3] / nt, q[4] / nt, q[5] / nt, q[6] / nt, q[15],
-                        q[8] / nh, q[9] / nh, q[10] / nh, q[11] / nh, q[12] / nh, q[13] / nh);
+                        q[8] / nh, q[9] / nh, q[10] / nh, q[11] / nh, q[12] / nh, q[13] / nh, q[14] / nh);
             }
         }
         *energy_out = energy;
@@ -652,6 +663,13 @@ struct Solver : SolverBase {
         count_launch();
         SB_CUDA(cudaMemcpyAsync(out, d.p, d.bytes(), cudaMemcpyDeviceToHost, stream));
         SB_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    void counters(double *out) override
+    {
+        out[0] = total_kernel_ms;
+        out[1] = (double)total_kernel_count;
+        out[2] = setup_ms;
     }
 
     void info(int64_t *out) override
@@ -714,7 +732,11 @@ int sb_trws_grid_set_weights(sb_trws_grid *g, const double *alphas)
 }
 int sb_trws_grid_synth(sb_trws_grid *g, uint64_t seed)
 {
-    SB_GRID_ENTRY("sb_trws_grid_synth", true, g->impl->synth(seed));
+    SB_GRID_ENTRY("sb_trws_grid_synth", true, g->impl->synth(seed, 0, 0, 0, 0));
+}
+int sb_trws_grid_synth_window(sb_trws_grid *g, uint64_t seed, int scene_H, int scene_W, int r_off, int c_off)
+{
+    SB_GRID_ENTRY("sb_trws_grid_synth_window", true, g->impl->synth(seed, scene_H, scene_W, r_off, c_off));
 }
 int sb_trws_grid_finalize(sb_trws_grid *g)
 {
@@ -754,6 +776,10 @@ int sb_trws_grid_pass(sb_trws_grid *g, int pass, int mode, double *acc)
 {
     SB_GRID_ENTRY("sb_trws_grid_pass", acc && (pass == 0 || pass == 1) && mode >= 0 && mode <= 3,
                   g->impl->run_one_pass(pass, mode, acc));
+}
+int sb_trws_grid_counters(sb_trws_grid *g, double *out)
+{
+    SB_GRID_ENTRY("sb_trws_grid_counters", out, g->impl->counters(out));
 }
 int sb_trws_grid_info(sb_trws_grid *g, int64_t *info)
 {

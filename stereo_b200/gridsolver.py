@@ -66,8 +66,14 @@ class TrwsGrid:
         assert a.size == self.E
         check(lib().sb_trws_grid_set_weights(self._h, a.ctypes.data_as(_dp)))
 
-    def synth(self, seed):
-        check(lib().sb_trws_grid_synth(self._h, ctypes.c_uint64(int(seed))))
+    def synth(self, seed, scene=None, offset=(0, 0)):
+        """Seeded synthetic problem generated on the device; with ``scene=(Hs, Ws)`` this solver's grid is the
+        window at ``offset`` of that larger scene."""
+        if scene is None:
+            check(lib().sb_trws_grid_synth(self._h, ctypes.c_uint64(int(seed))))
+        else:
+            check(lib().sb_trws_grid_synth_window(self._h, ctypes.c_uint64(int(seed)), int(scene[0]), int(scene[1]),
+                                                  int(offset[0]), int(offset[1])))
 
     def finalize(self):
         check(lib().sb_trws_grid_finalize(self._h))
@@ -98,6 +104,12 @@ class TrwsGrid:
         check(lib().sb_trws_grid_info(self._h, out))
         keys = ("hbm_bytes", "nodes_stored", "row_lo", "row_hi", "ctas_fwd", "ctas_bwd", "smem_per_cta", "LP")
         return dict(zip(keys, [int(v) for v in out]))
+
+    def counters(self):
+        """Cumulative (sweep kernel ms, sweep launches, set-up ms) since creation."""
+        out = (ctypes.c_double * 3)()
+        check(lib().sb_trws_grid_counters(self._h, out))
+        return float(out[0]), int(out[1]), float(out[2])
 
     # ---- solve
     def reset(self):

@@ -158,3 +158,84 @@ def rd_problem(H, W, seed=0, kernel=1, mode="stereo", tol=0.02):
     pc = (lambda a, b: w * np.minimum(np.abs(a - b), tol)) if kernel == 1 else (lambda a, b: w * np.minimum((a - b) ** 2, tol))
     return dict(U0=U0, U1=U1, E00=pc(q, qp), E01=pc(nq, qp), E10=pc(q, nqp), E11=pc(nq, nqp),
                 connectivity=np.stack([ind1, ind2]), cur=cur, new=new, weights=w, tol=tol)
+
+
+# ---------------------------------------------------------------------------
+# numpy mirror of the ON-DEVICE synthetic generator (csrc/gtrws_solve.cu: gsynth_kernel), used
+# where no GPU code may run (bench.py --impl reference).  Same hashes, same float32 formulas; the
+# device may contract a*b+c into an FMA, so own disparities can differ in the last bit.
+def _hash32(x):
+    x = np.asarray(x, dtype=np.uint64) & 0xFFFFFFFF
+    x ^= x >> 16
+    x = (x * 0x7FEB352D) & 0xFFFFFFFF
+    x ^= x >> 15
+    x = (x * 0x846CA68B) & 0xFFFFFFFF
+    x ^= x >> 16
+    return x
+
+
+def _hash3(seed, a, b, c):
+    m = 0xFFFFFFFF
+    a, b, c = (np.asarray(v, dtype=np.uint64) for v in (a, b, c))
+    h = _hash32((np.uint64(seed) ^ ((a * 0x9E3779B9) & m)) & m)
+    h = _hash32((h ^ ((b * 0x85EBCA6B) & m)) & m)
+    return _hash32((h ^ ((c * 0xC2B2AE35) & m)) & m)
+
+
+def _u01(h):
+    return (np.asarray(h, dtype=np.uint64) >> 8).astype(np.float32) * np.float32(1.0 / 16777216.0)
+
+
+def grid_synth_np(seed, H, W, L, kernel=1, scene=None, offset=(0, 0)):
+    """(unary, own, gx, gy) as L x N float32-valued float64 arrays (MATLAB node order) and alphas (E) of the
+    h x w window at `offset` of the scene; see TrwsGrid.synth."""
+    Hs, Ws = scene if scene is not None else (H, W)
+    seed = int(seed)
+    seed32 = (seed ^ (seed >> 32)) & 0xFFFFFFFF
+    rr, cc = np.meshgrid(np.arange(H) + offset[0], np.arange(W) + offset[1], indexing="ij")
+    r = rr.T.reshape(-1).astype(np.int64)      # MATLAB node order u = r + H c
+    c = cc.T.reshape(-1).astype(np.int64)
+    f32 = np.float32
+
+    def plane_of(lab):
+        lab = np.broadcast_to(np.asarray(lab, dtype=np.int64), r.shape)
+        hs = _hash3(seed32, 0x51, lab, 0)
+        cw = 16 + (hs & 127).astype(np.int64)
+        ch = 16 + ((hs >> 8) & 127).astype(np.int64)
+        cx, cy = c // cw, r // ch
+        hc = _hash3(seed32, (0x52 + lab) & 0xFFFFFFFF, cx, cy)
+        gx = (_u01(_hash32(hc ^ 1)) - f32(0.5)) * f32(0.16) / f32(Ws)
+        gy = (_u01(_hash32(hc ^ 2)) - f32(0.5)) * f32(0.16) / f32(Hs)
+        d = _u01(_hash32(hc ^ 3))
+        dx = c.astype(f32) - (cx.astype(f32) + f32(0.5)) * cw.astype(f32)
+        dy = r.astype(f32) - (cy.astype(f32) + f32(0.5)) * ch.astype(f32)
+        own = (d + gx * dx + gy * dy).astype(f32)
+        fp = (lab % 4) == 0
+        own = np.where(fp, ((lab.astype(f32) + f32(0.5)) / f32(L)).astype(f32), own)
+        return own, np.where(fp, f32(0), gx).astype(f32), np.where(fp, f32(0), gy).astype(f32)
+
+    N = H * W
+    unary = np.empty((L, N))
+    own = np.empty((L, N))
+    gx = np.empty((L, N))
+    gy = np.empty((L, N))
+    for l in range(L):
+        if l == L - 1 and L > 2:
+            pick = (_hash3(seed32, 0x53, r, c) % np.uint64(L - 1)).astype(np.int64)
+            o, a, b = plane_of(pick)
+        else:
+            o, a, b = plane_of(l)
+        own[l], gx[l], gy[l] = o, a, b
+        unary[l] = _u01(_hash3(seed32, (0x54 + l) & 0xFFFFFFFF, r, c)) * f32(0.69314718)
+    # weights: pair (node, down) -> l = 0 hash, (node, right) -> l = 1 hash; reference term order
+    def wt(which, rr_, cc_):
+        w = np.where(_u01(_hash3(seed32, 0x55 + which, rr_, cc_)) < f32(0.8), f32(108.0), f32(9.0)) * f32(2.0)
+        if kernel == 2:
+            w = w / f32(0.02)
+        return w.astype(np.float64)
+    R, C = np.meshgrid(np.arange(H - 1) + offset[0], np.arange(W) + offset[1], indexing="ij")
+    wv = wt(0, R.T.reshape(-1), C.T.reshape(-1))
+    R, C = np.meshgrid(np.arange(H) + offset[0], np.arange(W - 1) + offset[1], indexing="ij")
+    wh = wt(1, R.T.reshape(-1), C.T.reshape(-1))
+    alphas = np.concatenate([wv, wv, wh, wh])
+    return unary, own, gx, gy, alphas

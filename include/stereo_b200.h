@@ -232,6 +232,17 @@ SB_API void sb_trws_grid_destroy(sb_trws_grid *g);
  * need two steps, (messages pushed to rank - 1) * 1e6 + (messages pushed to rank + 1).  12 values. */
 SB_API int sb_trws_grid_plan_stats(int H, int W, int rank, int world, int64_t *stats);
 
+/* One Edge::UpdateMessage (typeStereoLinear.h:329-487 / typeStereoQuadratic.h:329-501) run by the sweep
+ * kernels' own device routine on one warp -- the unit-level known-answer entry:
+ *   msg_out[j] = min(vTrunc, min_i gamma*Di[i] - msg[i] + alpha*|dst_pos[j] - src_pos[i]|^kernel) - vMin.
+ * Known deviation: on EXACT ties h_j - h_k == alpha*(q_k - q_j) the reference's cone envelope drops cone k
+ * (its `s <= qj -> break` path, typeStereoLinear.h:443-446) and so returns values ABOVE the exact min-plus
+ * message; the device computes the exact minimum.  Continuous data never ties; integer-valued unaries with
+ * integer positions do (tests/test_update_message_gpu.py quantifies it). */
+SB_API int sb_trws_update_message(int kernel, int L, const double *Di, const double *msg,
+                           const double *src_pos, const double *dst_pos, double alpha, double lambda,
+                           double gamma, int precision, double *msg_out, double *vmin_out);
+
 /* Node ordering of MRFEnergy::SetAutomaticOrdering (cpp/trw-s/ordering.cpp:7-157)
  * on the H x W grid: ordering[r + H*c] in [0, H*W).  Closed form for H,W >= 4
  * (SURVEY Appendix A.1), literal greedy scan otherwise.  Host-only. */
@@ -259,7 +270,11 @@ SB_API int sb_grid_from_connectivity(int64_t N, int64_t E, const uint32_t *conn,
  * the labelling with unlabelled -> 0; roof-dual lower bound; number of nodes unlabelled
  * after Solve + ComputeWeakPersistencies (before Improve).
  * The connectivity must be the dispmap_super grid, else SB_ENOTGRID.  Improve draws its node
- * permutation from libc rand() exactly like QPBO_extra.cpp:13-27. */
+ * permutation from libc rand() exactly like QPBO_extra.cpp:13-27.
+ * Known deviation: with improve != 0 and unlabelled nodes, `lower_bound` is the roof-dual bound of the
+ * problem (what Solve yields); the reference evaluates ComputeTwiceLowerBound (QPBO.cpp:897-917) on the
+ * residual graph its forced-label max-flows leave behind (QPBO_extra.cpp:1151-1232), a number that
+ * depends on the particular augmenting paths BK took.  Labels, energy and num_unlabelled agree. */
 SB_API int sb_rd_solve(int64_t N, int64_t E, const double *U0, const double *U1,
                 const double *E00, const double *E01, const double *E10, const double *E11,
                 const uint32_t *conn, int improve,

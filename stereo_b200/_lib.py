@@ -95,6 +95,7 @@ def lib():
         L.sb_trws_grid_destroy.argtypes = [vp]
         L.sb_trws_grid_destroy.restype = None
         L.sb_trws_grid_plan_stats.argtypes = [c_int, c_int, c_int, c_int, POINTER(c_int64)]
+        L.sb_trws_update_message.argtypes = [c_int, c_int, _dp, _dp, _dp, _dp, c_double, c_double, c_double, c_int, _dp, _dp]
         ip, i64, dbl = c_int, c_int64, c_double
         L.sb_rd_solve.argtypes = [c_int64, c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _up, c_int, _dp, _dp, _dp, _dp]
         L.sb_ncc_volume.argtypes = [ip, ip, ip, _dp, _dp, ip, _dp, ip, _dp]

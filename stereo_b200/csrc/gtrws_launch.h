@@ -24,12 +24,21 @@ struct GTablesLaunch {
     cudaStream_t stream;
 };
 
+struct GUpdateLaunch {
+    int precision, kern, L;
+    const double *Di, *msg, *src, *dst;   // device
+    double alpha, lambda, gamma;
+    double *msg_out, *vmin_out;           // device
+    cudaStream_t stream;
+};
+
 struct GOps {
     int K;
     int (*blocks_per_sm)(int precision, int kern, int pass);
     void (*sweep)(const GSweepLaunch &);
     void (*tables)(const GTablesLaunch &);   // pad rows, node ranks, pair tables
     size_t (*smem_bytes)(int precision);
+    void (*update_message)(const GUpdateLaunch &);
 };
 
 const GOps *gops_for_labels(int L);

@@ -792,6 +792,30 @@ void sb_trws_grid_destroy(sb_trws_grid *g)
     delete g;
 }
 
+// One UpdateMessage on the device (unit-level known-answer tests against tests/golden/update_message.npz)
+int sb_trws_update_message(int kernel, int L, const double *Di, const double *msg, const double *src_pos, const double *dst_pos,
+                           double alpha, double lambda, double gamma, int precision, double *msg_out, double *vmin_out)
+{
+    return sb::guarded([&] {
+        SB_REQUIRE(kernel == 1 || kernel == 2, SB_EINVAL, "Unsupported kernel");
+        SB_REQUIRE(Di && msg && src_pos && dst_pos && msg_out && vmin_out && L >= 1, SB_EINVAL, "sb_trws_update_message: bad arguments");
+        const sb::gtrws::GOps *ops = sb::gtrws::gops_for_labels(L);
+        SB_REQUIRE(ops, SB_EUNSUP, "sb_trws_update_message: %d labels exceed SB_MAX_LABELS=%d", L, SB_MAX_LABELS);
+        sb::require_device();
+        sb::DevBuf<double> d((size_t)5 * L + 1);
+        const double *src[4] = {Di, msg, src_pos, dst_pos};
+        for (int i = 0; i < 4; i++) SB_CUDA(cudaMemcpy(d.p + (size_t)i * L, src[i], (size_t)L * 8, cudaMemcpyHostToDevice));
+        sb::gtrws::GUpdateLaunch a;
+        a.precision = precision; a.kern = kernel; a.L = L;
+        a.Di = d.p; a.msg = d.p + L; a.src = d.p + 2 * L; a.dst = d.p + 3 * L;
+        a.alpha = alpha; a.lambda = lambda; a.gamma = gamma;
+        a.msg_out = d.p + 4 * L; a.vmin_out = d.p + 5 * L; a.stream = 0;
+        ops->update_message(a);
+        SB_CUDA(cudaMemcpy(msg_out, a.msg_out, (size_t)L * 8, cudaMemcpyDeviceToHost));
+        SB_CUDA(cudaMemcpy(vmin_out, a.vmin_out, 8, cudaMemcpyDeviceToHost));
+    });
+}
+
 // host-only: schedule statistics of the grid-native plan (tests)
 int sb_trws_grid_plan_stats(int H, int W, int rank, int world, int64_t *stats)
 {

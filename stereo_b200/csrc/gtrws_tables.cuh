@@ -140,5 +140,50 @@ __global__ void __launch_bounds__(WARPS * 32) gpair_tables_kernel(const REAL *__
     }
 }
 
+// One Edge::UpdateMessage on the device (unit-level known-answer tests; sb_trws_update_message): one warp,
+// source positions src (cones rooted there), destination positions dst, Di = the gamma-unscaled node sum,
+// msg in / out.  Ranks and merge counts are built the way the table kernels build them.
+template <typename REAL, int K, int KERN>
+__global__ void gupdate_message_kernel(int L, const double *__restrict__ Di_in, const double *__restrict__ msg_in,
+                                       const double *__restrict__ src, const double *__restrict__ dst, double alpha, double lambda,
+                                       double gamma, double *__restrict__ msg_out, double *__restrict__ vmin_out)
+{
+    constexpr int LP = 32 * K;
+    __shared__ REAL sh[2][LP];
+    __shared__ trws::Pair<REAL> P[trws::scratch_pairs<K>()];
+    const int lane = threadIdx.x;
+    REAL Di[K], m[K], s[K], x[K];
+    REAL smax = -Lim<REAL>::big(), xmax = -Lim<REAL>::big();
+    for (int l = 0; l < L; l++) { smax = max(smax, (REAL)src[l]); xmax = max(xmax, (REAL)dst[l]); }
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const int l = lane * K + k;
+        Di[k] = l < L ? (REAL)Di_in[l] : REAL(0);
+        m[k] = l < L ? (REAL)msg_in[l] : REAL(0);
+        s[k] = l < L ? (REAL)src[l] : smax + REAL(1);
+        x[k] = l < L ? (REAL)dst[l] : xmax + REAL(1);
+        sh[0][l] = s[k];
+        sh[1][l] = x[k];
+    }
+    if (lane == 0) {
+        trws::Pair<REAL> t;
+        t.a = Lim<REAL>::big();
+        t.b = REAL(0);
+        P[0] = t;
+        P[trws::phys<K>(LP)] = t;
+    }
+    __syncwarp();
+    uint8_t rk[K], cn[K];
+    rank_rows<REAL, K>(sh[0], lane, rk);
+    count_rows<REAL, K>(sh[1], sh[0], lane, cn);   // #{src <= dst[l]}
+    REAL vmin;
+    if constexpr (KERN == 1) vmin = trws::update_linear<REAL, K>((REAL)gamma, (REAL)alpha, (REAL)lambda, L, lane, Di, m, s, rk, x, cn, P);
+    else vmin = trws::update_quadratic<REAL, K>((REAL)gamma, (REAL)alpha, (REAL)lambda, L, lane, Di, m, s, rk, x, cn, P);
+#pragma unroll
+    for (int k = 0; k < K; k++)
+        if (lane * K + k < L) msg_out[lane * K + k] = (double)m[k];
+    if (lane == 0) *vmin_out = (double)vmin;
+}
+
 } // namespace gtrws
 } // namespace sb

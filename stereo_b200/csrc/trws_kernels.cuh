@@ -300,8 +300,9 @@ template <int K> __host__ __device__ constexpr int scratch_pairs() { return 2 + 
 // and merge counts.
 
 // Truncated linear: msg[j] = min(vTrunc, min_i H_i + alpha |x_j - s_i|)
-// (typeStereoLinear.h:375-480; equality with the reference's cone envelope is
-// SURVEY.md 3.3 [probe] and tests/test_trws_message.py).
+// (typeStereoLinear.h:375-480).  Equal to the reference's cone envelope except on exact ties
+// h_j - h_k == alpha (q_k - q_j), where the reference drops cone k and returns values above the exact
+// minimum (include/stereo_b200.h, sb_trws_update_message; tests/test_update_message_gpu.py).
 template <typename REAL, int K>
 __device__ __forceinline__ REAL update_linear(REAL gamma, REAL alpha, REAL lambda, int L, int lane,
                                               const REAL (&Di)[K], REAL (&m)[K], const REAL (&s)[K],

@@ -27,9 +27,10 @@
 //     operands from shared memory when the update runs, so they hold no prefetched operands in
 //     registers and more strip walkers fit an SM.
 //
-// CTA = 4 term warps + 1 helper warp, one strip (the boundary ring, then one per interior row) at a
+// CTA = 4 term warps + 2 helper warps (alternating steps), one strip (the boundary ring, then one per interior row) at a
 // time from an atomic ticket, one persistent launch per pass.
 #pragma once
+#include <type_traits>
 #include "trws_kernels.cuh"
 #include "gtrws_plan.h"
 
@@ -44,7 +45,8 @@ using trws::MODE_SEND;
 using trws::MODE_ROUND;
 
 constexpr int NTW = 4;                       // term warps
-constexpr int CTA_THREADS = (NTW + 1) * 32;  // + helper warp
+constexpr int NHW = 2;                       // helper warps: helper h prepares the steps of parity h
+constexpr int CTA_THREADS = (NTW + NHW) * 32;
 enum { NF_D = 0, NF_GX = 1, NF_OWN = 2, NF_GY = 3 };
 
 template <typename REAL>
@@ -60,8 +62,11 @@ struct GProblem {
     unsigned long long *selbox;  // [pairs][2]  (the sender's rounded label | epoch << 32)
     REAL lambda;
     const GSeg *segs;
-    const int32_t *seg_ptr, *strip_len;
+    const int32_t *seg_ptr, *strip_len, *is_ring;   // strips in processing order of the pass
     int S;
+    unsigned long long *save;          // [save slots][LP][sizeof(REAL) / 4]: saved node totals (32 value bits | epoch << 32)
+    int *ring_smid;                    // forward pass: 1 + SM id of the CTA that walks the first ring strip
+    int isolate_ring;                  // forward pass: CTAs that share that SM leave (the ring is the serial bottleneck)
     int world;
     REAL *peer_msg[2];                 // rank - 1 / rank + 1 (peer mapped)
     unsigned long long *peer_selbox[2];
@@ -74,9 +79,142 @@ struct GProblem {
     int mode;
     long long *prof;                   // optional cycle counters
     int prof_warp;                     // term warp they are taken on
-    int gate;                          // > 1: every `gate` steps a strip waits until its upstream strip is `gate` nodes ahead
+    int head_strip;                    // profile: the first interior strip of the pass is reported on its own
+    unsigned poll_ns;                  // back-off between two polls of a dependency that has not arrived
     int *rec;                          // SB_TRWS_RECORD: host-mapped flight recorder [cta][5 warps][4], else null
 };
+
+// ---------------------------------------------------------------- lane <-> label map
+// Rows are label-contiguous in memory.  A lane owns its K labels in BLOCKS of 16 / 8 / 4 bytes: block b covers the
+// labels [off_b, off_b + 32 w_b) and gives lane l the w_b labels off_b + w_b l ... -- so every vector access of a
+// warp touches 32 consecutive chunks (no shared-memory bank conflicts, fully coalesced global sectors), where
+// "K consecutive labels per lane" made 32-byte lane strides (2-way conflicts on every row read at K = 8).
+template <typename REAL, int K> struct LaneMap {
+    static constexpr int CW = 16 / (int)sizeof(REAL);     // labels per 16-byte chunk
+    // width of the block that holds slot k, its first slot and its first label
+    static __host__ __device__ constexpr int blk_w(int k)
+    {
+        int k0 = 0, rem = K;
+        while (rem >= CW) { if (k < k0 + CW) return CW; k0 += CW; rem -= CW; }
+        for (int w = CW / 2; w >= 1; w /= 2)
+            if (rem >= w) { if (k < k0 + w) return w; k0 += w; rem -= w; }
+        return 1;
+    }
+    static __host__ __device__ constexpr int blk_k0(int k)
+    {
+        int k0 = 0, rem = K;
+        while (rem >= CW) { if (k < k0 + CW) return k0; k0 += CW; rem -= CW; }
+        for (int w = CW / 2; w >= 1; w /= 2)
+            if (rem >= w) { if (k < k0 + w) return k0; k0 += w; rem -= w; }
+        return k0;
+    }
+    static __device__ __forceinline__ int label(int lane, int k) { return 32 * blk_k0(k) + blk_w(k) * lane + (k - blk_k0(k)); }
+    // (lane, slot) that own label x
+    static __device__ __forceinline__ void owner(int x, int &lane, int &slot)
+    {
+        lane = 0; slot = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            if (k == blk_k0(k)) {   // first slot of a block
+                const int w = blk_w(k), off = 32 * k;
+                if (x >= off && x < off + 32 * w) { lane = (x - off) / w; slot = k + (x - off) % w; }
+            }
+        }
+    }
+    static __device__ __forceinline__ unsigned valid_mask(int lane, int L)
+    {
+        unsigned v = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) v |= (label(lane, k) < L ? 1u : 0u) << k;
+        return v;
+    }
+};
+
+// compile-time loop over the slots 0 .. K-1 (the block structure is a compile-time property of the slot)
+template <int K0, int KEND, typename F> __device__ __forceinline__ void static_for(F &&f)
+{
+    if constexpr (K0 < KEND) {
+        f(std::integral_constant<int, K0>{});
+        static_for<K0 + 1, KEND>(f);
+    }
+}
+
+// this lane's K values of a shared-memory row / to one
+template <typename REAL, int K> __device__ __forceinline__ void lrow_lds(REAL (&r)[K], const REAL *row, int lane)
+{
+    typedef LaneMap<REAL, K> LM;
+    static_for<0, K>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        if constexpr (k == LM::blk_k0(k)) {
+            constexpr int w = LM::blk_w(k);
+            constexpr int bytes = w * (int)sizeof(REAL);
+            const REAL *q = row + 32 * k + w * lane;
+            if constexpr (bytes == 16) {
+                const float4 v = *reinterpret_cast<const float4 *>(q);
+                if constexpr (sizeof(REAL) == 4) { r[k] = v.x; r[k + 1] = v.y; r[k + 2] = v.z; r[k + 3] = v.w; }
+                else {
+                    r[k] = __hiloint2double(__float_as_int(v.y), __float_as_int(v.x));
+                    r[k + 1] = __hiloint2double(__float_as_int(v.w), __float_as_int(v.z));
+                }
+            } else if constexpr (bytes == 8) {
+                const float2 v = *reinterpret_cast<const float2 *>(q);
+                if constexpr (sizeof(REAL) == 4) { r[k] = v.x; r[k + 1] = v.y; }
+                else r[k] = __hiloint2double(__float_as_int(v.y), __float_as_int(v.x));
+            } else {
+                r[k] = *q;
+            }
+        }
+    });
+}
+template <typename REAL, int K> __device__ __forceinline__ void lrow_sts(REAL *row, const REAL (&r)[K], int lane)
+{
+    typedef LaneMap<REAL, K> LM;
+    static_for<0, K>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        if constexpr (k == LM::blk_k0(k)) {
+            constexpr int w = LM::blk_w(k);
+            constexpr int bytes = w * (int)sizeof(REAL);
+            REAL *q = row + 32 * k + w * lane;
+            if constexpr (bytes == 16) {
+                float4 v;
+                if constexpr (sizeof(REAL) == 4) { v.x = r[k]; v.y = r[k + 1]; v.z = r[k + 2]; v.w = r[k + 3]; }
+                else {
+                    v.x = __int_as_float(__double2loint(r[k])); v.y = __int_as_float(__double2hiint(r[k]));
+                    v.z = __int_as_float(__double2loint(r[k + 1])); v.w = __int_as_float(__double2hiint(r[k + 1]));
+                }
+                *reinterpret_cast<float4 *>(q) = v;
+            } else if constexpr (bytes == 8) {
+                float2 v;
+                if constexpr (sizeof(REAL) == 4) { v.x = r[k]; v.y = r[k + 1]; }
+                else { v.x = __int_as_float(__double2loint(r[k])); v.y = __int_as_float(__double2hiint(r[k])); }
+                *reinterpret_cast<float2 *>(q) = v;
+            } else {
+                *q = r[k];
+            }
+        }
+    });
+}
+// this lane's K bytes of a shared-memory byte row
+template <typename REAL, int K> __device__ __forceinline__ void lrow_ldb(uint8_t (&r)[K], const uint8_t *row, int lane)
+{
+    typedef LaneMap<REAL, K> LM;
+    static_for<0, K>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        if constexpr (k == LM::blk_k0(k)) {
+            constexpr int w = LM::blk_w(k);
+            const uint8_t *q = row + 32 * k + w * lane;
+            if constexpr (w == 4) {
+                const unsigned v = *reinterpret_cast<const unsigned *>(q);
+                r[k] = (uint8_t)v; r[k + 1] = (uint8_t)(v >> 8); r[k + 2] = (uint8_t)(v >> 16); r[k + 3] = (uint8_t)(v >> 24);
+            } else if constexpr (w == 2) {
+                const unsigned short v = *reinterpret_cast<const unsigned short *>(q);
+                r[k] = (uint8_t)v; r[k + 1] = (uint8_t)(v >> 8);
+            } else {
+                r[k] = *q;
+            }
+        }
+    });
+}
 
 // ---------------------------------------------------------------- tagged message words
 template <typename REAL> struct Tag;
@@ -95,79 +233,115 @@ template <> struct Tag<double> {
     static __device__ __forceinline__ double val(double v) { return fabs(v); }
 };
 
-// K consecutive message words of this lane, L2-coherent relaxed loads (the words are written by
-// other SMs / GPUs during this launch).  Each word validates itself, so per-word atomicity suffices.
-template <typename REAL, int K, bool SYS> __device__ __forceinline__ void ld_words(REAL (&r)[K], const REAL *p)
+// This lane's K message words of a row in global memory (LaneMap blocks), L2-coherent relaxed accesses: the words
+// are written by other SMs / GPUs during this launch, and each word validates itself, so per-word atomicity suffices.
+template <int BYTES, bool SYS> __device__ __forceinline__ void ld_relaxed(unsigned (&w)[BYTES / 4], const void *p)
 {
-    if constexpr (sizeof(REAL) == 4) {
-        if constexpr (K % 4 == 0) {
-#pragma unroll
-            for (int i = 0; i < K / 4; i++) {
-                unsigned a, b, c, d;
-                if constexpr (SYS) asm volatile("ld.relaxed.sys.global.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p + 4 * i) : "memory");
-                else asm volatile("ld.relaxed.gpu.global.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p + 4 * i) : "memory");
-                r[4 * i] = __uint_as_float(a); r[4 * i + 1] = __uint_as_float(b); r[4 * i + 2] = __uint_as_float(c); r[4 * i + 3] = __uint_as_float(d);
-            }
-        } else if constexpr (K % 2 == 0) {
-#pragma unroll
-            for (int i = 0; i < K / 2; i++) {
-                unsigned a, b;
-                if constexpr (SYS) asm volatile("ld.relaxed.sys.global.v2.b32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(p + 2 * i) : "memory");
-                else asm volatile("ld.relaxed.gpu.global.v2.b32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(p + 2 * i) : "memory");
-                r[2 * i] = __uint_as_float(a); r[2 * i + 1] = __uint_as_float(b);
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < K; i++) {
-                unsigned a;
-                if constexpr (SYS) asm volatile("ld.relaxed.sys.global.b32 %0, [%1];" : "=r"(a) : "l"(p + i) : "memory");
-                else asm volatile("ld.relaxed.gpu.global.b32 %0, [%1];" : "=r"(a) : "l"(p + i) : "memory");
-                r[i] = __uint_as_float(a);
-            }
-        }
+    if constexpr (BYTES == 16) {
+        if constexpr (SYS) asm volatile("ld.relaxed.sys.global.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(p) : "memory");
+        else asm volatile("ld.relaxed.gpu.global.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(p) : "memory");
+    } else if constexpr (BYTES == 8) {
+        if constexpr (SYS) asm volatile("ld.relaxed.sys.global.v2.b32 {%0,%1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "l"(p) : "memory");
+        else asm volatile("ld.relaxed.gpu.global.v2.b32 {%0,%1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "l"(p) : "memory");
     } else {
+        if constexpr (SYS) asm volatile("ld.relaxed.sys.global.b32 %0, [%1];" : "=r"(w[0]) : "l"(p) : "memory");
+        else asm volatile("ld.relaxed.gpu.global.b32 %0, [%1];" : "=r"(w[0]) : "l"(p) : "memory");
+    }
+}
+template <int BYTES, bool SYS> __device__ __forceinline__ void st_relaxed(void *p, const unsigned (&w)[BYTES / 4])
+{
+    if constexpr (BYTES == 16) {
+        if constexpr (SYS) asm volatile("st.relaxed.sys.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+        else asm volatile("st.relaxed.gpu.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+    } else if constexpr (BYTES == 8) {
+        if constexpr (SYS) asm volatile("st.relaxed.sys.global.v2.b32 [%0], {%1,%2};" ::"l"(p), "r"(w[0]), "r"(w[1]) : "memory");
+        else asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1,%2};" ::"l"(p), "r"(w[0]), "r"(w[1]) : "memory");
+    } else {
+        if constexpr (SYS) asm volatile("st.relaxed.sys.global.b32 [%0], %1;" ::"l"(p), "r"(w[0]) : "memory");
+        else asm volatile("st.relaxed.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(w[0]) : "memory");
+    }
+}
+template <typename REAL> __device__ __forceinline__ REAL words_to_real(const unsigned *w)
+{
+    if constexpr (sizeof(REAL) == 4) return __uint_as_float(w[0]);
+    else return __hiloint2double((int)w[1], (int)w[0]);
+}
+template <typename REAL> __device__ __forceinline__ void real_to_words(unsigned *w, REAL v)
+{
+    if constexpr (sizeof(REAL) == 4) w[0] = __float_as_uint(v);
+    else { w[0] = (unsigned)__double2loint(v); w[1] = (unsigned)__double2hiint(v); }
+}
+// `row` = first label of the row
+template <typename REAL, int K, bool SYS> __device__ __forceinline__ void ld_words(REAL (&r)[K], const REAL *row, int lane)
+{
+    typedef LaneMap<REAL, K> LM;
+    constexpr int WR = (int)sizeof(REAL) / 4;
+    static_for<0, K>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        if constexpr (k == LM::blk_k0(k)) {
+            constexpr int w = LM::blk_w(k);
+            constexpr int NW = w * WR;          // 32-bit words of this block per lane: 4, 2 or 1
+            const REAL *q = row + 32 * k + w * lane;
+            unsigned u[NW];
+            ld_relaxed<NW * 4, SYS>(u, q);
 #pragma unroll
-        for (int i = 0; i < K; i++) {
-            unsigned long long a;
-            if constexpr (SYS) asm volatile("ld.relaxed.sys.global.b64 %0, [%1];" : "=l"(a) : "l"(p + i) : "memory");
-            else asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(a) : "l"(p + i) : "memory");
-            r[i] = __longlong_as_double((long long)a);
+            for (int i = 0; i < w; i++) r[k + i] = words_to_real<REAL>(u + i * WR);
+        }
+    });
+}
+template <typename REAL, int K, bool SYS> __device__ __forceinline__ void st_words(REAL *row, const REAL (&r)[K], int lane)
+{
+    typedef LaneMap<REAL, K> LM;
+    constexpr int WR = (int)sizeof(REAL) / 4;
+    static_for<0, K>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        if constexpr (k == LM::blk_k0(k)) {
+            constexpr int w = LM::blk_w(k);
+            constexpr int NW = w * WR;
+            REAL *q = row + 32 * k + w * lane;
+            unsigned u[NW];
+#pragma unroll
+            for (int i = 0; i < w; i++) real_to_words<REAL>(u + i * WR, r[k + i]);
+            st_relaxed<NW * 4, SYS>(q, u);
+        }
+    });
+}
+
+// Saved node totals (GF_SAVE -> GF_DEFERRED): 32 value bits + launch epoch per 64-bit word, so a word validates
+// itself (doubles travel as two words).
+template <typename REAL, int K> __device__ __forceinline__ void save_total(unsigned long long *slot, const REAL (&v)[K], int lane, unsigned epoch)
+{
+    constexpr int WPR = (int)sizeof(REAL) / 4;
+    unsigned long long *p = slot + (size_t)lane * K * WPR;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        if constexpr (WPR == 1) {
+            trws::st_mbox(p + k, (unsigned long long)__float_as_uint((float)v[k]) | ((unsigned long long)epoch << 32));
+        } else {
+            trws::st_mbox(p + 2 * k, (unsigned long long)(unsigned)__double2loint((double)v[k]) | ((unsigned long long)epoch << 32));
+            trws::st_mbox(p + 2 * k + 1, (unsigned long long)(unsigned)__double2hiint((double)v[k]) | ((unsigned long long)epoch << 32));
         }
     }
 }
-// K consecutive message words of this lane to global memory (relaxed, L2; SYS: a peer GPU's memory)
-template <typename REAL, int K, bool SYS> __device__ __forceinline__ void st_words(REAL *p, const REAL (&r)[K])
+template <typename REAL, int K> __device__ __forceinline__ void poll_total(const unsigned long long *slot, REAL (&v)[K], int lane, unsigned epoch)
 {
-    if constexpr (sizeof(REAL) == 4) {
-        if constexpr (K % 4 == 0) {
+    constexpr int WPR = (int)sizeof(REAL) / 4;
+    const unsigned long long *p = slot + (size_t)lane * K * WPR;
+    unsigned long long w[K * WPR];
+    for (;;) {
+        bool ok = true;
 #pragma unroll
-            for (int i = 0; i < K / 4; i++) {
-                const unsigned a = __float_as_uint(r[4 * i]), b = __float_as_uint(r[4 * i + 1]), c = __float_as_uint(r[4 * i + 2]), d = __float_as_uint(r[4 * i + 3]);
-                if constexpr (SYS) asm volatile("st.relaxed.sys.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p + 4 * i), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-                else asm volatile("st.relaxed.gpu.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p + 4 * i), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-            }
-        } else if constexpr (K % 2 == 0) {
-#pragma unroll
-            for (int i = 0; i < K / 2; i++) {
-                const unsigned a = __float_as_uint(r[2 * i]), b = __float_as_uint(r[2 * i + 1]);
-                if constexpr (SYS) asm volatile("st.relaxed.sys.global.v2.b32 [%0], {%1,%2};" ::"l"(p + 2 * i), "r"(a), "r"(b) : "memory");
-                else asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1,%2};" ::"l"(p + 2 * i), "r"(a), "r"(b) : "memory");
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < K; i++) {
-                const unsigned a = __float_as_uint(r[i]);
-                if constexpr (SYS) asm volatile("st.relaxed.sys.global.b32 [%0], %1;" ::"l"(p + i), "r"(a) : "memory");
-                else asm volatile("st.relaxed.gpu.global.b32 [%0], %1;" ::"l"(p + i), "r"(a) : "memory");
-            }
+        for (int q = 0; q < K * WPR; q++) {
+            w[q] = trws::ld_mbox(p + q);
+            ok = ok && ((unsigned)(w[q] >> 32) == epoch);
         }
-    } else {
+        if (__all_sync(0xffffffffu, ok)) break;
+        __nanosleep(200);
+    }
 #pragma unroll
-        for (int i = 0; i < K; i++) {
-            const unsigned long long a = (unsigned long long)__double_as_longlong(r[i]);
-            if constexpr (SYS) asm volatile("st.relaxed.sys.global.b64 [%0], %1;" ::"l"(p + i), "l"(a) : "memory");
-            else asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p + i), "l"(a) : "memory");
-        }
+    for (int k = 0; k < K; k++) {
+        if constexpr (WPR == 1) v[k] = (REAL)__uint_as_float((unsigned)w[k]);
+        else v[k] = (REAL)__hiloint2double((int)(unsigned)w[2 * k + 1], (int)(unsigned)w[2 * k]);
     }
 }
 
@@ -206,12 +380,12 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 struct StepGeo {
     int u;
     unsigned roles;
-    int gamma_den, next_dir, flags;
+    int gamma_den, next_dir, flags, save;
     unsigned peer;   // 8 bits per direction
 };
 struct SegWalker {
     const GSeg *segs;
-    int sg, i, n, u0, du;
+    int sg, i, n, u0, du, save0;
     unsigned roles, peer;
     int gamma_den, next_dir, flags;
     __device__ __forceinline__ void load()
@@ -223,12 +397,14 @@ struct SegWalker {
         next_dir = (int)(signed char)((b.x >> 16) & 0xff);
         flags = (b.x >> 24) & 0xff;
         peer = (unsigned)b.y;
+        save0 = b.z;
         i = 0;
     }
     __device__ __forceinline__ void init(const GSeg *s, int sg0) { segs = s; sg = sg0; load(); }
     __device__ __forceinline__ void get(StepGeo &g) const
     {
         g.u = u0 + i * du; g.roles = roles; g.gamma_den = gamma_den; g.next_dir = next_dir; g.flags = flags; g.peer = peer;
+        g.save = save0 + i;
     }
     // to the next step (the caller guarantees there is one)
     __device__ __forceinline__ void advance()
@@ -271,17 +447,20 @@ template <typename REAL, int K, int NS> __host__ __device__ constexpr size_t gsw
 {
     // stages + 2 sets of {BASE, DIB0, RMS} + 2 x {CM0, CM1, CC0, CC1} + DI_SAVE + scratch pairs + mbarriers
     return (size_t)NS * StageLayout<REAL, K>::BYTES + (size_t)(6 + 8 + 1) * 32 * K * sizeof(REAL) +
-           (size_t)NTW * trws::scratch_pairs<K>() * sizeof(Pair<REAL>) + 2 * NS * 8;
+           (size_t)NTW * trws::scratch_pairs<K>() * sizeof(Pair<REAL>) + (2 * NS + 2) * 8;
 }
 
-template <int ID> __device__ __forceinline__ void full_sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(CTA_THREADS) : "memory"); }
-template <int ID> __device__ __forceinline__ void full_arrive() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(CTA_THREADS) : "memory"); }
+// the four term warps among themselves (carry rows of the previous step are complete)
+template <int ID> __device__ __forceinline__ void term_sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(NTW * 32) : "memory"); }
 
 // resident CTAs per SM the register budget is set for
+// resident CTAs per SM the register budget is set for (setmaxnreg re-division between the term warpgroup and the
+// helpers was tried: ptxas 12.9 keeps allocating under the launch cap and spills, so the budget is uniform)
 template <typename REAL, int K> __host__ __device__ constexpr int gsweep_min_blocks()
 {
-    if (sizeof(REAL) == 8) return K <= 2 ? 3 : K <= 4 ? 2 : 1;
-    return K <= 2 ? 6 : K <= 3 ? 5 : K <= 4 ? 4 : K <= 6 ? 4 : 3;
+    if (sizeof(REAL) == 8) return K <= 2 ? 2 : 1;
+    // measured on a B200 (1980x2880x192 / 1024x2048x256): one CTA more per SM with ~1-2 KB of spills is 20 % slower
+    return K <= 2 ? 5 : K <= 4 ? 4 : K <= 6 ? 3 : 2;
 }
 
 template <typename REAL, int K, int KERN, int PASS, int NS>
@@ -310,7 +489,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
     Pair<REAL> *P = reinterpret_cast<Pair<REAL> *>(rows + (size_t)15 * LP) + (size_t)(is_term ? warp : 0) * trws::scratch_pairs<K>();
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(
         reinterpret_cast<unsigned char *>(rows + (size_t)15 * LP) + (size_t)NTW * trws::scratch_pairs<K>() * sizeof(Pair<REAL>));
-    unsigned long long *bar_full = bars, *bar_free = bars + NS;
+    unsigned long long *bar_full = bars, *bar_free = bars + NS, *bar_base = bars + 2 * NS;
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -318,6 +497,8 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
             mbar_init(bar_full + s, 1);
             mbar_init(bar_free + s, NTW);
         }
+        mbar_init(bar_base + 0, 1);
+        mbar_init(bar_base + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (is_term && lane == 0) {
@@ -328,24 +509,49 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
         P[trws::phys<K>(LP)] = t;
     }
     __syncthreads();
-
     double acc_energy = 0.0, acc_lb = 0.0;
     // flight recorder (debugging hangs): where every warp is -- strip, step, phase -- in host-mapped memory
     auto record = [&](int strip, int step, int phase, int extra) {
         if (p.rec && lane == 0) {
-            volatile int *r = p.rec + ((size_t)blockIdx.x * (NTW + 1) + warp) * 4;
+            volatile int *r = p.rec + ((size_t)blockIdx.x * (NTW + NHW) + warp) * 4;
             r[0] = strip; r[1] = step; r[2] = phase; r[3] = extra;
         }
     };
-    long long gstep0 = 0;   // node steps this CTA has walked before the current strip (stage ring position)
+    unsigned gstep0 = 0;    // node steps this CTA has walked before the current strip (stage ring position); 32-bit:
+                            // the stage / phase arithmetic below is a division by NS per use
 
+    // Forward pass: the first strip is the boundary ring, a serial chain everything else waits for.  CTA 0 takes it
+    // without a ticket and publishes its SM; CTAs that landed on the same SM leave, so the chain has the SM alone.
+    bool first_round = true;
+    if (PASS == PASS_FWD && p.isolate_ring) {
+        __shared__ int s_leave;
+        if (threadIdx.x == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            s_leave = 0;
+            if (blockIdx.x == 0) {
+                *reinterpret_cast<volatile int *>(p.ring_smid) = (int)smid + 1;
+            } else {
+                int v;
+                while ((v = *reinterpret_cast<volatile int *>(p.ring_smid)) == 0) __nanosleep(100);
+                s_leave = (v == (int)smid + 1);
+            }
+        }
+        __syncthreads();
+        if (s_leave) return;
+    }
     for (;;) {
-        if (threadIdx.x == 0) s_ticket = atomicAdd(p.ticket, 1);
+        if (threadIdx.x == 0) {
+            if (PASS == PASS_FWD && p.isolate_ring) s_ticket = (first_round && blockIdx.x == 0) ? 0 : atomicAdd(p.ticket, 1) + 1;
+            else s_ticket = atomicAdd(p.ticket, 1);
+        }
+        first_round = false;
         __syncthreads();
         const int ts = s_ticket;
         __syncthreads();
         if (ts >= p.S) break;
-        const int fs = (PASS == PASS_BWD) ? p.S - 1 - ts : ts;
+        const int fs = ts;   // strips are listed in processing order
+        const bool ring_strip = __ldg(p.is_ring + fs) != 0;
         const int sg0 = __ldg(p.seg_ptr + fs);
         const int n_steps = __ldg(p.strip_len + fs);
         if (n_steps <= 0) continue;
@@ -357,6 +563,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
             SegWalker wk;
             wk.init(p.segs, sg0);
             int xs = 0;
+            const unsigned valid = LaneMap<REAL, K>::valid_mask(lane, p.L);
             // optional phase timers (SB_TRWS_PROFILE): term warp 0 -> wait FULL, wait stage, node total + rounding,
             // operands, update, stores
             const bool prof_on = (p.prof != nullptr) && w == p.prof_warp;
@@ -370,10 +577,10 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
                 }
             };
             for (int node = 0; node < n_steps; node++) {
-                const long long gs = gstep0 + node;
+                const unsigned gs = gstep0 + (unsigned)node;
                 const int st = (int)(gs % NS);
                 const unsigned ph = (unsigned)((gs / NS) & 1);
-                const int par = node & 1;
+                const int par = (int)(gs & 1u);     // sets / carry rows / hand-over barriers alternate with the CTA's step count
                 StepGeo g;
                 wk.get(g);
                 if (node + 1 < n_steps) wk.advance();
@@ -383,23 +590,26 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
                 // ---- rows of this node are ready (helper), every term warp has finished the previous step
                 tick(6);
                 record(fs, node, 1, (int)g.roles);
-                if (par) full_sync<2>(); else full_sync<1>();
+                if (par) term_sync<2>(); else term_sync<1>();
                 tick(0);
                 record(fs, node, 2, st);
-                mbar_wait(bar_full + st, ph);   // the bulk copies of this stage, as seen by THIS thread
+                // the helper's rows of this step; it waited for the stage's bulk copies before it built them, so they
+                // are visible here as well (complete_tx -> helper's wait -> its arrive -> this wait)
+                mbar_wait(bar_base + par, (unsigned)((gs >> 1) & 1u));
                 record(fs, node, 3, st);
                 tick(1);
                 REAL Di[K];
-                if (g.flags & GF_SECOND) {
-                    trws::row_lds<REAL, K>(Di, di_save, lane);
+                if (g.flags & GF_DEFERRED) {
+                    // deferred sends of a node that sends on more than two pairs: its total, as saved by the main strip
+                    lrow_lds<REAL, K>(Di, set_ptr(par, R_BASE), lane);
                 } else {
-                    trws::row_lds<REAL, K>(Di, set_ptr(par, R_BASE), lane);
+                    lrow_lds<REAL, K>(Di, set_ptr(par, R_BASE), lane);
                     const int cd = dir_with_role(g.roles, ROLE_CARRY);
                     if (cd >= 0 && do_send) {
 #pragma unroll
                         for (int jj = 0; jj < 2; jj++) {
                             REAL v[K];
-                            trws::row_lds<REAL, K>(v, carry_ptr(par, jj), lane);
+                            lrow_lds<REAL, K>(v, carry_ptr(par, jj), lane);
 #pragma unroll
                             for (int k = 0; k < K; k++) Di[k] += v[k];
                         }
@@ -407,13 +617,13 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
                     if (do_round) {
                         // minimize.cpp:240-260: DiB = D + sum_{lower nb} V(x_nb, .), Dr = DiB + forward messages
                         REAL dib[K], rms[K];
-                        trws::row_lds<REAL, K>(dib, set_ptr(par, R_DIB0), lane);
-                        trws::row_lds<REAL, K>(rms, set_ptr(par, R_RMS), lane);
+                        lrow_lds<REAL, K>(dib, set_ptr(par, R_DIB0), lane);
+                        lrow_lds<REAL, K>(rms, set_ptr(par, R_RMS), lane);
                         if (cd >= 0) {
 #pragma unroll
                             for (int jj = 0; jj < 2; jj++) {
                                 REAL v[K];
-                                trws::row_lds<REAL, K>(v, carry_ptr(par, 2 + jj), lane);
+                                lrow_lds<REAL, K>(v, carry_ptr(par, 2 + jj), lane);
 #pragma unroll
                                 for (int k = 0; k < K; k++) dib[k] += v[k];
                             }
@@ -423,7 +633,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
                         int bi = 0x7fffffff;
 #pragma unroll
                         for (int k = 0; k < K; k++) {
-                            const int lbl = lane * K + k;
+                            const int lbl = LaneMap<REAL, K>::label(lane, k);
                             const REAL dr = dib[k] + rms[k];
                             if (lbl < p.L && dr < best) { best = dr; bi = lbl; }
                         }
@@ -431,11 +641,13 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
                         bi = trws::warp_min_s32(best == wbest ? bi : 0x7fffffff);
                         xs = bi;
                         if (w == 0) {
+                            int ol, os;
+                            LaneMap<REAL, K>::owner(bi, ol, os);
                             REAL dv = dib[0];
 #pragma unroll
                             for (int k = 1; k < K; k++)
-                                if (k == bi % K) dv = dib[k];
-                            dv = __shfl_sync(0xffffffffu, dv, bi / K);
+                                if (k == os) dv = dib[k];
+                            dv = __shfl_sync(0xffffffffu, dv, ol);
                             if (lane == 0) {
                                 p.sol[g.u] = bi;
                                 acc_energy += (double)dv;
@@ -447,13 +659,13 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
                         REAL vmin = BIG;
 #pragma unroll
                         for (int k = 0; k < K; k++)
-                            if (lane * K + k < p.L) vmin = min(vmin, Di[k]);
+                            if ((valid >> k) & 1u) vmin = min(vmin, Di[k]);
                         vmin = trws::warp_min(vmin);
 #pragma unroll
                         for (int k = 0; k < K; k++) Di[k] -= vmin;
                         if (w == 0) acc_lb += (double)vmin;
                     }
-                    if ((g.flags & GF_FIRST) && w == 0) trws::row_sts<REAL, K>(di_save, Di, lane);
+                    if ((g.flags & GF_SAVE) && w == 0) save_total<REAL, K>(p.save + (size_t)g.save * LP * (sizeof(REAL) / 4), Di, lane, p.epoch);
                 }
                 if (prof_on) { tclk += (long long)(Di[0] != Di[0]); tick(2); }
                 // ---- my send term: pair in send slot `slot`, term j of it
@@ -472,15 +684,15 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
                     uint8_t rk[K], cn[K];
                     {
                         const REAL *MS = reinterpret_cast<const REAL *>(sp + SL::OFF_MS) + (size_t)(slot * 2 + j) * LP;
-                        trws::row_lds<REAL, K>(m, MS, lane);
+                        lrow_lds<REAL, K>(m, MS, lane);
 #pragma unroll
                         for (int k = 0; k < K; k++) m[k] = Tag<REAL>::val(m[k]);
                         REAL own_me[K], g_me[K], own_nb[K], g_nb[K];
-                        trws::row_lds<REAL, K>(own_me, NF + NF_OWN * LP, lane);
+                        lrow_lds<REAL, K>(own_me, NF + NF_OWN * LP, lane);
                         const REAL *nb_own, *nb_g;
                         if (to_next) {
                             // the receiver is the next node of the strip: its rows are (or will shortly be) in the next stage
-                            const long long gn = gs + 1;
+                            const unsigned gn = gs + 1;
                             const int stn = (int)(gn % NS);
                             record(fs, node, 4, stn);
                             mbar_wait(bar_full + stn, (unsigned)((gn / NS) & 1));
@@ -493,32 +705,29 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
                             nb_own = XN + (vert ? 0 : 1) * LP;
                             nb_g = XN + (vert ? 1 : 0) * LP;
                         }
-                        trws::row_lds<REAL, K>(own_nb, nb_own, lane);
-                        trws::PackedBytes<K> rkp, cnp;
+                        lrow_lds<REAL, K>(own_nb, nb_own, lane);
                         const uint8_t *PB = sp + SL::OFF_PB + (size_t)slot * 3 * LP;
                         if (tail) {
                             // my positions: my planes at the receiver's point (qprim); receiver's: its own (q)
-                            trws::row_lds<REAL, K>(g_me, NF + (vert ? NF_GY : NF_GX) * LP, lane);
+                            lrow_lds<REAL, K>(g_me, NF + (vert ? NF_GY : NF_GX) * LP, lane);
 #pragma unroll
                             for (int k = 0; k < K; k++) {
                                 s[k] = sd == 0 ? own_me[k] + g_me[k] : own_me[k] - g_me[k];
                                 x[k] = own_nb[k];
                             }
-                            rkp.load_shared(PB + 2 * LP + lane * K);
-                            cnp.load_shared(PB + 0 * LP + lane * K);
+                            lrow_ldb<REAL, K>(rk, PB + 2 * LP, lane);
+                            lrow_ldb<REAL, K>(cn, PB + 0 * LP, lane);
                         } else {
                             // I am the head: my own disparities (q); receiver's planes at my point (qprim)
-                            trws::row_lds<REAL, K>(g_nb, nb_g, lane);
+                            lrow_lds<REAL, K>(g_nb, nb_g, lane);
 #pragma unroll
                             for (int k = 0; k < K; k++) {
                                 s[k] = own_me[k];
                                 x[k] = sd == 0 ? own_nb[k] - g_nb[k] : own_nb[k] + g_nb[k];
                             }
-                            rkp.load_shared(sp + SL::OFF_NB + lane * K);
-                            cnp.load_shared(PB + 1 * LP + lane * K);
+                            lrow_ldb<REAL, K>(rk, sp + SL::OFF_NB, lane);
+                            lrow_ldb<REAL, K>(cn, PB + 1 * LP, lane);
                         }
-                        rkp.unpack(rk);
-                        cnp.unpack(cn);
                     }
                     // the stage of this step is no longer needed by this warp
                     __syncwarp();
@@ -526,11 +735,13 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
                     if (prof_on) { tclk += (long long)(x[0] != x[0]) + (long long)(m[0] != m[0]); tick(3); }
                     if (do_round) {
                         // position of the rounded label on this term, for the receiver's rounding
+                        int ol, os;
+                        LaneMap<REAL, K>::owner(xs, ol, os);
                         REAL sv = s[0];
 #pragma unroll
                         for (int k = 1; k < K; k++)
-                            if (k == xs % K) sv = s[k];
-                        sv = __shfl_sync(0xffffffffu, sv, xs / K);
+                            if (k == os) sv = s[k];
+                        sv = __shfl_sync(0xffffffffu, sv, ol);
                         if (lane == 0 && !to_next) {
                             // fp32: the word carries the position itself; fp64 (64 value bits do not fit beside the
                             // tag): the label, and the receiver recomputes the position from my plane rows
@@ -544,26 +755,26 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
                             REAL cc[K];
 #pragma unroll
                             for (int k = 0; k < K; k++) cc[k] = alpha * trws::smooth<REAL, KERN>(x[k] - sv, p.lambda);
-                            trws::row_sts<REAL, K>(carry_ptr(par ^ 1, 2 + j), cc, lane);
+                            lrow_sts<REAL, K>(carry_ptr(par ^ 1, 2 + j), cc, lane);
                         }
                     }
                     if (do_send) {
                         REAL vmin;
                         if constexpr (KERN == 1)
-                            vmin = trws::update_linear<REAL, K>(gamma, alpha, p.lambda, p.L, lane, Di, m, s, rk, x, cn, P);
+                            vmin = trws::update_linear<REAL, K>(gamma, alpha, p.lambda, valid, lane, Di, m, s, rk, x, cn, P);
                         else
-                            vmin = trws::update_quadratic<REAL, K>(gamma, alpha, p.lambda, p.L, lane, Di, m, s, rk, x, cn, P);
+                            vmin = trws::update_quadratic<REAL, K>(gamma, alpha, p.lambda, valid, p.L, lane, Di, m, s, rk, x, cn, P);
                         if (PASS == PASS_BWD) acc_lb += (double)vmin;
                         if (prof_on) { tclk += (long long)(m[0] != m[0]); tick(4); }
-                        if (to_next) trws::row_sts<REAL, K>(carry_ptr(par ^ 1, j), m, lane);
+                        if (to_next) lrow_sts<REAL, K>(carry_ptr(par ^ 1, j), m, lane);
 #pragma unroll
                         for (int k = 0; k < K; k++) m[k] = Tag<REAL>::put(m[k], tag);
-                        REAL *dst = p.msg + term * LP + lane * K;
+                        REAL *dst = p.msg + term * LP;
                         if (p.world > 1) {
-                            st_words<REAL, K, true>(dst, m);
-                            if (peer >= 0) st_words<REAL, K, true>(p.peer_msg[peer] + (term + 4 * p.peer_dn[peer]) * LP + lane * K, m);
+                            st_words<REAL, K, true>(dst, m, lane);
+                            if (peer >= 0) st_words<REAL, K, true>(p.peer_msg[peer] + (term + 4 * p.peer_dn[peer]) * LP, m, lane);
                         } else {
-                            st_words<REAL, K, false>(dst, m);
+                            st_words<REAL, K, false>(dst, m, lane);
                         }
                         tick(5);
                     }
@@ -574,71 +785,27 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
             }
             if (prof_on && lane == 0) {
                 tick(6);
-                const int grp = (fs == 0) ? 0 : 1;
-                for (int q = 0; q < 8; q++) atomicAdd((unsigned long long *)p.prof + grp * 16 + q, (unsigned long long)tp[q]);
+                const int grp = ring_strip ? 0 : (fs == p.head_strip ? 2 : 1);
+                for (int q = 0; q < 8; q++) atomicAdd((unsigned long long *)p.prof + grp * 24 + q, (unsigned long long)tp[q]);
             }
         } else {
             // ============================================================ helper warp
+            // helper `hid` prepares the steps whose (CTA-lifetime) step count has parity hid: two helpers, so that
+            // a helper has two step times for its serial work (polls, sums, hand-over, copy issue)
+            const int hid = warp - NTW;
+            const int first = (int)((gstep0 ^ (unsigned)hid) & 1u);   // first own step of this strip
             SegWalker wk, pf;
             wk.init(p.segs, sg0);
             pf.init(p.segs, sg0);
-            int pf_node = 0;   // next step whose bulk copies are to be issued
-            auto issue = [&](int node) {
-                const long long gs = gstep0 + node;
-                const int st = (int)(gs % NS);
-                // the stage was last used NS steps ago: the term warps must have taken their operands from it
-                record(fs, node, 13, st);
-                if (gs >= NS) mbar_wait(bar_free + st, (unsigned)(((gs / NS) - 1) & 1));
-                record(fs, node, 15, st);
-                StepGeo g;
-                pf.get(g);
-                if (node + 1 < n_steps) pf.advance();
-                unsigned char *sp = stage_ptr(st);
-                // lane 0: node rows, lane 1: rank row, lanes 2..7: send slot (lane-2)/3 {messages, byte rows, neighbour rows}
-                const void *src = nullptr;
-                void *dst = nullptr;
-                unsigned bytes = 0;
-                if (lane == 0) {
-                    src = p.nodeF + (long long)g.u * 4 * LP; dst = sp + SL::OFF_NF; bytes = 4 * SL::ROW;
-                } else if (lane == 1) {
-                    src = p.nodeB + (long long)g.u * LP; dst = sp + SL::OFF_NB; bytes = LP;
-                } else if (lane < 8) {
-                    const int sl = (lane - 2) / 3, what = (lane - 2) % 3;
-                    const int d = dir_with_role(g.roles, ROLE_SEND0 + sl);
-                    if (d >= 0) {
-                        const long long pair = pair_of(g.u, d, W);
-                        if (what == 0) {
-                            src = p.msg + pair * 2 * LP; dst = sp + SL::OFF_MS + (size_t)sl * 2 * SL::ROW; bytes = 2 * SL::ROW;
-                        } else if (what == 1) {
-                            src = p.pairB + (pair * 2 + side_of(d)) * 3 * LP; dst = sp + SL::OFF_PB + (size_t)sl * 3 * LP; bytes = 3 * LP;
-                        } else if (d != g.next_dir) {
-                            const long long nb = nb_of(g.u, d, W);
-                            src = p.nodeF + nb * 4 * LP + (vertical(d) ? NF_OWN : NF_GX) * LP;
-                            dst = sp + SL::OFF_XN + (size_t)sl * 2 * SL::ROW; bytes = 2 * SL::ROW;
-                        }
-                    }
-                }
-                unsigned total = bytes;
-#pragma unroll
-                for (int o = 4; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-                if (lane == 0) mbar_expect_tx(bar_full + st, total);
-                __syncwarp();
-                if (bytes) bulk_g2s(dst, src, bytes, bar_full + st);
-                // rows the helper will poll for that step: pull them towards the L2 (where the sender ran long
-                // ago -- the ring in the backward pass -- they have left it)
-                if (lane >= 8 && lane < 12 && do_send) {
-                    const int d = lane - 8;
-                    if (role_of(g.roles, d) == ROLE_POLL) {
-                        const char *row = reinterpret_cast<const char *>(p.msg + pair_of(g.u, d, W) * 2 * LP);
-                        for (int t = 0; t < 2 * SL::ROW; t += 128) trws::prefetch_l2(row + t);
-                    }
-                }
+            int wk_pos = 0, pf_pos = 0;
+            auto seek = [&](SegWalker &w_, int &pos, int target) {
+                while (pos < target && pos + 1 < n_steps) { w_.advance(); pos++; }
             };
-            for (; pf_node < PD && pf_node < n_steps; pf_node++) issue(pf_node);
-            // helper phase timers: issue (incl. wait for a free stage), wait stage, static sum, message polls,
-            // rounding polls, write + arrive
-            const bool prof_on = p.prof != nullptr;
-            long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            int pf_node = first;   // next own step whose bulk copies are to be issued
+            // helper phase timers: wait for a free stage, wait stage, static sum, message polls, rounding polls,
+            // write + arrive, gate, issue work
+            const bool prof_on = p.prof != nullptr && hid == 0;
+            long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tsteps = 0, tretry = 0;
             long long tclk = prof_on ? clock64() : 0;
             auto tick = [&](int which) {
                 if (prof_on) {
@@ -648,51 +815,111 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
                 }
             };
 
-            for (int node = 0; node < n_steps; node++) {
-                const long long gs = gstep0 + node;
+            // Bulk-copy descriptors.  Within a segment every source address is affine in the step index, so each
+            // lane works its copy out ONCE per segment (lane 0: node rows, 1: rank row, 2..7: send slot (lane-2)/3
+            // {messages, byte rows, neighbour rows}, 8..11: rows to pull towards the L2 for the polls) and a step costs
+            // one multiply-add, one expect_tx and one copy instruction.
+            int d_seg = -1;                 // segment the descriptors below belong to
+            const char *d_src = nullptr;    // source of the segment's first step
+            long long d_stride = 0;         // ... advancing by this per step
+            unsigned d_dst = 0, d_bytes = 0, d_total = 0;
+            auto describe = [&]() {
+                StepGeo g;
+                pf.get(g);
+                const long long u0 = pf.u0, du = pf.du;
+                d_src = nullptr; d_stride = 0; d_dst = 0; d_bytes = 0;
+                auto node_row = [&](long long uu) { return reinterpret_cast<const char *>(p.nodeF + uu * 4 * LP); };
+                if (lane == 0) {
+                    d_src = node_row(u0); d_stride = du * 4 * LP * (long long)sizeof(REAL); d_dst = SL::OFF_NF; d_bytes = 4 * SL::ROW;
+                } else if (lane == 1) {
+                    d_src = reinterpret_cast<const char *>(p.nodeB + u0 * LP); d_stride = du * LP; d_dst = SL::OFF_NB; d_bytes = LP;
+                } else if (lane < 8) {
+                    const int sl = (lane - 2) / 3, what = (lane - 2) % 3;
+                    const int d = dir_with_role(g.roles, ROLE_SEND0 + sl);
+                    if (d >= 0) {
+                        const long long pair0 = pair_of(u0, d, W);     // pair ids advance by 2 du per step
+                        if (what == 0) {
+                            d_src = reinterpret_cast<const char *>(p.msg + pair0 * 2 * LP); d_stride = 2 * du * 2 * LP * (long long)sizeof(REAL);
+                            d_dst = SL::OFF_MS + sl * 2 * SL::ROW; d_bytes = 2 * SL::ROW;
+                        } else if (what == 1) {
+                            d_src = reinterpret_cast<const char *>(p.pairB + (pair0 * 2 + side_of(d)) * 3 * LP); d_stride = 2 * du * 2 * 3 * LP;
+                            d_dst = SL::OFF_PB + sl * 3 * LP; d_bytes = 3 * LP;
+                        } else if (d != g.next_dir) {
+                            d_src = node_row(nb_of(u0, d, W)) + (vertical(d) ? NF_OWN : NF_GX) * SL::ROW;
+                            d_stride = du * 4 * LP * (long long)sizeof(REAL);
+                            d_dst = SL::OFF_XN + sl * 2 * SL::ROW; d_bytes = 2 * SL::ROW;
+                        }
+                    }
+                } else if (lane < 12 && do_send && !(g.flags & GF_DEFERRED)) {
+                    const int d = lane - 8;
+                    if (role_of(g.roles, d) == ROLE_POLL) {
+                        d_src = reinterpret_cast<const char *>(p.msg + pair_of(u0, d, W) * 2 * LP);
+                        d_stride = 2 * du * 2 * LP * (long long)sizeof(REAL);
+                        d_bytes = 2 * SL::ROW;   // prefetch only (no stage slot)
+                    }
+                }
+                unsigned total = lane < 8 ? d_bytes : 0u;
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+                d_total = __shfl_sync(0xffffffffu, total, 0);
+                d_seg = pf.sg;
+            };
+            auto issue = [&](int node) {
+                const unsigned gs = gstep0 + (unsigned)node;
+                const int st = (int)(gs % NS);
+                // the stage was last used NS steps ago: the term warps must have taken their operands from it
+                record(fs, node, 13, st);
+                tick(5);
+                // (first use of a stage: the barrier is in its initial phase, and waiting for the parity of the phase
+                // before it returns at once)
+                mbar_wait(bar_free + st, (unsigned)(((gs / NS) + 1) & 1));
+                record(fs, node, 15, st);
+                tick(0);
+                seek(pf, pf_pos, node);
+                if (pf.sg != d_seg) describe();
+                const char *src = d_src + (long long)pf.i * d_stride;
+                if (lane == 0) mbar_expect_tx(bar_full + st, d_total);
+                __syncwarp();
+                if (d_bytes) {
+                    if (lane < 8) bulk_g2s(stage_ptr(st) + d_dst, src, d_bytes, bar_full + st);
+                    else asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(d_bytes) : "memory");
+                }
+            };
+            if (pf_node < n_steps) { issue(pf_node); pf_node += 2; }    // (PD = 2: one own step ahead)
+            int pre_d = -1;
+            unsigned long long pre_wv = 0;
+            REAL pre_v0[K], pre_v1[K];
+#pragma unroll
+            for (int k = 0; k < K; k++) { pre_v0[k] = REAL(0); pre_v1[k] = REAL(0); }
+            for (int node = first; node < n_steps; node += 2) {
+                const unsigned gs = gstep0 + (unsigned)node;
                 const int st = (int)(gs % NS);
                 const unsigned ph = (unsigned)((gs / NS) & 1);
-                const int par = node & 1;
+                const int par = (int)(gs & 1u);     // == hid
                 StepGeo g;
+                seek(wk, wk_pos, node);
                 wk.get(g);
-                const int wk_i = wk.i, wk_n = wk.n, wk_du = wk.du;
-                if (node + 1 < n_steps) wk.advance();
                 record(fs, node, 11, st);
                 mbar_wait(bar_full + st, ph);
                 record(fs, node, 16, (int)g.roles);
-                // Set `par` and the named barrier of this parity were last used by step node - 2: the term warps
-                // have all passed both once they have taken their operands of that step.  issue() at the end of the
-                // previous step waited for exactly that; where nothing was issued there (end of a strip), wait here.
-                if (node >= 2 && node - 1 + PD >= n_steps) {
-                    const long long g2 = gs - 2;
+                // Set `par` and its hand-over barrier were last used by step node - 2: the term warps have all passed
+                // both once they have taken their operands of that step.
+                if (node >= 2) {
+                    const unsigned g2 = gs - 2;
                     record(fs, node, 14, 0);
                     mbar_wait(bar_free + (int)(g2 % NS), (unsigned)((g2 / NS) & 1));
                 }
                 tick(1);
-                // Slack gate.  A strip's step waits for its upstream strip's step, which waits for ITS upstream's ...:
-                // with every hand-over taken at the last moment, the jitter of all strips above accumulates (a
-                // last-passage lattice).  Every `gate` steps this strip therefore waits until the upstream strip is
-                // `gate` nodes ahead, so that the polls of the steps in between succeed at once.
-                if (p.gate > 1 && do_send && !g.flags && (wk_i % p.gate) == 0 && wk_i + p.gate - 1 < wk_n) {
-                    const long long ua = (long long)g.u + (long long)(p.gate - 1) * wk_du;
-                    for (int d = 0; d < 4; d++) {
-                        if (role_of(g.roles, d) != ROLE_POLL) continue;
-                        const REAL *mrow = p.msg + pair_of(ua, d, W) * 2 * LP + lane * K;
-                        for (;;) {
-                            REAL a0[1], a1[1];
-                            if (p.world > 1) { ld_words<REAL, 1, true>(a0, mrow); ld_words<REAL, 1, true>(a1, mrow + LP); }
-                            else { ld_words<REAL, 1, false>(a0, mrow); ld_words<REAL, 1, false>(a1, mrow + LP); }
-                            if (__all_sync(0xffffffffu, Tag<REAL>::ok(a0[0], tag) && Tag<REAL>::ok(a1[0], tag))) break;
-                            __nanosleep(100);
-                        }
-                    }
-                }
                 tick(6);
-                if (!(g.flags & GF_SECOND)) {
+                if (g.flags & GF_DEFERRED) {
+                    REAL base[K];
+                    poll_total<REAL, K>(p.save + (size_t)g.save * LP * (sizeof(REAL) / 4), base, lane, p.epoch);
+                    lrow_sts<REAL, K>(set_ptr(par, R_BASE), base, lane);
+                } else {
                     const unsigned char *sp = stage_ptr(st);
                     const REAL *NF = reinterpret_cast<const REAL *>(sp + SL::OFF_NF);
                     REAL base[K], dib[K], rms[K];
-                    trws::row_lds<REAL, K>(base, NF + NF_D * LP, lane);
+                    lrow_lds<REAL, K>(base, NF + NF_D * LP, lane);
 #pragma unroll
                     for (int k = 0; k < K; k++) { dib[k] = base[k]; rms[k] = REAL(0); }
                     // old messages of the send pairs (they are incoming messages of this node)
@@ -702,7 +929,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
 #pragma unroll
                         for (int jj = 0; jj < 2; jj++) {
                             REAL v[K];
-                            trws::row_lds<REAL, K>(v, reinterpret_cast<const REAL *>(sp + SL::OFF_MS) + (size_t)(sl * 2 + jj) * LP, lane);
+                            lrow_lds<REAL, K>(v, reinterpret_cast<const REAL *>(sp + SL::OFF_MS) + (size_t)(sl * 2 + jj) * LP, lane);
 #pragma unroll
                             for (int k = 0; k < K; k++) { const REAL a = Tag<REAL>::val(v[k]); base[k] += a; rms[k] += a; }
                         }
@@ -712,12 +939,12 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
                         const int role = role_of(g.roles, d);
                         if (role != ROLE_ADD && role != ROLE_POLL) continue;
                         const long long pair = pair_of(g.u, d, W);
-                        const REAL *mrow = p.msg + pair * 2 * LP + lane * K;
+                        const REAL *mrow = p.msg + pair * 2 * LP;
                         if (role == ROLE_ADD) {
 #pragma unroll
                             for (int jj = 0; jj < 2; jj++) {
                                 REAL v[K];
-                                ld_words<REAL, K, false>(v, mrow + jj * LP);
+                                ld_words<REAL, K, false>(v, mrow + jj * LP, lane);
 #pragma unroll
                                 for (int k = 0; k < K; k++) { const REAL a = Tag<REAL>::val(v[k]); base[k] += a; rms[k] += a; }
                             }
@@ -732,21 +959,33 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
                         REAL v0[K], v1[K];
 #pragma unroll
                         for (int k = 0; k < K; k++) { v0[k] = REAL(0); v1[k] = REAL(0); }
+                        // the first round of polls of this pair was issued a step ago (behind the previous hand-over,
+                        // in flight while the bulk copies were issued): use those words first
+                        bool preloaded = pre_d == d;
+                        if (preloaded) {
+                            wv = pre_wv;
+#pragma unroll
+                            for (int k = 0; k < K; k++) { v0[k] = pre_v0[k]; v1[k] = pre_v1[k]; }
+                        }
                         record(fs, node, 12, d);
                         for (;;) {
-                            if (!have_sel) wv = p.world > 1 ? trws::ld_mbox_sys(sb) : trws::ld_mbox(sb);
+                            if (!have_sel && !preloaded) wv = p.world > 1 ? trws::ld_mbox_sys(sb) : trws::ld_mbox(sb);
                             bool ok = true;
                             if (do_send) {
-                                if (p.world > 1) { ld_words<REAL, K, true>(v0, mrow); ld_words<REAL, K, true>(v1, mrow + LP); }
-                                else { ld_words<REAL, K, false>(v0, mrow); ld_words<REAL, K, false>(v1, mrow + LP); }
+                                if (!preloaded) {
+                                    if (p.world > 1) { ld_words<REAL, K, true>(v0, mrow, lane); ld_words<REAL, K, true>(v1, mrow + LP, lane); }
+                                    else { ld_words<REAL, K, false>(v0, mrow, lane); ld_words<REAL, K, false>(v1, mrow + LP, lane); }
+                                }
 #pragma unroll
                                 for (int k = 0; k < K; k++) ok = ok && Tag<REAL>::ok(v0[k], tag) && Tag<REAL>::ok(v1[k], tag);
                             }
                             if (!have_sel) {
                                 if ((unsigned)(wv >> 32) == p.epoch) have_sel = true; else ok = false;
                             }
+                            preloaded = false;
                             if (__all_sync(0xffffffffu, ok)) break;
-                            __nanosleep(20);
+                            tretry++;
+                            __nanosleep(p.poll_ns);
                         }
                         if (do_send) {
 #pragma unroll
@@ -774,8 +1013,8 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
                             }
                             __syncwarp();
                             REAL own_me[K], g_me[K];
-                            trws::row_lds<REAL, K>(own_me, NF + NF_OWN * LP, lane);
-                            trws::row_lds<REAL, K>(g_me, NF + (vertical(d) ? NF_GY : NF_GX) * LP, lane);
+                            lrow_lds<REAL, K>(own_me, NF + NF_OWN * LP, lane);
+                            lrow_lds<REAL, K>(g_me, NF + (vertical(d) ? NF_GY : NF_GX) * LP, lane);
 #pragma unroll
                             for (int jj = 0; jj < 2; jj++) {
                                 const REAL aj = __shfl_sync(0xffffffffu, al, jj), sj = __shfl_sync(0xffffffffu, sel, jj);
@@ -789,27 +1028,54 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
                             if (prof_on) { tclk += (long long)(dib[0] != dib[0]); tick(4); }
                         }
                     }
-                    trws::row_sts<REAL, K>(set_ptr(par, R_BASE), base, lane);
+                    lrow_sts<REAL, K>(set_ptr(par, R_BASE), base, lane);
                     if (do_round) {
-                        trws::row_sts<REAL, K>(set_ptr(par, R_DIB0), dib, lane);
-                        trws::row_sts<REAL, K>(set_ptr(par, R_RMS), rms, lane);
+                        lrow_sts<REAL, K>(set_ptr(par, R_DIB0), dib, lane);
+                        lrow_sts<REAL, K>(set_ptr(par, R_RMS), rms, lane);
                     }
                 }
                 record(fs, node, 17, 0);
-                if (par) full_arrive<2>(); else full_arrive<1>();
+                // hand-over: an mbarrier arrive (a named-barrier arrive also waits for the warp's outstanding copies)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_base + par);
                 tick(5);
                 // bulk copies of the step PD ahead: behind the hand-over, so that the helper runs up to two steps
                 // ahead of the term warps (the stage it refills was released when they STARTED step node - 1)
-                if (pf_node < n_steps) { issue(pf_node); pf_node++; }
-                tick(0);
-                if (prof_on) tp[7]++;
+                // first round of polls of the NEXT step: in flight while the bulk copies below are issued
+                pre_d = -1;
+                if (node + 2 < n_steps) {
+                    StepGeo gn;
+                    seek(wk, wk_pos, node + 2);
+                    wk.get(gn);
+                    if (!(gn.flags & GF_DEFERRED)) {
+                        const int dn = dir_with_role(gn.roles, ROLE_POLL);
+                        if (dn >= 0) {
+                            const long long pairn = pair_of(gn.u, dn, W);
+                            const REAL *mrow = p.msg + pairn * 2 * LP;
+                            if (do_send) {
+                                if (p.world > 1) { ld_words<REAL, K, true>(pre_v0, mrow, lane); ld_words<REAL, K, true>(pre_v1, mrow + LP, lane); }
+                                else { ld_words<REAL, K, false>(pre_v0, mrow, lane); ld_words<REAL, K, false>(pre_v1, mrow + LP, lane); }
+                            }
+                            if (do_round && lane < 2) {
+                                const unsigned long long *sb = p.selbox + pairn * 2 + (lane & 1);
+                                pre_wv = p.world > 1 ? trws::ld_mbox_sys(sb) : trws::ld_mbox(sb);
+                            }
+                            pre_d = dn;
+                        }
+                    }
+                }
+                if (pf_node < n_steps) { issue(pf_node); pf_node += 2; }
+                tick(7);
+                tsteps++;
             }
             if (prof_on && lane == 0) {
-                const int grp = (fs == 0) ? 0 : 1;
-                for (int q = 0; q < 8; q++) atomicAdd((unsigned long long *)p.prof + grp * 16 + 8 + q, (unsigned long long)tp[q]);
+                const int grp = ring_strip ? 0 : (fs == p.head_strip ? 2 : 1);
+                for (int q = 0; q < 8; q++) atomicAdd((unsigned long long *)p.prof + grp * 24 + 8 + q, (unsigned long long)tp[q]);
+                atomicAdd((unsigned long long *)p.prof + grp * 24 + 16, (unsigned long long)tsteps);
+                atomicAdd((unsigned long long *)p.prof + grp * 24 + 17, (unsigned long long)tretry);
             }
         }
-        gstep0 += n_steps;
+        gstep0 += (unsigned)n_steps;
         record(fs, n_steps, 99, 0);
     }
     if (is_term && lane == 0) {

@@ -32,7 +32,7 @@ namespace {
 struct Step {
     int u;            // local node id
     uint32_t roles;
-    int gamma_den, next_dir, flags;
+    int gamma_den, next_dir, flags, save;
     uint8_t peer[4];
 };
 
@@ -76,12 +76,41 @@ void build_gpass_plan(int H, int W, int pass, int rank, int world, GPassPlan &pl
     plan.segs.clear();
     plan.seg_ptr.clear();
     plan.strip_len.clear();
-    std::vector<Step> steps;
-    for (int fs = 0; fs < S; fs++) {
+    plan.is_ring.clear();
+    plan.save_slots = 0;
+    auto emit = [&](const std::vector<Step> &steps, bool ring) {
+        plan.seg_ptr.push_back((int32_t)plan.segs.size());
+        plan.strip_len.push_back((int32_t)steps.size());
+        plan.is_ring.push_back(ring ? 1 : 0);
+        // fold runs of identical shape, constant node stride and consecutive scratch slots
+        size_t i = 0;
+        while (i < steps.size()) {
+            GSeg g;
+            std::memset(&g, 0, sizeof(g));
+            g.u0 = steps[i].u; g.du = 0; g.n = 1;
+            g.roles = steps[i].roles; g.gamma_den = (int16_t)steps[i].gamma_den; g.next_dir = (int8_t)steps[i].next_dir;
+            g.flags = (uint8_t)steps[i].flags; g.save0 = steps[i].save;
+            std::memcpy(g.peer, steps[i].peer, 4);
+            size_t j = i + 1;
+            if (j < steps.size() && same_shape(steps[i], steps[j]) && (!steps[i].flags || steps[j].save == steps[i].save + 1)) {
+                g.du = steps[j].u - steps[i].u;
+                while (j < steps.size() && same_shape(steps[i], steps[j]) &&
+                       steps[j].u == g.u0 + (int64_t)(j - i) * g.du &&
+                       (!steps[i].flags || steps[j].save == steps[i].save + (int)(j - i))) j++;
+                g.n = (int32_t)(j - i);
+            }
+            plan.segs.push_back(g);
+            i = j;
+        }
+    };
+    std::vector<Step> steps, aux;
+    for (int k = 0; k < S; k++) {
+        const int fs = pass == 0 ? k : S - 1 - k;     // processing order of this pass
         if (rank >= 0 && s.owner[fs] != rank) continue;
         const int64_t sb = s.strip_ptr[fs], se = s.strip_ptr[fs + 1], len = se - sb;
         auto node_at = [&](int64_t i) { return (int)s.nodes[pass == 0 ? sb + i : se - 1 - i]; };
         steps.clear();
+        aux.clear();
         for (int64_t i = 0; i < len; i++) {
             const int u = node_at(i);
             const int u_prev = i > 0 ? node_at(i - 1) : -1, u_next = i + 1 < len ? node_at(i + 1) : -1;
@@ -98,12 +127,20 @@ void build_gpass_plan(int H, int W, int pass, int rank, int world, GPassPlan &pl
             base.u = local_id(u);
             base.gamma_den = std::max(1, std::max(nF, nB));
             base.next_dir = -1;
-            // send directions, the one towards the next strip node LAST (its messages are handed over
-            // through shared memory by the step right before that node)
+            // send directions by urgency: the next strip node first, then the receivers in the order this pass
+            // reaches them (ascending node order forward, descending backward)
             int sd[4], ns = 0;
-            for (int d = 0; d < 4; d++)
-                if (((send_mask >> d) & 1u) && d != d_next) sd[ns++] = d;
             if (d_next >= 0) sd[ns++] = d_next;
+            {
+                int cand[4], nc = 0;
+                for (int d = 0; d < 4; d++)
+                    if (((send_mask >> d) & 1u) && d != d_next) cand[nc++] = d;
+                std::sort(cand, cand + nc, [&](int a, int b) {
+                    const int32_t oa = order[nb_ref(u, a)], ob = order[nb_ref(u, b)];
+                    return pass == 0 ? oa < ob : oa > ob;
+                });
+                for (int q = 0; q < nc; q++) sd[ns++] = cand[q];
+            }
             for (int d = 0; d < 4; d++)
                 if ((send_mask >> d) & 1u) {
                     if (rank >= 0) {
@@ -114,50 +151,65 @@ void build_gpass_plan(int H, int W, int pass, int rank, int world, GPassPlan &pl
                     }
                 }
             auto role_set = [](uint32_t &roles, int d, int role) { roles |= (uint32_t)role << (4 * d); };
-            uint32_t dep_roles = 0;
+            Step st = base;
             for (int d = 0; d < 4; d++)
-                if ((dep_mask >> d) & 1u) role_set(dep_roles, d, d == d_prev ? ROLE_CARRY : ROLE_POLL);
-            if (ns <= 2) {
-                Step st = base;
-                st.roles = dep_roles;
-                for (int q = 0; q < ns; q++) role_set(st.roles, sd[q], ROLE_SEND0 + q);
-                st.next_dir = d_next;
+                if ((dep_mask >> d) & 1u) role_set(st.roles, d, d == d_prev ? ROLE_CARRY : ROLE_POLL);
+            // the to-next pair goes into send slot 1 (its warps also hand the carry rows over), the other into slot 0
+            auto is_ring_node = [&](int v) { const int r = v % H, c = v / H; return r == 0 || r == H - 1 || c == 0 || c == W - 1; };
+            bool urgent_extra = false;   // a send beyond the first two goes to an INTERIOR node: the wavefront waits for it
+            for (int q = 2; q < ns; q++)
+                if (!is_ring_node(nb_ref(u, sd[q]))) urgent_extra = true;
+            if (ns > 2 && urgent_extra) {
+                // split in place: this step sends on the two most urgent pairs that do not lead to the next strip
+                // node and saves the node total; the step right behind it sends on the rest, the to-next pair included
+                // (so the carry rows are still written by the step before the next node)
+                SB_REQUIRE(pass == 1, SB_EUNSUP, "sb_trws_grid: a forward node sends on more than two pairs");
+                int oth[4], no = 0;
+                for (int q = 0; q < ns; q++)
+                    if (sd[q] != d_next) oth[no++] = sd[q];
+                st.flags = GF_SAVE;
+                st.save = plan.save_slots++;
+                role_set(st.roles, oth[0], ROLE_SEND0);
+                role_set(st.roles, oth[1], ROLE_SEND1);
+                Step ax = base;
+                ax.flags = GF_DEFERRED;
+                ax.save = st.save;
+                int slot = 0;
+                for (int q = 2; q < no; q++) { role_set(st.roles, oth[q], ROLE_ADD); role_set(ax.roles, oth[q], ROLE_SEND0 + slot++); }
+                if (d_next >= 0) {
+                    role_set(st.roles, d_next, ROLE_ADD);
+                    role_set(ax.roles, d_next, slot == 0 ? ROLE_SEND0 : ROLE_SEND1);
+                    ax.next_dir = d_next;
+                }
                 steps.push_back(st);
-            } else {
-                Step a = base, b = base;
-                a.roles = dep_roles;
-                a.flags = GF_FIRST;
-                role_set(a.roles, sd[0], ROLE_SEND0);
-                role_set(a.roles, sd[1], ROLE_SEND1);
-                for (int q = 2; q < ns; q++) role_set(a.roles, sd[q], ROLE_ADD);
-                b.flags = GF_SECOND;
-                for (int q = 2; q < ns; q++) role_set(b.roles, sd[q], ROLE_SEND0 + (q - 2));
-                b.next_dir = d_next;
-                steps.push_back(a);
-                steps.push_back(b);
+                steps.push_back(ax);
+                continue;
             }
+            const int kept = std::min(ns, 2);
+            if (kept == 2) { role_set(st.roles, sd[1], ROLE_SEND0); role_set(st.roles, sd[0], ROLE_SEND1); }
+            else if (kept == 1) role_set(st.roles, sd[0], ROLE_SEND0);
+            st.next_dir = d_next;
+            if (ns > 2) {
+                // the sends beyond two all go to ring nodes, which only the far end of the pass needs: they run at
+                // the end of the strip, from the saved node total
+                SB_REQUIRE(pass == 1, SB_EUNSUP, "sb_trws_grid: a forward node sends on more than two pairs");
+                st.flags = GF_SAVE;
+                st.save = plan.save_slots++;
+                for (int q = 2; q < ns; q++) role_set(st.roles, sd[q], ROLE_ADD);
+                Step ax = base;
+                ax.flags = GF_DEFERRED;
+                ax.save = st.save;
+                for (int q = 2; q < ns; q++) role_set(ax.roles, sd[q], ROLE_SEND0 + (q - 2));
+                aux.push_back(ax);
+            }
+            steps.push_back(st);
         }
-        plan.seg_ptr.push_back((int32_t)plan.segs.size());
-        plan.strip_len.push_back((int32_t)steps.size());
-        // fold runs of identical shape and constant stride
-        size_t i = 0;
-        while (i < steps.size()) {
-            GSeg g;
-            std::memset(&g, 0, sizeof(g));
-            g.u0 = steps[i].u; g.du = 0; g.n = 1;
-            g.roles = steps[i].roles; g.gamma_den = (int16_t)steps[i].gamma_den; g.next_dir = (int8_t)steps[i].next_dir;
-            g.flags = (uint8_t)steps[i].flags;
-            std::memcpy(g.peer, steps[i].peer, 4);
-            size_t j = i + 1;
-            // two-step nodes stay segments of their own (their second step repeats the node id)
-            if (!steps[i].flags && j < steps.size() && same_shape(steps[i], steps[j])) {
-                g.du = steps[j].u - steps[i].u;
-                while (j < steps.size() && same_shape(steps[i], steps[j]) &&
-                       steps[j].u == g.u0 + (int64_t)(j - i) * g.du) j++;
-                g.n = (int32_t)(j - i);
-            }
-            plan.segs.push_back(g);
-            i = j;
+        // the deferred sends run at the END of the same strip, by the same CTA: nothing but the far end of the pass
+        // (the boundary ring) waits for them, and a strip of their own would only park a CTA until its row starts
+        steps.insert(steps.end(), aux.begin(), aux.end());
+        {
+            const int u0 = node_at(0), r0 = u0 % H, c0 = u0 / H;
+            emit(steps, r0 == 0 || r0 == H - 1 || c0 == 0 || c0 == W - 1);
         }
     }
     plan.seg_ptr.push_back((int32_t)plan.segs.size());

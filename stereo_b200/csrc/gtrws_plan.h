@@ -21,8 +21,9 @@ enum { ROLE_NONE = 0,
        ROLE_POLL = 4,    // receives: waits for the neighbour's two messages of this pass (tagged words)
        ROLE_CARRY = 5 }; // receives from the previous node of the strip through shared memory
 
-enum { GF_SECOND = 1,    // second step of a node that sends on more than two pairs: node total taken from the first
-       GF_FIRST = 2 };   // first step of such a node: saves the node total
+enum { GF_SAVE = 1,      // the node sends on more than two pairs: the extra pairs are only summed here (ROLE_ADD), the node
+                         // total is saved to a scratch slot and the extra sends run at the end of the strip
+       GF_DEFERRED = 2 };// such a deferred step: node total taken from the scratch slot, no dependencies
 
 // A run of node steps with identical roles and a constant node stride (32 bytes).
 struct GSeg {
@@ -32,14 +33,17 @@ struct GSeg {
     int8_t next_dir;         // direction of the next strip node when it is a send target, else -1
     uint8_t flags;           // GF_*
     uint8_t peer[4];         // per direction: 0 receiver local, 1 on rank - 1, 2 on rank + 1
-    int32_t pad[2];
+    int32_t save0;           // GF_SAVE / GF_DEFERRED: scratch slot of the segment's first node (slots advance by 1)
+    int32_t pad;
 };
 static_assert(sizeof(GSeg) == 32, "GSeg layout");
 
 struct GPassPlan {
     std::vector<GSeg> segs;
     std::vector<int32_t> seg_ptr;    // per strip of this rank (schedule order)
-    std::vector<int32_t> strip_len;  // node STEPS per strip (a two-step node counts twice)
+    std::vector<int32_t> strip_len;  // node steps per strip
+    std::vector<int32_t> is_ring;    // the strip is (a piece of) the boundary ring
+    int32_t save_slots = 0;          // scratch slots for saved node totals
 };
 
 // Band geometry of rank `rank` of `world`: rows it sweeps [r_lo, r_hi), rows it stores [r_base, r_top)
@@ -47,7 +51,9 @@ struct GPassPlan {
 struct Band { int r_lo, r_hi, r_base, r_top; };
 Band band_rows(int H, int rank, int world);
 
-// pass 0 forward, 1 backward.  rank < 0: whole grid on one GPU.
+// pass 0 forward, 1 backward.  rank < 0: whole grid on one GPU.  Strips are listed in PROCESSING order of the pass
+// (the backward sweep runs the forward schedule in reverse); the deferred sends of a strip's nodes (GF_DEFERRED
+// steps) follow its regular steps.
 void build_gpass_plan(int H, int W, int pass, int rank, int world, GPassPlan &plan);
 
 } // namespace gtrws

@@ -43,7 +43,7 @@ double now_ms()
 
 struct Ctrl {
     int ticket;
-    int pad;
+    int ring_smid;
     double acc[2];
 };
 
@@ -67,9 +67,10 @@ template <typename T> struct RawBuf {
 };
 
 struct GridPlanDev {
-    int S = 0;
+    int S[2] = {0, 0};
+    int save_slots = 0;
     DevBuf<GSeg> segs[2];
-    DevBuf<int32_t> seg_ptr[2], strip_len[2];
+    DevBuf<int32_t> seg_ptr[2], strip_len[2], is_ring[2];
 };
 
 std::shared_ptr<GridPlanDev> grid_plan(int dev, int H, int W, int rank, int world)
@@ -84,10 +85,13 @@ std::shared_ptr<GridPlanDev> grid_plan(int dev, int H, int W, int rank, int worl
     for (int pass = 0; pass < 2; pass++) {
         GPassPlan plan;
         build_gpass_plan(H, W, pass, world > 1 ? rank : -1, world, plan);
-        gp->S = (int)plan.strip_len.size();
+        gp->S[pass] = (int)plan.strip_len.size();
+        gp->save_slots = std::max(gp->save_slots, (int)plan.save_slots);
         gp->segs[pass].alloc(std::max<size_t>(plan.segs.size(), 1));
         gp->seg_ptr[pass].alloc(plan.seg_ptr.size());
         gp->strip_len[pass].alloc(std::max<size_t>(plan.strip_len.size(), 1));
+        gp->is_ring[pass].alloc(std::max<size_t>(plan.is_ring.size(), 1));
+        SB_CUDA(cudaMemcpy(gp->is_ring[pass].p, plan.is_ring.data(), plan.is_ring.size() * 4, cudaMemcpyHostToDevice));
         SB_CUDA(cudaMemcpy(gp->segs[pass].p, plan.segs.data(), plan.segs.size() * sizeof(GSeg), cudaMemcpyHostToDevice));
         SB_CUDA(cudaMemcpy(gp->seg_ptr[pass].p, plan.seg_ptr.data(), plan.seg_ptr.size() * 4, cudaMemcpyHostToDevice));
         SB_CUDA(cudaMemcpy(gp->strip_len[pass].p, plan.strip_len.data(), plan.strip_len.size() * 4, cudaMemcpyHostToDevice));
@@ -301,7 +305,7 @@ struct Solver : SolverBase {
     cudaStream_t stream = 0;
     RawBuf<REAL> dNodeF, dMsg, dAlpha;
     RawBuf<uint8_t> dNodeB, dPairB;
-    RawBuf<unsigned long long> dSelBox;
+    RawBuf<unsigned long long> dSelBox, dSave;
     RawBuf<int32_t> dSol;
     RawBuf<unsigned char> dCtrl;
     RawBuf<long long> dProf;
@@ -312,6 +316,7 @@ struct Solver : SolverBase {
     void *peer_ptr[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     GProblem<REAL> P;
     int grid_fwd = 1, grid_bwd = 1;
+    bool isolate = false;
     unsigned launch_epoch = 0, pass_counter = 0;
     Ctrl *hc = nullptr;   // pinned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -348,6 +353,8 @@ struct Solver : SolverBase {
         dSelBox.alloc((size_t)Nloc * 4);
         dSol.alloc((size_t)Nloc);
         dCtrl.alloc(sizeof(Ctrl));
+        dSave.alloc((size_t)std::max(plan->save_slots, 1) * LP * (sizeof(REAL) / 4));
+        SB_CUDA(cudaMemsetAsync(dSave.p, 0, dSave.bytes(), stream));
         SB_CUDA(cudaMemsetAsync(dNodeF.p, 0, dNodeF.bytes(), stream));
         SB_CUDA(cudaMemsetAsync(dAlpha.p, 0, dAlpha.bytes(), stream));
         SB_CUDA(cudaMemsetAsync(dSelBox.p, 0, dSelBox.bytes(), stream));
@@ -359,22 +366,23 @@ struct Solver : SolverBase {
         P.H = H; P.W = W; P.L = L; P.LP = LP; P.rows = rows; P.Nloc = Nloc;
         P.nodeF = dNodeF.p; P.nodeB = dNodeB.p; P.msg = dMsg.p; P.pairB = dPairB.p; P.alpha = dAlpha.p;
         P.selbox = dSelBox.p; P.lambda = (REAL)tol;
-        P.S = plan->S; P.world = world; P.sol = dSol.p;
+        P.S = plan->S[0]; P.world = world; P.sol = dSol.p; P.save = dSave.p;
         Ctrl *ctrl = reinterpret_cast<Ctrl *>(dCtrl.p);
-        P.ticket = &ctrl->ticket; P.acc = ctrl->acc;
+        P.ticket = &ctrl->ticket; P.acc = ctrl->acc; P.ring_smid = &ctrl->ring_smid;
 
         if (getenv("SB_TRWS_PROFILE")) {
-            dProf.alloc(64);
+            dProf.alloc(144);
             SB_CUDA(cudaMemsetAsync(dProf.p, 0, dProf.bytes(), stream));
             P.prof = dProf.p;
             P.prof_warp = (atoi(getenv("SB_TRWS_PROFILE")) - 1) & 3;
         }
         if (const char *e = getenv("SB_TRWS_WATCHDOG_MS")) watchdog_ms = atof(e);
-        P.gate = 1;
-        if (const char *e = getenv("SB_GTRWS_GATE")) P.gate = std::max(1, atoi(e));
+        P.poll_ns = 100;
+        if (const char *e = getenv("SB_GTRWS_POLL_NS")) P.poll_ns = (unsigned)std::max(0, atoi(e));
+
         if (getenv("SB_TRWS_RECORD")) {
             rec_ctas = 1024;
-            SB_CUDA(cudaHostAlloc((void **)&rec_host, (size_t)rec_ctas * 5 * 4 * sizeof(int), cudaHostAllocMapped));
+            SB_CUDA(cudaHostAlloc((void **)&rec_host, (size_t)rec_ctas * 6 * 4 * sizeof(int), cudaHostAllocMapped));
             SB_CUDA(cudaHostGetDevicePointer((void **)&P.rec, rec_host, 0));
         }
         auto grid_for = [&](int pass) {
@@ -382,14 +390,24 @@ struct Solver : SolverBase {
             SB_REQUIRE(bps >= 1, SB_ECUDA, "sb_trws_grid: sweep kernel does not fit on an SM");
             long long g = (long long)bps * num_sms;
             if (const char *e = getenv("SB_GTRWS_CTAS_PER_SM")) g = std::max(1, std::min(bps, atoi(e))) * (long long)num_sms;
-            if (g > P.S) g = P.S;
+            const int Sp = plan->S[pass == PASS_FWD ? 0 : 1];
+            if (g > Sp) g = Sp;
+            // even waves: a CTA walks one strip (image row) at a time, so with S strips and g walkers the pass takes
+            // ceil(S / g) rounds whatever g is within that bracket -- the fewest walkers that keep the round count
+            // leave the least contention per SM and no mostly-idle last round
+            if (!getenv("SB_GTRWS_NO_EVEN_WAVES") && g >= 1) {
+                const long long rounds = (Sp + g - 1) / g;
+                g = (Sp + rounds - 1) / rounds;
+            }
             if (rec_host && g > rec_ctas) g = rec_ctas;
             // two strip walkers must be in flight: (H-3,1) waits for (H-2,1) (trws_order.cpp)
-            SB_REQUIRE(P.S < 2 || g >= 2, SB_ECUDA, "sb_trws_grid: fewer than two resident CTAs");
+            SB_REQUIRE(Sp < 2 || g >= 2, SB_ECUDA, "sb_trws_grid: fewer than two resident CTAs");
             return (int)std::max<long long>(g, 1);
         };
         grid_fwd = grid_for(PASS_FWD);
         grid_bwd = grid_for(PASS_BWD);
+        // the ring chain gets an SM of its own when there are CTAs to spare (at least three per SM)
+        isolate = grid_fwd >= 3 * num_sms && !getenv("SB_GTRWS_NO_ISOLATE");
         reset();
         SB_CUDA(cudaStreamSynchronize(stream));
         setup_ms = now_ms() - t0;
@@ -519,14 +537,19 @@ struct Solver : SolverBase {
         P.epoch = ++launch_epoch;
         P.mode = mode;
         const int pi = pass == PASS_FWD ? 0 : 1;
-        if (dProf.p) P.prof = dProf.p + 32 * pi;
+        if (dProf.p) P.prof = dProf.p + 72 * pi;
+        P.head_strip = pass == PASS_FWD ? (world > 1 ? -1 : 1) : 0;
+        if (const char *e = getenv("SB_PROF_STRIP")) P.head_strip = atoi(e);
         P.segs = plan->segs[pi].p;
         P.seg_ptr = plan->seg_ptr[pi].p;
         P.strip_len = plan->strip_len[pi].p;
+        P.is_ring = plan->is_ring[pi].p;
+        P.S = plan->S[pi];
+        P.isolate_ring = (pass == PASS_FWD && isolate) ? 1 : 0;
         GSweepLaunch sl;
         sl.precision = precision; sl.kern = kernel; sl.pass = pass; sl.problem = &P;
         sl.grid = pass == PASS_FWD ? grid_fwd : grid_bwd; sl.stream = stream;
-        if (rec_host) std::memset(rec_host, 0xff, (size_t)rec_ctas * 5 * 4 * sizeof(int));
+        if (rec_host) std::memset(rec_host, 0xff, (size_t)rec_ctas * 6 * 4 * sizeof(int));
         SB_CUDA(cudaEventRecord(ev0, stream));
         ops->sweep(sl);
         SB_CUDA(cudaEventRecord(ev1, stream));
@@ -543,8 +566,8 @@ struct Solver : SolverBase {
                 if (rec_host)
                     for (int c = 0; c < sl.grid && c < rec_ctas; c++) {
                         fprintf(stderr, "[sb record] cta %d:", c);
-                        for (int w = 0; w < 5; w++) {
-                            const int *r = rec_host + ((size_t)c * 5 + w) * 4;
+                        for (int w = 0; w < 6; w++) {
+                            const int *r = rec_host + ((size_t)c * 6 + w) * 4;
                             fprintf(stderr, " w%d(strip %d step %d ph %d x%x)", w, r[0], r[1], r[2], r[3]);
                         }
                         fprintf(stderr, "\n");
@@ -627,16 +650,16 @@ struct Solver : SolverBase {
         }
         const double solve_ms = timer.stop_ms();
         if (P.prof) {
-            long long h[64];
+            long long h[144];
             SB_CUDA(cudaMemcpy(h, dProf.p, sizeof(h), cudaMemcpyDeviceToHost));
             SB_CUDA(cudaMemsetAsync(dProf.p, 0, sizeof(h), stream));
-            for (int g = 0; g < 4; g++) {
-                const long long *q = h + 16 * g;
-                const double nt = q[7] ? (double)q[7] : 1, nh = q[15] ? (double)q[15] : 1;
+            for (int g = 0; g < 6; g++) {
+                const long long *q = h + 24 * g;
+                const double nt = q[7] ? (double)q[7] : 1, nh = q[16] ? (double)q[16] : 1;
                 fprintf(stderr, "[sb gprofile] %s %s term (%lld steps): waitFULL=%.0f waitstage=%.0f total+round=%.0f operands=%.0f update=%.0f "
-                        "stores=%.0f tail=%.0f | helper (%lld): issue=%.0f waitstage=%.0f static=%.0f msgpoll=%.0f roundpoll=%.0f write=%.0f gate=%.0f cyc/step\n",
-                        g >= 2 ? "bwd" : "fwd", (g & 1) ? "rows" : "ring", q[7], q[0] / nt, q[1] / nt, q[2] / nt, q[3] / nt, q[4] / nt, q[5] / nt, q[6] / nt, q[15],
-                        q[8] / nh, q[9] / nh, q[10] / nh, q[11] / nh, q[12] / nh, q[13] / nh, q[14] / nh);
+                        "stores=%.0f tail=%.0f | helper (%lld): waitfree=%.0f waitstage=%.0f static=%.0f msgpoll=%.0f roundpoll=%.0f write=%.0f gate=%.0f issuework=%.0f cyc/step, %.2f poll retries/step\n",
+                        g >= 3 ? "bwd" : "fwd", (g % 3) == 0 ? "ring" : (g % 3) == 1 ? "rows" : "head row", q[7], q[0] / nt, q[1] / nt, q[2] / nt, q[3] / nt, q[4] / nt, q[5] / nt, q[6] / nt, q[16],
+                        q[8] / nh, q[9] / nh, q[10] / nh, q[11] / nh, q[12] / nh, q[13] / nh, q[14] / nh, q[15] / nh, q[17] / nh);
             }
         }
         *energy_out = energy;
@@ -827,8 +850,8 @@ int sb_trws_grid_plan_stats(int H, int W, int rank, int world, int64_t *stats)
             int64_t steps = 0, nodes = 0, two = 0, peer_up = 0, peer_down = 0;
             for (const auto &s : plan.segs) {
                 steps += s.n;
-                if (!(s.flags & sb::gtrws::GF_SECOND)) nodes += s.n;
-                if (s.flags & sb::gtrws::GF_FIRST) two += s.n;
+                if (!(s.flags & sb::gtrws::GF_DEFERRED)) nodes += s.n;
+                if (s.flags & sb::gtrws::GF_SAVE) two += s.n;
                 for (int d = 0; d < 4; d++) {
                     if (s.peer[d] == 1) peer_up += s.n;
                     if (s.peer[d] == 2) peer_down += s.n;

@@ -177,8 +177,11 @@ __global__ void gupdate_message_kernel(int L, const double *__restrict__ Di_in, 
     rank_rows<REAL, K>(sh[0], lane, rk);
     count_rows<REAL, K>(sh[1], sh[0], lane, cn);   // #{src <= dst[l]}
     REAL vmin;
-    if constexpr (KERN == 1) vmin = trws::update_linear<REAL, K>((REAL)gamma, (REAL)alpha, (REAL)lambda, L, lane, Di, m, s, rk, x, cn, P);
-    else vmin = trws::update_quadratic<REAL, K>((REAL)gamma, (REAL)alpha, (REAL)lambda, L, lane, Di, m, s, rk, x, cn, P);
+    unsigned valid = 0;
+#pragma unroll
+    for (int k = 0; k < K; k++) valid |= (lane * K + k < L ? 1u : 0u) << k;
+    if constexpr (KERN == 1) vmin = trws::update_linear<REAL, K>((REAL)gamma, (REAL)alpha, (REAL)lambda, valid, lane, Di, m, s, rk, x, cn, P);
+    else vmin = trws::update_quadratic<REAL, K>((REAL)gamma, (REAL)alpha, (REAL)lambda, valid, L, lane, Di, m, s, rk, x, cn, P);
 #pragma unroll
     for (int k = 0; k < K; k++)
         if (lane * K + k < L) msg_out[lane * K + k] = (double)m[k];

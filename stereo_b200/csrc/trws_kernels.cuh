@@ -303,8 +303,9 @@ template <int K> __host__ __device__ constexpr int scratch_pairs() { return 2 + 
 // (typeStereoLinear.h:375-480).  Equal to the reference's cone envelope except on exact ties
 // h_j - h_k == alpha (q_k - q_j), where the reference drops cone k and returns values above the exact
 // minimum (include/stereo_b200.h, sb_trws_update_message; tests/test_update_message_gpu.py).
+// `valid`: bit k set iff this lane's k-th label is a real label (< L); the caller owns the lane <-> label map.
 template <typename REAL, int K>
-__device__ __forceinline__ REAL update_linear(REAL gamma, REAL alpha, REAL lambda, int L, int lane,
+__device__ __forceinline__ REAL update_linear(REAL gamma, REAL alpha, REAL lambda, unsigned valid, int lane,
                                               const REAL (&Di)[K], REAL (&m)[K], const REAL (&s)[K],
                                               const uint8_t (&rk)[K], const REAL (&x)[K],
                                               const uint8_t (&cn)[K], Pair<REAL> *P)
@@ -314,7 +315,7 @@ __device__ __forceinline__ REAL update_linear(REAL gamma, REAL alpha, REAL lambd
     REAL hmin = BIG;
 #pragma unroll
     for (int k = 0; k < K; k++) {
-        h[k] = (lane * K + k < L) ? gamma * Di[k] - m[k] : BIG;
+        h[k] = ((valid >> k) & 1u) ? gamma * Di[k] - m[k] : BIG;
         hmin = min(hmin, h[k]);
     }
     hmin = warp_min(hmin);
@@ -405,7 +406,7 @@ __device__ __forceinline__ REAL update_linear(REAL gamma, REAL alpha, REAL lambd
         const Pair<REAL> hi = P[phys<K>(c)];
         const REAL v = min(vTrunc, min(lo.a + alpha * fabs(x[k] - lo.b), hi.a + alpha * fabs(x[k] - hi.b)));
         m[k] = v;
-        if (lane * K + k < L) vmin = min(vmin, v);
+        if ((valid >> k) & 1u) vmin = min(vmin, v);
     }
     vmin = warp_min(vmin);
 #pragma unroll
@@ -419,7 +420,7 @@ __device__ __forceinline__ REAL update_linear(REAL gamma, REAL alpha, REAL lambd
 // cost at least vTrunc, so each destination scans outward from its merge
 // position in the sorted sources and stops at the truncation radius.
 template <typename REAL, int K>
-__device__ __forceinline__ REAL update_quadratic(REAL gamma, REAL alpha, REAL lambda, int L, int lane,
+__device__ __forceinline__ REAL update_quadratic(REAL gamma, REAL alpha, REAL lambda, unsigned valid, int L, int lane,
                                                  const REAL (&Di)[K], REAL (&m)[K], const REAL (&s)[K],
                                                  const uint8_t (&rk)[K], const REAL (&x)[K],
                                                  const uint8_t (&cn)[K], Pair<REAL> *P)
@@ -428,7 +429,7 @@ __device__ __forceinline__ REAL update_quadratic(REAL gamma, REAL alpha, REAL la
     REAL hmin = BIG;
 #pragma unroll
     for (int k = 0; k < K; k++) {
-        const REAL h = (lane * K + k < L) ? gamma * Di[k] - m[k] : BIG;
+        const REAL h = ((valid >> k) & 1u) ? gamma * Di[k] - m[k] : BIG;
         hmin = min(hmin, h);
         Pair<REAL> t;
         t.a = h;
@@ -448,7 +449,7 @@ __device__ __forceinline__ REAL update_quadratic(REAL gamma, REAL alpha, REAL la
 #pragma unroll
     for (int k = 0; k < K; k++) {
         REAL best = vTrunc;
-        if (lane * K + k < L) {
+        if ((valid >> k) & 1u) {
             const int c = cn[k];
             const REAL xk = x[k];
             for (int j = c - 1; j >= 0; j--) {
@@ -807,10 +808,13 @@ __global__ void __launch_bounds__(cta_threads(NHW), (sizeof(REAL) == 4 && K <= 4
                     uint8_t rk[K], cn[K];
                     o.rkp.unpack(rk);
                     o.cnp.unpack(cn);
+                    unsigned valid = 0;
+#pragma unroll
+                    for (int k = 0; k < K; k++) valid |= (lane * K + k < p.L ? 1u : 0u) << k;
                     if constexpr (KERN == 1)
-                        vmin = update_linear<REAL, K>(gamma, o.alpha, p.lambda, p.L, lane, Di, o.m, o.s, rk, o.x, cn, P);
+                        vmin = update_linear<REAL, K>(gamma, o.alpha, p.lambda, valid, lane, Di, o.m, o.s, rk, o.x, cn, P);
                     else
-                        vmin = update_quadratic<REAL, K>(gamma, o.alpha, p.lambda, p.L, lane, Di, o.m, o.s, rk, o.x, cn, P);
+                        vmin = update_quadratic<REAL, K>(gamma, o.alpha, p.lambda, valid, p.L, lane, Di, o.m, o.s, rk, o.x, cn, P);
                     if constexpr (MBOX) {
                         if (!to_next) {   // the receiver is in another strip: it polls these words
                             if (peer >= 0) {

@@ -169,10 +169,14 @@ SB_API int sb_trws_pass(sb_trws_solver *s, int pass, int mode, double *acc /* 2 
  * from three numbers per label and node (own disparity, disparity step per column / row), which
  * replaces the per-edge q / q' / order storage of typeStereoLinear.h:274-311.  State is 45 bytes per
  * label and node (fp32), so BASELINE config 5 (1980 x 2880 x 192) fits one B200 and config 4
- * (4096 x 4096 x 256) fits eight, each rank holding only its own row band (+ one halo row).
+ * (4096 x 4096 x 256) fits eight, each rank holding only its own column band (+ one halo column per
+ * inner side).  The bands are COLUMN bands because the sweep's strips run along the image rows
+ * (ordering.cpp:7-157 orders the interior row by row, right to left): a rank sweeps its piece of row r
+ * while its right-hand neighbour already sweeps row r + 1 -- the ranks are the stages of a pipeline --
+ * where row bands would make them take turns (row r + 1 waits for row r).
  *
- *   sb_trws_grid_create      rank `rank` of `world` row bands (world = 1: the whole grid); H, W >= 4;
- *                            kernel / tol / options as sb_trws_solve
+ *   sb_trws_grid_create      rank `rank` of `world` column bands (world = 1: the whole grid); H, W >= 4,
+ *                            W >= 4 world; kernel / tol / options as sb_trws_solve
  *   sb_trws_grid_set_labels  proposals l0 .. l0+nl-1: planes = nl consecutive 4 x N arrays ([a; b; c; d0]
  *                            per pixel, MATLAB node order), unary = nl x N (proposal-major);
  *                            d_min / d_step = the disparity normalisation of
@@ -184,7 +188,7 @@ SB_API int sb_trws_pass(sb_trws_solver *s, int pass, int mode, double *acc /* 2 
  *   sb_trws_grid_finalize    builds the sort-rank / merge-count tables (the argsort loop of
  *                            trws_mex.cpp:84-119) on the device; call after the labels are set
  *   sb_trws_grid_get_label   one stored proposal back out: 4 x N doubles [unary | own disparity | step per
- *                            column | step per row] (N each, MATLAB node order; rows this rank does not
+ *                            column | step per row] (N each, MATLAB node order; nodes this rank does not
  *                            store are 0) -- inspection / parity tests
  *   sb_trws_grid_get_weights the stored weights, E doubles in the reference's term order
  *   sb_trws_grid_minimize    Minimize_TRW_S (minimize.cpp:7-116), world = 1 only; continues from the
@@ -192,17 +196,27 @@ SB_API int sb_trws_pass(sb_trws_solver *s, int pass, int mode, double *acc /* 2 
  *                            iteration t runs inside the forward sweep of t + 1, so after an early stop
  *                            the resident messages are half an iteration ahead of the reference's
  *                            (the returned labels / energy / bound are those of iteration t)
- *   sb_trws_grid_get_labels  N doubles, 1-based, MATLAB node order; rows this rank does not sweep are 0
- *   sb_trws_grid_pass / _ipc_export (2 x 64 bytes: message and selected-position arrays) / _ipc_attach:
- *                            the row-banded multi-GPU protocol of sb_trws_pass, on sharded state: the
- *                            messages of the vertical terms that cross a band boundary are stored by both
- *                            ranks and written by the sender into both copies (its own, and the neighbour's
- *                            over NVLink); a message word carries the parity of the pass counter in its
- *                            sign bit (min-normalised messages are >= 0), so the receiver polls its own
- *                            copy -- no mailbox array, no flag, no fence
- *   sb_trws_grid_info        info[0] = bytes of HBM state on this rank, [1] = nodes stored, [2], [3] = rows
- *                            swept [lo, hi), [4], [5] = persistent CTAs (forward, backward), [6] = dynamic
- *                            shared memory per CTA, [7] = padded label count */
+ *   sb_trws_grid_get_labels  N doubles, 1-based, MATLAB node order; nodes this rank does not sweep are 0
+ *   sb_trws_grid_pass / _ipc_export (2 x 64 bytes: message and selected-position arrays) / _ipc_attach
+ *                            (`up` = rank - 1, the band to the left; `down` = rank + 1):
+ *                            the multi-GPU protocol of sb_trws_pass, on sharded state: the messages of the
+ *                            horizontal terms that cross a band boundary are stored by both ranks and
+ *                            written by the sender into both copies (its own, and the neighbour's over
+ *                            NVLink); a message word carries the parity of the pass counter in its sign
+ *                            bit (min-normalised messages are >= 0), so the receiver polls its own copy --
+ *                            no mailbox array, no flag, no fence
+ *   sb_trws_grid_launch_pass / _wait: the same pass, asynchronous: launch only enqueues, wait blocks
+ *                            until every launched pass has finished and returns (energy, bound
+ *                            contribution) per pass in launch order.  Because every message word
+ *                            validates itself the ranks need no barrier between passes: with a fixed
+ *                            iteration count (max_relgap = 0) a rank launches all its passes at once and
+ *                            the per-pass sums are all-reduced once at the end
+ *   sb_trws_grid_attach_local neighbours that are solvers of the SAME process on the same device (several
+ *                            ranks sharing one GPU: how a one-GPU box runs the banded sweep); `share` =
+ *                            solvers that sweep concurrently (each takes 1/share of the resident CTAs)
+ *   sb_trws_grid_info        info[0] = bytes of HBM state on this rank, [1] = nodes stored, [2], [3] =
+ *                            columns swept [lo, hi), [4], [5] = persistent CTAs (forward, backward), [6] =
+ *                            dynamic shared memory per CTA, [7] = padded label count */
 typedef struct sb_trws_grid sb_trws_grid;
 SB_API int sb_trws_grid_create(int kernel, int H, int W, int L, double tol, const sb_trws_options *opt,
                         int rank, int world, sb_trws_grid **out);
@@ -223,6 +237,9 @@ SB_API int sb_trws_grid_get_labels(sb_trws_grid *g, double *labels);
 SB_API int sb_trws_grid_ipc_export(sb_trws_grid *g, unsigned char *handles /* 128 bytes */);
 SB_API int sb_trws_grid_ipc_attach(sb_trws_grid *g, const unsigned char *up, const unsigned char *down);
 SB_API int sb_trws_grid_pass(sb_trws_grid *g, int pass, int mode, double *acc /* 2 */);
+SB_API int sb_trws_grid_launch_pass(sb_trws_grid *g, int pass, int mode);
+SB_API int sb_trws_grid_wait(sb_trws_grid *g, double *acc /* 2 x max_passes, may be null */, int max_passes, int *n_passes);
+SB_API int sb_trws_grid_attach_local(sb_trws_grid *g, sb_trws_grid *up, sb_trws_grid *down, int share);
 SB_API int sb_trws_grid_info(sb_trws_grid *g, int64_t *info /* 8 */);
 /* cumulative since creation: out[0] = ms spent in sweep kernels (CUDA events around every launch on the solver
  * stream), out[1] = sweep launches, out[2] = set-up ms (uploads, table build) */

@@ -90,6 +90,9 @@ def lib():
         L.sb_trws_grid_ipc_export.argtypes = [vp, ctypes.c_char_p]
         L.sb_trws_grid_ipc_attach.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p]
         L.sb_trws_grid_pass.argtypes = [vp, c_int, c_int, _dp]
+        L.sb_trws_grid_launch_pass.argtypes = [vp, c_int, c_int]
+        L.sb_trws_grid_wait.argtypes = [vp, _dp, c_int, POINTER(c_int)]
+        L.sb_trws_grid_attach_local.argtypes = [vp, vp, vp, c_int]
         L.sb_trws_grid_info.argtypes = [vp, POINTER(c_int64)]
         L.sb_trws_grid_counters.argtypes = [vp, _dp]
         L.sb_trws_grid_destroy.argtypes = [vp]

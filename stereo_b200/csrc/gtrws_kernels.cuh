@@ -16,7 +16,8 @@
 //     per neighbour pair (two terms): two message rows + 6 byte rows (sort rank of each
 //     term's tail positions, two merge-count rows per term)                       (2 x 14 B / label)
 //     => 45 bytes per label and node, against 100 in the MATLAB-layout path;
-//   * node ids are row-major and band-local, so a row band (multi-GPU) is a contiguous slab;
+//   * node ids are row-major and band-local: a rank of a multi-GPU run stores its column band (plus one halo
+//     column per inner side) as a grid of its own width, and the sweep only ever sees that local grid;
 //   * a message word carries its own validity: min-normalised messages are >= 0, so the SIGN BIT is
 //     free, and every message slot is written exactly once per sending pass -- the sweep stores
 //     messages with the sign bit = parity of the pass counter, and a receiver in another strip (another
@@ -70,7 +71,8 @@ struct GProblem {
     int world;
     REAL *peer_msg[2];                 // rank - 1 / rank + 1 (peer mapped)
     unsigned long long *peer_selbox[2];
-    long long peer_dn[2];              // their local node id of my local node u is u + peer_dn
+    int peer_dW[2];                    // the peer's local node id of my local node u = r W + c is u + r peer_dW + peer_dc
+    long long peer_dc[2];              // (the bands differ in width and in their first stored column)
     int32_t *sol;                      // [Nloc]
     unsigned epoch;                    // launch counter: tag of the selbox words
     unsigned tag;                      // 0 / 1: sign the messages of this pass carry
@@ -430,6 +432,13 @@ __device__ __forceinline__ long long pair_of(long long u, int d, int W)
 __device__ __forceinline__ int side_of(int d) { return (d == DIR_DOWN || d == DIR_RIGHT) ? 0 : 1; }
 __device__ __forceinline__ bool vertical(int d) { return d == DIR_UP || d == DIR_DOWN; }
 
+// index of my term `term` (= 4 x owner node + 2 x [horizontal] + j) in the arrays of neighbour rank `peer`
+template <typename REAL> __device__ __forceinline__ long long peer_term(const GProblem<REAL> &p, long long term, int peer)
+{
+    const long long uo = term >> 2;
+    return term + 4 * ((uo / p.W) * (long long)p.peer_dW[peer] + p.peer_dc[peer]);
+}
+
 // ---------------------------------------------------------------- shared memory plan
 template <typename REAL, int K> struct StageLayout {
     static constexpr int LP = 32 * K;
@@ -748,7 +757,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
                             unsigned lo;
                             if constexpr (sizeof(REAL) == 4) lo = __float_as_uint((float)sv); else lo = (unsigned)xs;
                             const unsigned long long wv = (unsigned long long)lo | ((unsigned long long)p.epoch << 32);
-                            if (peer >= 0) trws::st_mbox_sys(p.peer_selbox[peer] + (term + 4 * p.peer_dn[peer]), wv);
+                            if (peer >= 0) trws::st_mbox_sys(p.peer_selbox[peer] + peer_term(p, term, peer), wv);
                             else trws::st_mbox(p.selbox + term, wv);
                         }
                         if (to_next) {
@@ -772,7 +781,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
                         REAL *dst = p.msg + term * LP;
                         if (p.world > 1) {
                             st_words<REAL, K, true>(dst, m, lane);
-                            if (peer >= 0) st_words<REAL, K, true>(p.peer_msg[peer] + (term + 4 * p.peer_dn[peer]) * LP, m, lane);
+                            if (peer >= 0) st_words<REAL, K, true>(p.peer_msg[peer] + peer_term(p, term, peer) * LP, m, lane);
                         } else {
                             st_words<REAL, K, false>(dst, m, lane);
                         }

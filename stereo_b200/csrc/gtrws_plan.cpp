@@ -11,19 +11,18 @@
 namespace sb {
 namespace gtrws {
 
-Band band_rows(int H, int rank, int world)
+Band band_window(int H, int W, int rank, int world)
 {
     Band b;
-    if (rank < 0 || world <= 1) {
-        b.r_lo = 0; b.r_hi = H; b.r_base = 0; b.r_top = H;
-        return b;
-    }
-    // rows r with band_of_row(r) == rank, band_of_row(r) = floor(r * world / H)
-    auto first_row = [&](int k) { return (int)(((long long)k * H + world - 1) / world); };
-    b.r_lo = first_row(rank);
-    b.r_hi = first_row(rank + 1);
-    b.r_base = std::max(0, b.r_lo - 1);
-    b.r_top = std::min(H, b.r_hi + 1);
+    b.r_lo = 0; b.r_hi = H; b.r_base = 0; b.r_top = H;
+    b.c_lo = 0; b.c_hi = W; b.c_base = 0; b.c_top = W;
+    if (rank < 0 || world <= 1) return b;
+    // columns c with band_of_col(c) == rank, band_of_col(c) = floor(c * world / W)
+    auto first_col = [&](int k) { return (int)(((long long)k * W + world - 1) / world); };
+    b.c_lo = first_col(rank);
+    b.c_hi = first_col(rank + 1);
+    b.c_base = std::max(0, b.c_lo - 1);
+    b.c_top = std::min(W, b.c_hi + 1);
     return b;
 }
 
@@ -53,8 +52,9 @@ void build_gpass_plan(int H, int W, int pass, int rank, int world, GPassPlan &pl
     std::vector<uint8_t> info;
     build_node_info(H, W, order, info);
     Schedule s;
-    build_schedule(H, W, order, s, world);
-    const Band band = band_rows(H, rank, world);
+    build_schedule_cols(H, W, order, s, world);
+    const Band band = band_window(H, W, rank, world);
+    const int Wl = band.width();
     const int S = (int)s.strip_ptr.size() - 1;
     const int64_t N = (int64_t)H * W;
     std::vector<int32_t> strip_of((size_t)N);
@@ -69,8 +69,9 @@ void build_gpass_plan(int H, int W, int pass, int rank, int world, GPassPlan &pl
     };
     auto local_id = [&](int u) {
         const int r = u % H, c = u / H;
-        SB_REQUIRE(r >= band.r_base && r < band.r_top, SB_EUNSUP, "sb_trws_grid: node outside the band's storage");
-        return (r - band.r_base) * W + c;
+        SB_REQUIRE(r >= band.r_base && r < band.r_top && c >= band.c_base && c < band.c_top, SB_EUNSUP,
+                   "sb_trws_grid: node outside the band's storage");
+        return (r - band.r_base) * Wl + (c - band.c_base);
     };
 
     plan.segs.clear();

@@ -32,7 +32,7 @@ struct GSeg {
     int16_t gamma_den;       // max(nF, nB): gamma = 1 / gamma_den (treeProbabilities.cpp:28-45)
     int8_t next_dir;         // direction of the next strip node when it is a send target, else -1
     uint8_t flags;           // GF_*
-    uint8_t peer[4];         // per direction: 0 receiver local, 1 on rank - 1, 2 on rank + 1
+    uint8_t peer[4];         // per direction: 0 receiver local, 1 on rank - 1 (the band to the left), 2 on rank + 1
     int32_t save0;           // GF_SAVE / GF_DEFERRED: scratch slot of the segment's first node (slots advance by 1)
     int32_t pad;
 };
@@ -46,10 +46,17 @@ struct GPassPlan {
     int32_t save_slots = 0;          // scratch slots for saved node totals
 };
 
-// Band geometry of rank `rank` of `world`: rows it sweeps [r_lo, r_hi), rows it stores [r_base, r_top)
-// (one halo row on each inner side).
-struct Band { int r_lo, r_hi, r_base, r_top; };
-Band band_rows(int H, int rank, int world);
+// Band geometry of rank `rank` of `world`.  The grid is split into COLUMN bands (trws_order.h,
+// build_schedule_cols): the rank sweeps the columns [c_lo, c_hi) of every row and stores [c_base, c_top)
+// (one halo column on each inner side); local node id = r * (c_top - c_base) + (c - c_base).  The row fields
+// cover the whole grid (kept so that a window is described the same way in both directions).
+struct Band {
+    int r_lo, r_hi, r_base, r_top;
+    int c_lo, c_hi, c_base, c_top;
+    int width() const { return c_top - c_base; }
+    int rows() const { return r_top - r_base; }
+};
+Band band_window(int H, int W, int rank, int world);
 
 // pass 0 forward, 1 backward.  rank < 0: whole grid on one GPU.  Strips are listed in PROCESSING order of the pass
 // (the backward sweep runs the forward schedule in reverse); the deferred sends of a strip's nodes (GF_DEFERRED

@@ -108,15 +108,15 @@ std::shared_ptr<GridPlanDev> grid_plan(int dev, int H, int W, int rank, int worl
 // (dispmap_super.m:318-328, dispmap_globalstereo.m:336-345), gx / gy = its change per column / row.
 template <typename REAL>
 __global__ void gfill_labels_kernel(const double *__restrict__ planes, const double *__restrict__ unary, int nl, int l0,
-                                    int H, int W, int r_base, int rows, int LP, double d_min, double d_step,
+                                    int H, int W, int r_base, int rows, int c_base, int Wl, int LP, double d_min, double d_step,
                                     REAL *__restrict__ nodeF, int *bad)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long Nloc = (long long)rows * W;
+    const long long Nloc = (long long)rows * Wl;
     if (t >= Nloc * nl) return;
     const int ll = (int)(t % nl);
     const long long v = t / nl;
-    const int r = r_base + (int)(v / W), c = (int)(v % W);
+    const int r = r_base + (int)(v / Wl), c = c_base + (int)(v % Wl);
     const long long u = r + (long long)H * c;
     const long long N = (long long)H * W;
     const double *pl = planes + ((long long)ll * N + u) * 4;
@@ -137,14 +137,15 @@ __global__ void gfill_labels_kernel(const double *__restrict__ planes, const dou
 // alphas in the reference's term order (dispmap_super.m:284-294: vertical down, vertical up, horizontal
 // right, horizontal left, each column-major over the start node) -> alpha[pair][j]
 template <typename REAL>
-__global__ void gweights_kernel(const double *__restrict__ alphas, int H, int W, int r_base, int rows, REAL *__restrict__ alpha)
+__global__ void gweights_kernel(const double *__restrict__ alphas, int H, int W, int r_base, int rows, int c_base, int Wl,
+                                REAL *__restrict__ alpha)
 {
     const long long pr = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long Nloc = (long long)rows * W;
+    const long long Nloc = (long long)rows * Wl;
     if (pr >= 2 * Nloc) return;
     const long long v = pr >> 1;
     const int dirn = (int)(pr & 1);
-    const int r = r_base + (int)(v / W), c = (int)(v % W);
+    const int r = r_base + (int)(v / Wl), c = c_base + (int)(v % Wl);
     const long long nV = (long long)(H - 1) * W, nH = (long long)H * (W - 1);
     REAL a0 = REAL(0), a1 = REAL(0);
     if (dirn == 0) {
@@ -163,22 +164,24 @@ __global__ void gweights_kernel(const double *__restrict__ alphas, int H, int W,
 }
 
 // rounded labels of the rows this rank sweeps -> doubles, 1-based, MATLAB node order (trws_mex.cpp:134-139)
-__global__ void glabels_kernel(const int32_t *__restrict__ sol, int H, int W, int r_base, int r_lo, int r_hi, double *__restrict__ out)
+__global__ void glabels_kernel(const int32_t *__restrict__ sol, int H, Band b, double *__restrict__ out)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long n = (long long)(r_hi - r_lo) * W;
+    const int wo = b.c_hi - b.c_lo;
+    const long long n = (long long)(b.r_hi - b.r_lo) * wo;
     if (t >= n) return;
-    const int r = r_lo + (int)(t / W), c = (int)(t % W);
-    out[r + (long long)H * c] = (double)(sol[(long long)(r - r_base) * W + c] + 1);
+    const int r = b.r_lo + (int)(t / wo), c = b.c_lo + (int)(t % wo);
+    out[r + (long long)H * c] = (double)(sol[(long long)(r - b.r_base) * (b.c_top - b.c_base) + (c - b.c_base)] + 1);
 }
 
 // one stored label plane back out (inspection / parity tests): 4 x N doubles, rows not stored -> 0
 template <typename REAL>
-__global__ void gget_label_kernel(const REAL *__restrict__ nodeF, int l, int H, int W, int r_base, int rows, int LP, double *__restrict__ out)
+__global__ void gget_label_kernel(const REAL *__restrict__ nodeF, int l, int H, int W, int r_base, int rows, int c_base, int Wl, int LP,
+                                  double *__restrict__ out)
 {
     const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= (long long)rows * W) return;
-    const int r = r_base + (int)(v / W), c = (int)(v % W);
+    if (v >= (long long)rows * Wl) return;
+    const int r = r_base + (int)(v / Wl), c = c_base + (int)(v % Wl);
     const long long u = r + (long long)H * c, N = (long long)H * W;
     const REAL *rec = nodeF + v * 4 * LP + l;
     out[u] = (double)rec[NF_D * LP];
@@ -188,13 +191,14 @@ __global__ void gget_label_kernel(const REAL *__restrict__ nodeF, int l, int H, 
 }
 
 template <typename REAL>
-__global__ void gget_weights_kernel(const REAL *__restrict__ alpha, int H, int W, int r_base, int rows, double *__restrict__ out)
+__global__ void gget_weights_kernel(const REAL *__restrict__ alpha, int H, int W, int r_base, int rows, int c_base, int Wl,
+                                    double *__restrict__ out)
 {
     const long long pr = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pr >= 2LL * rows * W) return;
+    if (pr >= 2LL * rows * Wl) return;
     const long long v = pr >> 1;
     const int dirn = (int)(pr & 1);
-    const int r = r_base + (int)(v / W), c = (int)(v % W);
+    const int r = r_base + (int)(v / Wl), c = c_base + (int)(v % Wl);
     const long long nV = (long long)(H - 1) * W, nH = (long long)H * (W - 1);
     if (dirn == 0) {
         if (r + 1 < r_base + rows) {
@@ -202,7 +206,7 @@ __global__ void gget_weights_kernel(const REAL *__restrict__ alpha, int H, int W
             out[e] = (double)alpha[pr * 2];
             out[nV + e] = (double)alpha[pr * 2 + 1];
         }
-    } else if (c + 1 < W) {
+    } else if (c + 1 < c_base + Wl) {
         const long long e = 2 * nV + (long long)c * H + r;
         out[e] = (double)alpha[pr * 2];
         out[nH + e] = (double)alpha[pr * 2 + 1];
@@ -226,7 +230,7 @@ __device__ __forceinline__ unsigned hash3(unsigned seed, unsigned a, unsigned b,
 __device__ __forceinline__ float u01(unsigned h) { return (float)(h >> 8) * (1.0f / 16777216.0f); }
 
 template <typename REAL>
-__global__ void gsynth_kernel(unsigned seed, int kern, int Hs, int Ws, int r_off, int c_off, int Wloc, int L, int r_base, int rows, int LP,
+__global__ void gsynth_kernel(unsigned seed, int kern, int Hs, int Ws, int r_off, int c_off, int Wloc, int L, int r_base, int rows, int c_base, int LP,
                               REAL *__restrict__ nodeF, REAL *__restrict__ alpha)
 {
     // (Hs, Ws): the grid the synthetic scene is defined on; the solver's own grid is the window of it that
@@ -236,7 +240,7 @@ __global__ void gsynth_kernel(unsigned seed, int kern, int Hs, int Ws, int r_off
     if (t >= Nloc * L) return;
     const int l = (int)(t % L);
     const long long v = t / L;
-    const int r = r_off + r_base + (int)(v / Wloc), c = c_off + (int)(v % Wloc);
+    const int r = r_off + r_base + (int)(v / Wloc), c = c_off + c_base + (int)(v % Wloc);
     const int H = Hs, W = Ws;
     auto plane_of = [&](int lab, float &own, float &gx, float &gy) {
         if (lab % 4 == 0) {
@@ -289,6 +293,10 @@ struct SolverBase {
     virtual void ipc_export(unsigned char *out) = 0;
     virtual void ipc_attach(const unsigned char *up, const unsigned char *down) = 0;
     virtual void run_one_pass(int pass, int mode, double *acc) = 0;
+    virtual void launch_one_pass(int pass, int mode) = 0;
+    virtual int wait_all(double *acc, int max_passes) = 0;
+    virtual void *raw_ptr(int which) = 0;
+    virtual void attach_local(SolverBase *up, SolverBase *down, int share) = 0;
     virtual void info(int64_t *out) = 0;
     virtual void counters(double *out) = 0;
     double setup_ms = 0;
@@ -298,7 +306,7 @@ template <typename REAL>
 struct Solver : SolverBase {
     int kernel, H, W, L, K, LP, precision, rank, world;
     Band band;
-    int rows;
+    int rows, Wl;      // rows and columns stored on this rank
     int64_t Nloc, N, E;
     bool fuse, finalized = false;
     const GOps *ops;
@@ -319,7 +327,6 @@ struct Solver : SolverBase {
     bool isolate = false;
     unsigned launch_epoch = 0, pass_counter = 0;
     Ctrl *hc = nullptr;   // pinned
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double kernel_ms = 0, total_kernel_ms = 0;
     int64_t kernel_count = 0, total_kernel_count = 0;
 
@@ -335,10 +342,13 @@ struct Solver : SolverBase {
         LP = 32 * K;
         N = (int64_t)H * W;
         E = 2 * ((int64_t)(H - 1) * W + (int64_t)H * (W - 1));
-        SB_REQUIRE(world == 1 || world <= H / 2, SB_EUNSUP, "sb_trws_grid: at least two rows per rank");
-        band = band_rows(H, world > 1 ? rank : -1, world);
-        rows = band.r_top - band.r_base;
-        Nloc = (int64_t)rows * W;
+        SB_REQUIRE(world == 1 || world <= W / 4, SB_EUNSUP, "sb_trws_grid: at least four columns per rank");
+        band = band_window(H, W, world > 1 ? rank : -1, world);
+        rows = band.rows();
+        Wl = band.width();
+        Nloc = (int64_t)rows * Wl;
+        // several ranks may live in one process (sb_trws_grid_attach_local): their sweeps must run concurrently
+        if (world > 1) SB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         SB_REQUIRE(Nloc < (1LL << 30), SB_EUNSUP, "sb_trws_grid: too many nodes per rank");
         int dev = 0, num_sms = 0;
         SB_CUDA(cudaGetDevice(&dev));
@@ -359,11 +369,10 @@ struct Solver : SolverBase {
         SB_CUDA(cudaMemsetAsync(dAlpha.p, 0, dAlpha.bytes(), stream));
         SB_CUDA(cudaMemsetAsync(dSelBox.p, 0, dSelBox.bytes(), stream));
         SB_CUDA(cudaMallocHost((void **)&hc, sizeof(Ctrl)));
-        SB_CUDA(cudaEventCreate(&ev0));
-        SB_CUDA(cudaEventCreate(&ev1));
+        SB_CUDA(cudaMallocHost((void **)&hq, sizeof(Ctrl) * MAX_PENDING));
 
         std::memset(&P, 0, sizeof(P));
-        P.H = H; P.W = W; P.L = L; P.LP = LP; P.rows = rows; P.Nloc = Nloc;
+        P.H = H; P.W = Wl; P.L = L; P.LP = LP; P.rows = rows; P.Nloc = Nloc;
         P.nodeF = dNodeF.p; P.nodeB = dNodeB.p; P.msg = dMsg.p; P.pairB = dPairB.p; P.alpha = dAlpha.p;
         P.selbox = dSelBox.p; P.lambda = (REAL)tol;
         P.S = plan->S[0]; P.world = world; P.sol = dSol.p; P.save = dSave.p;
@@ -418,9 +427,12 @@ struct Solver : SolverBase {
         for (int d = 0; d < 2; d++)
             for (int a = 0; a < 2; a++)
                 if (peer_ptr[d][a]) cudaIpcCloseMemHandle(peer_ptr[d][a]);
+        if (stream) { cudaStreamSynchronize(stream); }
         if (hc) cudaFreeHost(hc);
-        if (ev0) cudaEventDestroy(ev0);
-        if (ev1) cudaEventDestroy(ev1);
+        if (hq) cudaFreeHost(hq);
+        for (const Pending &pd : pending) { cudaEventDestroy(pd.e0); cudaEventDestroy(pd.e1); }
+        for (cudaEvent_t e : event_pool) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
     }
 
     void set_labels(int l0, int nl, const double *planes, const double *unary, double d_min, double d_step) override
@@ -439,8 +451,8 @@ struct Solver : SolverBase {
             SB_CUDA(cudaMemcpyAsync(dPl.p, planes + (size_t)g0 * 4 * N, (size_t)ng * 4 * N * 8, cudaMemcpyHostToDevice, stream));
             SB_CUDA(cudaMemcpyAsync(dUn.p, unary + (size_t)g0 * N, (size_t)ng * N * 8, cudaMemcpyHostToDevice, stream));
             const long long tot = Nloc * ng;
-            gfill_labels_kernel<REAL><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(dPl.p, dUn.p, ng, l0 + g0, H, W, band.r_base, rows, LP,
-                                                                                         d_min, d_step, dNodeF.p, dBad.p);
+            gfill_labels_kernel<REAL><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(dPl.p, dUn.p, ng, l0 + g0, H, W, band.r_base, rows, band.c_base,
+                                                                                         Wl, LP, d_min, d_step, dNodeF.p, dBad.p);
             SB_CUDA(cudaGetLastError());
             count_launch();
         }
@@ -460,7 +472,7 @@ struct Solver : SolverBase {
         const double t0 = now_ms();
         DevBuf<double> dA((size_t)E);
         SB_CUDA(cudaMemcpyAsync(dA.p, alphas, (size_t)E * 8, cudaMemcpyHostToDevice, stream));
-        gweights_kernel<REAL><<<(unsigned)((2 * Nloc + 255) / 256), 256, 0, stream>>>(dA.p, H, W, band.r_base, rows, dAlpha.p);
+        gweights_kernel<REAL><<<(unsigned)((2 * Nloc + 255) / 256), 256, 0, stream>>>(dA.p, H, W, band.r_base, rows, band.c_base, Wl, dAlpha.p);
         SB_CUDA(cudaGetLastError());
         count_launch();
         SB_CUDA(cudaStreamSynchronize(stream));
@@ -474,8 +486,8 @@ struct Solver : SolverBase {
         SB_REQUIRE(r_off >= 0 && c_off >= 0 && r_off + H <= Hs && c_off + W <= Ws, SB_EINVAL,
                    "sb_trws_grid_synth: window (%d,%d)+%dx%d outside the %dx%d scene", r_off, c_off, H, W, Hs, Ws);
         const long long tot = Nloc * L;
-        gsynth_kernel<REAL><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>((unsigned)(seed ^ (seed >> 32)), kernel, Hs, Ws, r_off, c_off, W, L,
-                                                                               band.r_base, rows, LP, dNodeF.p, dAlpha.p);
+        gsynth_kernel<REAL><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>((unsigned)(seed ^ (seed >> 32)), kernel, Hs, Ws, r_off, c_off, Wl, L,
+                                                                               band.r_base, rows, band.c_base, LP, dNodeF.p, dAlpha.p);
         SB_CUDA(cudaGetLastError());
         count_launch();
         SB_CUDA(cudaStreamSynchronize(stream));
@@ -488,7 +500,7 @@ struct Solver : SolverBase {
         const double t0 = now_ms();
         GTablesLaunch tl;
         tl.precision = precision; tl.nodeF = dNodeF.p; tl.nodeB = dNodeB.p; tl.pairB = dPairB.p;
-        tl.W = W; tl.rows = rows; tl.L = L; tl.stream = stream;
+        tl.W = Wl; tl.rows = rows; tl.L = L; tl.stream = stream;
         ops->tables(tl);
         SB_CUDA(cudaStreamSynchronize(stream));
         finalized = true;
@@ -500,7 +512,7 @@ struct Solver : SolverBase {
         SB_REQUIRE(l >= 0 && l < L && out, SB_EINVAL, "sb_trws_grid_get_label: bad arguments");
         DevBuf<double> d((size_t)4 * N);
         SB_CUDA(cudaMemsetAsync(d.p, 0, d.bytes(), stream));
-        gget_label_kernel<REAL><<<(unsigned)((Nloc + 255) / 256), 256, 0, stream>>>(dNodeF.p, l, H, W, band.r_base, rows, LP, d.p);
+        gget_label_kernel<REAL><<<(unsigned)((Nloc + 255) / 256), 256, 0, stream>>>(dNodeF.p, l, H, W, band.r_base, rows, band.c_base, Wl, LP, d.p);
         SB_CUDA(cudaGetLastError());
         count_launch();
         SB_CUDA(cudaMemcpyAsync(out, d.p, d.bytes(), cudaMemcpyDeviceToHost, stream));
@@ -512,7 +524,7 @@ struct Solver : SolverBase {
         SB_REQUIRE(out, SB_EINVAL, "sb_trws_grid_get_weights: null pointer");
         DevBuf<double> d((size_t)E);
         SB_CUDA(cudaMemsetAsync(d.p, 0, d.bytes(), stream));
-        gget_weights_kernel<REAL><<<(unsigned)((2 * Nloc + 255) / 256), 256, 0, stream>>>(dAlpha.p, H, W, band.r_base, rows, d.p);
+        gget_weights_kernel<REAL><<<(unsigned)((2 * Nloc + 255) / 256), 256, 0, stream>>>(dAlpha.p, H, W, band.r_base, rows, band.c_base, Wl, d.p);
         SB_CUDA(cudaGetLastError());
         count_launch();
         SB_CUDA(cudaMemcpyAsync(out, d.p, d.bytes(), cudaMemcpyDeviceToHost, stream));
@@ -527,9 +539,29 @@ struct Solver : SolverBase {
         pass_counter = 0;
     }
 
-    void run_pass(int pass, int mode)
+    // One pass = memset of the control block, the persistent sweep launch, the control block back to a pinned slot.
+    // launch_pass only enqueues (the ranks of a multi-GPU run are not separated by host round trips: a message word
+    // validates itself, so a rank simply runs ahead until it needs a word its neighbour has not written yet);
+    // wait_passes synchronises, with the watchdog, and accounts the launch times.
+    struct Pending { cudaEvent_t e0, e1; };
+    std::vector<Pending> pending;            // launched, not yet waited for
+    std::vector<cudaEvent_t> event_pool;
+    Ctrl *hq = nullptr;                      // pinned: control blocks of the pending passes
+    static constexpr int MAX_PENDING = 256;
+    int last_grid = 0, last_pass = 0, last_mode = 0;
+
+    cudaEvent_t get_event()
+    {
+        if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
+        cudaEvent_t e;
+        SB_CUDA(cudaEventCreate(&e));
+        return e;
+    }
+
+    void launch_pass(int pass, int mode)
     {
         SB_REQUIRE(finalized, SB_EINVAL, "sb_trws_grid: call sb_trws_grid_finalize after the labels are set");
+        SB_REQUIRE((int)pending.size() < MAX_PENDING, SB_EINVAL, "sb_trws_grid: too many passes in flight (wait first)");
         SB_CUDA(cudaMemsetAsync(dCtrl.p, 0, dCtrl.bytes(), stream));
         const bool sends = pass == PASS_BWD || (mode & MODE_SEND);
         if (sends) ++pass_counter;
@@ -549,40 +581,62 @@ struct Solver : SolverBase {
         GSweepLaunch sl;
         sl.precision = precision; sl.kern = kernel; sl.pass = pass; sl.problem = &P;
         sl.grid = pass == PASS_FWD ? grid_fwd : grid_bwd; sl.stream = stream;
+        last_grid = sl.grid; last_pass = pass; last_mode = mode;
         if (rec_host) std::memset(rec_host, 0xff, (size_t)rec_ctas * 6 * 4 * sizeof(int));
-        SB_CUDA(cudaEventRecord(ev0, stream));
+        Pending pd;
+        pd.e0 = get_event();
+        pd.e1 = get_event();
+        SB_CUDA(cudaEventRecord(pd.e0, stream));
         ops->sweep(sl);
-        SB_CUDA(cudaEventRecord(ev1, stream));
-        SB_CUDA(cudaMemcpyAsync(hc, dCtrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
-        {
-            // watchdog: a sweep that does not finish (a dependency that never arrives) cannot be cancelled --
-            // report where it stands and leave, instead of hanging the caller forever
-            const double t_start = now_ms();
-            cudaError_t q;
-            while ((q = cudaStreamQuery(stream)) == cudaErrorNotReady && now_ms() - t_start < watchdog_ms) usleep(50);
-            if (q == cudaErrorNotReady) {
-                fprintf(stderr, "[sb_trws_grid] sweep pass=%d mode=%d epoch=%u tag=%u grid=%d did not finish within %.0f ms: HANG\n",
-                        pass, mode, P.epoch, P.tag, sl.grid, watchdog_ms);
-                if (rec_host)
-                    for (int c = 0; c < sl.grid && c < rec_ctas; c++) {
-                        fprintf(stderr, "[sb record] cta %d:", c);
-                        for (int w = 0; w < 6; w++) {
-                            const int *r = rec_host + ((size_t)c * 6 + w) * 4;
-                            fprintf(stderr, " w%d(strip %d step %d ph %d x%x)", w, r[0], r[1], r[2], r[3]);
-                        }
-                        fprintf(stderr, "\n");
+        SB_CUDA(cudaEventRecord(pd.e1, stream));
+        SB_CUDA(cudaMemcpyAsync(hq + pending.size(), dCtrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
+        pending.push_back(pd);
+    }
+
+    // acc: 2 doubles (energy, lower-bound contribution) per pending pass, in launch order (may be null)
+    void wait_passes(double *acc)
+    {
+        // watchdog: a sweep that does not finish (a dependency that never arrives) cannot be cancelled --
+        // report where it stands and leave, instead of hanging the caller forever
+        const double t_start = now_ms();
+        const double limit = watchdog_ms * (double)std::max<size_t>(pending.size(), 1);
+        cudaError_t q;
+        while ((q = cudaStreamQuery(stream)) == cudaErrorNotReady && now_ms() - t_start < limit) usleep(50);
+        if (q == cudaErrorNotReady) {
+            fprintf(stderr, "[sb_trws_grid] rank %d/%d: %zu pass(es) in flight (last: pass=%d mode=%d epoch=%u tag=%u grid=%d) did not finish within %.0f ms: HANG\n",
+                    rank, world, pending.size(), last_pass, last_mode, P.epoch, P.tag, last_grid, limit);
+            if (rec_host)
+                for (int c = 0; c < last_grid && c < rec_ctas; c++) {
+                    fprintf(stderr, "[sb record] cta %d:", c);
+                    for (int w = 0; w < 6; w++) {
+                        const int *r = rec_host + ((size_t)c * 6 + w) * 4;
+                        fprintf(stderr, " w%d(strip %d step %d ph %d x%x)", w, r[0], r[1], r[2], r[3]);
                     }
-                fflush(stderr);
-                _exit(3);
-            }
+                    fprintf(stderr, "\n");
+                }
+            fflush(stderr);
+            _exit(3);
         }
         SB_CUDA(cudaStreamSynchronize(stream));
-        float ms = 0;
-        SB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-        kernel_ms += ms;
-        kernel_count++;
-        total_kernel_ms += ms;
-        total_kernel_count++;
+        for (size_t i = 0; i < pending.size(); i++) {
+            float ms = 0;
+            SB_CUDA(cudaEventElapsedTime(&ms, pending[i].e0, pending[i].e1));
+            kernel_ms += ms;
+            kernel_count++;
+            total_kernel_ms += ms;
+            total_kernel_count++;
+            event_pool.push_back(pending[i].e0);
+            event_pool.push_back(pending[i].e1);
+            if (acc) { acc[2 * i] = hq[i].acc[0]; acc[2 * i + 1] = hq[i].acc[1]; }
+        }
+        if (!pending.empty()) *hc = hq[pending.size() - 1];
+        pending.clear();
+    }
+
+    void run_pass(int pass, int mode)
+    {
+        launch_pass(pass, mode);
+        wait_passes(nullptr);
     }
 
     void ipc_export(unsigned char *out) override
@@ -593,6 +647,37 @@ struct Solver : SolverBase {
         SB_CUDA(cudaIpcGetMemHandle(&h[1], dSelBox.p));
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
         std::memcpy(out, h, sizeof(h));
+    }
+
+    void set_peer_geometry(int d, int peer_rank)
+    {
+        const Band pb = band_window(H, W, peer_rank, world);
+        P.peer_dW[d] = pb.width() - Wl;
+        P.peer_dc[d] = (long long)band.c_base - pb.c_base;
+    }
+
+    void *raw_ptr(int which) override { return which == 0 ? (void *)dMsg.p : (void *)dSelBox.p; }
+
+    // neighbours that live in the SAME process and on the same device (several ranks on one GPU: how the
+    // one-GPU test box exercises the banded sweep).  `share` solvers run their sweeps concurrently, so each
+    // takes its part of the resident-CTA budget.
+    void attach_local(SolverBase *up, SolverBase *down, int share) override
+    {
+        SB_REQUIRE(world > 1, SB_EINVAL, "sb_trws_grid_attach_local: the solver was not created for several ranks");
+        SolverBase *src[2] = {up, down};
+        for (int d = 0; d < 2; d++) {
+            if (!src[d]) continue;
+            const int peer_rank = d == 0 ? rank - 1 : rank + 1;
+            SB_REQUIRE(peer_rank >= 0 && peer_rank < world, SB_EINVAL, "sb_trws_grid_attach_local: no such neighbour");
+            P.peer_msg[d] = static_cast<REAL *>(src[d]->raw_ptr(0));
+            P.peer_selbox[d] = static_cast<unsigned long long *>(src[d]->raw_ptr(1));
+            set_peer_geometry(d, peer_rank);
+        }
+        if (share > 1) {
+            grid_fwd = std::max(2, grid_fwd / share);
+            grid_bwd = std::max(2, grid_bwd / share);
+            isolate = false;
+        }
     }
 
     void ipc_attach(const unsigned char *up, const unsigned char *down) override
@@ -609,8 +694,7 @@ struct Solver : SolverBase {
                 SB_CUDA(cudaIpcOpenMemHandle(&peer_ptr[d][a], h[a], cudaIpcMemLazyEnablePeerAccess));
             P.peer_msg[d] = static_cast<REAL *>(peer_ptr[d][0]);
             P.peer_selbox[d] = static_cast<unsigned long long *>(peer_ptr[d][1]);
-            const Band pb = band_rows(H, peer_rank, world);
-            P.peer_dn[d] = (long long)(band.r_base - pb.r_base) * W;
+            set_peer_geometry(d, peer_rank);
         }
     }
 
@@ -619,6 +703,14 @@ struct Solver : SolverBase {
         run_pass(pass == 0 ? PASS_FWD : PASS_BWD, mode);
         acc[0] = hc->acc[0];
         acc[1] = hc->acc[1];
+    }
+    void launch_one_pass(int pass, int mode) override { launch_pass(pass == 0 ? PASS_FWD : PASS_BWD, mode); }
+    int wait_all(double *acc, int max_passes) override
+    {
+        const int n = (int)pending.size();
+        SB_REQUIRE(!acc || max_passes >= n, SB_EINVAL, "sb_trws_grid_wait: %d passes in flight, room for %d", n, max_passes);
+        wait_passes(acc);
+        return n;
     }
 
     // minimize.cpp:31-113 (same driver as trws_solve.cu)
@@ -680,8 +772,8 @@ struct Solver : SolverBase {
     {
         DevBuf<double> d((size_t)N);
         SB_CUDA(cudaMemsetAsync(d.p, 0, d.bytes(), stream));
-        const long long n = (long long)(band.r_hi - band.r_lo) * W;
-        glabels_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dSol.p, H, W, band.r_base, band.r_lo, band.r_hi, d.p);
+        const long long n = (long long)(band.r_hi - band.r_lo) * (band.c_hi - band.c_lo);
+        glabels_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dSol.p, H, band, d.p);
         SB_CUDA(cudaGetLastError());
         count_launch();
         SB_CUDA(cudaMemcpyAsync(out, d.p, d.bytes(), cudaMemcpyDeviceToHost, stream));
@@ -699,8 +791,8 @@ struct Solver : SolverBase {
     {
         out[0] = (int64_t)(dNodeF.bytes() + dNodeB.bytes() + dMsg.bytes() + dPairB.bytes() + dAlpha.bytes() + dSelBox.bytes() + dSol.bytes());
         out[1] = Nloc;
-        out[2] = band.r_lo;
-        out[3] = band.r_hi;
+        out[2] = band.c_lo;
+        out[3] = band.c_hi;
         out[4] = grid_fwd;
         out[5] = grid_bwd;
         out[6] = (int64_t)ops->smem_bytes(precision);
@@ -800,6 +892,18 @@ int sb_trws_grid_pass(sb_trws_grid *g, int pass, int mode, double *acc)
     SB_GRID_ENTRY("sb_trws_grid_pass", acc && (pass == 0 || pass == 1) && mode >= 0 && mode <= 3,
                   g->impl->run_one_pass(pass, mode, acc));
 }
+int sb_trws_grid_launch_pass(sb_trws_grid *g, int pass, int mode)
+{
+    SB_GRID_ENTRY("sb_trws_grid_launch_pass", (pass == 0 || pass == 1) && mode >= 0 && mode <= 3, g->impl->launch_one_pass(pass, mode));
+}
+int sb_trws_grid_wait(sb_trws_grid *g, double *acc, int max_passes, int *n_passes)
+{
+    SB_GRID_ENTRY("sb_trws_grid_wait", true, { const int n = g->impl->wait_all(acc, max_passes); if (n_passes) *n_passes = n; });
+}
+int sb_trws_grid_attach_local(sb_trws_grid *g, sb_trws_grid *up, sb_trws_grid *down, int share)
+{
+    SB_GRID_ENTRY("sb_trws_grid_attach_local", true, g->impl->attach_local(up ? up->impl : nullptr, down ? down->impl : nullptr, share));
+}
 int sb_trws_grid_counters(sb_trws_grid *g, double *out)
 {
     SB_GRID_ENTRY("sb_trws_grid_counters", out, g->impl->counters(out));
@@ -853,6 +957,8 @@ int sb_trws_grid_plan_stats(int H, int W, int rank, int world, int64_t *stats)
                 if (!(s.flags & sb::gtrws::GF_DEFERRED)) nodes += s.n;
                 if (s.flags & sb::gtrws::GF_SAVE) two += s.n;
                 for (int d = 0; d < 4; d++) {
+                    const int role = (int)((s.roles >> (4 * d)) & 15u);
+                    if (role != sb::gtrws::ROLE_SEND0 && role != sb::gtrws::ROLE_SEND1) continue;
                     if (s.peer[d] == 1) peer_up += s.n;
                     if (s.peer[d] == 2) peer_down += s.n;
                 }

@@ -255,6 +255,46 @@ void build_schedule(int H, int W, const std::vector<int32_t> &ordering, Schedule
     }
 }
 
+void build_schedule_cols(int H, int W, const std::vector<int32_t> &ordering, Schedule &s, int world)
+{
+    if (world <= 1) { build_schedule(H, W, ordering, s, 1); return; }
+    SB_REQUIRE(H >= 4 && W >= 4 && world <= W / 4, SB_EUNSUP,
+               "column-banded sweeps need a regular grid with at least four columns per rank");
+    s.nodes.clear();
+    s.strip_ptr.clear();
+    s.owner.clear();
+    s.nodes.reserve((int64_t)H * W);
+    s.world = world;
+    const int64_t ring = 2LL * H + 2LL * W - 4;
+    std::vector<int32_t> ringnodes(ring);
+    auto put = [&](int r, int c) { const int64_t u = r + (int64_t)H * c; ringnodes[ordering[u]] = (int32_t)u; };
+    for (int r = 0; r < H; r++) { put(r, 0); put(r, W - 1); }
+    for (int c = 1; c < W - 1; c++) { put(0, c); put(H - 1, c); }
+    for (int64_t k = 0; k < ring; k++) {
+        const int own = band_of_col(ringnodes[k] / H, W, world);
+        if (k == 0 || own != s.owner.back()) {
+            s.strip_ptr.push_back((int64_t)s.nodes.size());
+            s.owner.push_back(own);
+        }
+        s.nodes.push_back(ringnodes[k]);
+    }
+    // interior rows run right to left: the piece of the last rank first
+    for (int r = 1; r <= H - 2; r++) {
+        int cur = -1;
+        for (int c = W - 2; c >= 1; c--) {
+            const int own = band_of_col(c, W, world);
+            if (own != cur) {
+                s.strip_ptr.push_back((int64_t)s.nodes.size());
+                s.owner.push_back(own);
+                cur = own;
+            }
+            s.nodes.push_back((int32_t)(r + (int64_t)H * c));
+        }
+    }
+    s.strip_ptr.push_back((int64_t)s.nodes.size());
+    s.regular = true;
+}
+
 
 // ---------------------------------------------------------------------------
 // Segment descriptors (trws_sched.h).

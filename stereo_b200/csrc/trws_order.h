@@ -32,6 +32,13 @@ inline int band_of_row(int r, int H, int world) { return (int)(((long long)r * w
 // world > 1 (regular grids only): the ring strip is cut at the band boundaries and every strip
 // gets an owner.
 void build_schedule(int H, int W, const std::vector<int32_t> &ordering, Schedule &s, int world = 1);
+// Rank that owns image column c when the columns are split into `world` contiguous bands.
+inline int band_of_col(int c, int W, int world) { return (int)(((long long)c * world) / W); }
+// Column-banded variant (grid-native path, gtrws_plan.cpp): the strips run ALONG the image rows, so
+// cutting every strip at the column-band boundaries turns the ranks into the stages of a pipeline -- rank g
+// works on its piece of row r while rank g + 1 already works on row r + 1 -- where row bands would make
+// the ranks take turns (row r + 1 waits for row r).  The ring is cut wherever its owner changes.
+void build_schedule_cols(int H, int W, const std::vector<int32_t> &ordering, Schedule &s, int world);
 
 // Segment descriptors of one pass (trws_sched.h): segment range of forward strip fs =
 // [seg_ptr[fs], seg_ptr[fs + 1]).  pass 0 = forward sweep,

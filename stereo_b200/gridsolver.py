@@ -4,8 +4,10 @@
 solver when it does NOT first expand its proposals into the L x E arrays ``q`` / ``qprim``: L
 plane proposals (4 x N each), an L x N unary slab and the E smooth weights.  The positions
 q(:,p) = d(plane@ind2, pt ind2), qprim(:,p) = d(plane@ind1, pt ind2) (dispmap_super.m:180-183) are
-recomputed on the device.  With ``world > 1`` every rank holds and sweeps one row band
-(torch.distributed plumbing as in multigpu.py; the halo is peer stores over NVLink).
+recomputed on the device.  With ``world > 1`` every rank holds and sweeps one COLUMN band
+(torch.distributed plumbing as in multigpu.py; the halo is peer stores over NVLink): the strips of
+the sweep run along the image rows, so the ranks work as the stages of a pipeline.
+``TrwsGridLocalGroup`` runs the same banded sweep with all ranks in ONE process on one device.
 
 ``positions_from_labels`` rebuilds q / qprim in numpy from the planes AS STORED on the device
 (``get_label``), so a parity test can hand the reference solver bit-identical inputs.
@@ -25,13 +27,13 @@ MODE_SEND, MODE_ROUND = 1, 2
 
 
 class TrwsGrid:
-    def __init__(self, kernel, H, W, L, tol, options=None, group=None, rank=0, world=1):
+    def __init__(self, kernel, H, W, L, tol, options=None, group=None, rank=0, world=1, local=False):
         self.H, self.W, self.L = int(H), int(W), int(L)
         self.N = self.H * self.W
         self.E = 2 * ((self.H - 1) * self.W + self.H * (self.W - 1))
         self.group = group
         self.dist = None
-        if group is not None or world > 1:
+        if (group is not None or world > 1) and not local:
             import torch
             import torch.distributed as dist
             self.dist, self.torch = dist, torch
@@ -77,7 +79,7 @@ class TrwsGrid:
 
     def finalize(self):
         check(lib().sb_trws_grid_finalize(self._h))
-        if self.world > 1 and not self._attached:
+        if self.world > 1 and not self._attached and self.dist is not None:
             mine = ctypes.create_string_buffer(128)
             check(lib().sb_trws_grid_ipc_export(self._h, mine))
             gathered = [None] * self.world
@@ -102,7 +104,7 @@ class TrwsGrid:
     def info(self):
         out = (ctypes.c_int64 * 8)()
         check(lib().sb_trws_grid_info(self._h, out))
-        keys = ("hbm_bytes", "nodes_stored", "row_lo", "row_hi", "ctas_fwd", "ctas_bwd", "smem_per_cta", "LP")
+        keys = ("hbm_bytes", "nodes_stored", "col_lo", "col_hi", "ctas_fwd", "ctas_bwd", "smem_per_cta", "LP")
         return dict(zip(keys, [int(v) for v in out]))
 
     def counters(self):
@@ -114,8 +116,52 @@ class TrwsGrid:
     # ---- solve
     def reset(self):
         check(lib().sb_trws_grid_reset(self._h))
-        if self.world > 1:
+        if self.world > 1 and self.dist is not None:
             self.dist.barrier(group=self.group)
+
+    # asynchronous passes: launch only enqueues; wait returns [(energy, bound contribution)] per launched pass
+    def launch(self, which, mode):
+        check(lib().sb_trws_grid_launch_pass(self._h, which, mode))
+
+    def wait(self, max_passes=256):
+        acc = (ctypes.c_double * (2 * max_passes))()
+        n = ctypes.c_int()
+        check(lib().sb_trws_grid_wait(self._h, acc, max_passes, ctypes.byref(n)))
+        return [(acc[2 * i], acc[2 * i + 1]) for i in range(n.value)]
+
+    @staticmethod
+    def pass_list(fuse, iters):
+        """(pass, mode) sequence of `iters` iterations under max_relgap = 0 (minimize.cpp:31-113; with fused
+        rounding the rounding of iteration t rides in the forward sweep of t + 1)."""
+        seq = []
+        for it in range(1, iters + 1):
+            seq.append((0, MODE_SEND | (MODE_ROUND if (fuse and it > 1) else 0)))
+            seq.append((1, 0))
+            if (not fuse) or it >= iters:
+                seq.append((0, MODE_ROUND))
+        return seq
+
+    def _minimize_async(self, iters):
+        """Fixed iteration count on several ranks: every rank launches all its passes at once (the message words
+        validate themselves, so no barrier separates the passes) and the sums are all-reduced once."""
+        seq = self.pass_list(self.fuse, iters)
+        accs = []
+        for i0 in range(0, len(seq), 200):
+            for which, mode in seq[i0:i0 + 200]:
+                self.launch(which, mode)
+            accs += self.wait()
+        t = self.torch.tensor(accs, dtype=self.torch.float64)
+        dev = "cuda" if self.dist.get_backend(self.group) == "nccl" else "cpu"
+        t = t.to(dev)
+        self.dist.all_reduce(t, group=self.group)
+        t = t.cpu()
+        energy = lb = 0.0
+        for (which, mode), row in zip(seq, t.tolist()):
+            if which == 0 and (mode & MODE_ROUND):
+                energy = row[0]
+            if which == 1:
+                lb = row[1]
+        return energy, lb, float(iters)
 
     def _pass(self, which, mode):
         acc = (ctypes.c_double * 2)()
@@ -139,6 +185,8 @@ class TrwsGrid:
             self.timing = _timing_dict(tm)
             return e.value, lb.value, it.value
         iter_max = int(maxiter)
+        if max_relgap <= 0.0 and iter_max >= 1:
+            return self._minimize_async(iter_max)
         energy = lb = 0.0
         it = 1
         while True:
@@ -157,7 +205,7 @@ class TrwsGrid:
     def labels(self, gather=True):
         out = np.zeros(self.N, dtype=np.float64)
         check(lib().sb_trws_grid_get_labels(self._h, out.ctypes.data_as(_dp)))
-        if self.world > 1 and gather:
+        if self.world > 1 and gather and self.dist is not None:
             t = self.torch.from_numpy(out)
             dev = "cuda" if self.dist.get_backend(self.group) == "nccl" else "cpu"
             t = t.to(dev)
@@ -175,6 +223,59 @@ class TrwsGrid:
             self.close()
         except Exception:
             pass
+
+
+class TrwsGridLocalGroup:
+    """All `world` ranks of a banded sweep as solvers of THIS process on the current device, their sweeps running
+    concurrently on separate streams (sb_trws_grid_attach_local).  The ranks exchange their boundary messages
+    exactly as over NVLink -- sender writes into the receiver's arrays, receiver polls self-validating words --
+    so a one-GPU box exercises the multi-GPU protocol, cross-band dependencies included."""
+
+    def __init__(self, kernel, H, W, L, tol, world, options=None):
+        self.world = int(world)
+        self.ranks = [TrwsGrid(kernel, H, W, L, tol, options, rank=r, world=self.world, local=True) for r in range(self.world)]
+        self.fuse = self.ranks[0].fuse
+        self.N = self.ranks[0].N
+
+    def each(self, fn):
+        return [fn(g) for g in self.ranks]
+
+    def finalize(self):
+        for g in self.ranks:
+            g.finalize()
+        for r, g in enumerate(self.ranks):
+            up = self.ranks[r - 1]._h if r > 0 else None
+            down = self.ranks[r + 1]._h if r + 1 < self.world else None
+            check(lib().sb_trws_grid_attach_local(g._h, up, down, self.world))
+            g._attached = True
+
+    def minimize(self, iters):
+        seq = TrwsGrid.pass_list(self.fuse, int(iters))
+        tot = np.zeros((len(seq), 2))
+        for i0 in range(0, len(seq), 200):
+            part = seq[i0:i0 + 200]
+            for which, mode in part:
+                for g in self.ranks:
+                    g.launch(which, mode)
+            for g in self.ranks:
+                tot[i0:i0 + len(part)] += np.asarray(g.wait()).reshape(len(part), 2)
+        energy = lb = 0.0
+        for (which, mode), row in zip(seq, tot):
+            if which == 0 and (mode & MODE_ROUND):
+                energy = row[0]
+            if which == 1:
+                lb = row[1]
+        return float(energy), float(lb), float(iters)
+
+    def labels(self):
+        out = np.zeros(self.N)
+        for g in self.ranks:
+            out += g.labels(gather=False)     # nodes a rank does not sweep are 0
+        return out
+
+    def close(self):
+        for g in self.ranks:
+            g.close()
 
 
 def trws_grid(kernel, unary, proposals, weights, tol, H, W, options=None, d_min=0.0, d_step=1.0):

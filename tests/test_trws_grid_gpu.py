@@ -156,3 +156,59 @@ def test_memory_footprint():
     g.close()
     per = info["hbm_bytes"] / (64 * 96 * 64)
     assert 45.0 <= per <= 46.5, per
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("H,W,L,it,world", [(12, 17, 8, 5, 2), (24, 31, 16, 6, 3), (9, 40, 40, 4, 4), (40, 64, 70, 3, 4),
+                                            (31, 33, 130, 3, 2), (16, 64, 24, 4, 8)])
+def test_column_bands_one_gpu(H, W, L, it, world, kernel):
+    """The multi-GPU sweep (column bands, boundary messages written into the neighbour's arrays, self-validating
+    words, passes launched without barriers) with all ranks on THIS device: same labels / energy / bound as the
+    single-rank sweep of the same problem."""
+    from stereo_b200.gridsolver import TrwsGridLocalGroup
+    pr = synth.trws_problem(H, W, L, seed=7 * H + W + world, kernel=kernel)
+    ref = TrwsGrid(kernel, H, W, L, pr["tol"])
+    ref.set_labels(0, pr["planes"], pr["unary"])
+    ref.set_weights(pr["alphas"])
+    ref.finalize()
+    e1, lb1, _ = ref.minimize(it, 0.0)
+    lab1 = ref.labels()
+    ref.close()
+    grp = TrwsGridLocalGroup(kernel, H, W, L, pr["tol"], world)
+    try:
+        grp.each(lambda g: g.set_labels(0, pr["planes"], pr["unary"]))
+        grp.each(lambda g: g.set_weights(pr["alphas"]))
+        grp.finalize()
+        cols = [(g.info()["col_lo"], g.info()["col_hi"]) for g in grp.ranks]
+        assert cols[0][0] == 0 and cols[-1][1] == W and all(cols[i][1] == cols[i + 1][0] for i in range(world - 1))
+        e, lb, _ = grp.minimize(it)
+        lab = grp.labels()
+    finally:
+        grp.close()
+    # the bands sum their energy / bound contributions in a different order: summation-order differences only
+    assert abs(e - e1) <= 1e-5 * abs(e1) and abs(lb - lb1) <= 1e-5 * abs(lb1)
+    assert np.mean(lab == lab1) >= 0.999
+
+
+def test_column_bands_one_gpu_f64_exact():
+    from stereo_b200.gridsolver import TrwsGridLocalGroup
+    H, W, L, it, world = 21, 34, 24, 6, 3
+    pr = synth.trws_problem(H, W, L, seed=11, kernel=1)
+    ref = TrwsGrid(1, H, W, L, pr["tol"], dict(precision="f64"))
+    ref.set_labels(0, pr["planes"], pr["unary"])
+    ref.set_weights(pr["alphas"])
+    ref.finalize()
+    e1, lb1, _ = ref.minimize(it, 0.0)
+    lab1 = ref.labels()
+    ref.close()
+    grp = TrwsGridLocalGroup(1, H, W, L, pr["tol"], world, dict(precision="f64"))
+    try:
+        grp.each(lambda g: g.set_labels(0, pr["planes"], pr["unary"]))
+        grp.each(lambda g: g.set_weights(pr["alphas"]))
+        grp.finalize()
+        e, lb, _ = grp.minimize(it)
+        lab = grp.labels()
+    finally:
+        grp.close()
+    assert abs(e - e1) <= 1e-12 * abs(e1) and abs(lb - lb1) <= 1e-12 * abs(lb1)
+    assert np.array_equal(lab, lab1)

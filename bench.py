@@ -284,7 +284,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the QPBO / NCC side measurements (N = 1 only)")
     ap.add_argument("--mode", default="banded", choices=["banded", "independent"],
-                    help="N > 1: ONE problem swept row-banded across the GPUs (strong scaling, default) or one "
+                    help="N > 1: ONE problem swept in column bands across the GPUs (strong scaling, default) or one "
                          "independent fusion per GPU (weak scaling)")
     args = ap.parse_args()
 
@@ -301,8 +301,10 @@ def main():
               "entry": "sb_trws_grid_* (plane-native, 45 B of HBM per label and node)",
               "l2": "working set (tens of GB) exceeds the 126 MB L2; no explicit flush",
               "parallelism": "1 GPU" if world == 1 else (
-                  f"one problem, {world} row bands, static data sharded, boundary messages pushed over NVLink into the "
-                  f"neighbour's HBM (sign-tagged words), one NCCL all-reduce of (energy, bound) per pass" if banded
+                  f"one problem, {world} column bands (the ranks are pipeline stages along the row strips of the sweep), all "
+                  f"state sharded, boundary messages pushed over NVLink into the neighbour's HBM (sign-tagged words), every "
+                  f"rank launches all passes of a step at once, one NCCL all-reduce of the per-pass (energy, bound) sums per step"
+                  if banded
                   else f"{world} independent fusions (one per GPU)")}
 
     # ------------------------------------------------------------------ reference arm

@@ -1,4 +1,4 @@
-"""Row-banded grid-native TRW-S on N GPUs vs the single-GPU sweep (run under torchrun):
+"""Column-banded grid-native TRW-S on N GPUs vs the single-GPU sweep (run under torchrun):
    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/mg_grid_check.py H W L iters [kernel]"""
 import os
 import sys

@@ -536,6 +536,8 @@ struct Solver : SolverBase {
     {
         SB_CUDA(cudaMemsetAsync(dSol.p, 0, dSol.bytes(), stream));
         SB_CUDA(cudaMemsetAsync(dMsg.p, 0, dMsg.bytes(), stream));
+        // (a neighbouring rank writes into these arrays: the caller's barrier must find them cleared)
+        if (world > 1) SB_CUDA(cudaStreamSynchronize(stream));
         pass_counter = 0;
     }
 

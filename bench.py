@@ -251,25 +251,96 @@ def extras():
             q["labels_identical_to_reference"] = bool(np.array_equal(rl, lab))
     except Exception as ex:
         q["reference_error"] = str(ex)[:100]
+    # the same fusion through the grid-native call (tables built on the device): host-pinned inputs, then with
+    # every array resident on the device (what a fusion loop that keeps its fields on the GPU pays)
+    try:
+        # plane fields as pinned 4 x N column-major buffers ((N, 4) C-order memory, passed as its (4, N) transposed view)
+        gin = tuple(pin(rp[k].T).reshape(H * W, 4).T if rp[k].ndim == 2 else pin(rp[k]) for k in ("cur", "new", "U0", "U1", "weights"))
+        sb.binary_fusion_grid(H, W, 1, gin[0], gin[1], gin[2], gin[3], gin[4], rp["tol"])
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            glab, ge, glb, gnu, gst = sb.binary_fusion_grid(H, W, 1, gin[0], gin[1], gin[2], gin[3], gin[4], rp["tol"])
+        dtg = (time.perf_counter() - t0) / reps
+        dev = [torch.from_numpy(np.ascontiguousarray(x.T) if x.ndim == 2 else x).cuda() for x in gin]
+        dlab = torch.zeros(H * W, dtype=torch.float64, device="cuda")
+        ptrs = dict(zip(("assignment", "proposal", "U0", "U1", "weights"), [t.data_ptr() for t in dev]))
+        ptrs["labels"] = dlab.data_ptr()
+        torch.cuda.synchronize()
+        sb.binary_fusion_grid(H, W, 1, None, None, None, None, None, rp["tol"], device_ptrs=ptrs)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            _, de, dlb, dnu, dst = sb.binary_fusion_grid(H, W, 1, None, None, None, None, None, rp["tol"], device_ptrs=ptrs)
+        torch.cuda.synchronize()
+        dtd = (time.perf_counter() - t0) / reps
+        N_ = H * W
+        # 176 N bytes of state traffic per push / relabel round
+        q["grid_native"] = {"api": "stereo_b200.binary_fusion_grid(...) -> sb_binary_fusion_grid (plane fields + unaries + weights in; "
+                                   "pairwise tables built on the device)",
+                            "ms_per_fusion_host_pinned": dtg * 1e3, "h2d_bytes": int(sum(x.nbytes for x in gin)), "d2h_bytes": int(N_ * 8),
+                            "ms_per_fusion_device_resident": dtd * 1e3, "push_relabel_rounds": dst["rounds"],
+                            "global_relabels": dst["relabels"], "bfs_sweeps": dst["bfs_sweeps"], "solve_ms": dst["solve_ms"],
+                            "state_gbs_over_solve": 176.0 * N_ * dst["rounds"] / (dst["solve_ms"] * 1e-3) / 1e9,
+                            "energy": de, "labels_equal_table_entry_fraction": float(np.mean(glab == lab)),
+                            "note": "tables are rebuilt in fp64 on the device from the plane fields; the host-table entry above got "
+                                    "NumPy-built tables (last-bit differences can flip tie labels)"}
+    except Exception as ex:
+        q["grid_native_error"] = str(ex)[:200]
     out["qpbo_fusion"] = q
     im0, im1, _ = synth.stereo_pair(H, W, 127, seed=0xB203)
     d = np.arange(128, dtype=np.float64)
-    builders.ncc_volume(im0, im1, d[:4], 4)
+    builders.NccVolume(im0, im1, d[:4], 4).close()
     t0 = time.perf_counter()
-    vol = builders.ncc_volume(im0, im1, d, 4)
-    dt = time.perf_counter() - t0
-    n = {"workload": f"synthetic {H}x{W} pair, 128 levels, 9x9 window", "ms": dt * 1e3,
-         "volume_gb_fp32": H * W * 128 * 4 / 1e9, "api": "builders.ncc_volume -> sb_ncc_volume, host buffers, "
-         "double volume back to the host"}
+    vh = builders.NccVolume(im0, im1, d, 4)
+    t_create = time.perf_counter() - t0
+    vi = vh.info()
+    t0 = time.perf_counter()
+    best = vh.best_disp()
+    t_wta = time.perf_counter() - t0
+    algo = 4.0 * H * W * 128 + 2 * 3 * H * W            # fp32 volume write + the two uint8 images
+    pk, pk_src = peaks()
+    n = {"workload": f"synthetic {H}x{W} 8-bit pair, 128 integer levels, 9x9 window (BASELINE configs[2])",
+         "api": "builders.NccVolume -> sb_ncc_vol_create (volume stays on the device), .best_disp() -> sb_ncc_vol_best_disp",
+         "create_ms_host_images_in": t_create * 1e3, "wta_ms_best_disp_out": t_wta * 1e3,
+         "volume_kernels_ms": vi["kernel_ms"], "one_pass_kernel": vi["one_pass"], "volume_gb_fp32": H * W * 128 * 4 / 1e9,
+         "roofline": {"bound": "hbm", "achieved": algo / (vi["kernel_ms"] * 1e-3) / 1e9, "peak": pk, "unit": "GB/s",
+                      "frac": algo / (vi["kernel_ms"] * 1e-3) / 1e9 / pk, "peak_source": pk_src,
+                      "note": "algorithmic bytes 4 H W D + 6 H W over the CUDA-event time of ALL volume kernels (packing, window "
+                              "statistics of both images, the level kernel)"}}
     try:
         from oracle import stereo_np
         t0 = time.perf_counter()
         ref = stereo_np.compute_ncc(im0, im1, d[:2], 4)
         n["numpy_restatement_ms_extrapolated_1core"] = (time.perf_counter() - t0) * 1e3 * 64
-        n["max_abs_diff_first_levels"] = float(np.abs(ref - vol[:, :, :2]).max())
+        vol2 = builders.ncc_volume(im0, im1, d[:2], 4)
+        n["max_abs_diff_first_levels"] = float(np.abs(ref - vol2).max())
     except Exception as ex:
         n["reference_error"] = str(ex)[:100]
+    vh.close()
     out["ncc_volume"] = n
+    # BASELINE configs[0] plumbing (example_ncc.m:13-46) at its shape: volume -> WTA initial solution -> one QPBO fusion
+    # with a fronto-parallel proposal, through the dispmap_ncc mirror
+    try:
+        h1, w1 = 375, 450
+        a0, a1, _ = synth.stereo_pair(h1, w1, 60, seed=0xB201)
+        lv = np.arange(0, 61, 4, dtype=np.float64)
+        sb.dispmap_ncc([a0, a1], lv, 1, 40.0, 8.0 * 4, patchsize=2)
+        t0 = time.perf_counter()
+        dm = sb.dispmap_ncc([a0, a1], lv, 1, 40.0, 8.0 * 4, patchsize=2)
+        t_dm = time.perf_counter() - t0
+        prop = np.zeros((4, h1 * w1))
+        prop[2] = 1
+        prop[3] = -30.0
+        e_before = dm.energy()
+        t0 = time.perf_counter()
+        dm.binary_fusion(prop)
+        t_fu = time.perf_counter() - t0
+        out["cfg1_pipeline"] = {"workload": f"synthetic {h1}x{w1} pair, levels 0:4:60, 5x5 window, unary_weight 40, tol 32, kernel 1 "
+                                            "(BASELINE configs[0] with a synthetic pair: teddy is not on the GPU box)",
+                                "construct_ms_volume_wta_energy": t_dm * 1e3, "volume_kernels_ms": dm._vol.info()["kernel_ms"],
+                                "binary_fusion_ms": t_fu * 1e3, "energy_before": e_before, "energy_after": dm.energy(),
+                                "fusion_stats": dm.last_fusion_stats}
+    except Exception as ex:
+        out["cfg1_pipeline_error"] = str(ex)[:200]
     return out
 
 

@@ -297,6 +297,24 @@ SB_API int sb_rd_solve(int64_t N, int64_t E, const double *U0, const double *U1,
                 const uint32_t *conn, int improve,
                 double *labels, double *energy, double *lower_bound, double *num_unlabelled);
 
+/* dispmap_super.binary_fusion (dispmap_super.m:61-84) as one grid-native call: the four
+ * tables of all_pairwise_costs (dispmap_super.m:236-262) are built ON the device from the two plane fields
+ * and feed the QPBO build directly, so neither the 4 x E table doubles nor the 2 x E connectivity cross the
+ * host boundary (14 N doubles in instead of 23 N + the connectivity).
+ *   assignment, proposal  4 x N plane fields ([a; b; c; d0] per pixel, MATLAB node order)
+ *   U0, U1                N   unary cost of keeping / of taking the proposal (dispmap_super.m:66-67)
+ *   weights               E   smooth weights, the reference's term order
+ *   kernel, tol, d_min, d_step   as sb_pairwise_tables
+ *   on_device             != 0: every array pointer (inputs and `labels`) is a DEVICE pointer -- a fusion loop
+ *                         that keeps its fields resident pays no copies at all
+ *   labels / energy / lower_bound / num_unlabelled   as sb_rd_solve
+ *   stats (may be null)   [0] push / relabel rounds, [1] exact relabellings, [2] BFS sweeps, [3] ms from the
+ *                         graph build to the labels */
+SB_API int sb_binary_fusion_grid(int H, int W, int kernel, const double *assignment, const double *proposal,
+                          const double *U0, const double *U1, const double *weights, double tol, double d_min,
+                          double d_step, int improve, int on_device, double *labels, double *energy,
+                          double *lower_bound, double *num_unlabelled, double *stats /* 4 */);
+
 /* ------------------------------------------- cost volume / unary / pairwise builders
  *
  * The dense arrays dispmap_super.binary_fusion / simultaneous_fusion hand to rd() / trws()
@@ -310,6 +328,21 @@ SB_API int sb_rd_solve(int64_t N, int64_t E, const double *U0, const double *U1,
  * (2*patchsize+1)^2 x 3 window; the reference hard-codes patchsize = 2 (dispmap_ncc.m:24). */
 SB_API int sb_ncc_volume(int H, int W, int C, const double *im0, const double *im1,
                   int D, const double *disparities, int patchsize, double *ncc_out);
+/* The same volume kept ON the device (fp32, H x W x D) behind a handle, for the methods that only sample it
+ * (dispmap_ncc.m:107-115, 208-276): nothing of size H x W x D crosses the host boundary unless sb_ncc_vol_get asks.
+ * For 8-bit images and integer disparities (every case the reference's examples run, example_ncc.m:13-16) the
+ * volume comes from ONE pass over the two images for all levels (ncc_volume.cu: exact integer running window
+ * sums, image columns staged by TMA tensor-map copies); otherwise from the general per-level kernel.
+ *   sb_ncc_vol_best_disp / _sample  = sb_ncc_best_disp / sb_ncc_sample on the resident volume (bit-identical)
+ *   sb_ncc_vol_info   info[0] = ms the volume kernels took, [1] = 1 if the one-pass kernel ran, [2] = bytes held */
+typedef struct sb_ncc_vol sb_ncc_vol;
+SB_API int sb_ncc_vol_create(int H, int W, int C, const double *im0, const double *im1,
+                      int D, const double *disparities, int patchsize, sb_ncc_vol **out);
+SB_API int sb_ncc_vol_get(sb_ncc_vol *v, double *ncc_out /* H x W x D */);
+SB_API int sb_ncc_vol_best_disp(sb_ncc_vol *v, double *best_disp);
+SB_API int sb_ncc_vol_sample(sb_ncc_vol *v, const double *disps, double unary_weight, int as_unary, double *out);
+SB_API int sb_ncc_vol_info(sb_ncc_vol *v, double *info /* 3 */);
+SB_API void sb_ncc_vol_destroy(sb_ncc_vol *v);
 /* dispmap_ncc.best_disp_from_ncc (dispmap_ncc.m:208-221): WTA level + parabola refinement. */
 SB_API int sb_ncc_best_disp(int H, int W, int D, const double *ncc, const double *disparities,
                      double *best_disp);

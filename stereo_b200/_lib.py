@@ -101,7 +101,16 @@ def lib():
         L.sb_trws_update_message.argtypes = [c_int, c_int, _dp, _dp, _dp, _dp, c_double, c_double, c_double, c_int, _dp, _dp]
         ip, i64, dbl = c_int, c_int64, c_double
         L.sb_rd_solve.argtypes = [c_int64, c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _up, c_int, _dp, _dp, _dp, _dp]
+        L.sb_binary_fusion_grid.argtypes = [ip, ip, ip, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p, dbl, dbl, dbl, ip, ip, ctypes.c_void_p, _dp, _dp, _dp, _dp]
         L.sb_ncc_volume.argtypes = [ip, ip, ip, _dp, _dp, ip, _dp, ip, _dp]
+        L.sb_ncc_vol_create.argtypes = [ip, ip, ip, _dp, _dp, ip, _dp, ip, POINTER(vp)]
+        L.sb_ncc_vol_get.argtypes = [vp, _dp]
+        L.sb_ncc_vol_best_disp.argtypes = [vp, _dp]
+        L.sb_ncc_vol_sample.argtypes = [vp, _dp, dbl, ip, _dp]
+        L.sb_ncc_vol_info.argtypes = [vp, _dp]
+        L.sb_ncc_vol_destroy.argtypes = [vp]
+        L.sb_ncc_vol_destroy.restype = None
         L.sb_ncc_best_disp.argtypes = [ip, ip, ip, _dp, _dp, _dp]
         L.sb_ncc_sample.argtypes = [ip, ip, ip, _dp, _dp, _dp, dbl, ip, _dp]
         L.sb_plane_disparity.argtypes = [i64, _dp, _dp, dbl, dbl, _dp]

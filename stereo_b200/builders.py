@@ -28,6 +28,57 @@ def ncc_volume(im0, im1, disparities, patchsize=2):
     return out
 
 
+class NccVolume:
+    """The NCC volume of dispmap_ncc.compute_ncc kept ON the device (``sb_ncc_vol_*``): ``best_disp`` and ``sample``
+    are dispmap_ncc.best_disp_from_ncc / sample_ncc_from_disp (dispmap_ncc.m:208-245) on the resident volume;
+    ``get()`` copies it out as (H, W, D) doubles only when asked."""
+
+    def __init__(self, im0, im1, disparities, patchsize=2):
+        import ctypes
+        im0, im1 = _f(im0), _f(im1)
+        self.H, self.W, C = im0.shape
+        assert im1.shape == im0.shape
+        self.disparities = _f(np.asarray(disparities).reshape(-1))
+        self.D = self.disparities.size
+        self._h = ctypes.c_void_p()
+        check(lib().sb_ncc_vol_create(self.H, self.W, C, _p(im0), _p(im1), self.D, _p(self.disparities), int(patchsize),
+                                      ctypes.byref(self._h)))
+
+    def info(self):
+        import ctypes
+        out = (ctypes.c_double * 3)()
+        check(lib().sb_ncc_vol_info(self._h, out))
+        return dict(kernel_ms=out[0], one_pass=bool(out[1]), bytes=int(out[2]))
+
+    def get(self):
+        out = np.zeros((self.H, self.W, self.D), dtype=np.float64, order="F")
+        check(lib().sb_ncc_vol_get(self._h, _p(out)))
+        return out
+
+    def best_disp(self):
+        out = np.zeros((self.H, self.W), dtype=np.float64, order="F")
+        check(lib().sb_ncc_vol_best_disp(self._h, _p(out)))
+        return out
+
+    def sample(self, disps, unary_weight=1.0, as_unary=False):
+        x = _f(np.asarray(disps).reshape(-1, order="F"))
+        assert x.size == self.H * self.W
+        out = np.zeros((self.H, self.W), dtype=np.float64, order="F")
+        check(lib().sb_ncc_vol_sample(self._h, _p(x), float(unary_weight), int(bool(as_unary)), _p(out)))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().sb_ncc_vol_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def ncc_best_disp(ncc, disparities):
     """dispmap_ncc.best_disp_from_ncc (dispmap_ncc.m:208-221) -> (H, W)."""
     ncc = _f(ncc)

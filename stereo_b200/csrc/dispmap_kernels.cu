@@ -429,6 +429,42 @@ double device_sum(const double *d, long long n)
     return s;
 }
 
+double compute_ncc_volume(int H, int W, const double *d_im0, const double *d_im1, const double *h_im0, const double *h_im1, int D,
+                          const double *h_disps, const double *d_disps, int patchsize, float *vol, bool *fast);
+
+// The general volume kernel (any disparities, any pixel values): one CTA per 64 x 16 tile of one level.
+int ncc_volume_general(int H, int W, const double *d_im0, const double *d_im1, int D, const double *h_disps, const double *d_disps,
+                       int patchsize, bool exact32, float *vol)
+{
+    (void)h_disps;
+    const long long N = (long long)H * W;
+    const int HR = NCC_TR + 2 * patchsize, HC = NCC_TC + 2 * patchsize;
+    dim3 grid((H + NCC_TR - 1) / NCC_TR, (W + NCC_TC - 1) / NCC_TC, D);
+    if (exact32) {
+        // 8-bit integer images, integer disparities, every window sum < 2^24: exact in fp32
+        DevBuf<float> f0((size_t)N * 3), f1((size_t)N * 3), sR((size_t)N), sRR((size_t)N);
+        to_float_kernel<<<blocks_for(N * 3), 256>>>(d_im0, f0.p, N * 3);
+        to_float_kernel<<<blocks_for(N * 3), 256>>>(d_im1, f1.p, N * 3);
+        ncc_ref_sums_kernel<float><<<blocks_for(N), 256>>>(f0.p, H, W, patchsize, sR.p, sRR.p);
+        const size_t smem = (size_t)(3 * HR * HC + 3 * HR * NCC_TC) * sizeof(float);
+        SB_CUDA(cudaFuncSetAttribute(ncc_volume_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ncc_volume_kernel<float><<<grid, 256, smem>>>(f0.p, f1.p, H, W, patchsize, d_disps, sR.p, sRR.p, vol);
+        SB_CUDA(cudaGetLastError());
+        SB_CUDA(cudaDeviceSynchronize());
+        count_launch(4);
+    } else {
+        DevBuf<double> sR((size_t)N), sRR((size_t)N);
+        ncc_ref_sums_kernel<double><<<blocks_for(N), 256>>>(d_im0, H, W, patchsize, sR.p, sRR.p);
+        const size_t smem = (size_t)(3 * HR * HC + 3 * HR * NCC_TC) * sizeof(double);
+        SB_CUDA(cudaFuncSetAttribute(ncc_volume_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ncc_volume_kernel<double><<<grid, 256, smem>>>(d_im0, d_im1, H, W, patchsize, d_disps, sR.p, sRR.p, vol);
+        SB_CUDA(cudaGetLastError());
+        SB_CUDA(cudaDeviceSynchronize());
+        count_launch(2);
+    }
+    return 0;
+}
+
 } // namespace dm
 } // namespace sb
 
@@ -437,58 +473,124 @@ using namespace sb::dm;
 
 extern "C" {
 
+// ---------------------------------------------------------------- NCC volume: host-array entry and device-resident handle
+struct sb_ncc_vol {
+    int H, W, D;
+    sb::DevBuf<float> vol;         // [D][W][H]
+    sb::DevBuf<double> disps;
+    std::vector<double> hdisps;
+    double kernel_ms;
+    int fast;
+};
+
+static void ncc_volume_build(int H, int W, int C, const double *im0, const double *im1, int D, const double *disparities,
+                             int patchsize, sb_ncc_vol &v)
+{
+    SB_REQUIRE(H >= 1 && W >= 1 && D >= 1 && im0 && im1 && disparities, SB_EINVAL, "sb_ncc_volume: bad arguments");
+    SB_REQUIRE(C == 3, SB_EINVAL, "sb_ncc_volume: images must have 3 channels (dispmap_ncc.m:125-131)");
+    SB_REQUIRE(patchsize >= 0 && patchsize <= NCC_PMAX, SB_EUNSUP, "sb_ncc_volume: patchsize %d outside [0, %d]", patchsize, NCC_PMAX);
+    require_device();
+    const long long N = (long long)H * W;
+    DevBuf<double> raw0, raw1;
+    upload(raw0, im0, (size_t)N * 3);
+    upload(raw1, im1, (size_t)N * 3);
+    upload(v.disps, disparities, (size_t)D);
+    v.hdisps.assign(disparities, disparities + D);
+    v.H = H; v.W = W; v.D = D;
+    v.vol.alloc((size_t)N * D);
+    bool fast = false;
+    v.kernel_ms = compute_ncc_volume(H, W, raw0.p, raw1.p, im0, im1, D, disparities, v.disps.p, patchsize, v.vol.p, &fast);
+    v.fast = fast ? 1 : 0;
+}
+
+static void ncc_volume_to_host(const sb_ncc_vol &v, double *ncc_out)
+{
+    // back to the MATLAB layout in doubles, one level at a time (bounded staging)
+    const long long N = (long long)v.H * v.W;
+    DevBuf<double> stage((size_t)N);
+    for (int i = 0; i < v.D; i++) {
+        to_double_kernel<<<blocks_for(N), 256>>>(v.vol.p + (size_t)i * N, stage.p, N);
+        SB_CUDA(cudaMemcpy(ncc_out + (size_t)i * N, stage.p, (size_t)N * 8, cudaMemcpyDeviceToHost));
+    }
+    count_launch(v.D);
+}
+
 int sb_ncc_volume(int H, int W, int C, const double *im0, const double *im1, int D, const double *disparities,
                   int patchsize, double *ncc_out)
 {
     return guarded([&] {
-        SB_REQUIRE(H >= 1 && W >= 1 && D >= 1 && im0 && im1 && disparities && ncc_out, SB_EINVAL, "sb_ncc_volume: bad arguments");
-        SB_REQUIRE(C == 3, SB_EINVAL, "sb_ncc_volume: images must have 3 channels (dispmap_ncc.m:125-131)");
-        SB_REQUIRE(patchsize >= 0 && patchsize <= NCC_PMAX, SB_EUNSUP, "sb_ncc_volume: patchsize %d outside [0, %d]", patchsize, NCC_PMAX);
-        require_device();
-        const long long N = (long long)H * W;
-        DevBuf<double> raw0, raw1, dd;
-        upload(raw0, im0, (size_t)N * 3);
-        upload(raw1, im1, (size_t)N * 3);
-        upload(dd, disparities, (size_t)D);
-        // exact fp32 path: 8-bit integer images and integer disparities (every window sum < 2^24)
-        bool exact32 = true;
-        for (int i = 0; i < D && exact32; i++) exact32 = disparities[i] == std::floor(disparities[i]);
-        for (long long i = 0; i < N * 3 && exact32; i++)
-            exact32 = im0[i] >= 0 && im0[i] <= 255 && im0[i] == std::floor(im0[i]) && im1[i] >= 0 && im1[i] <= 255 &&
-                      im1[i] == std::floor(im1[i]);
-        DevBuf<float> vol((size_t)N * D);
-        const int HR = NCC_TR + 2 * patchsize, HC = NCC_TC + 2 * patchsize;
-        dim3 grid((H + NCC_TR - 1) / NCC_TR, (W + NCC_TC - 1) / NCC_TC, D);
-        if (exact32) {
-            DevBuf<float> f0((size_t)N * 3), f1((size_t)N * 3), sR((size_t)N), sRR((size_t)N);
-            to_float_kernel<<<blocks_for(N * 3), 256>>>(raw0.p, f0.p, N * 3);
-            to_float_kernel<<<blocks_for(N * 3), 256>>>(raw1.p, f1.p, N * 3);
-            ncc_ref_sums_kernel<float><<<blocks_for(N), 256>>>(f0.p, H, W, patchsize, sR.p, sRR.p);
-            const size_t smem = (size_t)(3 * HR * HC + 3 * HR * NCC_TC) * sizeof(float);
-            SB_CUDA(cudaFuncSetAttribute(ncc_volume_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ncc_volume_kernel<float><<<grid, 256, smem>>>(f0.p, f1.p, H, W, patchsize, dd.p, sR.p, sRR.p, vol.p);
-            SB_CUDA(cudaGetLastError());
-            SB_CUDA(cudaDeviceSynchronize());
-            count_launch(4);
-        } else {
-            DevBuf<double> sR((size_t)N), sRR((size_t)N);
-            ncc_ref_sums_kernel<double><<<blocks_for(N), 256>>>(raw0.p, H, W, patchsize, sR.p, sRR.p);
-            const size_t smem = (size_t)(3 * HR * HC + 3 * HR * NCC_TC) * sizeof(double);
-            SB_CUDA(cudaFuncSetAttribute(ncc_volume_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ncc_volume_kernel<double><<<grid, 256, smem>>>(raw0.p, raw1.p, H, W, patchsize, dd.p, sR.p, sRR.p, vol.p);
-            SB_CUDA(cudaGetLastError());
-            SB_CUDA(cudaDeviceSynchronize());
-            count_launch(2);
-        }
-        // back to the MATLAB layout in doubles, one level at a time (bounded staging)
-        DevBuf<double> stage((size_t)N);
-        for (int i = 0; i < D; i++) {
-            to_double_kernel<<<blocks_for(N), 256>>>(vol.p + (size_t)i * N, stage.p, N);
-            SB_CUDA(cudaMemcpy(ncc_out + (size_t)i * N, stage.p, (size_t)N * 8, cudaMemcpyDeviceToHost));
-        }
-        count_launch(D);
+        SB_REQUIRE(ncc_out, SB_EINVAL, "sb_ncc_volume: bad arguments");
+        sb_ncc_vol v;
+        ncc_volume_build(H, W, C, im0, im1, D, disparities, patchsize, v);
+        ncc_volume_to_host(v, ncc_out);
     });
 }
+
+int sb_ncc_vol_create(int H, int W, int C, const double *im0, const double *im1, int D, const double *disparities,
+                      int patchsize, sb_ncc_vol **out)
+{
+    return guarded([&] {
+        SB_REQUIRE(out, SB_EINVAL, "sb_ncc_vol_create: null output");
+        *out = nullptr;
+        sb_ncc_vol *v = new sb_ncc_vol();
+        try {
+            ncc_volume_build(H, W, C, im0, im1, D, disparities, patchsize, *v);
+        } catch (...) {
+            delete v;
+            throw;
+        }
+        *out = v;
+    });
+}
+
+int sb_ncc_vol_get(sb_ncc_vol *v, double *ncc_out)
+{
+    return guarded([&] {
+        SB_REQUIRE(v && ncc_out, SB_EINVAL, "sb_ncc_vol_get: null pointer");
+        ncc_volume_to_host(*v, ncc_out);
+    });
+}
+
+int sb_ncc_vol_best_disp(sb_ncc_vol *v, double *best_disp)
+{
+    return guarded([&] {
+        SB_REQUIRE(v && best_disp, SB_EINVAL, "sb_ncc_vol_best_disp: null pointer");
+        const long long N = (long long)v->H * v->W;
+        DevBuf<double> out((size_t)N);
+        ncc_best_disp_kernel<float><<<blocks_for(N), 256>>>(v->vol.p, N, v->D, v->disps.p, out.p);
+        SB_CUDA(cudaGetLastError());
+        count_launch();
+        SB_CUDA(cudaMemcpy(best_disp, out.p, (size_t)N * 8, cudaMemcpyDeviceToHost));
+    });
+}
+
+int sb_ncc_vol_sample(sb_ncc_vol *v, const double *disps, double unary_weight, int as_unary, double *out)
+{
+    return guarded([&] {
+        SB_REQUIRE(v && disps && out, SB_EINVAL, "sb_ncc_vol_sample: null pointer");
+        const long long N = (long long)v->H * v->W;
+        double dmin = v->hdisps[0], dmax = v->hdisps[0];
+        for (int i = 1; i < v->D; i++) { dmin = std::min(dmin, v->hdisps[i]); dmax = std::max(dmax, v->hdisps[i]); }
+        DevBuf<double> x, o((size_t)N);
+        upload(x, disps, (size_t)N);
+        ncc_sample_kernel<float><<<blocks_for(N), 256>>>(v->vol.p, N, v->D, v->disps.p, dmin, dmax, x.p, unary_weight, as_unary, o.p);
+        SB_CUDA(cudaGetLastError());
+        count_launch();
+        SB_CUDA(cudaMemcpy(out, o.p, (size_t)N * 8, cudaMemcpyDeviceToHost));
+    });
+}
+
+int sb_ncc_vol_info(sb_ncc_vol *v, double *info)
+{
+    return guarded([&] {
+        SB_REQUIRE(v && info, SB_EINVAL, "sb_ncc_vol_info: null pointer");
+        info[0] = v->kernel_ms;
+        info[1] = (double)v->fast;
+        info[2] = (double)v->vol.bytes();
+    });
+}
+
+void sb_ncc_vol_destroy(sb_ncc_vol *v) { delete v; }
 
 int sb_ncc_best_disp(int H, int W, int D, const double *ncc, const double *disparities, double *best_disp)
 {
@@ -592,6 +694,21 @@ int sb_photo_unary(int H, int W, int C, const double *im0, const double *im1, co
         SB_CUDA(cudaMemcpy(U, o.p, (size_t)N * 8, cudaMemcpyDeviceToHost));
     });
 }
+
+} // extern "C"
+
+namespace sb {
+// device pointers in, device pointers out (sb_binary_fusion_grid, qpbo.cu)
+void launch_pairwise_tables(int H, int W, int kernel, const double *cur, const double *prop, const double *weights, double tol,
+                            double d_min, double d_step, long long E, double *E00, double *E01, double *E10, double *E11)
+{
+    pairwise_tables_kernel<<<blocks_for(E), 256>>>(H, W, kernel, cur, prop, weights, tol, d_min, d_step, E, E00, E01, E10, E11);
+    SB_CUDA(cudaGetLastError());
+    count_launch();
+}
+} // namespace sb
+
+extern "C" {
 
 int sb_pairwise_tables(int H, int W, int kernel, const double *assignment, const double *proposal,
                        const double *weights, double tol, double d_min, double d_step, double *E00, double *E01,

@@ -548,9 +548,171 @@ void weak_persistencies(const Graph &g, const std::vector<double> &r, const std:
         }
 }
 
+
+// The four pairwise tables and the unaries of one fusion, resident on the device
+struct DeviceProblem {
+    int H, W;
+    int64_t N, E;
+    const double *U0, *U1;
+    const double *Et[4];     // E00, E01, E10, E11 in the reference's term order
+    const unsigned *conn;    // 2 x E, 0-based
+};
+
+// connectivity of dispmap_super.construct_neighborhood (dispmap_super.m:284-294), 0-based
+__global__ void grid_conn_kernel(int H, int W, long long E, unsigned *__restrict__ conn)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= E) return;
+    const long long nV = (long long)(H - 1) * W, nH = (long long)H * (W - 1);
+    long long a, b;
+    if (p < 2 * nV) {
+        const long long e = p < nV ? p : p - nV;
+        const long long c = e / (H - 1), r = e % (H - 1);
+        const long long up = r + (long long)H * c;
+        if (p < nV) { a = up; b = up + 1; } else { a = up + 1; b = up; }
+    } else {
+        const long long q = p - 2 * nV;
+        const long long e = q < nH ? q : q - nH;
+        if (q < nH) { a = e; b = e + H; } else { a = e + H; b = e; }
+    }
+    conn[2 * p] = (unsigned)a;
+    conn[2 * p + 1] = (unsigned)b;
+}
+
+__global__ void labels_to_double_kernel(const int *__restrict__ lab, long long N, double *__restrict__ out)
+{
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < N) out[u] = (double)lab[u];
+}
+
+// rd_mex.cpp:55-100 from device-resident inputs.  lab: final labels on the host (always filled);
+// dlabels: optional DEVICE array of N doubles that receives them as well; stats (optional, 4 doubles):
+// push/relabel rounds, exact relabellings, BFS sweeps, milliseconds from the graph build to the labels.
+void solve_device(const DeviceProblem &dp, int improve, std::vector<int> &lab, double *dlabels, double *energy,
+                  double *lower_bound, double *num_unlabelled, double *stats)
+{
+    const int H = dp.H, W = dp.W;
+    const int64_t N = dp.N, E = dp.E;
+    const double *dU0 = dp.U0, *dU1 = dp.U1;
+    Solver S;
+    S.alloc(H, W);
+    Graph &g = S.g;
+    DevBuf<double> pci((size_t)std::max<long long>(g.nP, 1)), pcj((size_t)std::max<long long>(g.nP, 1)),
+        pt00((size_t)std::max<long long>(g.nP, 1));
+    const bool prof = getenv("SB_QPBO_PROFILE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_a = now();
+    const double t_begin = t_a;
+    if (g.nP) build_pairs_kernel<<<nblk(g.nP), 256>>>(g, dp.Et[0], dp.Et[1], dp.Et[2], dp.Et[3], pci.p, pcj.p, pt00.p);
+    build_nodes_kernel<<<nblk(N), 256>>>(g, dU0, dU1, pci.p, pcj.p);
+    init_preflow_kernel<<<nblk(2 * N), 256>>>(g);
+    SB_CUDA(cudaGetLastError());
+    count_launch(3);
+    SB_CUDA(cudaMemcpy(S.r0.p, S.r.p, S.r.bytes(), cudaMemcpyDeviceToDevice));
+
+    if (prof) { cudaDeviceSynchronize(); fprintf(stderr, "[sb qpbo] build %.1f ms\n", now() - t_a); t_a = now(); }
+    // ---- Solve(): maximum preflow, sink-reachable set, strong labels
+    S.maxflow<false>();
+    if (prof) { cudaDeviceSynchronize(); fprintf(stderr, "[sb qpbo] maxflow %.1f ms\n", now() - t_a); t_a = now(); }
+    labels_kernel<<<nblk(N), 256>>>(g, S.label.p);
+    count_launch();
+    lab.resize((size_t)N);
+    SB_CUDA(cudaMemcpy(lab.data(), S.label.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
+    // open nodes that are trivially weakly persistent are settled on the device
+    int complex_open = 0;
+    {
+        SB_CUDA(cudaMemsetAsync(S.flag.p, 0, 2 * sizeof(int)));
+        isolated_open_kernel<<<nblk(N), 256>>>(g, S.label.p, S.flag.p);
+        count_launch();
+        SB_CUDA(cudaMemcpy(&complex_open, S.flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+    }
+
+    // ---- lower bound: (initial bound + flow value) / 2 (ComputeTwiceLowerBound, QPBO.cpp:897-917)
+    {
+        DevBuf<double> terms((size_t)(2 * N + g.nP));
+        bound_terms_kernel<<<nblk(N + g.nP), 256>>>(g, dU0, pt00.p, terms.p);
+        count_launch();
+        double twice = device_sum(terms.p, N + g.nP);
+        flow_terms_kernel<<<nblk(2 * N + g.nP), 256>>>(g, S.r0.p, terms.p);
+        count_launch();
+        twice += device_sum(terms.p, 2 * N + g.nP);
+        *lower_bound = twice / 2;
+    }
+
+    // ---- ComputeWeakPersistencies() on the nodes Solve left open
+    if (complex_open == 0) {
+        SB_CUDA(cudaMemcpy(lab.data(), S.label.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
+    } else {
+        S.maxflow<true>();   // a true flow: stranded excess back to the source
+        std::vector<double> hr((size_t)std::max<long long>(g.nP, 1) * 4);
+        std::vector<unsigned char> hsub((size_t)std::max<long long>(g.nP, 1));
+        SB_CUDA(cudaMemcpy(hr.data(), S.r.p, hr.size() * 8, cudaMemcpyDeviceToHost));
+        SB_CUDA(cudaMemcpy(hsub.data(), S.sub.p, hsub.size(), cudaMemcpyDeviceToHost));
+        weak_persistencies(g, hr, hsub, lab);
+    }
+    double nun = 0;
+    for (int64_t u = 0; u < N; u++) nun += lab[u] < 0;   // rd_mex.cpp:83-88
+    *num_unlabelled = nun;
+
+    // ---- Improve() (QPBO_extra.cpp:1151-1232): fix still-ambiguous nodes one by one to
+    // label 0 in a libc rand() permutation, re-solving after each
+    if (improve && nun > 0) {
+        std::vector<int> perm((size_t)N);
+        for (int64_t i = 0; i < N; i++) perm[i] = (int)i;
+        for (int64_t i = 0; i + 1 < N; i++) {   // ComputeRandomPermutation, QPBO_extra.cpp:13-27
+            int64_t j = i + (int64_t)((rand() / (1.0 + (double)RAND_MAX)) * (double)(N - i));
+            if (j > N - 1) j = N - 1;
+            std::swap(perm[j], perm[i]);
+        }
+        S.maxflow<false>();
+        labels_kernel<<<nblk(N), 256>>>(g, S.label.p);
+        std::vector<int> cur((size_t)N);
+        SB_CUDA(cudaMemcpy(cur.data(), S.label.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
+        DevBuf<double> dsat(1);
+        for (int64_t pi = 0; pi < N; pi++) {
+            const int u = perm[pi];
+            if (cur[u] >= 0) continue;     // what_segment(i) != what_segment(i'): decided
+            double sat = 0;
+            saturation_kernel<<<1, 1>>>(g, u, dsat.p);
+            SB_CUDA(cudaMemcpy(&sat, dsat.p, 8, cudaMemcpyDeviceToHost));
+            add_unary_kernel<<<1, 1>>>(g, u, sat);   // user_label == 0: forbid label 1
+            count_launch(2);
+            S.maxflow<false>();
+            labels_kernel<<<nblk(N), 256>>>(g, S.label.p);
+            count_launch();
+            SB_CUDA(cudaMemcpy(cur.data(), S.label.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
+        }
+        for (int64_t u = 0; u < N; u++) lab[u] = cur[u] < 0 ? 0 : cur[u];   // ambiguous -> user_label (0)
+    }
+
+    if (prof) fprintf(stderr, "[sb qpbo] labels+bound+weak %.1f ms\n", now() - t_a);
+    if (prof)
+        fprintf(stderr, "[sb qpbo] %dx%d: %lld push/relabel rounds, %lld global relabels, %lld bfs sweeps\n", H, W,
+                (long long)S.rounds, (long long)S.relabels, (long long)S.bfs_sweeps);
+    if (stats) {
+        stats[0] = (double)S.rounds; stats[1] = (double)S.relabels; stats[2] = (double)S.bfs_sweeps;
+        stats[3] = now() - t_begin;
+    }
+    // ---- energy of the labelling (unlabelled -> 0), ComputeTwiceEnergy / 2
+    {
+        SB_CUDA(cudaMemcpy(S.label.p, lab.data(), (size_t)N * 4, cudaMemcpyHostToDevice));
+        DevBuf<double> terms((size_t)(N + E));
+        energy_terms_kernel<<<nblk(N + E), 256>>>(N, E, dp.conn, S.label.p, dU0, dU1, dp.Et[0], dp.Et[1], dp.Et[2], dp.Et[3], terms.p);
+        count_launch();
+        *energy = device_sum(terms.p, N + E);
+        if (dlabels) {
+            labels_to_double_kernel<<<nblk(N), 256>>>(S.label.p, N, dlabels);
+            count_launch();
+            SB_CUDA(cudaDeviceSynchronize());
+        }
+    }
+}
+
 } // namespace qpbo
 
 bool grid_from_connectivity(int64_t N, int64_t E, const uint32_t *conn, int &H, int &W);
+void launch_pairwise_tables(int H, int W, int kernel, const double *cur, const double *prop, const double *weights, double tol,
+                            double d_min, double d_step, long long E, double *E00, double *E01, double *E10, double *E11);
 
 } // namespace sb
 
@@ -573,119 +735,66 @@ int sb_rd_solve(int64_t N, int64_t E, const double *U0, const double *U1, const 
                    "sb_rd_solve: connectivity (N=%lld, E=%lld) is not the 4-connected dispmap_super grid; "
                    "general graphs are not supported on the GPU path", (long long)N, (long long)E);
         require_device();
-        Solver S;
-        S.alloc(H, W);
-        Graph &g = S.g;
-        DevBuf<double> dU0, dU1, dE[4], pci((size_t)std::max<long long>(g.nP, 1)), pcj((size_t)std::max<long long>(g.nP, 1)),
-            pt00((size_t)std::max<long long>(g.nP, 1));
+        DevBuf<double> dU0, dU1, dE[4];
         DevBuf<unsigned> dconn;
         auto up = [&](DevBuf<double> &b, const double *hsrc, size_t n) {
             b.alloc(std::max<size_t>(n, 1));
             if (n) SB_CUDA(cudaMemcpy(b.p, hsrc, n * 8, cudaMemcpyHostToDevice));
         };
-        const bool prof = getenv("SB_QPBO_PROFILE") != nullptr;
-        auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-        double t_a = now();
         up(dU0, U0, (size_t)N); up(dU1, U1, (size_t)N);
         up(dE[0], E00, (size_t)E); up(dE[1], E01, (size_t)E); up(dE[2], E10, (size_t)E); up(dE[3], E11, (size_t)E);
         dconn.alloc((size_t)std::max<int64_t>(2 * E, 1));
         if (E) SB_CUDA(cudaMemcpy(dconn.p, conn, (size_t)E * 8, cudaMemcpyHostToDevice));
-        if (g.nP) build_pairs_kernel<<<nblk(g.nP), 256>>>(g, dE[0].p, dE[1].p, dE[2].p, dE[3].p, pci.p, pcj.p, pt00.p);
-        build_nodes_kernel<<<nblk(N), 256>>>(g, dU0.p, dU1.p, pci.p, pcj.p);
-        init_preflow_kernel<<<nblk(2 * N), 256>>>(g);
-        SB_CUDA(cudaGetLastError());
-        count_launch(3);
-        SB_CUDA(cudaMemcpy(S.r0.p, S.r.p, S.r.bytes(), cudaMemcpyDeviceToDevice));
-
-        if (prof) { cudaDeviceSynchronize(); fprintf(stderr, "[sb qpbo] upload+build %.1f ms\n", now() - t_a); t_a = now(); }
-        // ---- Solve(): maximum preflow, sink-reachable set, strong labels
-        S.maxflow<false>();
-        if (prof) { cudaDeviceSynchronize(); fprintf(stderr, "[sb qpbo] maxflow %.1f ms\n", now() - t_a); t_a = now(); }
-        labels_kernel<<<nblk(N), 256>>>(g, S.label.p);
-        count_launch();
-        std::vector<int> lab((size_t)N);
-        SB_CUDA(cudaMemcpy(lab.data(), S.label.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
-        // open nodes that are trivially weakly persistent are settled on the device
-        int complex_open = 0;
-        {
-            SB_CUDA(cudaMemsetAsync(S.flag.p, 0, 2 * sizeof(int)));
-            isolated_open_kernel<<<nblk(N), 256>>>(g, S.label.p, S.flag.p);
-            count_launch();
-            SB_CUDA(cudaMemcpy(&complex_open, S.flag.p, sizeof(int), cudaMemcpyDeviceToHost));
-        }
-
-        // ---- lower bound: (initial bound + flow value) / 2 (ComputeTwiceLowerBound, QPBO.cpp:897-917)
-        {
-            DevBuf<double> terms((size_t)(2 * N + g.nP));
-            bound_terms_kernel<<<nblk(N + g.nP), 256>>>(g, dU0.p, pt00.p, terms.p);
-            count_launch();
-            double twice = device_sum(terms.p, N + g.nP);
-            flow_terms_kernel<<<nblk(2 * N + g.nP), 256>>>(g, S.r0.p, terms.p);
-            count_launch();
-            twice += device_sum(terms.p, 2 * N + g.nP);
-            *lower_bound = twice / 2;
-        }
-
-        // ---- ComputeWeakPersistencies() on the nodes Solve left open
-        if (complex_open == 0) {
-            SB_CUDA(cudaMemcpy(lab.data(), S.label.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
-        } else {
-            S.maxflow<true>();   // a true flow: stranded excess back to the source
-            std::vector<double> hr((size_t)std::max<long long>(g.nP, 1) * 4);
-            std::vector<unsigned char> hsub((size_t)std::max<long long>(g.nP, 1));
-            SB_CUDA(cudaMemcpy(hr.data(), S.r.p, hr.size() * 8, cudaMemcpyDeviceToHost));
-            SB_CUDA(cudaMemcpy(hsub.data(), S.sub.p, hsub.size(), cudaMemcpyDeviceToHost));
-            weak_persistencies(g, hr, hsub, lab);
-        }
-        double nun = 0;
-        for (int64_t u = 0; u < N; u++) nun += lab[u] < 0;   // rd_mex.cpp:83-88
-        *num_unlabelled = nun;
-
-        // ---- Improve() (QPBO_extra.cpp:1151-1232): fix still-ambiguous nodes one by one to
-        // label 0 in a libc rand() permutation, re-solving after each
-        if (improve && nun > 0) {
-            std::vector<int> perm((size_t)N);
-            for (int64_t i = 0; i < N; i++) perm[i] = (int)i;
-            for (int64_t i = 0; i + 1 < N; i++) {   // ComputeRandomPermutation, QPBO_extra.cpp:13-27
-                int64_t j = i + (int64_t)((rand() / (1.0 + (double)RAND_MAX)) * (double)(N - i));
-                if (j > N - 1) j = N - 1;
-                std::swap(perm[j], perm[i]);
-            }
-            S.maxflow<false>();
-            labels_kernel<<<nblk(N), 256>>>(g, S.label.p);
-            std::vector<int> cur((size_t)N);
-            SB_CUDA(cudaMemcpy(cur.data(), S.label.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
-            DevBuf<double> dsat(1);
-            for (int64_t pi = 0; pi < N; pi++) {
-                const int u = perm[pi];
-                if (cur[u] >= 0) continue;     // what_segment(i) != what_segment(i'): decided
-                double sat = 0;
-                saturation_kernel<<<1, 1>>>(g, u, dsat.p);
-                SB_CUDA(cudaMemcpy(&sat, dsat.p, 8, cudaMemcpyDeviceToHost));
-                add_unary_kernel<<<1, 1>>>(g, u, sat);   // user_label == 0: forbid label 1
-                count_launch(2);
-                S.maxflow<false>();
-                labels_kernel<<<nblk(N), 256>>>(g, S.label.p);
-                count_launch();
-                SB_CUDA(cudaMemcpy(cur.data(), S.label.p, (size_t)N * 4, cudaMemcpyDeviceToHost));
-            }
-            for (int64_t u = 0; u < N; u++) lab[u] = cur[u] < 0 ? 0 : cur[u];   // ambiguous -> user_label (0)
-        }
-
-        if (prof) fprintf(stderr, "[sb qpbo] labels+bound+weak %.1f ms\n", now() - t_a);
-        if (prof)
-            fprintf(stderr, "[sb qpbo] %dx%d: %lld push/relabel rounds, %lld global relabels, %lld bfs sweeps\n", H, W,
-                    (long long)S.rounds, (long long)S.relabels, (long long)S.bfs_sweeps);
-        // ---- energy of the labelling (unlabelled -> 0), ComputeTwiceEnergy / 2
-        {
-            SB_CUDA(cudaMemcpy(S.label.p, lab.data(), (size_t)N * 4, cudaMemcpyHostToDevice));
-            DevBuf<double> terms((size_t)(N + E));
-            energy_terms_kernel<<<nblk(N + E), 256>>>(N, E, dconn.p, S.label.p, dU0.p, dU1.p, dE[0].p, dE[1].p, dE[2].p,
-                                                      dE[3].p, terms.p);
-            count_launch();
-            *energy = device_sum(terms.p, N + E);
-        }
+        DeviceProblem dp{H, W, N, E, dU0.p, dU1.p, {dE[0].p, dE[1].p, dE[2].p, dE[3].p}, dconn.p};
+        std::vector<int> lab;
+        solve_device(dp, improve, lab, nullptr, energy, lower_bound, num_unlabelled, nullptr);
         for (int64_t u = 0; u < N; u++) labels[u] = (double)lab[u];
+    });
+}
+
+// dispmap_super.binary_fusion (dispmap_super.m:61-84) as ONE call on the grid: the four pairwise tables of
+// all_pairwise_costs (dispmap_super.m:236-262) are built on the device from the two plane fields and go straight
+// into the QPBO build -- the 4 x E doubles of tables (and the 2 x E connectivity) never exist on the host.
+int sb_binary_fusion_grid(int H, int W, int kernel, const double *assignment, const double *proposal, const double *U0,
+                          const double *U1, const double *weights, double tol, double d_min, double d_step, int improve,
+                          int on_device, double *labels, double *energy, double *lower_bound, double *num_unlabelled,
+                          double *stats)
+{
+    return guarded([&] {
+        SB_REQUIRE(H >= 1 && W >= 1, SB_EINVAL, "sb_binary_fusion_grid: bad sizes H=%d W=%d", H, W);
+        SB_REQUIRE(kernel == 1 || kernel == 2, SB_EINVAL, "Unkown kernel type");   // dispmap_super.m:232-233
+        SB_REQUIRE(assignment && proposal && U0 && U1 && weights && labels && energy && lower_bound && num_unlabelled, SB_EINVAL,
+                   "sb_binary_fusion_grid: null pointer");
+        SB_REQUIRE(d_step != 0.0, SB_EINVAL, "sb_binary_fusion_grid: d_step == 0");
+        const int64_t N = (int64_t)H * W, E = 2 * ((int64_t)(H - 1) * W + (int64_t)H * (W - 1));
+        SB_REQUIRE(N < (1LL << 30), SB_EUNSUP, "sb_binary_fusion_grid: too many nodes");
+        require_device();
+        DevBuf<double> bcur, bprop, bU0, bU1, bw, tables((size_t)std::max<int64_t>(4 * E, 1)), dlab;
+        DevBuf<unsigned> dconn((size_t)std::max<int64_t>(2 * E, 1));
+        const double *cur = assignment, *prop = proposal, *u0 = U0, *u1 = U1, *wt = weights;
+        if (!on_device) {
+            auto up = [&](DevBuf<double> &b, const double *hsrc, size_t n) -> const double * {
+                b.alloc(std::max<size_t>(n, 1));
+                if (n) SB_CUDA(cudaMemcpyAsync(b.p, hsrc, n * 8, cudaMemcpyHostToDevice, 0));
+                return b.p;
+            };
+            cur = up(bcur, assignment, (size_t)N * 4); prop = up(bprop, proposal, (size_t)N * 4);
+            u0 = up(bU0, U0, (size_t)N); u1 = up(bU1, U1, (size_t)N); wt = up(bw, weights, (size_t)E);
+        }
+        if (E) {
+            launch_pairwise_tables(H, W, kernel, cur, prop, wt, tol, d_min, d_step, E, tables.p, tables.p + E, tables.p + 2 * E,
+                                   tables.p + 3 * E);
+            grid_conn_kernel<<<nblk(E), 256>>>(H, W, E, dconn.p);
+            SB_CUDA(cudaGetLastError());
+            count_launch();
+        }
+        DeviceProblem dp{H, W, N, E, u0, u1, {tables.p, tables.p + E, tables.p + 2 * E, tables.p + 3 * E}, dconn.p};
+        std::vector<int> lab;
+        double *dlabels = nullptr;
+        if (on_device) dlabels = labels;
+        solve_device(dp, improve, lab, dlabels, energy, lower_bound, num_unlabelled, stats);
+        if (!on_device)
+            for (int64_t u = 0; u < N; u++) labels[u] = (double)lab[u];
     });
 }
 

@@ -10,7 +10,7 @@ import numpy as np
 
 from . import builders
 from .grid import construct_neighborhood, get_points
-from .solvers import rd, trws
+from .solvers import binary_fusion_grid, rd, trws
 
 
 class dispmap_super:
@@ -24,6 +24,8 @@ class dispmap_super:
         self.maxiter = 1000              # dispmap_super.m:9
         self._max_relgap = 1e-4          # :10
         self._improve = False            # :13
+        self.grid_native = True          # binary_fusion through sb_binary_fusion_grid (tables built on the device)
+        self.last_fusion_stats = None
         self._assignment = None
         self.stored_energy = np.inf
         ind1, ind2 = construct_neighborhood(*self.sz)
@@ -77,11 +79,17 @@ class dispmap_super:
         proposal = np.asarray(proposal, dtype=np.float64)
         if proposal.shape != self._assignment.shape:
             raise ValueError("Binary fusion: Proposals is of wrong size")
-        E00, E01, E10, E11 = self.all_pairwise_costs(self._assignment, proposal)
         U0 = self.unary_cost(self._assignment)
         U1 = self.unary_cost(proposal)
-        connectivity = np.stack([self.neighborhood["ind1"], self.neighborhood["ind2"]]).astype(np.uint32)
-        labelling, e, lb, num_unlabelled = rd(U0, U1, E00, E01, E10, E11, connectivity, dict(improve=self.improve))
+        if self.grid_native:
+            # the tables of all_pairwise_costs are built on the device and feed the solver directly
+            labelling, e, lb, num_unlabelled, self.last_fusion_stats = binary_fusion_grid(
+                self.sz[0], self.sz[1], self.smoothness_kernel, self._assignment, proposal, U0, U1, self.smooth_weights,
+                self.tol, self.d_min, self.d_step, dict(improve=self.improve))
+        else:
+            E00, E01, E10, E11 = self.all_pairwise_costs(self._assignment, proposal)
+            connectivity = np.stack([self.neighborhood["ind1"], self.neighborhood["ind2"]]).astype(np.uint32)
+            labelling, e, lb, num_unlabelled = rd(U0, U1, E00, E01, E10, E11, connectivity, dict(improve=self.improve))
         a = self._assignment.copy()
         take = labelling == 1
         a[:, take] = proposal[:, take]
@@ -181,8 +189,16 @@ class dispmap_ncc(dispmap_super):
             raise ValueError("Tolerance weight must be positive")
         self._unary_weight = unary_weight
         self._tol = tol
-        self.ncc = builders.ncc_volume(self.images[0], self.images[1], self.disparities, patchsize)  # :24
+        # :24 -- the volume stays on the device; `ncc` (the reference's public property) copies it out on first use
+        self._vol = builders.NccVolume(self.images[0], self.images[1], self.disparities, patchsize)
+        self._ncc_host = None
         self.init_solution()                                                                        # :27
+
+    @property
+    def ncc(self):
+        if self._ncc_host is None:
+            self._ncc_host = self._vol.get()
+        return self._ncc_host
 
     @property
     def tol(self):
@@ -212,10 +228,10 @@ class dispmap_ncc(dispmap_super):
     def unary_cost(self, assignment):
         """dispmap_ncc.m:107-115."""
         disps = self.disparitymap_from_assignment(assignment)
-        return builders.ncc_sample(self.ncc, self.disparities, disps, self.unary_weight, True).reshape(-1, order="F")
+        return self._vol.sample(disps, self.unary_weight, True).reshape(-1, order="F")
 
     def best_disp_from_ncc(self):
-        return builders.ncc_best_disp(self.ncc, self.disparities)
+        return self._vol.best_disp()
 
     def init_solution(self):
         """dispmap_ncc.m:199-207."""

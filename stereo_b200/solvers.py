@@ -196,6 +196,43 @@ def rd(U0, U1, E00, E01, E10, E11, connectivity, options=None):
     return solution, e.value, lb.value, nu.value
 
 
+def binary_fusion_grid(H, W, kernel, assignment, proposal, U0, U1, weights, tol, d_min=0.0, d_step=1.0, options=None,
+                       device_ptrs=None):
+    """dispmap_super.binary_fusion (dispmap_super.m:61-84) as one grid-native call (``sb_binary_fusion_grid``):
+    the tables of all_pairwise_costs are built on the device.  assignment / proposal: 4 x N; U0 / U1: N; weights: E
+    (the reference's term order).  Returns (labelling N float64 in {0, 1, negative}, energy, lower_bound,
+    num_unlabelled, stats) with stats = dict(rounds, relabels, bfs_sweeps, solve_ms).
+
+    ``device_ptrs``: dict of integer device addresses (assignment, proposal, U0, U1, weights, labels) -- the
+    arrays stay where they are; the labelling is then written to the ``labels`` address and None is returned
+    in its place."""
+    N = int(H) * int(W)
+    improve = bool(_opt(options, "improve", False))
+    e, lb, nu = c_double(), c_double(), c_double()
+    stats = (c_double * 4)()
+    if device_ptrs is not None:
+        args = [ctypes.c_void_p(int(device_ptrs[k])) for k in ("assignment", "proposal", "U0", "U1", "weights")]
+        out = ctypes.c_void_p(int(device_ptrs["labels"]))
+        solution = None
+        on_device = 1
+    else:
+        def planes(a):
+            # 4 x N in MATLAB (column-major) memory order; an F-contiguous (4, N) view is passed through untouched
+            a = np.asarray(a, dtype=np.float64)
+            assert a.shape == (4, N)
+            return np.asfortranarray(a)
+        arrs = [planes(assignment), planes(proposal),
+                _f(np.asarray(U0).reshape(-1)), _f(np.asarray(U1).reshape(-1)), _f(np.asarray(weights).reshape(-1))]
+        assert arrs[2].size == N and arrs[3].size == N
+        args = [ctypes.c_void_p(a.ctypes.data) for a in arrs]
+        solution = np.zeros(N, dtype=np.float64)
+        out = ctypes.c_void_p(solution.ctypes.data)
+        on_device = 0
+    check(lib().sb_binary_fusion_grid(int(H), int(W), int(kernel), *args, float(tol), float(d_min), float(d_step), int(improve),
+                                      on_device, out, ctypes.byref(e), ctypes.byref(lb), ctypes.byref(nu), stats))
+    return solution, e.value, lb.value, nu.value, dict(rounds=stats[0], relabels=stats[1], bfs_sweeps=stats[2], solve_ms=stats[3])
+
+
 def trws_grid_ordering(H, W):
     """m_ordering of SetAutomaticOrdering (ordering.cpp:7-157) on the H x W grid, as (H, W) int32."""
     out = np.zeros(H * W, dtype=np.int32)

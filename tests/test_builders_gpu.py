@@ -32,6 +32,34 @@ def test_ncc_volume(H, W, D, p, frac):
     assert np.array_equal(got == 0, ref == 0) or np.mean((got == 0) == (ref == 0)) > 0.999
 
 
+@pytest.mark.parametrize("H,W,disps,p", [(37, 53, list(range(8)), 2), (101, 300, list(range(0, 120, 3)), 4), (64, 200, list(range(0, 64, 4)), 2),
+                                         (7, 9, [0, 1, 2], 1), (33, 70, [5, 0, 17, 2], 8), (130, 96, list(range(20)), 3),
+                                         (50, 400, list(range(130)), 4)])
+def test_ncc_one_pass_kernel_equals_general(H, W, disps, p, monkeypatch):
+    """The one-pass volume kernel (exact integer window sums, TMA-staged ring, all levels per CTA) against the general
+    per-level kernel on the same 8-bit pair, and the device-resident handle against the host-array entry points."""
+    im0, im1, _ = synth.stereo_pair(H, W, max(disps) + 1, seed=H * 7 + W)
+    d = np.asarray(disps, dtype=np.float64)
+    vol = builders.NccVolume(im0, im1, d, p)
+    assert vol.info()["one_pass"]
+    fast = vol.get()
+    monkeypatch.setenv("SB_NCC_GENERAL", "1")
+    gen = builders.ncc_volume(im0, im1, d, p)
+    monkeypatch.delenv("SB_NCC_GENERAL")
+    cond = _np().ncc_conditioning(im0, im1, d, p)
+    ok = cond > 1e-6
+    # the general kernel combines fp32 sums in doubles with cancellation; the one-pass kernel has none
+    assert np.all(np.abs(fast - gen)[ok] <= 2e-5)
+    assert np.all(np.abs(fast) <= 1.0 + 1e-5)
+    ref = _np().compute_ncc(im0, im1, d, p)
+    assert np.all(np.abs(fast - ref)[ok] <= 1e-4 * np.maximum(np.abs(ref[ok]), 1e-2))
+    # handle methods == host-array entry points on the same volume
+    assert np.array_equal(vol.best_disp(), builders.ncc_best_disp(fast, d))
+    x = np.random.default_rng(1).random((H, W)) * (d.max() + 2) - 1
+    assert np.array_equal(vol.sample(x, 40.0, True), builders.ncc_sample(fast, d, x.reshape(-1, order="F"), 40.0, True))
+    vol.close()
+
+
 def test_ncc_sampling_and_wta():
     H, W, D = 33, 47, 9
     im0, im1, _ = synth.stereo_pair(H, W, D, seed=3)

@@ -122,3 +122,70 @@ def test_argument_validation():
     with pytest.raises(sb._lib.SbError) as ei:
         sb.rd(pr["U0"], pr["U1"], pr["E00"], pr["E01"], pr["E10"], pr["E11"], conn, {})
     assert ei.value.code == sb._lib.SB_ENOTGRID
+
+
+def _fusion_inputs(H, W, seed, kernel):
+    pr = synth.rd_problem(H, W, seed=seed, kernel=kernel, mode="stereo")
+    # the tables exactly as the device builds them (fp64, same kernel): both entries then see the same energy
+    t = sb.builders.pairwise_tables(H, W, kernel, pr["cur"], pr["new"], pr["weights"], pr["tol"], 0.0, 1.0)
+    return pr, t
+
+
+@pytest.mark.parametrize("H,W,seed,kernel,improve", [(12, 17, 1, 1, False), (23, 31, 2, 2, False), (48, 64, 3, 1, True),
+                                                     (5, 4, 4, 1, False), (64, 48, 5, 2, True), (1, 9, 6, 1, False)])
+def test_binary_fusion_grid_equals_rd_and_reference(H, W, seed, kernel, improve):
+    """sb_binary_fusion_grid (tables built on the device, no tables / connectivity on the host) == sb_rd_solve on the
+    same tables == the reference's rd_mex on them: labels bit-exact."""
+    from oracle import oracle
+    pr, (E00, E01, E10, E11) = _fusion_inputs(H, W, seed, kernel)
+    libc.srand(1)
+    lab, e, lb, nu, st = sb.binary_fusion_grid(H, W, kernel, pr["cur"], pr["new"], pr["U0"], pr["U1"], pr["weights"], pr["tol"],
+                                               options=dict(improve=improve))
+    libc.srand(1)
+    lab2, e2, lb2, nu2 = sb.rd(pr["U0"], pr["U1"], E00, E01, E10, E11, pr["connectivity"], dict(improve=improve))
+    assert np.array_equal(lab, lab2) and e == e2 and lb == lb2 and nu == nu2
+    assert st["rounds"] >= 0 and st["solve_ms"] > 0
+    if oracle.have_ref("rd"):
+        libc.srand(1)
+        r = oracle.rd_solve(pr["U0"], pr["U1"], E00, E01, E10, E11, (pr["connectivity"] - 1).T, improve=improve)
+        assert np.array_equal(lab, r[0])
+        assert abs(e - r[1]) <= 1e-9 * abs(r[1]) and nu == r[3]
+
+
+def test_binary_fusion_grid_device_pointers():
+    """The same call with every array resident on the device (on_device = 1): nothing is copied."""
+    import torch
+    H, W, kernel = 40, 56, 1
+    pr, _ = _fusion_inputs(H, W, 9, kernel)
+    lab, e, lb, nu, _ = sb.binary_fusion_grid(H, W, kernel, pr["cur"], pr["new"], pr["U0"], pr["U1"], pr["weights"], pr["tol"])
+    dev = {k: torch.from_numpy(np.asfortranarray(v).T.copy() if v.ndim == 2 else np.ascontiguousarray(v)).cuda()
+           for k, v in dict(assignment=pr["cur"], proposal=pr["new"], U0=pr["U0"], U1=pr["U1"], weights=pr["weights"]).items()}
+    out = torch.zeros(H * W, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    ptrs = {k: v.data_ptr() for k, v in dev.items()}
+    ptrs["labels"] = out.data_ptr()
+    none, e2, lb2, nu2, _ = sb.binary_fusion_grid(H, W, kernel, None, None, None, None, None, pr["tol"], device_ptrs=ptrs)
+    assert none is None and e2 == e and lb2 == lb and nu2 == nu
+    assert np.array_equal(out.cpu().numpy(), lab)
+
+
+def test_dispmap_binary_fusion_paths_agree():
+    """dispmap_super.binary_fusion through the grid-native call and through rd(...) on host tables."""
+    H, W = 24, 30
+    pr = synth.rd_problem(H, W, seed=5, kernel=1, mode="stereo")
+
+    class DM(sb.dispmap_super):
+        def unary_cost(self, a):
+            return pr["U0"] if np.array_equal(a, pr["cur"]) else pr["U1"]
+
+    res = []
+    for native in (True, False):
+        dm = DM([np.zeros((H, W, 3)), np.zeros((H, W, 3))], 1)
+        dm.smoothness_kernel = 1
+        dm.smooth_weights = pr["weights"]
+        dm.tol = pr["tol"]
+        dm.grid_native = native
+        dm._assignment = pr["cur"].copy()
+        out = dm.binary_fusion(pr["new"])
+        res.append((out, dm._assignment.copy()))
+    assert res[0][0] == res[1][0] and np.array_equal(res[0][1], res[1][1])

@@ -82,29 +82,36 @@ __global__ void window_stats_kernel(const unsigned *__restrict__ pk, int H, int 
 
 __device__ __forceinline__ unsigned s_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-// sum of v over the lanes lane - P .. lane + P (lane ids taken modulo 32: exact for P <= lane < 32 - P).  Windows of
-// length 2^k are doubled up by shuffles, the 2P + 1 window is assembled from them: 4-6 shuffles instead of the 7 of a
-// prefix scan.
-template <int P> __device__ __forceinline__ int vbox(int v)
-{
-    constexpr unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    // w2[i] = v[i] + v[i+1], w4[i] = v[i..i+3], w8[i] = v[i..i+7], w16[i] = v[i..i+15]
-    int acc = 0, start = -P;      // acc = sum over [lane + (-P), lane + start)
-    int wlen = 1, w = v;
-    int remaining = 2 * P + 1;
+// Sum of v over the lanes lane - P .. lane + P (lane ids modulo 32: exact for P <= lane < 32 - P).  Windows of
+// length 2^k are doubled up by shuffles and the 2P + 1 window is assembled from them (4-6 shuffles instead of the 7 of
+// a prefix scan); the source lanes are worked out once.
+template <int P> struct VBoxLanes {
+    int up[5];     // (lane + 2^b) & 31
+    int at[5];     // where the piece of length 2^b of the window starts, as a lane id
+    __device__ __forceinline__ explicit VBoxLanes(int lane)
+    {
+        int start = -P;
 #pragma unroll
-    for (int bit = 0; bit < 5; bit++) {
-        if (remaining & wlen) {
-            acc += __shfl_sync(FULL, w, (lane + start) & 31);
-            start += wlen;
+        for (int b = 0; b < 5; b++) {
+            up[b] = (lane + (1 << b)) & 31;
+            at[b] = (lane + start) & 31;
+            if ((2 * P + 1) & (1 << b)) start += 1 << b;
         }
-        if ((remaining >> (bit + 1)) == 0) break;
-        w += __shfl_sync(FULL, w, (lane + wlen) & 31);
-        wlen <<= 1;
     }
-    return acc;
-}
+    __device__ __forceinline__ int box(int v) const
+    {
+        constexpr unsigned FULL = 0xffffffffu;
+        constexpr int N = 2 * P + 1;
+        int acc = 0, w = v;
+#pragma unroll
+        for (int b = 0; b < 5; b++) {
+            if (N & (1 << b)) acc += __shfl_sync(FULL, w, at[b]);
+            if ((N >> (b + 1)) == 0) break;
+            w += __shfl_sync(FULL, w, up[b]);
+        }
+        return acc;
+    }
+};
 
 struct NccArgs {
     const unsigned *pk0;      // [W][Hp] packed reference image
@@ -179,16 +186,18 @@ ncc_levels_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_constant
         for (int xb = xb_first; xb <= j0; xb++) load_block(xb);
     for (int xb = xb_first; xb <= j0; xb++) wait_block(xb);
 
-    // this warp's levels
+    // this warp's levels (slots beyond the level count run on d = 0 and never store: no divergent paths in the loops)
     int dk[NV_LPW];
     int hs[NV_LPW];
 #pragma unroll
     for (int k = 0; k < NV_LPW; k++) {
         const int li = warp + NV_WARPS * k;
-        dk[k] = li < a.D ? a.disps[li] : -1;
+        dk[k] = li < a.D ? a.disps[li] : 0;
         hs[k] = 0;
     }
-    auto ring_idx = [&](int x) { return ((x >> 5) & (NV_SLOTS - 1)) * (NV_BLK * 32) + (x & 31) * 32 + lane; };
+    const int nlev = a.D > warp ? (a.D - warp + NV_WARPS - 1) / NV_WARPS : 0;
+    // ring word of absolute column x for this lane: the ring holds 8 x 32 = 256 columns of 32 rows
+    auto ring_idx = [&](int x) { return ((x & (NV_SLOTS * NV_BLK - 1)) << 5) + lane; };
     auto load_R = [&](int cin, unsigned &Rn, unsigned &Ro, unsigned &srv, float &rsa) {
         Rn = 0; Ro = 0; srv = 0; rsa = 0.f;
         if (row_in) {
@@ -199,6 +208,9 @@ ncc_levels_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_constant
             if (c >= 0 && c < W) { srv = __ldg(a.sR + (size_t)c * Hp + r); rsa = __ldg(a.rsA + (size_t)c * Hp + r); }
         }
     };
+    VBoxLanes<P> vl(lane);
+    float *const vol_lane = a.vol + (size_t)warp * W * H + r;       // level `warp`, column 0, this lane's row
+    const size_t lvl_stride = (size_t)NV_WARPS * W * H;
     unsigned nRn, nRo, nsr;
     float nrsa;
     load_R(cin_first, nRn, nRo, nsr, nrsa);
@@ -209,36 +221,46 @@ ncc_levels_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_constant
         if (threadIdx.x == 0 && j + 1 <= j1) load_block(j + 1);
         const int cb = max(cin_first, j * NV_BLK), ce = min(cin_last, j * NV_BLK + NV_BLK - 1);
         for (int cin = cb; cin <= ce; cin++) {
-            const unsigned Rn = nRn, Ro = nRo, srv = nsr;
+            const unsigned Rn = nRn, Ro = nRo, srv = nsr;     // (Rn = 0 right of the image, Ro = 0 during the warm-up)
             const float rsa = nrsa;
             load_R(cin + 1, nRn, nRo, nsr, nrsa);
-            const int c = cin - P;                       // output column of this step
-            const bool emit = c >= c0 && c < c1;
-            const bool border = c + P > W - 1;           // the window leaves the image on the right: T sums are truncated
+            // ---- horizontal running sums: column c_in enters the window, column c_in - (2P + 1) leaves
 #pragma unroll
             for (int k = 0; k < NV_LPW; k++) {
-                const int d = dk[k];
-                if (d < 0) continue;                      // (warp-uniform)
-                const int x = cin - d, xo = x - WIN;
-                const unsigned Tn = (x >= 0 && cin < W) ? ringT[ring_idx(x)] : 0u;
-                const unsigned To = (xo >= 0) ? ringT[ring_idx(xo)] : 0u;
+                const int x = cin - dk[k], xo = x - WIN;
+                const unsigned Tn = x >= 0 ? ringT[ring_idx(x)] : 0u;
+                const unsigned To = xo >= 0 ? ringT[ring_idx(xo)] : 0u;
                 hs[k] += (int)__dp4a(Rn, Tn, 0u) - (int)__dp4a(Ro, To, 0u);
-                if (!emit) continue;                      // (warp-uniform)
-                // vertical box over the lanes lane - P .. lane + P (wrap-around only reaches lanes that emit nothing)
-                const long long sRT = (long long)vbox<P>(hs[k]);
-                float v = 0.f;
-                const int xc = c - d;
-                if (xc >= 0) {
-                    unsigned sT;
-                    float rsb;
-                    if (!border) {
-                        sT = ringS[ring_idx(xc)];
-                        rsb = ringB[ring_idx(xc)];
-                    } else {
-                        // columns c' = c - P .. W - 1 of the shifted image only (x = c' - d)
+            }
+            const int c = cin - P;                       // output column of this step
+            if (c < c0 || c >= c1) continue;             // (warp-uniform)
+            float *const vcol = vol_lane + (size_t)c * H;
+            if (c + P <= W - 1) {
+#pragma unroll
+                for (int k = 0; k < NV_LPW; k++) {
+                    // vertical box over the lanes lane - P .. lane + P (wrap-around only reaches lanes that emit nothing)
+                    const long long sRT = (long long)vl.box(hs[k]);
+                    const int xc = c - dk[k];
+                    const unsigned sT = ringS[ring_idx(xc)];
+                    const float rsb = xc >= 0 ? ringB[ring_idx(xc)] : 0.f;      // left of the shifted image: ncc = 0
+                    const long long Cn = n3 * sRT - (long long)srv * (long long)sT;
+                    const float v = (float)Cn * rsa * rsb;
+                    if (out_lane && k < nlev) vcol[(size_t)k * lvl_stride] = v;
+                }
+            } else {
+                // the window leaves the image on the right: the sums of the shifted image are truncated at its last
+                // column (x = W - 1 - d), so they are taken from the ring directly
+#pragma unroll
+                for (int k = 0; k < NV_LPW; k++) {    // (unrolled: the running sums must stay in registers)
+                    if (k >= nlev) continue;
+                    const int d = dk[k];
+                    const long long sRT = (long long)vl.box(hs[k]);
+                    const int xc = c - d;
+                    float v = 0.f;
+                    if (xc >= 0) {
                         unsigned t1 = 0, t2 = 0;
                         for (int xx = max(xc - P, 0); xx <= W - 1 - d; xx++) {
-                            const unsigned *col = ringT + ((xx >> 5) & (NV_SLOTS - 1)) * (NV_BLK * 32) + (xx & 31) * 32;
+                            const unsigned *col = ringT + ((xx & (NV_SLOTS * NV_BLK - 1)) << 5);
 #pragma unroll
                             for (int dr = -P; dr <= P; dr++) {
                                 const int l2 = lane + dr;
@@ -248,13 +270,12 @@ ncc_levels_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_constant
                             }
                         }
                         const long long B = n3 * (long long)t2 - (long long)t1 * (long long)t1;
-                        sT = t1;
-                        rsb = B > 0 ? rsqrtf((float)B) : 0.f;
+                        const float rsb = B > 0 ? rsqrtf((float)B) : 0.f;
+                        const long long Cn = n3 * sRT - (long long)srv * (long long)t1;
+                        v = (float)Cn * rsa * rsb;
                     }
-                    const long long Cn = n3 * sRT - (long long)srv * (long long)sT;
-                    v = (float)Cn * rsa * rsb;
+                    if (out_lane) vcol[(size_t)k * lvl_stride] = v;
                 }
-                if (out_lane) a.vol[((size_t)(warp + NV_WARPS * k) * W + c) * H + r] = v;
             }
         }
     }

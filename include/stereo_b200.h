@@ -181,7 +181,8 @@ SB_API int sb_trws_pass(sb_trws_solver *s, int pass, int mode, double *acc /* 2 
  *                            per pixel, MATLAB node order), unary = nl x N (proposal-major);
  *                            d_min / d_step = the disparity normalisation of
  *                            dispmap_globalstereo.m:336-345 (0, 1 for dispmap_ncc / dispmap_super).
- *                            c == 0 -> SB_EINVAL "Infinite disparity" (dispmap_super.m:321-323)
+ *                            c == 0 -> SB_EINVAL "Infinite disparity" (dispmap_super.m:321-323).
+ *                            planes / unary (and alphas below) may be host OR device pointers (unified addressing)
  *   sb_trws_grid_set_weights alphas, E doubles in the reference's term order (trws_mex.cpp:35)
  *   sb_trws_grid_synth       fills every proposal, unary and weight with the seeded synthetic problem of
  *                            SURVEY 8(d) ON the device (for sizes whose inputs do not fit a host)

@@ -448,8 +448,10 @@ struct Solver : SolverBase {
         SB_CUDA(cudaMemsetAsync(dBad.p, 0, sizeof(int), stream));
         for (int g0 = 0; g0 < nl; g0 += grp) {
             const int ng = std::min(grp, nl - g0);
-            SB_CUDA(cudaMemcpyAsync(dPl.p, planes + (size_t)g0 * 4 * N, (size_t)ng * 4 * N * 8, cudaMemcpyHostToDevice, stream));
-            SB_CUDA(cudaMemcpyAsync(dUn.p, unary + (size_t)g0 * N, (size_t)ng * N * 8, cudaMemcpyHostToDevice, stream));
+            // (cudaMemcpyDefault: the proposals may already live on the device -- a fusion loop that keeps its plane
+            // fields resident passes device pointers)
+            SB_CUDA(cudaMemcpyAsync(dPl.p, planes + (size_t)g0 * 4 * N, (size_t)ng * 4 * N * 8, cudaMemcpyDefault, stream));
+            SB_CUDA(cudaMemcpyAsync(dUn.p, unary + (size_t)g0 * N, (size_t)ng * N * 8, cudaMemcpyDefault, stream));
             const long long tot = Nloc * ng;
             gfill_labels_kernel<REAL><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(dPl.p, dUn.p, ng, l0 + g0, H, W, band.r_base, rows, band.c_base,
                                                                                          Wl, LP, d_min, d_step, dNodeF.p, dBad.p);
@@ -471,7 +473,7 @@ struct Solver : SolverBase {
         SB_REQUIRE(alphas, SB_EINVAL, "sb_trws_grid_set_weights: null pointer");
         const double t0 = now_ms();
         DevBuf<double> dA((size_t)E);
-        SB_CUDA(cudaMemcpyAsync(dA.p, alphas, (size_t)E * 8, cudaMemcpyHostToDevice, stream));
+        SB_CUDA(cudaMemcpyAsync(dA.p, alphas, (size_t)E * 8, cudaMemcpyDefault, stream));
         gweights_kernel<REAL><<<(unsigned)((2 * Nloc + 255) / 256), 256, 0, stream>>>(dA.p, H, W, band.r_base, rows, band.c_base, Wl, dAlpha.p);
         SB_CUDA(cudaGetLastError());
         count_launch();

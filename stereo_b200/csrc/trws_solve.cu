@@ -173,6 +173,18 @@ struct Solver : SolverBase {
            int world_ = 1)
         : kernel(kernel_), L(L_), H(H_), W(W_), N(N_), E(E_), rank(rank_), world(world_)
     {
+        // a constructor that throws does not run the destructor: release what was acquired (pinned slot, events,
+        // IPC allocations) before the rejection ("q contains NaN", a CUDA error) reaches the caller
+        try {
+            init(unary, q, qprim, alphas, tol, opt);
+        } catch (...) {
+            release();
+            throw;
+        }
+    }
+
+    void init(const double *unary, const double *q, const double *qprim, const double *alphas, double tol, const sb_trws_options &opt)
+    {
         SB_REQUIRE(world == 1 || sizeof(REAL) == 4, SB_EUNSUP, "row-banded sweeps run in fp32 only");
         precision = sizeof(REAL) == 8 ? SB_F64 : SB_F32;
         fuse = opt.fuse_rounding != 0;
@@ -238,7 +250,15 @@ struct Solver : SolverBase {
             // table build of the other
             const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(E, (int64_t)(128u << 20) / (8 * (int64_t)L)));
             DevBuf<double> rq[2], rqp[2];
-            cudaStream_t ss[2] = {nullptr, nullptr};
+            struct SlabStreams {     // destroyed on every way out of this block, a throwing table build included
+                cudaStream_t s[2] = {nullptr, nullptr};
+                cudaStream_t &operator[](int b) { return s[b]; }
+                ~SlabStreams()
+                {
+                    for (int b = 0; b < 2; b++)
+                        if (s[b]) { cudaStreamSynchronize(s[b]); cudaStreamDestroy(s[b]); }
+                }
+            } ss;
             for (int b = 0; b < 2; b++) {
                 rq[b].alloc((size_t)slab * L);
                 rqp[b].alloc((size_t)slab * L);
@@ -259,10 +279,7 @@ struct Solver : SolverBase {
                 tl.bad = dBad.p; tl.stream = ss[which];
                 ops->tables(tl);
             }
-            for (int b = 0; b < 2; b++) {
-                SB_CUDA(cudaStreamSynchronize(ss[b]));
-                cudaStreamDestroy(ss[b]);
-            }
+            for (int b = 0; b < 2; b++) SB_CUDA(cudaStreamSynchronize(ss[b]));
             int bad = 0;
             SB_CUDA(cudaMemcpyAsync(&bad, dBad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
             SB_CUDA(cudaStreamSynchronize(stream));
@@ -316,18 +333,25 @@ struct Solver : SolverBase {
         setup_ms = now_ms() - t0;
     }
 
-    ~Solver() override
+    void release()
     {
         if (hc) pinned_pool().put(hc);
+        hc = nullptr;
         for (int d = 0; d < 2; d++)
-            for (int a = 0; a < 3; a++)
+            for (int a = 0; a < 3; a++) {
                 if (peer_ptr[d][a]) cudaIpcCloseMemHandle(peer_ptr[d][a]);
+                peer_ptr[d][a] = nullptr;
+            }
         if (ipc_msg) cudaFree(ipc_msg);
         if (ipc_mbox) cudaFree(ipc_mbox);
         if (ipc_selbox) cudaFree(ipc_selbox);
+        ipc_msg = nullptr; ipc_mbox = nullptr; ipc_selbox = nullptr;
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        ev0 = nullptr; ev1 = nullptr;
     }
+
+    ~Solver() override { release(); }
 
     // ZeroMessages (MRFEnergy.cpp:115-131) + fresh epoch flags
     void reset() override

@@ -63,6 +63,11 @@ class TrwsGrid:
         check(lib().sb_trws_grid_set_labels(self._h, int(l0), nl, pl.ctypes.data_as(_dp), un.ctypes.data_as(_dp),
                                             float(d_min), float(d_step)))
 
+    def set_labels_ptr(self, l0, nl, planes_ptr, unary_ptr, d_min=0.0, d_step=1.0):
+        """The same from raw addresses (host or device): nl proposals of 4 x N doubles (MATLAB layout) / nl x N unaries."""
+        check(lib().sb_trws_grid_set_labels(self._h, int(l0), int(nl), ctypes.cast(ctypes.c_void_p(int(planes_ptr)), _dp),
+                                            ctypes.cast(ctypes.c_void_p(int(unary_ptr)), _dp), float(d_min), float(d_step)))
+
     def set_weights(self, alphas):
         a = _f(np.asarray(alphas).reshape(-1))
         assert a.size == self.E

@@ -66,6 +66,8 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         const int H = (int)mxGetPr(a[0])[0], W = (int)mxGetPr(a[0])[1];
         const mwSize E = 2 * ((H - 1) * W + H * (W - 1));
         const bool has_prop = mxGetNumberOfElements(a[3]) > 0;
+        // MATLAB hands over max(nlhs, 1) output slots: never write past them
+        SB_MEX_ASSERT(has_prop ? nlhs == 4 : nlhs <= 1);
         for (int i = 0; i < (has_prop ? 4 : 1); i++) plhs[i] = sb_mex_matrix(1, E);
         sb_mex_check(sb_pairwise_tables(H, W, (int)scalar(a[1]), mxGetPr(a[2]), has_prop ? mxGetPr(a[3]) : NULL, mxGetPr(a[4]),
                                         scalar(a[5]), scalar(a[6]), scalar(a[7]), mxGetPr(plhs[0]),
@@ -76,6 +78,7 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         const int H = (int)mxGetPr(a[0])[0], W = (int)mxGetPr(a[0])[1];
         const mwSize E = 2 * ((H - 1) * W + H * (W - 1));
         const int L = (int)(mxGetNumberOfElements(a[1]) / ((size_t)4 * H * W));
+        SB_MEX_ASSERT(nlhs == 2);
         plhs[0] = sb_mex_matrix(L, E);
         plhs[1] = sb_mex_matrix(L, E);
         sb_mex_check(sb_fusion_positions(H, W, L, mxGetPr(a[1]), scalar(a[2]), scalar(a[3]), mxGetPr(plhs[0]), mxGetPr(plhs[1])));
@@ -88,5 +91,4 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
     } else {
         mexErrMsgTxt("sb_builders_mex: unknown operation");
     }
-    (void)nlhs;
 }

@@ -212,3 +212,43 @@ def test_column_bands_one_gpu_f64_exact():
         grp.close()
     assert abs(e - e1) <= 1e-12 * abs(e1) and abs(lb - lb1) <= 1e-12 * abs(lb1)
     assert np.array_equal(lab, lab1)
+
+
+def test_alternating_schedule_on_device():
+    """BASELINE configs[4]'s schedule at a small size (scripts/cfg5_alternating.py): binary fusions from device-resident
+    fields (sb_binary_fusion_grid, on_device) alternating with the grid TRW-S whose last label is re-set from a device
+    pointer.  A QPBO fusion move never increases the energy; the first TRW-S energy can be checked independently."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    import cfg5_alternating
+    out = cfg5_alternating.run(40, 56, 12, rounds=2, fusions=4, iters=8, verbose=False, check=True)
+    for rec in out["log"]:
+        # the solver's (fp32) energy is the energy of the assignment it hands back, evaluated independently in fp64
+        assert abs(rec["trws"]["energy"] - rec["trws"]["energy_of_assignment"]) <= 1e-4 * abs(rec["trws"]["energy_of_assignment"])
+        e = [f["energy"] for f in rec["fusions"]]
+        assert all(e[i + 1] <= e[i] * (1 + 1e-12) for i in range(len(e) - 1))
+        assert rec["trws"]["lower_bound"] <= rec["trws"]["energy"] * (1 + 1e-6)
+    # the simultaneous fusion starts from the fused assignment as one of its labels: it should not end far above it
+    assert out["log"][0]["trws"]["energy"] <= out["log"][0]["fusions"][-1]["energy"] * 1.05
+
+
+def test_set_labels_from_device_pointer():
+    import torch
+    H, W, L = 16, 20, 6
+    pr = synth.trws_problem(H, W, L, seed=5, kernel=1)
+    res = []
+    for on_dev in (False, True):
+        g = TrwsGrid(1, H, W, L, pr["tol"])
+        if on_dev:
+            pl = torch.from_numpy(np.ascontiguousarray(pr["planes"].transpose(0, 2, 1))).cuda()
+            un = torch.from_numpy(np.ascontiguousarray(pr["unary"])).cuda()
+            torch.cuda.synchronize()
+            g.set_labels_ptr(0, L, pl.data_ptr(), un.data_ptr())
+        else:
+            g.set_labels(0, pr["planes"], pr["unary"])
+        g.set_weights(pr["alphas"])
+        g.finalize()
+        res.append(g.minimize(5, 0.0) + (g.labels(),))
+        g.close()
+    assert res[0][:3] == res[1][:3] and np.array_equal(res[0][3], res[1][3])

@@ -158,3 +158,52 @@ def test_dispmap_ncc_class_end_to_end():
     dm.simultaneous_fusion(props)
     assert dm.energy() <= e1 + 1e-6 * abs(e1)
     assert dm.current_dispmap().shape == (H, W)
+
+
+def _teddy():
+    g = golden("teddy.npz")
+    return g["im2"].astype(np.float64), g["im6"].astype(np.float64)
+
+
+def test_teddy_ncc_pipeline():
+    """example_ncc.m:9-46 plumbing on the real Middlebury pair (BASELINE configs[0] shape, 375 x 450): the NCC volume
+    (one-pass kernel == general kernel == NumPy restatement on real data), the WTA initial solution, and fronto-parallel
+    fusion moves.  There is no MATLAB output to compare with; the anchors are photo-consistency of the WTA
+    disparity and monotone fusion energies."""
+    import os
+    im2, im6 = _teddy()
+    H, W, _ = im2.shape
+    disps = np.arange(0, 51, dtype=np.float64)               # example_ncc.m:12
+    dm = sb.dispmap_ncc([im2, im6], disps, 1, 40.0, 8.0)     # :13-19
+    assert dm._vol.info()["one_pass"]
+    fast = dm.ncc
+    os.environ["SB_NCC_GENERAL"] = "1"
+    try:
+        gen = builders.ncc_volume(im2, im6, disps[::10], 2)
+    finally:
+        del os.environ["SB_NCC_GENERAL"]
+    cond = _np().ncc_conditioning(im2, im6, disps[::10], 2) > 1e-6
+    assert cond.mean() > 0.8
+    assert np.all(np.abs(fast[:, :, ::10] - gen)[cond] <= 5e-5)
+    ref = _np().compute_ncc(im2, im6, disps[:3], 2)
+    c3 = _np().ncc_conditioning(im2, im6, disps[:3], 2) > 1e-6
+    assert np.all(np.abs(fast[:, :, :3] - ref)[c3] <= 1e-4 * np.maximum(np.abs(ref[c3]), 1e-2))
+    # WTA disparity: warping the right image by it must explain the left image far better than no disparity
+    best = dm.best_disp_from_ncc()
+    assert np.isfinite(best).all() and best.min() >= -1 and best.max() <= 51
+    cols = np.clip(np.round(np.arange(W)[None, :] - best).astype(int), 0, W - 1)
+    warped = im6[np.arange(H)[:, None], cols]
+    inner = (slice(8, H - 8), slice(60, W - 8))
+    mad_w = np.abs(warped - im2)[inner].mean()
+    mad_0 = np.abs(im6 - im2)[inner].mean()
+    assert mad_w < 0.5 * mad_0, (mad_w, mad_0)
+    # fusion moves with fronto-parallel proposals (example_ncc.m:35-46): energy never increases
+    e = [dm.energy()]
+    for d in range(0, 51, 10):
+        prop = np.zeros((4, H * W))
+        prop[2] = 1
+        prop[3] = -d
+        dm.binary_fusion(prop)
+        e.append(dm.energy())
+    assert all(e[i + 1] <= e[i] * (1 + 1e-12) for i in range(len(e) - 1)), e
+    assert e[-1] < e[0]

@@ -78,3 +78,13 @@ def test_port_equals_compiled_reference_live():
         a = oracle.trws_solve(*args, kind="reference")
         b = oracle.trws_solve(*args, kind="port")
         assert np.array_equal(a[0], b[0]) and a[1] == b[1] and a[2] == b[2] and a[3] == b[3]
+
+
+def test_teddy_fixture_integrity():
+    """tests/golden/teddy.npz (made by tests/golden/make_teddy.py from the reference's data/teddy) is the pair the
+    examples run on: shape and checksums as recorded when it was generated."""
+    import numpy as np
+    from util import golden
+    g = golden("teddy.npz")
+    assert g["im2"].shape == g["im6"].shape == (375, 450, 3) and g["im2"].dtype == np.uint8
+    assert int(g["im2"].astype(np.int64).sum()) == 60448401 and int(g["im6"].astype(np.int64).sum()) == 60462544

@@ -257,6 +257,69 @@ __global__ void bfs_sweep_kernel(Graph g)
         g.flag[1] = 1;
     }
 }
+// The same relaxation, run to a LOCAL fixed point on a 32 x 8 tile (both node copies) in shared memory before anything
+// is written back: one launch carries a distance across a whole tile instead of one node, so the number of global
+// sweeps drops from the residual graph's diameter to roughly diameter / tile size (long thin paths on 1980 x 2880
+// grids needed thousands of single-step sweeps).  Halo labels are read once and stay fixed during the launch; labels
+// only ever decrease towards the BFS distances, so any schedule reaches the same fixed point.
+constexpr int BT_R = 32, BT_C = 8;
+__global__ void __launch_bounds__(BT_R * BT_C) bfs_tile_kernel(Graph g)
+{
+    __shared__ int hs[2][BT_C + 2][BT_R + 2];
+    const int H = g.H, W = g.W;
+    const long long N = g.N;
+    const int r0 = (int)blockIdx.x * BT_R, c0 = (int)blockIdx.y * BT_C;
+    for (int i = threadIdx.x; i < 2 * (BT_C + 2) * (BT_R + 2); i += blockDim.x) {
+        const int lr = i % (BT_R + 2), lc = (i / (BT_R + 2)) % (BT_C + 2), sd = i / ((BT_R + 2) * (BT_C + 2));
+        const int r = r0 + lr - 1, c = c0 + lc - 1;
+        hs[sd][lc][lr] = (r >= 0 && r < H && c >= 0 && c < W) ? g.h[(long long)r + (long long)H * c + (sd ? N : 0)] : HINF;
+    }
+    const int lr = threadIdx.x % BT_R, lc = threadIdx.x / BT_R;
+    const int r = r0 + lr, c = c0 + lc;
+    const bool inside = r < H && c < W;
+    const long long u = (long long)r + (long long)H * c;
+    // the residual arcs out of my two nodes: the shared-memory cell of the head, or null
+    int *nb[2][4];
+    int hv[2] = {HINF, HINF};
+#pragma unroll
+    for (int sd = 0; sd < 2; sd++)
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            nb[sd][d] = nullptr;
+            if (!inside) continue;
+            const Arc a = arc_of(g, u + (sd ? N : 0), d);
+            if (!a.valid || !(g.r[4 * a.P + a.slot] > 0)) continue;
+            const int os = a.w >= N ? 1 : 0;
+            const int dr = d == 0 ? -1 : d == 1 ? 1 : 0, dc = d == 2 ? -1 : d == 3 ? 1 : 0;
+            nb[sd][d] = &hs[os][lc + 1 + dc][lr + 1 + dr];
+        }
+    __syncthreads();
+    if (inside) { hv[0] = hs[0][lc + 1][lr + 1]; hv[1] = hs[1][lc + 1][lr + 1]; }
+    bool any = false;
+    for (int it = 0; it < 2 * (BT_R + BT_C); it++) {
+        int best[2] = {hv[0], hv[1]};
+#pragma unroll
+        for (int sd = 0; sd < 2; sd++)
+#pragma unroll
+            for (int d = 0; d < 4; d++)
+                if (nb[sd][d]) {
+                    const int hw = *(volatile int *)nb[sd][d];
+                    if (hw < HINF && hw + 1 < best[sd]) best[sd] = hw + 1;
+                }
+        __syncthreads();
+        bool ch = false;
+#pragma unroll
+        for (int sd = 0; sd < 2; sd++)
+            if (best[sd] < hv[sd]) { hv[sd] = best[sd]; hs[sd][lc + 1][lr + 1] = best[sd]; ch = true; }
+        any = any || ch;
+        if (!__syncthreads_or(ch ? 1 : 0)) break;
+    }
+    if (any) {
+        g.h[u] = hv[0];
+        g.h[u + N] = hv[1];
+        g.flag[1] = 1;
+    }
+}
 __global__ void any_active_kernel(Graph g)
 {
     const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -422,9 +485,16 @@ struct Solver {
         count_launch();
         for (;;) {
             SB_CUDA(cudaMemsetAsync(flag.p, 0, 2 * sizeof(int)));
-            for (int k = 0; k < 16; k++) bfs_sweep_kernel<<<nb, 256>>>(g);
-            count_launch(16);
-            bfs_sweeps += 16;
+            if (getenv("SB_QPBO_PLAIN_BFS")) {
+                for (int k = 0; k < 16; k++) bfs_sweep_kernel<<<nb, 256>>>(g);
+                count_launch(16);
+                bfs_sweeps += 16;
+            } else {
+                const dim3 tg((g.H + BT_R - 1) / BT_R, (g.W + BT_C - 1) / BT_C);
+                for (int k = 0; k < 4; k++) bfs_tile_kernel<<<tg, BT_R * BT_C>>>(g);
+                count_launch(4);
+                bfs_sweeps += 4;
+            }
             SB_CUDA(cudaMemcpy(hflag, flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost));
             if (!hflag[1]) break;
         }

@@ -83,9 +83,10 @@ def reports(tag):
                     if k in d:
                         f.write(f"| {k} | {d[k]} | {units[hdr.index(k)]} |\n")
                 try:
-                    tr = float(d["dram__bytes_read.sum"].replace(",", "")) + float(d["dram__bytes_write.sum"].replace(",", ""))
-                    ur, uw = units[hdr.index("dram__bytes_read.sum")], units[hdr.index("dram__bytes_write.sum")]
-                    f.write(f"| dram traffic (read+write) | {tr:.3f} | {ur} (write in {uw}) |\n")
+                    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+                    tr = sum(float(d[k].replace(",", "")) * scale[units[hdr.index(k)]]
+                             for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                    f.write(f"| dram traffic (read+write) | {tr / 1e9:.3f} | Gbyte |\n")
                 except Exception:
                     pass
                 f.write("\n")

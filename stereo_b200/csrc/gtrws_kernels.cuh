@@ -469,7 +469,9 @@ template <typename REAL, int K> __host__ __device__ constexpr int gsweep_min_blo
 {
     if (sizeof(REAL) == 8) return K <= 2 ? 2 : 1;
     // measured on a B200 (1980x2880x192 / 1024x2048x256): one CTA more per SM with ~1-2 KB of spills is 20 % slower
-    return K <= 2 ? 5 : K <= 4 ? 4 : K <= 6 ? 3 : 2;
+    // (K <= 2: 5 CTAs per SM cost 70-120 spill instructions and were 7-14 % slower than 4 at 375x450x64 / 1080x1920x64;
+    // 3 instead of 4 loses 2-4 % at K = 3, 4; 2 instead of 3 loses 4 % at K = 6; 1 instead of 2 loses 16 % at K = 8)
+    return K <= 4 ? 4 : K <= 6 ? 3 : 2;
 }
 
 template <typename REAL, int K, int KERN, int PASS, int NS>

@@ -70,7 +70,9 @@ typedef struct sb_trws_options {
     int    precision;     /* SB_F32 (default) | SB_F64     */
     int    fuse_rounding; /* 1 (default): primal rounding of iteration t rides in the
                              forward sweep of t+1; 0: separate sweep   */
-    int    reserved[6];
+    int    col_blocks;    /* grid-native entry, world > 1: column blocks per rank (the blocks are dealt round robin
+                             to the ranks; 1 = contiguous bands); 0 = default (up to 4, blocks at least 16 columns wide) */
+    int    reserved[5];
 } sb_trws_options;
 
 SB_API void sb_trws_default_options(sb_trws_options *opt);
@@ -175,8 +177,9 @@ SB_API int sb_trws_pass(sb_trws_solver *s, int pass, int mode, double *acc /* 2 
  * while its right-hand neighbour already sweeps row r + 1 -- the ranks are the stages of a pipeline --
  * where row bands would make them take turns (row r + 1 waits for row r).
  *
- *   sb_trws_grid_create      rank `rank` of `world` column bands (world = 1: the whole grid); H, W >= 4,
- *                            W >= 4 world; kernel / tol / options as sb_trws_solve
+ *   sb_trws_grid_create      rank `rank` of `world` (world = 1: the whole grid): the columns are cut into blocks that
+ *                            are dealt round robin to the ranks (opt.col_blocks per rank); H, W >= 4, W >= 4 x the
+ *                            number of blocks; kernel / tol / options as sb_trws_solve
  *   sb_trws_grid_set_labels  proposals l0 .. l0+nl-1: planes = nl consecutive 4 x N arrays ([a; b; c; d0]
  *                            per pixel, MATLAB node order), unary = nl x N (proposal-major);
  *                            d_min / d_step = the disparity normalisation of
@@ -199,7 +202,8 @@ SB_API int sb_trws_pass(sb_trws_solver *s, int pass, int mode, double *acc /* 2 
  *                            (the returned labels / energy / bound are those of iteration t)
  *   sb_trws_grid_get_labels  N doubles, 1-based, MATLAB node order; nodes this rank does not sweep are 0
  *   sb_trws_grid_pass / _ipc_export (2 x 64 bytes: message and selected-position arrays) / _ipc_attach
- *                            (`up` = rank - 1, the band to the left; `down` = rank + 1):
+ *                            (`up` = rank (rank - 1) mod world, which owns the blocks to the left of mine; `down` =
+ *                            (rank + 1) mod world; with two ranks both are the same process):
  *                            the multi-GPU protocol of sb_trws_pass, on sharded state: the messages of the
  *                            horizontal terms that cross a band boundary are stored by both ranks and
  *                            written by the sender into both copies (its own, and the neighbour's over

@@ -30,7 +30,7 @@ class SbError(RuntimeError):
 
 class TrwsOptions(Structure):
     _fields_ = [("maxiter", c_double), ("max_relgap", c_double), ("precision", c_int),
-                ("fuse_rounding", c_int), ("reserved", c_int * 6)]
+                ("fuse_rounding", c_int), ("col_blocks", c_int), ("reserved", c_int * 5)]
 
 
 class TrwsTiming(Structure):

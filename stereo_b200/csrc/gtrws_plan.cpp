@@ -6,23 +6,35 @@
 #include "gtrws_plan.h"
 #include "trws_order.h"
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 
 namespace sb {
 namespace gtrws {
 
-Band band_window(int H, int W, int rank, int world)
+int default_col_blocks(int W, int world)
+{
+    if (world <= 1) return 1;
+    if (const char *e = getenv("SB_GTRWS_BLOCKS")) {
+        const int v = atoi(e);
+        if (v >= 1) return v;
+    }
+    return std::max(1, std::min(4, W / (16 * world)));
+}
+
+Band band_window(int H, int W, int rank, int world, int blocks)
 {
     Band b;
-    b.r_lo = 0; b.r_hi = H; b.r_base = 0; b.r_top = H;
-    b.c_lo = 0; b.c_hi = W; b.c_base = 0; b.c_top = W;
-    if (rank < 0 || world <= 1) return b;
-    // columns c with band_of_col(c) == rank, band_of_col(c) = floor(c * world / W)
-    auto first_col = [&](int k) { return (int)(((long long)k * W + world - 1) / world); };
-    b.c_lo = first_col(rank);
-    b.c_hi = first_col(rank + 1);
-    b.c_base = std::max(0, b.c_lo - 1);
-    b.c_top = std::min(W, b.c_hi + 1);
+    b.H = H; b.W = W; b.rank = rank < 0 ? 0 : rank; b.world = (rank < 0 || world <= 1) ? 1 : world;
+    if (b.world == 1) {
+        b.wb = W; b.Wl = W; b.nblocks = 1; b.NB = 1;
+        return b;
+    }
+    if (blocks <= 0) blocks = default_col_blocks(W, world);
+    b.wb = col_block_width(W, world, blocks);
+    b.Wl = b.wb + 2;
+    b.NB = (W + b.wb - 1) / b.wb;
+    b.nblocks = b.NB > b.rank ? (b.NB - b.rank + world - 1) / world : 0;
     return b;
 }
 
@@ -43,7 +55,7 @@ inline bool same_shape(const Step &a, const Step &b)
 
 } // namespace
 
-void build_gpass_plan(int H, int W, int pass, int rank, int world, GPassPlan &plan)
+void build_gpass_plan(int H, int W, int pass, int rank, int world, int blocks, GPassPlan &plan)
 {
     SB_REQUIRE(H >= 4 && W >= 4, SB_EUNSUP, "sb_trws_grid: the grid-native path needs H, W >= 4 (got %d x %d)", H, W);
     if (rank < 0) world = 1;
@@ -52,9 +64,10 @@ void build_gpass_plan(int H, int W, int pass, int rank, int world, GPassPlan &pl
     std::vector<uint8_t> info;
     build_node_info(H, W, order, info);
     Schedule s;
-    build_schedule_cols(H, W, order, s, world);
-    const Band band = band_window(H, W, rank, world);
-    const int Wl = band.width();
+    if (blocks <= 0) blocks = default_col_blocks(W, world);
+    build_schedule_cols(H, W, order, s, world, blocks);
+    const Band band = band_window(H, W, rank, world, blocks);
+    const int Wl = band.Wl;
     const int S = (int)s.strip_ptr.size() - 1;
     const int64_t N = (int64_t)H * W;
     std::vector<int32_t> strip_of((size_t)N);
@@ -69,9 +82,10 @@ void build_gpass_plan(int H, int W, int pass, int rank, int world, GPassPlan &pl
     };
     auto local_id = [&](int u) {
         const int r = u % H, c = u / H;
-        SB_REQUIRE(r >= band.r_base && r < band.r_top && c >= band.c_base && c < band.c_top, SB_EUNSUP,
-                   "sb_trws_grid: node outside the band's storage");
-        return (r - band.r_base) * Wl + (c - band.c_base);
+        if (band.world == 1) return r * Wl + c;
+        const int B = c / band.wb;
+        SB_REQUIRE(B % band.world == band.rank, SB_EUNSUP, "sb_trws_grid: node outside the rank's blocks");
+        return (B / band.world) * (H * Wl) + r * Wl + (c - B * band.wb + 1);
     };
 
     plan.segs.clear();
@@ -145,10 +159,13 @@ void build_gpass_plan(int H, int W, int pass, int rank, int world, GPassPlan &pl
             for (int d = 0; d < 4; d++)
                 if ((send_mask >> d) & 1u) {
                     if (rank >= 0) {
+                        // only horizontal terms cross a block boundary; the direction names the neighbour (with two
+                        // ranks the blocks to the left and to the right belong to the same one)
                         const int peer = s.owner[strip_of[nb_ref(u, d)]];
-                        if (peer == rank - 1) base.peer[d] = 1;
-                        else if (peer == rank + 1) base.peer[d] = 2;
-                        else SB_REQUIRE(peer == rank, SB_EUNSUP, "sb_trws_grid: a term spans non-adjacent ranks");
+                        if (peer != rank) {
+                            SB_REQUIRE(d == DIR_LEFT || d == DIR_RIGHT, SB_EUNSUP, "sb_trws_grid: a vertical term spans two ranks");
+                            base.peer[d] = d == DIR_LEFT ? 1 : 2;
+                        }
                     }
                 }
             auto role_set = [](uint32_t &roles, int d, int role) { roles |= (uint32_t)role << (4 * d); };

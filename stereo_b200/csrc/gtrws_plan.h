@@ -32,7 +32,7 @@ struct GSeg {
     int16_t gamma_den;       // max(nF, nB): gamma = 1 / gamma_den (treeProbabilities.cpp:28-45)
     int8_t next_dir;         // direction of the next strip node when it is a send target, else -1
     uint8_t flags;           // GF_*
-    uint8_t peer[4];         // per direction: 0 receiver local, 1 on rank - 1 (the band to the left), 2 on rank + 1
+    uint8_t peer[4];         // per direction: 0 receiver local, 1 on the rank that owns the block to the left, 2 ... to the right
     int32_t save0;           // GF_SAVE / GF_DEFERRED: scratch slot of the segment's first node (slots advance by 1)
     int32_t pad;
 };
@@ -46,22 +46,29 @@ struct GPassPlan {
     int32_t save_slots = 0;          // scratch slots for saved node totals
 };
 
-// Band geometry of rank `rank` of `world`.  The grid is split into COLUMN bands (trws_order.h,
-// build_schedule_cols): the rank sweeps the columns [c_lo, c_hi) of every row and stores [c_base, c_top)
-// (one halo column on each inner side); local node id = r * (c_top - c_base) + (c - c_base).  The row fields
-// cover the whole grid (kept so that a window is described the same way in both directions).
+// Storage geometry of rank `rank` of `world`.  The grid is split into COLUMN blocks of `wb` columns dealt round
+// robin to the ranks (trws_order.h, build_schedule_cols): the strips of the sweep run along the image rows, so the
+// ranks are the stages of a pipeline.  A rank stores each of its blocks as a grid of H rows x Wl = wb + 2 columns
+// (one halo column per side, unused at the image border), block after block:
+//   local node id = b * H * Wl + r * Wl + (c - B * wb + 1),   B = c / wb = rank + b * world.
+// world == 1: one block = the whole grid, no halo (Wl = W).
 struct Band {
-    int r_lo, r_hi, r_base, r_top;
-    int c_lo, c_hi, c_base, c_top;
-    int width() const { return c_top - c_base; }
-    int rows() const { return r_top - r_base; }
+    int H, W, rank, world;
+    int wb, Wl, nblocks, NB;
+    int block_id(int b) const { return world <= 1 ? 0 : rank + b * world; }
+    int c_base(int b) const { return world <= 1 ? 0 : block_id(b) * wb - 1; }                  // first STORED column (may be -1)
+    int c_lo(int b) const { return world <= 1 ? 0 : block_id(b) * wb; }                        // first owned column
+    int c_hi(int b) const { const int e = world <= 1 ? W : (block_id(b) + 1) * wb; return e < W ? e : W; }
+    long long nodes() const { return (long long)nblocks * H * Wl; }
 };
-Band band_window(int H, int W, int rank, int world);
+// blocks <= 0: the default (1 for one rank; up to 4 per rank when the blocks stay at least 16 columns wide)
+int default_col_blocks(int W, int world);
+Band band_window(int H, int W, int rank, int world, int blocks);
 
 // pass 0 forward, 1 backward.  rank < 0: whole grid on one GPU.  Strips are listed in PROCESSING order of the pass
 // (the backward sweep runs the forward schedule in reverse); the deferred sends of a strip's nodes (GF_DEFERRED
 // steps) follow its regular steps.
-void build_gpass_plan(int H, int W, int pass, int rank, int world, GPassPlan &plan);
+void build_gpass_plan(int H, int W, int pass, int rank, int world, int blocks, GPassPlan &plan);
 
 } // namespace gtrws
 } // namespace sb

@@ -73,18 +73,18 @@ struct GridPlanDev {
     DevBuf<int32_t> seg_ptr[2], strip_len[2], is_ring[2];
 };
 
-std::shared_ptr<GridPlanDev> grid_plan(int dev, int H, int W, int rank, int world)
+std::shared_ptr<GridPlanDev> grid_plan(int dev, int H, int W, int rank, int world, int blocks)
 {
     static std::mutex mu;
-    static std::map<std::tuple<int, int, int, int, int>, std::shared_ptr<GridPlanDev>> cache;
+    static std::map<std::tuple<int, int, int, int, int, int>, std::shared_ptr<GridPlanDev>> cache;
     std::lock_guard<std::mutex> lock(mu);
-    const auto key = std::make_tuple(dev, H, W, rank, world);
+    const auto key = std::make_tuple(dev, H, W, rank, world, blocks);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
     auto gp = std::make_shared<GridPlanDev>();
     for (int pass = 0; pass < 2; pass++) {
         GPassPlan plan;
-        build_gpass_plan(H, W, pass, world > 1 ? rank : -1, world, plan);
+        build_gpass_plan(H, W, pass, world > 1 ? rank : -1, world, blocks, plan);
         gp->S[pass] = (int)plan.strip_len.size();
         gp->save_slots = std::max(gp->save_slots, (int)plan.save_slots);
         gp->segs[pass].alloc(std::max<size_t>(plan.segs.size(), 1));
@@ -117,6 +117,7 @@ __global__ void gfill_labels_kernel(const double *__restrict__ planes, const dou
     const int ll = (int)(t % nl);
     const long long v = t / nl;
     const int r = r_base + (int)(v / Wl), c = c_base + (int)(v % Wl);
+    if (c < 0 || c >= W) return;      // unused halo column at the image border
     const long long u = r + (long long)H * c;
     const long long N = (long long)H * W;
     const double *pl = planes + ((long long)ll * N + u) * 4;
@@ -148,7 +149,9 @@ __global__ void gweights_kernel(const double *__restrict__ alphas, int H, int W,
     const int r = r_base + (int)(v / Wl), c = c_base + (int)(v % Wl);
     const long long nV = (long long)(H - 1) * W, nH = (long long)H * (W - 1);
     REAL a0 = REAL(0), a1 = REAL(0);
-    if (dirn == 0) {
+    if (c < 0 || c >= W) {
+        // unused halo column at the image border
+    } else if (dirn == 0) {
         if (r + 1 < H) {
             const long long e = (long long)c * (H - 1) + r;
             a0 = (REAL)alphas[e];
@@ -164,14 +167,15 @@ __global__ void gweights_kernel(const double *__restrict__ alphas, int H, int W,
 }
 
 // rounded labels of the rows this rank sweeps -> doubles, 1-based, MATLAB node order (trws_mex.cpp:134-139)
-__global__ void glabels_kernel(const int32_t *__restrict__ sol, int H, Band b, double *__restrict__ out)
+// (one column block: owned columns [c_lo, c_hi), stored from column c_base with Wl columns per row)
+__global__ void glabels_kernel(const int32_t *__restrict__ sol, int H, int c_lo, int c_hi, int c_base, int Wl, double *__restrict__ out)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int wo = b.c_hi - b.c_lo;
-    const long long n = (long long)(b.r_hi - b.r_lo) * wo;
+    const int wo = c_hi - c_lo;
+    const long long n = (long long)H * wo;
     if (t >= n) return;
-    const int r = b.r_lo + (int)(t / wo), c = b.c_lo + (int)(t % wo);
-    out[r + (long long)H * c] = (double)(sol[(long long)(r - b.r_base) * (b.c_top - b.c_base) + (c - b.c_base)] + 1);
+    const int r = (int)(t / wo), c = c_lo + (int)(t % wo);
+    out[r + (long long)H * c] = (double)(sol[(long long)r * Wl + (c - c_base)] + 1);
 }
 
 // one stored label plane back out (inspection / parity tests): 4 x N doubles, rows not stored -> 0
@@ -182,6 +186,7 @@ __global__ void gget_label_kernel(const REAL *__restrict__ nodeF, int l, int H, 
     const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= (long long)rows * Wl) return;
     const int r = r_base + (int)(v / Wl), c = c_base + (int)(v % Wl);
+    if (c < 0 || c >= W) return;
     const long long u = r + (long long)H * c, N = (long long)H * W;
     const REAL *rec = nodeF + v * 4 * LP + l;
     out[u] = (double)rec[NF_D * LP];
@@ -200,13 +205,14 @@ __global__ void gget_weights_kernel(const REAL *__restrict__ alpha, int H, int W
     const int dirn = (int)(pr & 1);
     const int r = r_base + (int)(v / Wl), c = c_base + (int)(v % Wl);
     const long long nV = (long long)(H - 1) * W, nH = (long long)H * (W - 1);
+    if (c < 0 || c >= W) return;
     if (dirn == 0) {
         if (r + 1 < r_base + rows) {
             const long long e = (long long)c * (H - 1) + r;
             out[e] = (double)alpha[pr * 2];
             out[nV + e] = (double)alpha[pr * 2 + 1];
         }
-    } else if (c + 1 < c_base + Wl) {
+    } else if (c + 1 < c_base + Wl && c + 1 < W) {
         const long long e = 2 * nV + (long long)c * H + r;
         out[e] = (double)alpha[pr * 2];
         out[nH + e] = (double)alpha[pr * 2 + 1];
@@ -230,7 +236,7 @@ __device__ __forceinline__ unsigned hash3(unsigned seed, unsigned a, unsigned b,
 __device__ __forceinline__ float u01(unsigned h) { return (float)(h >> 8) * (1.0f / 16777216.0f); }
 
 template <typename REAL>
-__global__ void gsynth_kernel(unsigned seed, int kern, int Hs, int Ws, int r_off, int c_off, int Wloc, int L, int r_base, int rows, int c_base, int LP,
+__global__ void gsynth_kernel(unsigned seed, int kern, int Hs, int Ws, int r_off, int c_off, int Wloc, int Wgrid, int L, int r_base, int rows, int c_base, int LP,
                               REAL *__restrict__ nodeF, REAL *__restrict__ alpha)
 {
     // (Hs, Ws): the grid the synthetic scene is defined on; the solver's own grid is the window of it that
@@ -240,7 +246,9 @@ __global__ void gsynth_kernel(unsigned seed, int kern, int Hs, int Ws, int r_off
     if (t >= Nloc * L) return;
     const int l = (int)(t % L);
     const long long v = t / L;
-    const int r = r_off + r_base + (int)(v / Wloc), c = c_off + c_base + (int)(v % Wloc);
+    const int cw = c_base + (int)(v % Wloc);     // column within the solver's own grid
+    if (cw < 0 || cw >= Wgrid) return;           // unused halo column at the image border
+    const int r = r_off + r_base + (int)(v / Wloc), c = c_off + cw;
     const int H = Hs, W = Ws;
     auto plane_of = [&](int lab, float &own, float &gx, float &gy) {
         if (lab % 4 == 0) {
@@ -306,7 +314,9 @@ template <typename REAL>
 struct Solver : SolverBase {
     int kernel, H, W, L, K, LP, precision, rank, world;
     Band band;
-    int rows, Wl;      // rows and columns stored on this rank
+    int rows, Wl;      // rows and columns stored per column block of this rank
+    int blocks = 1;    // column blocks per rank (block-cyclic bands)
+    int64_t blk_nodes = 0;
     int64_t Nloc, N, E;
     bool fuse, finalized = false;
     const GOps *ops;
@@ -343,17 +353,21 @@ struct Solver : SolverBase {
         N = (int64_t)H * W;
         E = 2 * ((int64_t)(H - 1) * W + (int64_t)H * (W - 1));
         SB_REQUIRE(world == 1 || world <= W / 4, SB_EUNSUP, "sb_trws_grid: at least four columns per rank");
-        band = band_window(H, W, world > 1 ? rank : -1, world);
-        rows = band.rows();
-        Wl = band.width();
-        Nloc = (int64_t)rows * Wl;
+        blocks = world > 1 ? (opt.col_blocks > 0 ? opt.col_blocks : default_col_blocks(W, world)) : 1;
+        SB_REQUIRE(world == 1 || world * blocks <= W / 4, SB_EUNSUP, "sb_trws_grid: at least four columns per column block");
+        band = band_window(H, W, world > 1 ? rank : -1, world, blocks);
+        SB_REQUIRE(band.nblocks >= 1, SB_EUNSUP, "sb_trws_grid: rank %d has no column block", rank);
+        rows = H;
+        Wl = band.Wl;
+        blk_nodes = (int64_t)H * Wl;
+        Nloc = band.nodes();
         // several ranks may live in one process (sb_trws_grid_attach_local): their sweeps must run concurrently
         if (world > 1) SB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         SB_REQUIRE(Nloc < (1LL << 30), SB_EUNSUP, "sb_trws_grid: too many nodes per rank");
         int dev = 0, num_sms = 0;
         SB_CUDA(cudaGetDevice(&dev));
         SB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        plan = grid_plan(dev, H, W, rank, world);
+        plan = grid_plan(dev, H, W, rank, world, blocks);
 
         dNodeF.alloc((size_t)Nloc * 4 * LP);
         dNodeB.alloc((size_t)Nloc * LP);
@@ -452,11 +466,13 @@ struct Solver : SolverBase {
             // fields resident passes device pointers)
             SB_CUDA(cudaMemcpyAsync(dPl.p, planes + (size_t)g0 * 4 * N, (size_t)ng * 4 * N * 8, cudaMemcpyDefault, stream));
             SB_CUDA(cudaMemcpyAsync(dUn.p, unary + (size_t)g0 * N, (size_t)ng * N * 8, cudaMemcpyDefault, stream));
-            const long long tot = Nloc * ng;
-            gfill_labels_kernel<REAL><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(dPl.p, dUn.p, ng, l0 + g0, H, W, band.r_base, rows, band.c_base,
-                                                                                         Wl, LP, d_min, d_step, dNodeF.p, dBad.p);
-            SB_CUDA(cudaGetLastError());
-            count_launch();
+            const long long tot = blk_nodes * ng;
+            for (int b = 0; b < band.nblocks; b++) {
+                gfill_labels_kernel<REAL><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(
+                    dPl.p, dUn.p, ng, l0 + g0, H, W, 0, rows, band.c_base(b), Wl, LP, d_min, d_step, dNodeF.p + (size_t)b * blk_nodes * 4 * LP, dBad.p);
+                SB_CUDA(cudaGetLastError());
+                count_launch();
+            }
         }
         int bad = 0;
         SB_CUDA(cudaMemcpyAsync(&bad, dBad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -474,9 +490,12 @@ struct Solver : SolverBase {
         const double t0 = now_ms();
         DevBuf<double> dA((size_t)E);
         SB_CUDA(cudaMemcpyAsync(dA.p, alphas, (size_t)E * 8, cudaMemcpyDefault, stream));
-        gweights_kernel<REAL><<<(unsigned)((2 * Nloc + 255) / 256), 256, 0, stream>>>(dA.p, H, W, band.r_base, rows, band.c_base, Wl, dAlpha.p);
-        SB_CUDA(cudaGetLastError());
-        count_launch();
+        for (int b = 0; b < band.nblocks; b++) {
+            gweights_kernel<REAL><<<(unsigned)((2 * blk_nodes + 255) / 256), 256, 0, stream>>>(dA.p, H, W, 0, rows, band.c_base(b), Wl,
+                                                                                              dAlpha.p + (size_t)b * blk_nodes * 4);
+            SB_CUDA(cudaGetLastError());
+            count_launch();
+        }
         SB_CUDA(cudaStreamSynchronize(stream));
         setup_ms += now_ms() - t0;
     }
@@ -487,11 +506,14 @@ struct Solver : SolverBase {
         if (Hs <= 0 || Ws <= 0) { Hs = H; Ws = W; r_off = 0; c_off = 0; }
         SB_REQUIRE(r_off >= 0 && c_off >= 0 && r_off + H <= Hs && c_off + W <= Ws, SB_EINVAL,
                    "sb_trws_grid_synth: window (%d,%d)+%dx%d outside the %dx%d scene", r_off, c_off, H, W, Hs, Ws);
-        const long long tot = Nloc * L;
-        gsynth_kernel<REAL><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>((unsigned)(seed ^ (seed >> 32)), kernel, Hs, Ws, r_off, c_off, Wl, L,
-                                                                               band.r_base, rows, band.c_base, LP, dNodeF.p, dAlpha.p);
-        SB_CUDA(cudaGetLastError());
-        count_launch();
+        const long long tot = blk_nodes * L;
+        for (int b = 0; b < band.nblocks; b++) {
+            gsynth_kernel<REAL><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(
+                (unsigned)(seed ^ (seed >> 32)), kernel, Hs, Ws, r_off, c_off, Wl, W, L, 0, rows, band.c_base(b), LP,
+                dNodeF.p + (size_t)b * blk_nodes * 4 * LP, dAlpha.p + (size_t)b * blk_nodes * 4);
+            SB_CUDA(cudaGetLastError());
+            count_launch();
+        }
         SB_CUDA(cudaStreamSynchronize(stream));
         finalized = false;
         setup_ms += now_ms() - t0;
@@ -502,7 +524,9 @@ struct Solver : SolverBase {
         const double t0 = now_ms();
         GTablesLaunch tl;
         tl.precision = precision; tl.nodeF = dNodeF.p; tl.nodeB = dNodeB.p; tl.pairB = dPairB.p;
-        tl.W = Wl; tl.rows = rows; tl.L = L; tl.stream = stream;
+        // (the blocks are stacked: to the table kernels they are one grid of nblocks * H rows; the pairs that would join
+        // two blocks are never read)
+        tl.W = Wl; tl.rows = rows * band.nblocks; tl.L = L; tl.stream = stream;
         ops->tables(tl);
         SB_CUDA(cudaStreamSynchronize(stream));
         finalized = true;
@@ -514,9 +538,12 @@ struct Solver : SolverBase {
         SB_REQUIRE(l >= 0 && l < L && out, SB_EINVAL, "sb_trws_grid_get_label: bad arguments");
         DevBuf<double> d((size_t)4 * N);
         SB_CUDA(cudaMemsetAsync(d.p, 0, d.bytes(), stream));
-        gget_label_kernel<REAL><<<(unsigned)((Nloc + 255) / 256), 256, 0, stream>>>(dNodeF.p, l, H, W, band.r_base, rows, band.c_base, Wl, LP, d.p);
-        SB_CUDA(cudaGetLastError());
-        count_launch();
+        for (int b = 0; b < band.nblocks; b++) {
+            gget_label_kernel<REAL><<<(unsigned)((blk_nodes + 255) / 256), 256, 0, stream>>>(dNodeF.p + (size_t)b * blk_nodes * 4 * LP, l, H, W, 0, rows,
+                                                                                            band.c_base(b), Wl, LP, d.p);
+            SB_CUDA(cudaGetLastError());
+            count_launch();
+        }
         SB_CUDA(cudaMemcpyAsync(out, d.p, d.bytes(), cudaMemcpyDeviceToHost, stream));
         SB_CUDA(cudaStreamSynchronize(stream));
     }
@@ -526,9 +553,12 @@ struct Solver : SolverBase {
         SB_REQUIRE(out, SB_EINVAL, "sb_trws_grid_get_weights: null pointer");
         DevBuf<double> d((size_t)E);
         SB_CUDA(cudaMemsetAsync(d.p, 0, d.bytes(), stream));
-        gget_weights_kernel<REAL><<<(unsigned)((2 * Nloc + 255) / 256), 256, 0, stream>>>(dAlpha.p, H, W, band.r_base, rows, band.c_base, Wl, d.p);
-        SB_CUDA(cudaGetLastError());
-        count_launch();
+        for (int b = 0; b < band.nblocks; b++) {
+            gget_weights_kernel<REAL><<<(unsigned)((2 * blk_nodes + 255) / 256), 256, 0, stream>>>(dAlpha.p + (size_t)b * blk_nodes * 4, H, W, 0, rows,
+                                                                                                  band.c_base(b), Wl, d.p);
+            SB_CUDA(cudaGetLastError());
+            count_launch();
+        }
         SB_CUDA(cudaMemcpyAsync(out, d.p, d.bytes(), cudaMemcpyDeviceToHost, stream));
         SB_CUDA(cudaStreamSynchronize(stream));
     }
@@ -655,9 +685,13 @@ struct Solver : SolverBase {
 
     void set_peer_geometry(int d, int peer_rank)
     {
-        const Band pb = band_window(H, W, peer_rank, world);
-        P.peer_dW[d] = pb.width() - Wl;
-        P.peer_dc[d] = (long long)band.c_base - pb.c_base;
+        // Every rank stores its blocks with the same pitch, so my node (b, r, cl) is the peer's (b', r, cl -+ wb): a send
+        // to the LEFT leaves through my halo column 0 = the peer's last owned column wb, a send to the RIGHT through my
+        // column wb = the peer's halo column 0; b' = b except where the block sequence wraps around the ranks.
+        (void)peer_rank;
+        P.peer_dW[d] = 0;
+        if (d == 0) P.peer_dc[d] = (rank == 0 ? -blk_nodes : 0) + band.wb;
+        else P.peer_dc[d] = (rank == world - 1 ? blk_nodes : 0) - band.wb;
     }
 
     void *raw_ptr(int which) override { return which == 0 ? (void *)dMsg.p : (void *)dSelBox.p; }
@@ -671,8 +705,7 @@ struct Solver : SolverBase {
         SolverBase *src[2] = {up, down};
         for (int d = 0; d < 2; d++) {
             if (!src[d]) continue;
-            const int peer_rank = d == 0 ? rank - 1 : rank + 1;
-            SB_REQUIRE(peer_rank >= 0 && peer_rank < world, SB_EINVAL, "sb_trws_grid_attach_local: no such neighbour");
+            const int peer_rank = (d == 0 ? rank - 1 + world : rank + 1) % world;    // the block sequence wraps around the ranks
             P.peer_msg[d] = static_cast<REAL *>(src[d]->raw_ptr(0));
             P.peer_selbox[d] = static_cast<unsigned long long *>(src[d]->raw_ptr(1));
             set_peer_geometry(d, peer_rank);
@@ -690,14 +723,20 @@ struct Solver : SolverBase {
         const unsigned char *src[2] = {up, down};
         for (int d = 0; d < 2; d++) {
             if (!src[d]) continue;
-            const int peer_rank = d == 0 ? rank - 1 : rank + 1;
-            SB_REQUIRE(peer_rank >= 0 && peer_rank < world, SB_EINVAL, "sb_trws_grid_ipc_attach: no such neighbour");
-            cudaIpcMemHandle_t h[2];
-            std::memcpy(h, src[d], sizeof(h));
-            for (int a = 0; a < 2; a++)
-                SB_CUDA(cudaIpcOpenMemHandle(&peer_ptr[d][a], h[a], cudaIpcMemLazyEnablePeerAccess));
-            P.peer_msg[d] = static_cast<REAL *>(peer_ptr[d][0]);
-            P.peer_selbox[d] = static_cast<unsigned long long *>(peer_ptr[d][1]);
+            const int peer_rank = (d == 0 ? rank - 1 + world : rank + 1) % world;    // the block sequence wraps around the ranks
+            void *ptr[2];
+            if (d == 1 && src[0] && std::memcmp(src[0], src[1], 2 * sizeof(cudaIpcMemHandle_t)) == 0) {
+                // two ranks: the neighbour on both sides is the same process, and a handle opens only once
+                ptr[0] = peer_ptr[0][0]; ptr[1] = peer_ptr[0][1];
+            } else {
+                cudaIpcMemHandle_t h[2];
+                std::memcpy(h, src[d], sizeof(h));
+                for (int a = 0; a < 2; a++)
+                    SB_CUDA(cudaIpcOpenMemHandle(&peer_ptr[d][a], h[a], cudaIpcMemLazyEnablePeerAccess));
+                ptr[0] = peer_ptr[d][0]; ptr[1] = peer_ptr[d][1];
+            }
+            P.peer_msg[d] = static_cast<REAL *>(ptr[0]);
+            P.peer_selbox[d] = static_cast<unsigned long long *>(ptr[1]);
             set_peer_geometry(d, peer_rank);
         }
     }
@@ -776,10 +815,14 @@ struct Solver : SolverBase {
     {
         DevBuf<double> d((size_t)N);
         SB_CUDA(cudaMemsetAsync(d.p, 0, d.bytes(), stream));
-        const long long n = (long long)(band.r_hi - band.r_lo) * (band.c_hi - band.c_lo);
-        glabels_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dSol.p, H, band, d.p);
-        SB_CUDA(cudaGetLastError());
-        count_launch();
+        for (int b = 0; b < band.nblocks; b++) {
+            const long long n = (long long)H * (band.c_hi(b) - band.c_lo(b));
+            if (n <= 0) continue;
+            glabels_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dSol.p + (size_t)b * blk_nodes, H, band.c_lo(b), band.c_hi(b), band.c_base(b),
+                                                                            Wl, d.p);
+            SB_CUDA(cudaGetLastError());
+            count_launch();
+        }
         SB_CUDA(cudaMemcpyAsync(out, d.p, d.bytes(), cudaMemcpyDeviceToHost, stream));
         SB_CUDA(cudaStreamSynchronize(stream));
     }
@@ -795,8 +838,8 @@ struct Solver : SolverBase {
     {
         out[0] = (int64_t)(dNodeF.bytes() + dNodeB.bytes() + dMsg.bytes() + dPairB.bytes() + dAlpha.bytes() + dSelBox.bytes() + dSol.bytes());
         out[1] = Nloc;
-        out[2] = band.c_lo;
-        out[3] = band.c_hi;
+        out[2] = band.c_lo(0);
+        out[3] = band.c_hi(0);
         out[4] = grid_fwd;
         out[5] = grid_bwd;
         out[6] = (int64_t)ops->smem_bytes(precision);
@@ -954,7 +997,7 @@ int sb_trws_grid_plan_stats(int H, int W, int rank, int world, int64_t *stats)
         SB_REQUIRE(stats, SB_EINVAL, "sb_trws_grid_plan_stats: null pointer");
         for (int pass = 0; pass < 2; pass++) {
             sb::gtrws::GPassPlan plan;
-            sb::gtrws::build_gpass_plan(H, W, pass, world > 1 ? rank : -1, world, plan);
+            sb::gtrws::build_gpass_plan(H, W, pass, world > 1 ? rank : -1, world, 0, plan);
             int64_t steps = 0, nodes = 0, two = 0, peer_up = 0, peer_down = 0;
             for (const auto &s : plan.segs) {
                 steps += s.n;

@@ -255,11 +255,13 @@ void build_schedule(int H, int W, const std::vector<int32_t> &ordering, Schedule
     }
 }
 
-void build_schedule_cols(int H, int W, const std::vector<int32_t> &ordering, Schedule &s, int world)
+void build_schedule_cols(int H, int W, const std::vector<int32_t> &ordering, Schedule &s, int world, int blocks)
 {
     if (world <= 1) { build_schedule(H, W, ordering, s, 1); return; }
-    SB_REQUIRE(H >= 4 && W >= 4 && world <= W / 4, SB_EUNSUP,
-               "column-banded sweeps need a regular grid with at least four columns per rank");
+    SB_REQUIRE(blocks >= 1 && H >= 4 && W >= 4 && world * blocks <= W / 4, SB_EUNSUP,
+               "column-banded sweeps need a regular grid with at least four columns per block");
+    const int wb = col_block_width(W, world, blocks);
+    SB_REQUIRE((W + wb - 1) / wb >= world, SB_EUNSUP, "column-banded sweeps: fewer column blocks than ranks");
     s.nodes.clear();
     s.strip_ptr.clear();
     s.owner.clear();
@@ -271,7 +273,7 @@ void build_schedule_cols(int H, int W, const std::vector<int32_t> &ordering, Sch
     for (int r = 0; r < H; r++) { put(r, 0); put(r, W - 1); }
     for (int c = 1; c < W - 1; c++) { put(0, c); put(H - 1, c); }
     for (int64_t k = 0; k < ring; k++) {
-        const int own = band_of_col(ringnodes[k] / H, W, world);
+        const int own = band_of_col(ringnodes[k] / H, wb, world);
         if (k == 0 || own != s.owner.back()) {
             s.strip_ptr.push_back((int64_t)s.nodes.size());
             s.owner.push_back(own);
@@ -282,7 +284,7 @@ void build_schedule_cols(int H, int W, const std::vector<int32_t> &ordering, Sch
     for (int r = 1; r <= H - 2; r++) {
         int cur = -1;
         for (int c = W - 2; c >= 1; c--) {
-            const int own = band_of_col(c, W, world);
+            const int own = band_of_col(c, wb, world);
             if (own != cur) {
                 s.strip_ptr.push_back((int64_t)s.nodes.size());
                 s.owner.push_back(own);

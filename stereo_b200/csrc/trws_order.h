@@ -32,13 +32,16 @@ inline int band_of_row(int r, int H, int world) { return (int)(((long long)r * w
 // world > 1 (regular grids only): the ring strip is cut at the band boundaries and every strip
 // gets an owner.
 void build_schedule(int H, int W, const std::vector<int32_t> &ordering, Schedule &s, int world = 1);
-// Rank that owns image column c when the columns are split into `world` contiguous bands.
-inline int band_of_col(int c, int W, int world) { return (int)(((long long)c * world) / W); }
+// Column blocks of the grid-native multi-GPU sweep: blocks of `wb` columns dealt round robin to the ranks (block B
+// belongs to rank B % world).  One block per rank = contiguous bands; several = block-cyclic, which shortens the
+// pipeline fill (a rank waits for (world - 1) BLOCKS of the first row, not for (world - 1) / world of it).
+inline int col_block_width(int W, int world, int blocks) { return (W + world * blocks - 1) / (world * blocks); }
+inline int band_of_col(int c, int wb, int world) { return (c / wb) % world; }
 // Column-banded variant (grid-native path, gtrws_plan.cpp): the strips run ALONG the image rows, so
 // cutting every strip at the column-band boundaries turns the ranks into the stages of a pipeline -- rank g
 // works on its piece of row r while rank g + 1 already works on row r + 1 -- where row bands would make
 // the ranks take turns (row r + 1 waits for row r).  The ring is cut wherever its owner changes.
-void build_schedule_cols(int H, int W, const std::vector<int32_t> &ordering, Schedule &s, int world);
+void build_schedule_cols(int H, int W, const std::vector<int32_t> &ordering, Schedule &s, int world, int blocks = 1);
 
 // Segment descriptors of one pass (trws_sched.h): segment range of forward strip fs =
 // [seg_ptr[fs], seg_ptr[fs + 1]).  pass 0 = forward sweep,

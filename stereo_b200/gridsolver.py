@@ -89,8 +89,9 @@ class TrwsGrid:
             check(lib().sb_trws_grid_ipc_export(self._h, mine))
             gathered = [None] * self.world
             self.dist.all_gather_object(gathered, bytes(mine.raw), group=self.group)
-            up = gathered[self.rank - 1] if self.rank > 0 else None
-            down = gathered[self.rank + 1] if self.rank + 1 < self.world else None
+            # the column blocks are dealt round robin, so the neighbours wrap around the ranks
+            up = gathered[(self.rank - 1) % self.world]
+            down = gathered[(self.rank + 1) % self.world]
             check(lib().sb_trws_grid_ipc_attach(self._h, up, down))
             self.dist.barrier(group=self.group)
             self._attached = True
@@ -249,8 +250,8 @@ class TrwsGridLocalGroup:
         for g in self.ranks:
             g.finalize()
         for r, g in enumerate(self.ranks):
-            up = self.ranks[r - 1]._h if r > 0 else None
-            down = self.ranks[r + 1]._h if r + 1 < self.world else None
+            up = self.ranks[(r - 1) % self.world]._h
+            down = self.ranks[(r + 1) % self.world]._h
             check(lib().sb_trws_grid_attach_local(g._h, up, down, self.world))
             g._attached = True
 

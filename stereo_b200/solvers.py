@@ -80,6 +80,7 @@ def _trws_options(options):
     prec = _opt(options, "precision", "f32")
     opt.precision = SB_F64 if prec in ("f64", SB_F64, "double") and prec != 0 else SB_F32
     opt.fuse_rounding = int(bool(_opt(options, "fuse_rounding", True)))
+    opt.col_blocks = int(_opt(options, "col_blocks", 0))      # grid-native multi-GPU: column blocks per rank (0 = default)
     return opt
 
 

@@ -71,7 +71,8 @@ typedef struct sb_trws_options {
     int    fuse_rounding; /* 1 (default): primal rounding of iteration t rides in the
                              forward sweep of t+1; 0: separate sweep   */
     int    col_blocks;    /* grid-native entry, world > 1: column blocks per rank (the blocks are dealt round robin
-                             to the ranks; 1 = contiguous bands); 0 = default (up to 4, blocks at least 16 columns wide) */
+                             to the ranks; 1 = contiguous bands); 0 = default (1: more blocks shorten the pipeline fill but
+                             add NVLink hand-overs to the critical path -- measured slower on 8 GPUs) */
     int    reserved[5];
 } sb_trws_options;
 

@@ -1,4 +1,5 @@
-"""N > 1 path.  CPU part (gloo, world_size 2): the host-side band partition of the sweep schedule
+"""N > 1 path.  CPU part (gloo, world_size 2-4): the host-side band partition of the sweep schedule (MATLAB-layout
+entry: row bands; grid-native entry: column blocks)
 -- every node swept by exactly one rank, boundary pushes of neighbouring ranks mirror each
 other.  GPU part (needs >= 2 devices; skipped on the single-GPU test box, run by hand with
 `gpurun --gpus 2 -- python -m torch.distributed.run ... scripts/mg_check.py`): banded sweep ==
@@ -58,6 +59,58 @@ def test_band_partition_gloo(world):
     port = 29600 + world + (os.getpid() % 200)
     shapes = [(12, 9), (48, 64), (375, 450)]
     procs = [ctx.Process(target=_worker, args=(r, world, port, shapes, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
+
+
+def _grid_plan_stats(H, W, rank, world):
+    from stereo_b200 import _lib
+    st = (ctypes.c_int64 * 12)()
+    _lib.check(_lib.lib().sb_trws_grid_plan_stats(H, W, rank, world, st))
+    return np.array(list(st))
+
+
+def _grid_worker(rank, world, port, shapes, blocks, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["SB_GTRWS_BLOCKS"] = str(blocks)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ok = True
+    for (H, W) in shapes:
+        st = torch.from_numpy(_grid_plan_stats(H, W, rank, world))
+        allst = [torch.zeros_like(st) for _ in range(world)]
+        dist.all_gather(allst, st)
+        if rank == 0:
+            a = np.stack([t.numpy() for t in allst])
+            wb = -(-W // (world * blocks))
+            NB = -(-W // wb)
+            for p in (0, 1):
+                left, right = a[:, 5 + 6 * p] // 1000000, a[:, 5 + 6 * p] % 1000000
+                ok &= int(a[:, 3 + 6 * p].sum()) == H * W            # every node swept by exactly one rank
+                ok &= int(left.sum() + right.sum()) == H * (NB - 1)   # every block boundary carries its H pairs once per pass
+            # what is pushed to the right in the forward pass comes back to the left in the backward pass
+            ok &= int((a[:, 5] % 1000000).sum()) == int((a[:, 11] // 1000000).sum())
+            ok &= int((a[:, 5] // 1000000).sum()) == int((a[:, 11] % 1000000).sum())
+    if rank == 0:
+        q.put(bool(ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,blocks", [(2, 1), (3, 1), (2, 3), (4, 2)])
+def test_grid_column_band_partition_gloo(world, blocks):
+    """Grid-native entry: the column-block partition of the sweep schedule (contiguous bands and block-cyclic)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + 10 * world + blocks + (os.getpid() % 200)
+    shapes = [(12, 40), (48, 64), (37, 130)]
+    procs = [ctx.Process(target=_grid_worker, args=(r, world, port, shapes, blocks, q)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:

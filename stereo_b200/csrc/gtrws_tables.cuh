@@ -72,21 +72,65 @@ __device__ __forceinline__ void count_rows(const REAL *A, const REAL *B, int lan
     for (int k = 0; k < K; k++) cn[k] = (uint8_t)min(c[k], 255);
 }
 
+// ---------------------------------------------------------------- sort-based tables (one warp per row)
+// The counting loops above are O(LP^2) per row; a grid of 1980 x 2880 nodes with 192 labels has 68 million rows.
+// A stable bitonic sort of (position, label) in shared memory gives the ranks in O(LP log^2 LP), and the merge
+// counts are upper bounds in the sorted rows (binary search): same integers, ~6x fewer instructions.
+template <int LP> __host__ __device__ constexpr int pow2_at_least() { int n = 32; while (n < LP) n <<= 1; return n; }
+
+// keys[0..LP) in, LPS - LP padding slots appended (+big); out: keys sorted ascending (ties: lower label first),
+// idx[pos] = label at sorted position pos.  One warp; keys / idx hold LPS entries.
+template <typename REAL, int LP, int LPS>
+__device__ __forceinline__ void warp_sort(REAL *keys, int *idx, int lane)
+{
+    for (int i = lane; i < LPS; i += 32) {
+        idx[i] = i;
+        if (i >= LP) keys[i] = Lim<REAL>::big();
+    }
+    __syncwarp();
+    for (int k = 2; k <= LPS; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < LPS / 2; t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));     // t with a zero bit inserted at position log2(j)
+                const int p = i | j;
+                const REAL a = keys[i], b = keys[p];
+                const int ia = idx[i], ib = idx[p];
+                const bool up = (i & k) == 0;
+                const bool a_after_b = (b < a) || (b == a && ib < ia);
+                if (a_after_b == up) {
+                    keys[i] = b; keys[p] = a;
+                    idx[i] = ib; idx[p] = ia;
+                }
+            }
+            __syncwarp();
+        }
+}
+// #{m < LP : S[m] <= v} for S sorted ascending
+template <typename REAL, int LP>
+__device__ __forceinline__ int upper_bound(const REAL *S, REAL v)
+{
+    int lo = 0, hi = LP;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (S[mid] <= v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
 // one warp per node: rank of own
 template <typename REAL, int K, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) gnode_tables_kernel(const REAL *__restrict__ nodeF, uint8_t *__restrict__ nodeB, long long Nloc)
 {
-    constexpr int LP = 32 * K;
-    __shared__ REAL sh[WARPS][LP];
+    constexpr int LP = 32 * K, LPS = pow2_at_least<LP>();
+    __shared__ REAL keys[WARPS][LPS];
+    __shared__ int idx[WARPS][LPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (long long v = (long long)blockIdx.x * WARPS + warp; v < Nloc; v += (long long)gridDim.x * WARPS) {
         const REAL *rec = nodeF + v * 4 * LP;
-#pragma unroll
-        for (int k = 0; k < K; k++) sh[warp][lane * K + k] = rec[NF_OWN * LP + lane * K + k];
+        for (int l = lane; l < LP; l += 32) keys[warp][l] = rec[NF_OWN * LP + l];
         __syncwarp();
-        uint8_t rk[K];
-        rank_rows<REAL, K>(sh[warp], lane, rk);
-        trws::ByteIO<K>::store(nodeB + v * LP + lane * K, rk);
+        warp_sort<REAL, LP, LPS>(keys[warp], idx[warp], lane);
+        for (int pos = lane; pos < LP; pos += 32) nodeB[v * LP + idx[warp][pos]] = (uint8_t)pos;
         __syncwarp();
     }
 }
@@ -96,11 +140,17 @@ __global__ void __launch_bounds__(WARPS * 32) gnode_tables_kernel(const REAL *__
 //   term 1: tail b, head a:  q1 = own_a,  qp1 = own_b - g_b
 // side record s (what node s of the pair needs when it sends): [cnt_q[s] | cnt_qp[1-s] | rank_tail[s]]
 //   cnt_q[j][l]  = #{m : qp_j[m] <= q_j[l]}     cnt_qp[j][l] = #{m : q_j[m] <= qp_j[l]}
+// Runs after gnode_tables_kernel: the sorted q rows come from the node ranks.
 template <typename REAL, int K, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) gpair_tables_kernel(const REAL *__restrict__ nodeF, uint8_t *__restrict__ pairB, int W, int rows)
+__global__ void __launch_bounds__(WARPS * 32) gpair_tables_kernel(const REAL *__restrict__ nodeF, const uint8_t *__restrict__ nodeB,
+                                                                  uint8_t *__restrict__ pairB, int W, int rows)
 {
-    constexpr int LP = 32 * K;
-    __shared__ REAL sh[WARPS][4][LP];
+    constexpr int LP = 32 * K, LPS = pow2_at_least<LP>();
+    __shared__ REAL q[WARPS][2][LP];       // q_j by label
+    __shared__ REAL qp[WARPS][2][LP];      // qp_j by label
+    __shared__ REAL sq[WARPS][2][LP];      // q_j sorted
+    __shared__ REAL sqp[WARPS][LPS];       // qp_j sorted (one term at a time)
+    __shared__ int idx[WARPS][LPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long Nloc = (long long)rows * W;
     for (long long pr = (long long)blockIdx.x * WARPS + warp; pr < 2 * Nloc; pr += (long long)gridDim.x * WARPS) {
@@ -110,33 +160,33 @@ __global__ void __launch_bounds__(WARPS * 32) gpair_tables_kernel(const REAL *__
         if (dirn == 0 ? (r + 1 >= rows) : (c + 1 >= W)) continue;
         const long long b = dirn == 0 ? a + W : a + 1;
         const REAL *ra = nodeF + a * 4 * LP, *rb = nodeF + b * 4 * LP;
+        const uint8_t *ka = nodeB + a * LP, *kb = nodeB + b * LP;
         const int gsel = dirn == 0 ? NF_GY : NF_GX;
-        REAL *q0 = sh[warp][0], *qp0 = sh[warp][1], *q1 = sh[warp][2], *qp1 = sh[warp][3];
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            const int l = lane * K + k;
+        for (int l = lane; l < LP; l += 32) {
             const REAL oa = ra[NF_OWN * LP + l], ob = rb[NF_OWN * LP + l];
-            q0[l] = ob;
-            qp0[l] = oa + ra[gsel * LP + l];
-            q1[l] = oa;
-            qp1[l] = ob - rb[gsel * LP + l];
+            q[warp][0][l] = ob;
+            qp[warp][0][l] = oa + ra[gsel * LP + l];
+            q[warp][1][l] = oa;
+            qp[warp][1][l] = ob - rb[gsel * LP + l];
+            sq[warp][0][kb[l]] = ob;      // rank of own: a permutation of 0 .. LP-1
+            sq[warp][1][ka[l]] = oa;
         }
         __syncwarp();
-        uint8_t out[K];
-        uint8_t *rec = pairB + pr * 6 * LP + lane * K;
-        count_rows<REAL, K>(q0, qp0, lane, out);    // cnt_q[0]
-        trws::ByteIO<K>::store(rec + 0 * LP, out);
-        count_rows<REAL, K>(qp1, q1, lane, out);    // cnt_qp[1]
-        trws::ByteIO<K>::store(rec + 1 * LP, out);
-        rank_rows<REAL, K>(qp0, lane, out);         // rank_tail[0]
-        trws::ByteIO<K>::store(rec + 2 * LP, out);
-        count_rows<REAL, K>(q1, qp1, lane, out);    // cnt_q[1]
-        trws::ByteIO<K>::store(rec + 3 * LP, out);
-        count_rows<REAL, K>(qp0, q0, lane, out);    // cnt_qp[0]
-        trws::ByteIO<K>::store(rec + 4 * LP, out);
-        rank_rows<REAL, K>(qp1, lane, out);         // rank_tail[1]
-        trws::ByteIO<K>::store(rec + 5 * LP, out);
-        __syncwarp();
+        uint8_t *rec = pairB + pr * 6 * LP;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            // record layout: term 0 -> rows 0 (cnt_q), 4 (cnt_qp), 2 (rank_tail); term 1 -> rows 3, 1, 5
+            const int row_cq = j == 0 ? 0 : 3, row_cqp = j == 0 ? 4 : 1, row_rk = j == 0 ? 2 : 5;
+            for (int l = lane; l < LP; l += 32) sqp[warp][l] = qp[warp][j][l];
+            __syncwarp();
+            warp_sort<REAL, LP, LPS>(sqp[warp], idx[warp], lane);
+            for (int pos = lane; pos < LP; pos += 32) rec[row_rk * LP + idx[warp][pos]] = (uint8_t)pos;
+            for (int l = lane; l < LP; l += 32) {
+                rec[row_cq * LP + l] = (uint8_t)min(upper_bound<REAL, LP>(sqp[warp], q[warp][j][l]), 255);
+                rec[row_cqp * LP + l] = (uint8_t)min(upper_bound<REAL, LP>(sq[warp][j], qp[warp][j][l]), 255);
+            }
+            __syncwarp();
+        }
     }
 }
 

@@ -73,7 +73,11 @@ typedef struct sb_trws_options {
     int    col_blocks;    /* grid-native entry, world > 1: column blocks per rank (the blocks are dealt round robin
                              to the ranks; 1 = contiguous bands); 0 = default (1: more blocks shorten the pipeline fill but
                              add NVLink hand-overs to the critical path -- measured slower on 8 GPUs) */
-    int    reserved[5];
+    int    latency_mode;  /* grid-native entry: 0 = automatic, 1 = always, -1 = never run the LATENCY build of the sweep
+                             kernel (one strip walker per SM, registers uncapped: shorter node steps, less throughput).
+                             Automatic: banded runs whose ranks hold so few nodes that the pass ends with the DAG's
+                             critical path (nodes per SM <= 1.25 (H + W)), DESIGN.md 6 */
+    int    reserved[4];
 } sb_trws_options;
 
 SB_API void sb_trws_default_options(sb_trws_options *opt);
@@ -247,6 +251,8 @@ SB_API int sb_trws_grid_launch_pass(sb_trws_grid *g, int pass, int mode);
 SB_API int sb_trws_grid_wait(sb_trws_grid *g, double *acc /* 2 x max_passes, may be null */, int max_passes, int *n_passes);
 SB_API int sb_trws_grid_attach_local(sb_trws_grid *g, sb_trws_grid *up, sb_trws_grid *down, int share);
 SB_API int sb_trws_grid_info(sb_trws_grid *g, int64_t *info /* 8 */);
+/* *on = 1 when this solver sweeps with the latency build (sb_trws_options.latency_mode) */
+SB_API int sb_trws_grid_latency_mode(sb_trws_grid *g, int *on);
 /* cumulative since creation: out[0] = ms spent in sweep kernels (CUDA events around every launch on the solver
  * stream), out[1] = sweep launches, out[2] = set-up ms (uploads, table build) */
 SB_API int sb_trws_grid_counters(sb_trws_grid *g, double *out /* 3 */);

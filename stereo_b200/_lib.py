@@ -30,7 +30,7 @@ class SbError(RuntimeError):
 
 class TrwsOptions(Structure):
     _fields_ = [("maxiter", c_double), ("max_relgap", c_double), ("precision", c_int),
-                ("fuse_rounding", c_int), ("col_blocks", c_int), ("reserved", c_int * 5)]
+                ("fuse_rounding", c_int), ("col_blocks", c_int), ("latency_mode", c_int), ("reserved", c_int * 4)]
 
 
 class TrwsTiming(Structure):
@@ -94,6 +94,7 @@ def lib():
         L.sb_trws_grid_wait.argtypes = [vp, _dp, c_int, POINTER(c_int)]
         L.sb_trws_grid_attach_local.argtypes = [vp, vp, vp, c_int]
         L.sb_trws_grid_info.argtypes = [vp, POINTER(c_int64)]
+        L.sb_trws_grid_latency_mode.argtypes = [vp, POINTER(c_int)]
         L.sb_trws_grid_counters.argtypes = [vp, _dp]
         L.sb_trws_grid_destroy.argtypes = [vp]
         L.sb_trws_grid_destroy.restype = None

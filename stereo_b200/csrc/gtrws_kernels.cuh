@@ -45,6 +45,14 @@ using trws::PASS_BWD;
 using trws::MODE_SEND;
 using trws::MODE_ROUND;
 
+// Diagnostics (SB_TRWS_PROFILE phase counters, SB_TRWS_RECORD flight recorder) cost ~8 % of the term warps'
+// instructions even when switched off at run time (predicated-off instructions still issue), so they are compiled
+// in only by  make EXTRA=-DSB_GTRWS_DIAG=1  (profiles/r2_phase_counters_cfg5.txt came from such a build).
+#ifndef SB_GTRWS_DIAG
+#define SB_GTRWS_DIAG 0
+#endif
+constexpr bool DIAG = SB_GTRWS_DIAG != 0;
+
 constexpr int NTW = 4;                       // term warps
 constexpr int NHW = 2;                       // helper warps: helper h prepares the steps of parity h
 constexpr int CTA_THREADS = (NTW + NHW) * 32;
@@ -474,8 +482,11 @@ template <typename REAL, int K> __host__ __device__ constexpr int gsweep_min_blo
     return K <= 4 ? 4 : K <= 6 ? 3 : 2;
 }
 
-template <typename REAL, int K, int KERN, int PASS, int NS>
-__global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) gsweep_kernel(const GProblem<REAL> p)
+// MB = resident CTAs per SM the registers are budgeted for: gsweep_min_blocks (throughput: as many strip walkers per SM
+// as pay) or 1 (latency: no register cap, no spills, one walker per SM -- for passes that run at the DAG's critical
+// path, i.e. the column-banded multi-GPU sweeps with few nodes per rank; gtrws_solve.cu picks)
+template <typename REAL, int K, int KERN, int PASS, int NS, int MB>
+__global__ void __launch_bounds__(CTA_THREADS, MB) gsweep_kernel(const GProblem<REAL> p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int s_ticket;
@@ -483,6 +494,8 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
     constexpr int LP = 32 * K;
     constexpr int PD = NS - 1;   // bulk copies are issued PD steps ahead
     const int lane = threadIdx.x & 31;
+    // (warp w issues from scheduler w & 3: the term warps 2, 3 of send slot 1 -- the sends to the next node of the strip,
+    // i.e. the dependent chain, gtrws_plan.cpp -- have their schedulers to themselves; the helpers share with slot 0)
     const int warp = threadIdx.x >> 5;
     const bool is_term = warp < NTW;
     const int W = p.W;
@@ -523,6 +536,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
     double acc_energy = 0.0, acc_lb = 0.0;
     // flight recorder (debugging hangs): where every warp is -- strip, step, phase -- in host-mapped memory
     auto record = [&](int strip, int step, int phase, int extra) {
+        if constexpr (!DIAG) return;
         if (p.rec && lane == 0) {
             volatile int *r = p.rec + ((size_t)blockIdx.x * (NTW + NHW) + warp) * 4;
             r[0] = strip; r[1] = step; r[2] = phase; r[3] = extra;
@@ -577,7 +591,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
             const unsigned valid = LaneMap<REAL, K>::valid_mask(lane, p.L);
             // optional phase timers (SB_TRWS_PROFILE): term warp 0 -> wait FULL, wait stage, node total + rounding,
             // operands, update, stores
-            const bool prof_on = (p.prof != nullptr) && w == p.prof_warp;
+            const bool prof_on = DIAG && (p.prof != nullptr) && w == p.prof_warp;
             long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             long long tclk = prof_on ? clock64() : 0;
             auto tick = [&](int which) {
@@ -815,7 +829,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (gsweep_min_blocks<REAL, K>())) g
             int pf_node = first;   // next own step whose bulk copies are to be issued
             // helper phase timers: wait for a free stage, wait stage, static sum, message polls, rounding polls,
             // write + arrive, gate, issue work
-            const bool prof_on = p.prof != nullptr && hid == 0;
+            const bool prof_on = DIAG && p.prof != nullptr && hid == 0;
             long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tsteps = 0, tretry = 0;
             long long tclk = prof_on ? clock64() : 0;
             auto tick = [&](int which) {

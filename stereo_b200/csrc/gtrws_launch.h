@@ -13,6 +13,7 @@ struct GSweepLaunch {
     int pass;            // PASS_FWD / PASS_BWD
     const void *problem; // GProblem<float> or GProblem<double>, host copy
     int grid;            // persistent CTAs (all co-resident)
+    int lat;             // 1: the latency build (one CTA per SM, registers uncapped)
     cudaStream_t stream;
 };
 
@@ -34,7 +35,7 @@ struct GUpdateLaunch {
 
 struct GOps {
     int K;
-    int (*blocks_per_sm)(int precision, int kern, int pass);
+    int (*blocks_per_sm)(int precision, int kern, int pass, int lat);
     void (*sweep)(const GSweepLaunch &);
     void (*tables)(const GTablesLaunch &);   // pad rows, node ranks, pair tables
     size_t (*smem_bytes)(int precision);

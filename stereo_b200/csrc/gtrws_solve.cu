@@ -306,6 +306,7 @@ struct SolverBase {
     virtual void *raw_ptr(int which) = 0;
     virtual void attach_local(SolverBase *up, SolverBase *down, int share) = 0;
     virtual void info(int64_t *out) = 0;
+    virtual int latency_build() const = 0;
     virtual void counters(double *out) = 0;
     double setup_ms = 0;
 };
@@ -334,6 +335,7 @@ struct Solver : SolverBase {
     void *peer_ptr[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     GProblem<REAL> P;
     int grid_fwd = 1, grid_bwd = 1;
+    int lat = 0;               // 1: latency build of the sweep (one CTA per SM, registers uncapped)
     bool isolate = false;
     unsigned launch_epoch = 0, pass_counter = 0;
     Ctrl *hc = nullptr;   // pinned
@@ -393,6 +395,9 @@ struct Solver : SolverBase {
         Ctrl *ctrl = reinterpret_cast<Ctrl *>(dCtrl.p);
         P.ticket = &ctrl->ticket; P.acc = ctrl->acc; P.ring_smid = &ctrl->ring_smid;
 
+        if ((getenv("SB_TRWS_PROFILE") || getenv("SB_TRWS_RECORD")) && !DIAG)
+            fprintf(stderr, "[stereo_b200] SB_TRWS_PROFILE / SB_TRWS_RECORD need the diagnostics build of the grid sweep: "
+                            "make -C stereo_b200/csrc clean all EXTRA=-DSB_GTRWS_DIAG=1\n");
         if (getenv("SB_TRWS_PROFILE")) {
             dProf.alloc(144);
             SB_CUDA(cudaMemsetAsync(dProf.p, 0, dProf.bytes(), stream));
@@ -408,8 +413,15 @@ struct Solver : SolverBase {
             SB_CUDA(cudaHostAlloc((void **)&rec_host, (size_t)rec_ctas * 6 * 4 * sizeof(int), cudaHostAllocMapped));
             SB_CUDA(cudaHostGetDevicePointer((void **)&P.rec, rec_host, 0));
         }
+        // Throughput or latency build?  A rank of a banded run with few nodes finishes its rows long before the DAG's
+        // critical path (the ring chain, then H + W dependent node steps) lets the pass end: there one walker per SM
+        // with uncapped registers (shorter node steps) wins, where a single GPU wants as many walkers as fit.
+        // The walkers of a latency pass have Nloc / SMs node steps each; the critical path of the rows is H + W.
+        lat = world > 1 && (double)Nloc / num_sms <= 1.25 * (double)(H + W);
+        if (opt.latency_mode) lat = opt.latency_mode > 0;
+        if (const char *e = getenv("SB_GTRWS_LAT")) lat = atoi(e) != 0;
         auto grid_for = [&](int pass) {
-            const int bps = ops->blocks_per_sm(precision, kernel, pass);
+            const int bps = ops->blocks_per_sm(precision, kernel, pass, lat);
             SB_REQUIRE(bps >= 1, SB_ECUDA, "sb_trws_grid: sweep kernel does not fit on an SM");
             long long g = (long long)bps * num_sms;
             if (const char *e = getenv("SB_GTRWS_CTAS_PER_SM")) g = std::max(1, std::min(bps, atoi(e))) * (long long)num_sms;
@@ -614,7 +626,7 @@ struct Solver : SolverBase {
         P.isolate_ring = (pass == PASS_FWD && isolate) ? 1 : 0;
         GSweepLaunch sl;
         sl.precision = precision; sl.kern = kernel; sl.pass = pass; sl.problem = &P;
-        sl.grid = pass == PASS_FWD ? grid_fwd : grid_bwd; sl.stream = stream;
+        sl.grid = pass == PASS_FWD ? grid_fwd : grid_bwd; sl.stream = stream; sl.lat = lat;
         last_grid = sl.grid; last_pass = pass; last_mode = mode;
         if (rec_host) std::memset(rec_host, 0xff, (size_t)rec_ctas * 6 * 4 * sizeof(int));
         Pending pd;
@@ -834,6 +846,7 @@ struct Solver : SolverBase {
         out[2] = setup_ms;
     }
 
+    int latency_build() const override { return lat; }
     void info(int64_t *out) override
     {
         out[0] = (int64_t)(dNodeF.bytes() + dNodeB.bytes() + dMsg.bytes() + dPairB.bytes() + dAlpha.bytes() + dSelBox.bytes() + dSol.bytes());
@@ -958,6 +971,10 @@ int sb_trws_grid_counters(sb_trws_grid *g, double *out)
 int sb_trws_grid_info(sb_trws_grid *g, int64_t *info)
 {
     SB_GRID_ENTRY("sb_trws_grid_info", info, g->impl->info(info));
+}
+int sb_trws_grid_latency_mode(sb_trws_grid *g, int *on)
+{
+    SB_GRID_ENTRY("sb_trws_grid_latency_mode", on, *on = g->impl->latency_build());
 }
 void sb_trws_grid_destroy(sb_trws_grid *g)
 {

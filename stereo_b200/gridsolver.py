@@ -111,7 +111,11 @@ class TrwsGrid:
         out = (ctypes.c_int64 * 8)()
         check(lib().sb_trws_grid_info(self._h, out))
         keys = ("hbm_bytes", "nodes_stored", "col_lo", "col_hi", "ctas_fwd", "ctas_bwd", "smem_per_cta", "LP")
-        return dict(zip(keys, [int(v) for v in out]))
+        d = dict(zip(keys, [int(v) for v in out]))
+        on = ctypes.c_int(0)
+        check(lib().sb_trws_grid_latency_mode(self._h, ctypes.byref(on)))
+        d["latency_build"] = int(on.value)
+        return d
 
     def counters(self):
         """Cumulative (sweep kernel ms, sweep launches, set-up ms) since creation."""

@@ -81,6 +81,7 @@ def _trws_options(options):
     opt.precision = SB_F64 if prec in ("f64", SB_F64, "double") and prec != 0 else SB_F32
     opt.fuse_rounding = int(bool(_opt(options, "fuse_rounding", True)))
     opt.col_blocks = int(_opt(options, "col_blocks", 0))      # grid-native multi-GPU: column blocks per rank (0 = default)
+    opt.latency_mode = int(_opt(options, "latency_mode", 0))  # grid-native: 0 auto, 1 / -1 force the latency build on / off
     return opt
 
 

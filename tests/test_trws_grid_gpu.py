@@ -191,6 +191,47 @@ def test_column_bands_one_gpu(H, W, L, it, world, blocks, kernel):
     assert np.mean(lab == lab1) >= 0.999
 
 
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("H,W,L,it,world", [(24, 31, 16, 5, 1), (18, 44, 64, 4, 2), (40, 64, 100, 3, 4), (21, 60, 192, 3, 3), (14, 48, 250, 2, 2)])
+def test_latency_build(H, W, L, it, world, kernel):
+    """sb_trws_options.latency_mode = 1: the sweep kernel built for one strip walker per SM (registers uncapped), which
+    the banded runs pick on their own when a rank holds few nodes.  Same DAG, same arithmetic: identical labels / energy /
+    bound to the throughput build (single rank), and the banded sweep on it agrees with the single-rank sweep."""
+    from stereo_b200.gridsolver import TrwsGridLocalGroup
+    pr = synth.trws_problem(H, W, L, seed=3 * H + W + world, kernel=kernel)
+    ref = TrwsGrid(kernel, H, W, L, pr["tol"], dict(latency_mode=-1))
+    assert ref.info()["latency_build"] == 0
+    ref.set_labels(0, pr["planes"], pr["unary"])
+    ref.set_weights(pr["alphas"])
+    ref.finalize()
+    e1, lb1, _ = ref.minimize(it, 0.0)
+    lab1 = ref.labels()
+    ref.close()
+    if world == 1:
+        g = TrwsGrid(kernel, H, W, L, pr["tol"], dict(latency_mode=1))
+        assert g.info()["latency_build"] == 1
+        g.set_labels(0, pr["planes"], pr["unary"])
+        g.set_weights(pr["alphas"])
+        g.finalize()
+        e, lb, _ = g.minimize(it, 0.0)
+        lab = g.labels()
+        g.close()
+        assert e == e1 and lb == lb1 and np.array_equal(lab, lab1)
+        return
+    grp = TrwsGridLocalGroup(kernel, H, W, L, pr["tol"], world, dict(latency_mode=1))
+    try:
+        assert all(g.info()["latency_build"] == 1 for g in grp.ranks)
+        grp.each(lambda g: g.set_labels(0, pr["planes"], pr["unary"]))
+        grp.each(lambda g: g.set_weights(pr["alphas"]))
+        grp.finalize()
+        e, lb, _ = grp.minimize(it)
+        lab = grp.labels()
+    finally:
+        grp.close()
+    assert abs(e - e1) <= 1e-5 * abs(e1) and abs(lb - lb1) <= 1e-5 * abs(lb1)
+    assert np.mean(lab == lab1) >= 0.999
+
+
 def test_column_bands_one_gpu_f64_exact():
     from stereo_b200.gridsolver import TrwsGridLocalGroup
     H, W, L, it, world = 21, 34, 24, 6, 3

@@ -386,6 +386,18 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// 1 / d for the small integers gamma's denominators are (treeProbabilities.cpp:35-45: at most 8 terms per side):
+// correctly rounded compile-time constants instead of a division (MUFU.RCP + fix-up call) on the dependent chain
+template <typename REAL> __device__ __forceinline__ REAL inv_small(int d)
+{
+    // (a constant-bank table: one indexed LDC)
+    static constexpr REAL tab[16] = {REAL(0),          REAL(1),          REAL(1) / REAL(2),  REAL(1) / REAL(3),
+                                     REAL(1) / REAL(4),  REAL(1) / REAL(5),  REAL(1) / REAL(6),  REAL(1) / REAL(7),
+                                     REAL(1) / REAL(8),  REAL(1) / REAL(9),  REAL(1) / REAL(10), REAL(1) / REAL(11),
+                                     REAL(1) / REAL(12), REAL(1) / REAL(13), REAL(1) / REAL(14), REAL(1) / REAL(15)};
+    return tab[d & 15];
+}
+
 // ---------------------------------------------------------------- geometry of a node step
 struct StepGeo {
     int u;
@@ -423,22 +435,30 @@ struct SegWalker {
     }
 };
 __device__ __forceinline__ int role_of(unsigned roles, int d) { return (roles >> (4 * d)) & 15; }
+// first direction whose role nibble equals `role`, else -1.  Branch-free: zero-nibble search in roles ^ (role x 0x1111);
+// the borrow of x - 0x1111 can only raise false flags ABOVE a true zero nibble, and the lowest flag is taken.
 __device__ __forceinline__ int dir_with_role(unsigned roles, int role)
 {
-#pragma unroll
-    for (int d = 0; d < 4; d++)
-        if (role_of(roles, d) == role) return d;
-    return -1;
+    const unsigned x = (roles & 0xffffu) ^ ((unsigned)role * 0x1111u);
+    const unsigned t = (x - 0x1111u) & ~x & 0x8888u;
+    return ((int)__ffs((int)t) - 1) >> 2;          // t == 0: (0 - 1) >> 2 = -1
 }
-__device__ __forceinline__ long long nb_of(long long u, int d, int W) { return d == DIR_UP ? u - W : d == DIR_DOWN ? u + W : d == DIR_LEFT ? u - 1 : u + 1; }
+// (DIR_UP = 0, DIR_DOWN = 1, DIR_LEFT = 2, DIR_RIGHT = 3: bit 1 = horizontal, bit 0 = towards larger ids)
+__device__ __forceinline__ long long nb_of(long long u, int d, int W)
+{
+    const int step = (d & 2) ? 1 : W;
+    return (d & 1) ? u + step : u - step;
+}
 // pair record of the neighbour pair in direction d: pairs are owned by their upper / left node
 __device__ __forceinline__ long long pair_of(long long u, int d, int W)
 {
-    return d == DIR_DOWN ? 2 * u : d == DIR_RIGHT ? 2 * u + 1 : d == DIR_UP ? 2 * (u - W) : 2 * (u - 1) + 1;
+    const int step = (d & 2) ? 1 : W;
+    return 2 * ((d & 1) ? u : u - step) + ((d >> 1) & 1);
 }
 // 0: I am the pair's first (upper / left) node, 1: its second.  Term j of a pair has tail = node j.
-__device__ __forceinline__ int side_of(int d) { return (d == DIR_DOWN || d == DIR_RIGHT) ? 0 : 1; }
-__device__ __forceinline__ bool vertical(int d) { return d == DIR_UP || d == DIR_DOWN; }
+__device__ __forceinline__ int side_of(int d) { return (d & 1) ^ 1; }
+__device__ __forceinline__ bool vertical(int d) { return (d & 2) == 0; }
+static_assert(DIR_UP == 0 && DIR_DOWN == 1 && DIR_LEFT == 2 && DIR_RIGHT == 3, "direction encoding");
 
 // index of my term `term` (= 4 x owner node + 2 x [horizontal] + j) in the arrays of neighbour rank `peer`
 template <typename REAL> __device__ __forceinline__ long long peer_term(const GProblem<REAL> &p, long long term, int peer)
@@ -601,15 +621,16 @@ __global__ void __launch_bounds__(CTA_THREADS, MB) gsweep_kernel(const GProblem<
                     tclk = now;
                 }
             };
-            for (int node = 0; node < n_steps; node++) {
+            // stage and phase of the CTA-lifetime step count gs = gstep0 + node, kept incrementally (gs % NS, gs / NS)
+            int st = (int)(gstep0 % NS);
+            unsigned ph = (unsigned)((gstep0 / NS) & 1);
+            for (int node = 0; node < n_steps; node++, ph ^= (unsigned)(st + 1 == NS), st = (st + 1 == NS) ? 0 : st + 1) {
                 const unsigned gs = gstep0 + (unsigned)node;
-                const int st = (int)(gs % NS);
-                const unsigned ph = (unsigned)((gs / NS) & 1);
                 const int par = (int)(gs & 1u);     // sets / carry rows / hand-over barriers alternate with the CTA's step count
                 StepGeo g;
                 wk.get(g);
                 if (node + 1 < n_steps) wk.advance();
-                const REAL gamma = REAL(1) / REAL(g.gamma_den);
+                const REAL gamma = inv_small<REAL>(g.gamma_den);
                 const unsigned char *sp = stage_ptr(st);
                 const REAL *NF = reinterpret_cast<const REAL *>(sp + SL::OFF_NF);
                 // ---- rows of this node are ready (helper), every term warp has finished the previous step
@@ -717,10 +738,10 @@ __global__ void __launch_bounds__(CTA_THREADS, MB) gsweep_kernel(const GProblem<
                         const REAL *nb_own, *nb_g;
                         if (to_next) {
                             // the receiver is the next node of the strip: its rows are (or will shortly be) in the next stage
-                            const unsigned gn = gs + 1;
-                            const int stn = (int)(gn % NS);
+                            const bool wrap = st + 1 == NS;
+                            const int stn = wrap ? 0 : st + 1;
                             record(fs, node, 4, stn);
-                            mbar_wait(bar_full + stn, (unsigned)((gn / NS) & 1));
+                            mbar_wait(bar_full + stn, ph ^ (unsigned)wrap);
                             record(fs, node, 5, stn);
                             const REAL *NFn = reinterpret_cast<const REAL *>(stage_ptr(stn) + SL::OFF_NF);
                             nb_own = NFn + NF_OWN * LP;
@@ -889,15 +910,21 @@ __global__ void __launch_bounds__(CTA_THREADS, MB) gsweep_kernel(const GProblem<
                 d_total = __shfl_sync(0xffffffffu, total, 0);
                 d_seg = pf.sg;
             };
+            // (stage, phase) of the step the next issue() refills and of the step the main loop prepares: both advance by 2
+            int ist = (int)((gstep0 + (unsigned)first) % NS);
+            unsigned iph = (unsigned)(((gstep0 + (unsigned)first) / NS) & 1);
+            int hst = ist;
+            unsigned hph = iph;
             auto issue = [&](int node) {
-                const unsigned gs = gstep0 + (unsigned)node;
-                const int st = (int)(gs % NS);
+                const int st = ist;
                 // the stage was last used NS steps ago: the term warps must have taken their operands from it
                 record(fs, node, 13, st);
                 tick(5);
                 // (first use of a stage: the barrier is in its initial phase, and waiting for the parity of the phase
                 // before it returns at once)
-                mbar_wait(bar_free + st, (unsigned)(((gs / NS) + 1) & 1));
+                mbar_wait(bar_free + st, iph ^ 1u);
+                ist += 2;
+                if (ist >= NS) { ist -= NS; iph ^= 1u; }
                 record(fs, node, 15, st);
                 tick(0);
                 seek(pf, pf_pos, node);
@@ -918,8 +945,10 @@ __global__ void __launch_bounds__(CTA_THREADS, MB) gsweep_kernel(const GProblem<
             for (int k = 0; k < K; k++) { pre_v0[k] = REAL(0); pre_v1[k] = REAL(0); }
             for (int node = first; node < n_steps; node += 2) {
                 const unsigned gs = gstep0 + (unsigned)node;
-                const int st = (int)(gs % NS);
-                const unsigned ph = (unsigned)((gs / NS) & 1);
+                const int st = hst;
+                const unsigned ph = hph;
+                hst += 2;
+                if (hst >= NS) { hst -= NS; hph ^= 1u; }
                 const int par = (int)(gs & 1u);     // == hid
                 StepGeo g;
                 seek(wk, wk_pos, node);
@@ -930,9 +959,9 @@ __global__ void __launch_bounds__(CTA_THREADS, MB) gsweep_kernel(const GProblem<
                 // Set `par` and its hand-over barrier were last used by step node - 2: the term warps have all passed
                 // both once they have taken their operands of that step.
                 if (node >= 2) {
-                    const unsigned g2 = gs - 2;
+                    // step gs - 2
                     record(fs, node, 14, 0);
-                    mbar_wait(bar_free + (int)(g2 % NS), (unsigned)((g2 / NS) & 1));
+                    mbar_wait(bar_free + (st >= 2 ? st - 2 : st + NS - 2), st >= 2 ? ph : ph ^ 1u);
                 }
                 tick(1);
                 tick(6);

@@ -285,12 +285,16 @@ template <int K> struct PackedBytes {
 // phys(LP) are the (+big, 0) sentinels for "no source on this side".
 // Even K gets one pad slot per K so the blocked per-lane reads are
 // bank-conflict free.
+// Only K = 2, 4, 8 are padded (there the pad index i / K is a shift).  K = 6 would need a division per access -- 24 of
+// them per update, ~100 integer instructions of the ~1100 a node step issues, measured -- to save a 2-way bank conflict
+// on the 12 blocked accesses, so it goes unpadded like the odd K.
+template <int K> __host__ __device__ constexpr bool scratch_padded() { return K % 2 == 0 && (K & (K - 1)) == 0; }
 template <int K> __device__ __forceinline__ int phys(int i)
 {
-    if constexpr (K % 2 == 0) return 1 + i + i / K;
+    if constexpr (scratch_padded<K>()) return 1 + i + i / K;
     else return 1 + i;
 }
-template <int K> __host__ __device__ constexpr int scratch_pairs() { return 2 + 32 * K + ((K % 2 == 0) ? 32 : 0); }
+template <int K> __host__ __device__ constexpr int scratch_pairs() { return 2 + 32 * K + (scratch_padded<K>() ? 32 : 0); }
 
 // ---------------------------------------------------------------- min-plus updates
 //
@@ -402,8 +406,14 @@ __device__ __forceinline__ REAL update_linear(REAL gamma, REAL alpha, REAL lambd
 #pragma unroll
     for (int k = 0; k < K; k++) {
         const int c = cn[k];
-        const Pair<REAL> lo = P[c ? phys<K>(c - 1) : 0];
-        const Pair<REAL> hi = P[phys<K>(c)];
+        Pair<REAL> lo, hi;
+        if constexpr (scratch_padded<K>()) {
+            lo = P[c ? phys<K>(c - 1) : 0];
+            hi = P[phys<K>(c)];
+        } else {        // unpadded: the sentinel in slot 0 is the element before sorted index 0
+            lo = P[c];
+            hi = P[c + 1];
+        }
         const REAL v = min(vTrunc, min(lo.a + alpha * fabs(x[k] - lo.b), hi.a + alpha * fabs(x[k] - hi.b)));
         m[k] = v;
         if ((valid >> k) & 1u) vmin = min(vmin, v);

@@ -327,6 +327,29 @@ SB_API int sb_binary_fusion_grid(int H, int W, int kernel, const double *assignm
                           double d_step, int improve, int on_device, double *labels, double *energy,
                           double *lower_bound, double *num_unlabelled, double *stats /* 4 */);
 
+/* dispmap_super.binary_fuse_until_convergence (dispmap_super.m:85-152) as ONE call over device-resident fields
+ * (SURVEY 8(f) rank 3): the reference's loop makes one MATLAB round trip per fusion (unary_cost x 2, all_pairwise_costs,
+ * rd); here the proposals and their unary costs go to the device once, every move is sb_binary_fusion_grid in
+ * device-pointer mode, a kernel adopts the accepted planes, and only the energy crosses the host per fusion.
+ *   proposals      n_proposals x (4 x N) plane fields        (proposal_cell, :91)
+ *   unaries        n_proposals x N   unary_cost of each proposal field (:66-67; per-pixel functions of the plane at
+ *                  that pixel in dispmap_ncc / dispmap_globalstereo, so the fused field's cost is a selection)
+ *   assignment     4 x N   in: the current assignment, out: the fused one
+ *   unary          N       in: unary_cost(assignment), out: that of the result
+ *   maxiter        self.maxiter (:107)
+ *   ids, n_ids     the visiting order the CALLER builds at :96-101 (1:n, then 5 maxiter randi draws, repeats removed):
+ *                  1-based proposal numbers.  The random stream stays MATLAB's own.
+ *   on_device      != 0: proposals, unaries, assignment, unary and weights are device pointers
+ *   energies       maxiter + 1 doubles: E of :104 / :128 (energies[0] = energy before the first move)
+ *   n_energies     number_of_iterations = length(E) (:151)
+ *   stats          (may be null) [0] fusion moves made, [1] push / relabel rounds, [2] solver ms, [3] pixels adopted
+ * The loop keeps the reference's bookkeeping: `iter = iter + 1` (:116) starts it at ids(2); a proposal is marked visited
+ * when a move leaves E unchanged, all marks are cleared when E changes, and it stops when every proposal is marked. */
+SB_API int sb_binary_fuse_until_convergence_grid(int H, int W, int kernel, int n_proposals, const double *proposals,
+                          const double *unaries, double *assignment, double *unary, const double *weights, double tol,
+                          double d_min, double d_step, int improve, int maxiter, const int32_t *ids, int64_t n_ids,
+                          int on_device, double *energies, int *n_energies, double *stats /* 4 */);
+
 /* ------------------------------------------- cost volume / unary / pairwise builders
  *
  * The dense arrays dispmap_super.binary_fusion / simultaneous_fusion hand to rd() / trws()
@@ -369,6 +392,22 @@ SB_API int sb_plane_disparity(int64_t M, const double *planes, const double *poi
 /* vgg_interp2(A, X, Y, 'linear', oobv) (imrender/vgg/vgg_interp2.cxx:246-322); B is n x col. */
 SB_API int sb_interp2_linear(const double *A, int h, int w, int col, const double *X, const double *Y,
                       int64_t n, double oobv, double *B);
+/* The window-matching volume of dispmap_globalstereo.segpln (dispmap_globalstereo.m:83-117): for
+ * every disparity level the photo cost ephoto(colour of images{a} at the point projected with that disparity - colour
+ * of the reference) summed over the images, box mean over the (2 window + 1)^2 window (conv2 'valid'), normalised by
+ * X(1) = ephoto(-1000 - R(1, 1, :)) * n_images, first maximum over the levels, matches scoring below min_corr (0.07 in
+ * the reference) set to disparity 0, symmetric padding back to H x W.
+ *   images   n_images x (H x W x C) doubles, images[0] the reference;  P  n_images x (3 x 4) camera matrices (column-major)
+ *   disps    D disparity levels (self.disps);  window = options.window;  col_thresh = options.col_thresh
+ *   corr     H x W: the winning disparity per pixel;  score (may be null)  (H - 2 window) x (W - 2 window): info.corr */
+SB_API int sb_segpln_wta(int H, int W, int C, int n_images, const double *images, const double *P, int D,
+                  const double *disps, int window, double col_thresh, double min_corr, double *corr, double *score);
+/* dispmap_globalstereo.preprocess, the part after the segmentation (dispmap_globalstereo.m:396-401):
+ * weights[p] = scale * (lambda_h if the two pixels of term p lie in the same segment else lambda_l), with
+ * scale = num_in / ((connect == 8) + 1), terms in dispmap_super.construct_neighborhood order.  segment: H x W uint32
+ * labels (vgg_segment_ms output, column-major).  The mean-shift segmentation itself stays the caller's. */
+SB_API int sb_smooth_weights(int H, int W, const uint32_t *segment, double lambda_h, double lambda_l, double scale,
+                      double *weights);
 /* dispmap_globalstereo.unary_cost + ephoto (dispmap_globalstereo.m:355-375,405).
  * P2 = self.P(:,:,2): the 4 x 3 transpose of the second camera matrix (:42). */
 SB_API int sb_photo_unary(int H, int W, int C, const double *im0, const double *im1, const double *P2,

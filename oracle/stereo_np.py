@@ -218,6 +218,55 @@ def photo_unary_cost(images, P2, assignment, d_min, d_step, col_thresh, interp2)
     return np.log(2.0) - np.log(np.exp((M ** 2).sum(axis=1) * (-1.0 / (col_thresh * colors))) + 1.0)
 
 
+# ----------------------------------------------------------------------------- f2 / f4
+def segpln_wta(images, P, disps, window, col_thresh, interp2, min_corr=0.07):
+    """The window-matching volume of dispmap_globalstereo.segpln (dispmap_globalstereo.m:83-117), literally: per image
+    and disparity the photo cost at the projected point, conv2(filt, filt', ., 'valid') with the 1 x (2 w + 1) average
+    filter, normalisation by X(1), first maximum over the levels, score < 0.07 -> 0, symmetric padding.
+    ``P``: 3 x 4 x n camera matrices; returns (corr H x W, volume (H-2w) x (W-2w) x D of normalised scores)."""
+    ims = [np.asarray(im, dtype=np.float64) for im in images]
+    ims = [im[:, :, None] if im.ndim == 2 else im for im in ims]
+    H, W, C = ims[0].shape
+    P = np.asarray(P, dtype=np.float64).reshape(3, 4, -1)
+    disps = np.asarray(disps, dtype=np.float64).reshape(-1)
+    w = int(window)
+    Rvec = ims[0].transpose(1, 0, 2).reshape(H * W, C)                     # reshape(double(R), [], sz(3)) (:74)
+    pts = get_points(H, W)
+    WC = np.stack([pts[0], pts[1], np.ones(H * W)], axis=1)                # :75-78
+
+    def ephoto(F):
+        return np.log(2.0) - np.log(np.exp((F ** 2).sum(axis=1) * (-1.0 / (col_thresh * C))) + 1.0)
+
+    f = 1.0 / (2 * w + 1)
+    corr = np.zeros((H - 2 * w, W - 2 * w, disps.size))
+    for a in range(len(ims)):
+        X = WC @ P[:, :3, a].T                                             # :89
+        P_ = P[:, 3, a]
+        for b, dv in enumerate(disps):
+            d = dv * P_                                                    # :95
+            Z = 1.0 / (X[:, 2] + d[2])
+            Y = interp2(ims[a], (X[:, 0] + d[0]) * Z, (X[:, 1] + d[1]) * Z, -1000.0)
+            Y = ephoto(Y - Rvec).reshape(W, H).T                           # reshape(Y, sz(1:2)) (:104)
+            hb = sum(Y[:, k:k + W - 2 * w] * f for k in range(2 * w + 1))
+            vb = sum(hb[k:k + H - 2 * w, :] * f for k in range(2 * w + 1))
+            corr[:, :, b] += vb
+    X1 = ephoto((-1000.0 - Rvec)[:1])[0] * len(ims)                        # :110
+    vol = (X1 - corr) / X1
+    idx = vol.argmax(axis=2)                                               # first maximum, like max(., [], 3)
+    best = np.take_along_axis(vol, idx[:, :, None], axis=2)[:, :, 0]
+    out = disps[idx]
+    out[best < min_corr] = 0
+    return np.pad(out, w, mode="symmetric"), vol
+
+
+def smooth_weights(H, W, segment, lambda_h, lambda_l, scale):
+    """dispmap_globalstereo.m:396-400."""
+    ind1, ind2 = construct_neighborhood(H, W)
+    seg = np.asarray(segment).reshape(-1, order="F")
+    same = seg[ind1 - 1] == seg[ind2 - 1]
+    return (same * lambda_h + (~same) * lambda_l) * scale
+
+
 # ----------------------------------------------------------------------------- a6 / a7
 def pairwise_cost(kernel, weights, tol, p, q):
     """dispmap_super.m:226-235."""

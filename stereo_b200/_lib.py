@@ -104,6 +104,11 @@ def lib():
         L.sb_rd_solve.argtypes = [c_int64, c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _up, c_int, _dp, _dp, _dp, _dp]
         L.sb_binary_fusion_grid.argtypes = [ip, ip, ip, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                             ctypes.c_void_p, dbl, dbl, dbl, ip, ip, ctypes.c_void_p, _dp, _dp, _dp, _dp]
+        L.sb_binary_fuse_until_convergence_grid.argtypes = [ip, ip, ip, ip, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                            ctypes.c_void_p, ctypes.c_void_p, dbl, dbl, dbl, ip, ip,
+                                                            POINTER(ctypes.c_int32), i64, ip, _dp, POINTER(c_int), _dp]
+        L.sb_segpln_wta.argtypes = [ip, ip, ip, ip, _dp, _dp, ip, _dp, ip, dbl, dbl, _dp, _dp]
+        L.sb_smooth_weights.argtypes = [ip, ip, POINTER(ctypes.c_uint32), dbl, dbl, dbl, _dp]
         L.sb_ncc_volume.argtypes = [ip, ip, ip, _dp, _dp, ip, _dp, ip, _dp]
         L.sb_ncc_vol_create.argtypes = [ip, ip, ip, _dp, _dp, ip, _dp, ip, POINTER(vp)]
         L.sb_ncc_vol_get.argtypes = [vp, _dp]

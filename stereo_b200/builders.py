@@ -137,6 +137,43 @@ def photo_unary(im0, im1, P2, planes, d_min, d_step, col_thresh):
     return out
 
 
+def segpln_wta(images, P, disps, window, col_thresh, min_corr=0.07, return_score=False):
+    """The window-matching volume of dispmap_globalstereo.segpln (dispmap_globalstereo.m:83-117): winner-takes-all
+    disparity per pixel (H x W; 0 where the best match scores below ``min_corr``).  images: list of H x W x C arrays,
+    images[0] the reference; P: 3 x 4 x n camera matrices (the constructor's argument); disps: self.disps."""
+    ims = [_f(np.asarray(im, dtype=np.float64)) for im in images]
+    if ims[0].ndim == 2:
+        ims = [im[:, :, None] for im in ims]
+    H, W, C = ims[0].shape
+    n = len(ims)
+    stack = np.ascontiguousarray(np.stack([im.reshape(-1, order="F") for im in ims]))       # n x (H W C), MATLAB order
+    P = np.asarray(P, dtype=np.float64)
+    if P.ndim == 2:
+        P = P[:, :, None]
+    assert P.shape == (3, 4, n)
+    Pm = np.ascontiguousarray(np.stack([P[:, :, a].reshape(-1, order="F") for a in range(n)]))
+    disps = np.ascontiguousarray(np.asarray(disps, dtype=np.float64).reshape(-1))
+    corr = np.zeros((H, W), dtype=np.float64, order="F")
+    score = np.zeros((H - 2 * window, W - 2 * window), dtype=np.float64, order="F")
+    check(lib().sb_segpln_wta(H, W, C, n, _p(stack), _p(Pm), disps.size, _p(disps), int(window), float(col_thresh),
+                              float(min_corr), _p(corr), _p(score)))
+    return (corr, score) if return_score else corr
+
+
+def smooth_weights(segment, lambda_h, lambda_l, scale=1.0):
+    """The smoothness weights of dispmap_globalstereo.preprocess (dispmap_globalstereo.m:396-401) from a segment label
+    image (H x W integers): scale * lambda_h inside a segment, scale * lambda_l across a boundary, E values in
+    construct_neighborhood order."""
+    seg = np.asfortranarray(np.asarray(segment).astype(np.uint32))
+    H, W = seg.shape
+    E = 2 * ((H - 1) * W + H * (W - 1))
+    out = np.zeros(E, dtype=np.float64)
+    if E:
+        check(lib().sb_smooth_weights(H, W, seg.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), float(lambda_h), float(lambda_l),
+                                      float(scale), _p(out)))
+    return out
+
+
 def pairwise_tables(H, W, kernel, assignment, proposal, weights, tol, d_min=0.0, d_step=1.0):
     """dispmap_super.all_pairwise_costs (dispmap_super.m:236-262) -> E00, E01, E10, E11
     (E00 only when proposal is None)."""

@@ -311,6 +311,109 @@ __global__ void photo_unary_kernel(const double *__restrict__ im0, const double 
     U[u] = log(2.0) - log(exp(acc * (-1.0 / (col_thresh * C))) + 1.0);
 }
 
+// ---- dispmap_globalstereo.segpln, the window-matching volume (dispmap_globalstereo.m:83-115) ----------------------
+// One disparity level at a time: photo cost of every pixel summed over the images (:86-103), separable box mean over
+// the (2 w + 1)^2 window ('valid', :104), normalisation (:110-111) and the running first-maximum (:114).
+// Pm = n_images x (3 x 4) camera matrices, column-major (the user's P(:, :, a)).
+__global__ void wta_cost_kernel(const double *__restrict__ images, int H, int W, int C, int n_images,
+                                const double *__restrict__ Pm, double disp, double col_thresh, double *__restrict__ cost)
+{
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long N = (long long)H * W;
+    if (u >= N) return;
+    const int r = (int)(u % H), c = (int)(u / H);
+    const double x = (double)(c + 1), y = (double)(r + 1);
+    const double *R = images;       // images{1} is the reference (dispmap_globalstereo.m:39-41)
+    double total = 0;
+    for (int a = 0; a < n_images; a++) {
+        const double *P = Pm + 12 * a;
+        double X[3];
+        for (int k = 0; k < 3; k++) X[k] = (x * P[k] + y * P[k + 3]) + P[k + 6];          // WC * P(:, 1:3, a)' (:89)
+        const double d1 = disp * P[9], d2 = disp * P[10], d3 = disp * P[11];               // :95
+        const double Z = 1.0 / (X[2] + d3);                                                 // :96
+        const double sx = (X[0] + d1) * Z, sy = (X[1] + d2) * Z;
+        const double *im = images + (size_t)a * N * C;
+        double acc = 0;
+        for (int j0 = 0; j0 < C; j0 += 4) {
+            const int cj = min(4, C - j0);
+            double m[4];
+            interp2_point(im + (size_t)j0 * N, H, W, cj, sx, sy, -1000.0, m);               // :99
+            for (int j = 0; j < cj; j++) {
+                const double dlt = m[j] - R[(size_t)(j0 + j) * N + u];
+                acc += dlt * dlt;
+            }
+        }
+        total += log(2.0) - log(exp(acc * (-1.0 / (col_thresh * C))) + 1.0);                // ephoto (:405)
+    }
+    cost[u] = total;
+}
+// horizontal pass of conv2(filt, filt', ., 'valid'): out is H x (W - 2 w)
+__global__ void wta_hbox_kernel(const double *__restrict__ cost, int H, int W, int w, double *__restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int Wi = W - 2 * w;
+    if (i >= (long long)H * Wi) return;
+    const int r = (int)(i % H), c = (int)(i / H);
+    const double f = 1.0 / (double)(2 * w + 1);
+    double s = 0;
+    for (int dc = 0; dc <= 2 * w; dc++) s += cost[(size_t)(c + dc) * H + r] * f;
+    out[i] = s;
+}
+// vertical pass + normalisation + running maximum; best / best_idx are (H - 2 w) x (W - 2 w)
+__global__ void wta_vbox_max_kernel(const double *__restrict__ hb, int H, int W, int w, double X1, int level,
+                                    double *__restrict__ best, int *__restrict__ best_idx)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int Hi = H - 2 * w, Wi = W - 2 * w;
+    if (i >= (long long)Hi * Wi) return;
+    const int r = (int)(i % Hi), c = (int)(i / Hi);
+    const double f = 1.0 / (double)(2 * w + 1);
+    double s = 0;
+    for (int dr = 0; dr <= 2 * w; dr++) s += hb[(size_t)c * H + r + dr] * f;
+    const double v = (X1 - s) / X1;                         // :111
+    if (level == 0 || v > best[i]) {                        // max(., [], 3): the first maximum (:114)
+        best[i] = v;
+        best_idx[i] = level;
+    }
+}
+// corr = disps(idx); corr(score < min_corr) = 0; padarray(corr, [w w], 'symmetric') (:115-117)
+__global__ void wta_finish_kernel(const double *__restrict__ best, const int *__restrict__ best_idx,
+                                  const double *__restrict__ disps, int H, int W, int w, double min_corr, double *__restrict__ out)
+{
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= (long long)H * W) return;
+    const int Hi = H - 2 * w, Wi = W - 2 * w;
+    int r = (int)(u % H) - w, c = (int)(u / H) - w;
+    if (r < 0) r = -r - 1;
+    if (r >= Hi) r = 2 * Hi - 1 - r;
+    if (c < 0) c = -c - 1;
+    if (c >= Wi) c = 2 * Wi - 1 - c;
+    const size_t i = (size_t)c * Hi + r;
+    out[u] = best[i] < min_corr ? 0.0 : disps[best_idx[i]];
+}
+
+// dispmap_globalstereo.preprocess, the smoothness weights (dispmap_globalstereo.m:398-401): lambda_h on the terms whose
+// two pixels share a segment, lambda_l on those that cross a segment boundary, both scaled by num_in / (connect == 8 + 1).
+__global__ void smooth_weights_kernel(const unsigned *__restrict__ segment, int H, int W, long long E, double w_same,
+                                      double w_cross, double *__restrict__ out)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= E) return;
+    long long i1, i2;
+    {
+        const long long nV = (long long)(H - 1) * W, nH = (long long)H * (W - 1);
+        if (p < 2 * nV) {
+            const long long k = p < nV ? p : p - nV;
+            const long long c = k / (H - 1), r = k % (H - 1);
+            i1 = r + (long long)H * c; i2 = i1 + 1;
+        } else {
+            const long long k0 = p - 2 * nV;
+            i1 = k0 < nH ? k0 : k0 - nH; i2 = i1 + H;
+        }
+    }
+    out[p] = segment[i1] == segment[i2] ? w_same : w_cross;
+}
+
 // Geometry of pairwise term p of the dispmap_super grid: tail / head node (0-based) and the
 // point of the head (dispmap_super.m:279-302 order).
 __device__ __forceinline__ void term_nodes(long long p, int H, int W, long long &i1, long long &i2)
@@ -667,6 +770,57 @@ int sb_interp2_linear(const double *A, int h, int w, int col, const double *X, c
     });
 }
 
+int sb_segpln_wta(int H, int W, int C, int n_images, const double *images, const double *P, int D, const double *disps,
+                  int window, double col_thresh, double min_corr, double *corr, double *score)
+{
+    return guarded([&] {
+        SB_REQUIRE(H >= 1 && W >= 1 && C >= 1 && n_images >= 1 && D >= 1 && images && P && disps && corr, SB_EINVAL,
+                   "sb_segpln_wta: bad arguments");
+        SB_REQUIRE(window >= 0 && 3 * window < H && 3 * window < W, SB_EINVAL,
+                   "sb_segpln_wta: window %d does not fit a %d x %d image (symmetric padding needs H, W > 3 window)", window, H, W);
+        require_device();
+        const long long N = (long long)H * W;
+        const int Hi = H - 2 * window, Wi = W - 2 * window;
+        DevBuf<double> im, dP, dd, cost((size_t)N), hb((size_t)H * Wi), best((size_t)Hi * Wi), out((size_t)N);
+        DevBuf<int> bidx((size_t)Hi * Wi);
+        upload(im, images, (size_t)n_images * N * C);
+        upload(dP, P, (size_t)12 * n_images);
+        upload(dd, disps, (size_t)D);
+        // X = ephoto(-1000 - Rvec) * numel(images); only X(1), the value at pixel (1, 1), is used (:110-111)
+        double acc = 0;
+        for (int j = 0; j < C; j++) { const double v = -1000.0 - images[(size_t)j * N]; acc += v * v; }
+        const double X1 = (std::log(2.0) - std::log(std::exp(acc * (-1.0 / (col_thresh * C))) + 1.0)) * n_images;
+        for (int b = 0; b < D; b++) {
+            wta_cost_kernel<<<blocks_for(N), 256>>>(im.p, H, W, C, n_images, dP.p, disps[b], col_thresh, cost.p);
+            wta_hbox_kernel<<<blocks_for((long long)H * Wi), 256>>>(cost.p, H, W, window, hb.p);
+            wta_vbox_max_kernel<<<blocks_for((long long)Hi * Wi), 256>>>(hb.p, H, W, window, X1, b, best.p, bidx.p);
+        }
+        wta_finish_kernel<<<blocks_for(N), 256>>>(best.p, bidx.p, dd.p, H, W, window, min_corr, out.p);
+        SB_CUDA(cudaGetLastError());
+        count_launch(3 * D + 1);
+        SB_CUDA(cudaMemcpy(corr, out.p, (size_t)N * 8, cudaMemcpyDeviceToHost));
+        if (score) SB_CUDA(cudaMemcpy(score, best.p, (size_t)Hi * Wi * 8, cudaMemcpyDeviceToHost));
+    });
+}
+
+int sb_smooth_weights(int H, int W, const uint32_t *segment, double lambda_h, double lambda_l, double scale, double *weights)
+{
+    return guarded([&] {
+        SB_REQUIRE(H >= 1 && W >= 1 && segment && weights, SB_EINVAL, "sb_smooth_weights: bad arguments");
+        require_device();
+        const long long N = (long long)H * W, E = 2 * ((long long)(H - 1) * W + (long long)H * (W - 1));
+        if (E == 0) return;
+        DevBuf<unsigned> seg((size_t)N);
+        DevBuf<double> o((size_t)E);
+        SB_CUDA(cudaMemcpyAsync(seg.p, segment, (size_t)N * 4, cudaMemcpyHostToDevice, 0));
+        // EW = EW * lambda_h + ~EW * lambda_l; EW = EW * (num_in / ((connect == 8) + 1))  (:399-400)
+        smooth_weights_kernel<<<blocks_for(E), 256>>>(seg.p, H, W, E, lambda_h * scale, lambda_l * scale, o.p);
+        SB_CUDA(cudaGetLastError());
+        count_launch();
+        SB_CUDA(cudaMemcpy(weights, o.p, (size_t)E * 8, cudaMemcpyDeviceToHost));
+    });
+}
+
 int sb_photo_unary(int H, int W, int C, const double *im0, const double *im1, const double *P2, const double *planes,
                    double d_min, double d_step, double col_thresh, double *U)
 {
@@ -705,6 +859,23 @@ void launch_pairwise_tables(int H, int W, int kernel, const double *cur, const d
     pairwise_tables_kernel<<<blocks_for(E), 256>>>(H, W, kernel, cur, prop, weights, tol, d_min, d_step, E, E00, E01, E10, E11);
     SB_CUDA(cudaGetLastError());
     count_launch();
+}
+// dispmap_super.update_energy (dispmap_super.m:263-274) on device-resident fields: sum of the unary costs plus the sum of the
+// (current, current) pairwise table.  Fixed partial sums added on the host: the same fields give the same bits.
+double device_energy(int H, int W, int kernel, const double *d_unary, const double *d_assignment, const double *d_weights,
+                     double tol, double d_min, double d_step)
+{
+    const long long N = (long long)H * W, E = 2 * ((long long)(H - 1) * W + (long long)H * (W - 1));
+    double e = dm::device_sum(d_unary, N);
+    if (E > 0) {
+        DevBuf<double> o((size_t)E);
+        pairwise_tables_kernel<<<blocks_for(E), 256>>>(H, W, kernel, d_assignment, nullptr, d_weights, tol, d_min, d_step, E, o.p,
+                                                       nullptr, nullptr, nullptr);
+        SB_CUDA(cudaGetLastError());
+        count_launch();
+        e += dm::device_sum(o.p, E);
+    }
+    return e;
 }
 } // namespace sb
 
@@ -765,19 +936,11 @@ int sb_energy(int H, int W, int kernel, const double *unary, const double *assig
         SB_REQUIRE(kernel == 1 || kernel == 2, SB_EINVAL, "Unkown kernel type");
         require_device();
         const long long N = (long long)H * W, E = 2 * ((long long)(H - 1) * W + (long long)H * (W - 1));
-        DevBuf<double> un, cur, wt, o((size_t)std::max<long long>(E, 1));
+        DevBuf<double> un, cur, wt;
         upload(un, unary, (size_t)N);
         upload(cur, assignment, (size_t)N * 4);
-        double e = device_sum(un.p, N);
-        if (E > 0) {
-            upload(wt, weights, (size_t)E);
-            pairwise_tables_kernel<<<blocks_for(E), 256>>>(H, W, kernel, cur.p, nullptr, wt.p, tol, d_min, d_step, E, o.p,
-                                                           nullptr, nullptr, nullptr);
-            SB_CUDA(cudaGetLastError());
-            count_launch();
-            e += device_sum(o.p, E);
-        }
-        *energy = e;
+        if (E > 0) upload(wt, weights, (size_t)E);
+        *energy = device_energy(H, W, kernel, un.p, cur.p, wt.p, tol, d_min, d_step);
     });
 }
 

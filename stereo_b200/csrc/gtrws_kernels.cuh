@@ -806,9 +806,11 @@ __global__ void __launch_bounds__(CTA_THREADS, MB) gsweep_kernel(const GProblem<
                     }
                     if (do_send) {
                         REAL vmin;
-                        if constexpr (KERN == 1)
-                            vmin = trws::update_linear<REAL, K>(gamma, alpha, p.lambda, valid, lane, Di, m, s, rk, x, cn, P);
-                        else
+                        if constexpr (KERN == 1) {
+                            // (L == 32 K, the usual case: the copy of the update without the label-validity tests)
+                            if (p.L == LP) vmin = trws::update_linear<REAL, K, true>(gamma, alpha, p.lambda, valid, lane, Di, m, s, rk, x, cn, P);
+                            else vmin = trws::update_linear<REAL, K, false>(gamma, alpha, p.lambda, valid, lane, Di, m, s, rk, x, cn, P);
+                        } else
                             vmin = trws::update_quadratic<REAL, K>(gamma, alpha, p.lambda, valid, p.L, lane, Di, m, s, rk, x, cn, P);
                         if (PASS == PASS_BWD) acc_lb += (double)vmin;
                         if (prof_on) { tclk += (long long)(m[0] != m[0]); tick(4); }

@@ -308,7 +308,8 @@ template <int K> __host__ __device__ constexpr int scratch_pairs() { return 2 + 
 // h_j - h_k == alpha (q_k - q_j), where the reference drops cone k and returns values above the exact
 // minimum (include/stereo_b200.h, sb_trws_update_message; tests/test_update_message_gpu.py).
 // `valid`: bit k set iff this lane's k-th label is a real label (< L); the caller owns the lane <-> label map.
-template <typename REAL, int K>
+// FULL: every label slot of the warp is a real label (L == 32 K): the `valid` tests fold away.
+template <typename REAL, int K, bool FULL = false>
 __device__ __forceinline__ REAL update_linear(REAL gamma, REAL alpha, REAL lambda, unsigned valid, int lane,
                                               const REAL (&Di)[K], REAL (&m)[K], const REAL (&s)[K],
                                               const uint8_t (&rk)[K], const REAL (&x)[K],
@@ -319,7 +320,7 @@ __device__ __forceinline__ REAL update_linear(REAL gamma, REAL alpha, REAL lambd
     REAL hmin = BIG;
 #pragma unroll
     for (int k = 0; k < K; k++) {
-        h[k] = ((valid >> k) & 1u) ? gamma * Di[k] - m[k] : BIG;
+        h[k] = (FULL || ((valid >> k) & 1u)) ? gamma * Di[k] - m[k] : BIG;
         hmin = min(hmin, h[k]);
     }
     hmin = warp_min(hmin);
@@ -416,7 +417,7 @@ __device__ __forceinline__ REAL update_linear(REAL gamma, REAL alpha, REAL lambd
         }
         const REAL v = min(vTrunc, min(lo.a + alpha * fabs(x[k] - lo.b), hi.a + alpha * fabs(x[k] - hi.b)));
         m[k] = v;
-        if ((valid >> k) & 1u) vmin = min(vmin, v);
+        if (FULL || ((valid >> k) & 1u)) vmin = min(vmin, v);
     }
     vmin = warp_min(vmin);
 #pragma unroll

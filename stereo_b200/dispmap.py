@@ -10,7 +10,7 @@ import numpy as np
 
 from . import builders
 from .grid import construct_neighborhood, get_points
-from .solvers import binary_fusion_grid, rd, trws
+from .solvers import binary_fuse_until_convergence_grid, binary_fusion_grid, rd, trws
 
 
 class dispmap_super:
@@ -25,6 +25,8 @@ class dispmap_super:
         self._max_relgap = 1e-4          # :10
         self._improve = False            # :13
         self.grid_native = True          # binary_fusion through sb_binary_fusion_grid (tables built on the device)
+        self.device_loop = True          # binary_fuse_until_convergence as one call (fields stay on the device)
+        self.fusion_energies = None
         self.last_fusion_stats = None
         self._assignment = None
         self.stored_energy = np.inf
@@ -107,6 +109,20 @@ class dispmap_super:
         keep = np.ones(ids.size, dtype=bool)
         keep[:-1][np.diff(ids) == 0] = False   # ids([diff(ids) == 0]) = 0; removed
         ids = ids[keep]
+        if self.grid_native and self.device_loop:
+            # the whole loop as one call on device-resident fields (sb_binary_fuse_until_convergence_grid); the visiting
+            # order stays the one drawn above
+            props = [np.asarray(p, dtype=np.float64) for p in proposal_cell]
+            for p in props:
+                if p.shape != self._assignment.shape:
+                    raise ValueError("Binary fusion: Proposals is of wrong size")
+            a, _, E, self.last_fusion_stats = binary_fuse_until_convergence_grid(
+                self.sz[0], self.sz[1], self.smoothness_kernel, props, [self.unary_cost(p) for p in props], self._assignment,
+                self.unary_cost(self._assignment), self.smooth_weights, self.tol, self.maxiter, ids, self.d_min, self.d_step,
+                dict(improve=self.improve))
+            self.assignment = a
+            self.fusion_energies = list(E)
+            return len(E)
         E = [self.energy()]
         visited = np.zeros(n, dtype=bool)
         for it in range(1, self.maxiter + 1):
@@ -125,6 +141,7 @@ class dispmap_super:
                 visited[ids[it1 - 1] - 1] = True
             if visited.all():
                 break
+        self.fusion_energies = list(E)
         return len(E)
 
     def simultaneous_fusion(self, proposal_cell):
@@ -286,18 +303,22 @@ class dispmap_globalstereo(dispmap_super):
         o = self.options
         self.improve = o.get("improve", 0) > 0
         num_in = len(self.images)
-        ind1, ind2 = self.neighborhood["ind1"], self.neighborhood["ind2"]
+        scale = num_in / ((o.get("connect", 4) == 8) + 1)
         if segment is None:
-            same = np.zeros(ind1.size, dtype=bool)
+            self.smooth_weights = np.full(self.neighborhood["ind1"].size, o["lambda_l"] * scale, dtype=np.float64)
         else:
-            seg = np.asarray(segment).reshape(-1, order="F")
-            same = seg[ind1 - 1] == seg[ind2 - 1]
-        EW = np.where(same, o["lambda_h"], o["lambda_l"]).astype(np.float64)
-        EW = EW * (num_in / ((o.get("connect", 4) == 8) + 1))
-        self.smooth_weights = EW
+            # :396-400 on the device (sb_smooth_weights)
+            self.smooth_weights = builders.smooth_weights(np.asarray(segment).reshape(self.sz), o["lambda_h"],
+                                                          o["lambda_l"], scale)
         if self._kernel == 2:
             self.smooth_weights = self.smooth_weights / self._tol
             self._tol = self._tol ** 2
+
+    def segpln_wta(self):
+        """The winner-takes-all window-matching disparity map segpln starts from (dispmap_globalstereo.m:83-117): the
+        input of its per-segment plane fits."""
+        P = np.transpose(self.P, (1, 0, 2))        # :66 (back to 3 x 4 x n)
+        return builders.segpln_wta(self.images, P, self.disps, self.options["window"], self.options["col_thresh"])
 
     def init_solution(self):
         a = np.zeros((4, self.sz[0] * self.sz[1]))

@@ -235,6 +235,32 @@ def binary_fusion_grid(H, W, kernel, assignment, proposal, U0, U1, weights, tol,
     return solution, e.value, lb.value, nu.value, dict(rounds=stats[0], relabels=stats[1], bfs_sweeps=stats[2], solve_ms=stats[3])
 
 
+def binary_fuse_until_convergence_grid(H, W, kernel, proposals, unaries, assignment, unary, weights, tol, maxiter, ids,
+                                       d_min=0.0, d_step=1.0, options=None):
+    """dispmap_super.binary_fuse_until_convergence (dispmap_super.m:85-152) as one call
+    (``sb_binary_fuse_until_convergence_grid``): proposals n x (4 x N), unaries n x N (unary_cost of each proposal),
+    assignment 4 x N and unary N (the current field and its unary cost), ids = the 1-based visiting order of :96-101.
+    Returns (assignment 4 x N, unary N, energies E, stats)."""
+    N = int(H) * int(W)
+    n = len(proposals)
+    props = np.ascontiguousarray(np.stack([np.asfortranarray(np.asarray(p, dtype=np.float64)).T for p in proposals]))  # n x N x 4
+    assert props.shape == (n, N, 4)
+    uns = np.ascontiguousarray(np.asarray(unaries, dtype=np.float64).reshape(n, N))
+    cur = np.ascontiguousarray(np.asarray(assignment, dtype=np.float64).T)        # N x 4 == MATLAB 4 x N memory
+    ucur = np.ascontiguousarray(np.asarray(unary, dtype=np.float64).reshape(N))
+    wt = _f(np.asarray(weights).reshape(-1))
+    ids = np.ascontiguousarray(np.asarray(ids, dtype=np.int32))
+    energies = np.zeros(int(maxiter) + 1, dtype=np.float64)
+    ne = ctypes.c_int(0)
+    stats = (c_double * 4)()
+    vp = ctypes.c_void_p
+    check(lib().sb_binary_fuse_until_convergence_grid(
+        int(H), int(W), int(kernel), n, vp(props.ctypes.data), vp(uns.ctypes.data), vp(cur.ctypes.data), vp(ucur.ctypes.data),
+        vp(wt.ctypes.data), float(tol), float(d_min), float(d_step), int(bool(_opt(options, "improve", False))), int(maxiter),
+        ids.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), int(ids.size), 0, energies.ctypes.data_as(_dp), ctypes.byref(ne), stats))
+    return cur.T.copy(), ucur, energies[:ne.value].copy(), dict(fusions=stats[0], rounds=stats[1], solve_ms=stats[2], adopted=stats[3])
+
+
 def trws_grid_ordering(H, W):
     """m_ordering of SetAutomaticOrdering (ordering.cpp:7-157) on the H x W grid, as (H, W) int32."""
     out = np.zeros(H * W, dtype=np.int32)

@@ -160,6 +160,115 @@ def test_dispmap_ncc_class_end_to_end():
     assert dm.current_dispmap().shape == (H, W)
 
 
+@pytest.mark.parametrize("n_images,window", [(2, 2), (3, 1), (2, 0)])
+def test_segpln_wta_volume(n_images, window):
+    """dispmap_globalstereo.segpln, the window-matching WTA disparity (dispmap_globalstereo.m:83-117), against the NumPy
+    restatement (the gather through the compiled vgg_interp2 where it is built): same disparity wherever the best level
+    wins by more than rounding, same scores; and the disparity found is the true one of the synthetic pair."""
+    from oracle import oracle
+    H, W = 36, 52
+    im0, im1, dtrue = synth.stereo_pair(H, W, 8, seed=11)
+    images = [im0, im1] + ([im1[:, ::-1].copy()] if n_images == 3 else [])
+    P = np.zeros((3, 4, n_images))
+    for a in range(n_images):
+        P[:, :3, a] = np.eye(3)
+    P[0, 3, 1] = -0.25                                   # example_global.m:17-18: 4 disparity units per pixel
+    if n_images == 3:
+        P[0, 3, 2] = 0.125
+    disps = np.arange(40.0, -1.0, -1.0)                  # descending, like self.disps (:48)
+    corr, score = builders.segpln_wta(images, P, disps, window, 30.0, return_score=True)
+
+    def interp(A, X, Y, oobv):
+        kind = "reference" if oracle.have_ref("interp2") else "port"
+        return oracle.interp2_linear(A, X, Y, oobv, kind=kind)
+    ref, vol = _np().segpln_wta(images, P, disps, window, 30.0, interp)
+    assert corr.shape == (H, W) and score.shape == vol.shape[:2]
+    assert np.allclose(score, vol.max(axis=2), rtol=1e-12, atol=1e-13)
+    top2 = np.sort(vol, axis=2)[:, :, -2:]
+    clear = np.pad((top2[:, :, 1] - top2[:, :, 0]) > 1e-9, window, mode="symmetric")
+    near_thresh = np.pad(np.abs(vol.max(axis=2) - 0.07) < 1e-9, window, mode="symmetric")
+    ok = clear & ~near_thresh
+    assert ok.mean() > 0.6
+    assert np.array_equal(corr[ok], ref[ok])
+    if n_images == 2 and window == 2:
+        # the pair is im1(r, c - d) = im0(r, c): with 4 units per pixel the winning level is about 4 d away from the borders
+        inner = (slice(6, H - 6), slice(14, W - 6))
+        found = corr[inner] > 0
+        assert found.mean() > 0.4
+        assert np.median(np.abs(corr[inner][found] / 4.0 - dtrue[inner][found])) <= 1.0
+
+
+def test_smooth_weights_from_segments():
+    """dispmap_globalstereo.preprocess (:396-401): lambda_h inside a segment, lambda_l across, scaled by the image count."""
+    H, W = 13, 17
+    rng = np.random.default_rng(2)
+    seg = (rng.integers(0, 3, size=(H, W)) + 7).astype(np.uint32)
+    got = builders.smooth_weights(seg, 5.0, 0.5, 2.0)
+    assert np.array_equal(got, _np().smooth_weights(H, W, seg, 5.0, 0.5, 2.0))
+    opts = dict(smoothness_kernel=1, disp_thresh=0.02, lambda_h=5.0, lambda_l=0.5, col_thresh=30.0, improve=0, window=1)
+    im0, im1, _ = synth.stereo_pair(H, W, 3, seed=1)
+    P = np.zeros((3, 4, 2))
+    P[:, :3, 0] = np.eye(3)
+    P[:, :3, 1] = np.eye(3)
+    P[0, 3, 1] = -0.25
+    dm = sb.dispmap_globalstereo([im0, im1], P, [0, 3], 4, opts, segment=seg, rng=np.random.default_rng(0))
+    assert np.array_equal(dm.smooth_weights, got)
+    w = dm.segpln_wta()
+    assert w.shape == (H, W) and set(np.unique(w)).issubset(set(dm.disps) | {0.0})
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_binary_fuse_until_convergence_device_loop(kernel):
+    """dispmap_super.binary_fuse_until_convergence (dispmap_super.m:85-152): the one-call loop over device-resident
+    fields (sb_binary_fuse_until_convergence_grid) follows the per-fusion loop of the class -- same visiting order, same
+    energies after every move, same final assignment -- including the reference's bookkeeping (starts at ids(2), stops
+    when every proposal has been tried without a change of E)."""
+    H, W = 30, 44
+    im0, im1, _ = synth.stereo_pair(H, W, 9, seed=5)
+    props = []
+    for i, d in enumerate((0.0, 2.0, 4.0, 6.0, 8.0)):
+        p = np.zeros((4, H * W))
+        p[0] = 0.01 * (i - 2)          # slanted planes: a x + b y + c d + d0 = 0
+        p[2] = 1
+        p[3] = -d - p[0] * W / 2
+        props.append(p)
+    runs = []
+    for device_loop in (False, True):
+        dm = sb.dispmap_ncc([im0, im1], np.arange(0, 10, dtype=np.float64), kernel, 40.0, 8.0 if kernel == 1 else 3.0)
+        dm.maxiter = 12
+        dm.device_loop = device_loop
+        n = dm.binary_fuse_until_convergence(props, rng=np.random.default_rng(3))
+        assert n == len(dm.fusion_energies)
+        runs.append((n, np.array(dm.fusion_energies), dm.assignment.copy(), dm.energy()))
+    (n0, e0, a0, f0), (n1, e1, a1, f1) = runs
+    assert n0 == n1 and n0 >= 3
+    assert np.allclose(e0, e1, rtol=1e-12, atol=0)
+    assert np.array_equal(a0, a1) and abs(f0 - f1) <= 1e-12 * abs(f0)
+    assert all(e1[i + 1] <= e1[i] * (1 + 1e-12) for i in range(len(e1) - 1)) and e1[-1] < e1[0]
+
+
+def test_binary_fuse_until_convergence_stops_when_all_visited():
+    """Proposals equal to the current assignment change nothing: every proposal is marked after one try and the loop
+    ends (dispmap_super.m:136-150) -- ids(1) is skipped by the reference's `iter = iter + 1`, so with n proposals the
+    1:n prefix leaves proposal 1 for the random tail."""
+    H, W = 12, 15
+    N = H * W
+    rng = np.random.default_rng(0)
+    cur = np.zeros((4, N))
+    cur[2] = 1
+    cur[3] = -3.0
+    un = rng.random(N)
+    w = np.ones(2 * ((H - 1) * W + H * (W - 1)))
+    ids = np.array([1, 2, 3, 2, 1, 3, 1], dtype=np.int32)
+    a, u, E, st = sb.binary_fuse_until_convergence_grid(H, W, 1, [cur, cur, cur], [un, un, un], cur, un, w, 0.5, 20, ids)
+    # visits ids(2)=2, ids(3)=3, ids(4)=2 (already marked: skipped), ids(5)=1 -> all marked
+    assert st["fusions"] == 3
+    assert len(E) == 4 and np.all(E == E[0])
+    assert np.array_equal(a, cur) and np.array_equal(u, un)
+    with pytest.raises(Exception):
+        sb.binary_fuse_until_convergence_grid(H, W, 1, [cur], [un], cur, un, w, 0.5, 5, np.array([1, 2], dtype=np.int32))
+
+
 def _teddy():
     g = golden("teddy.npz")
     return g["im2"].astype(np.float64), g["im6"].astype(np.float64)

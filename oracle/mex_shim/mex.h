@@ -166,6 +166,24 @@ static inline void mxDestroyArray(mxArray *a)
     free(a);
 }
 
+/* deep copy of a numeric array (mxDuplicateArray); structs are not needed by the gateways */
+static inline mxArray *mxDuplicateArray(const mxArray *src)
+{
+    mxArray *a = (mxArray *)calloc(1, sizeof(mxArray));
+    a->classid = src->classid;
+    a->ndim = src->ndim;
+    size_t n = 1;
+    for (int i = 0; i < SB_MX_MAXDIM; i++) a->dims[i] = src->dims[i];
+    for (int i = 0; i < src->ndim; i++) n *= (size_t)src->dims[i];
+    const size_t bytes = n * sb_mx_elsize(src->classid);
+    a->data = malloc(bytes ? bytes : 1);
+    if (bytes) memcpy(a->data, src->data, bytes);
+    a->owns_data = 1;
+    return a;
+}
+/* shrink the column count of a matrix in place (mxSetN keeps the allocation) */
+static inline void mxSetN(mxArray *a, mwSize n) { a->ndim = 2; a->dims[1] = n; }
+
 static inline void *mxMalloc(size_t n) { return malloc(n ? n : 1); }
 static inline void *mxCalloc(size_t n, size_t s) { return calloc(n ? n : 1, s ? s : 1); }
 static inline void mxFree(void *p) { free(p); }

@@ -38,6 +38,14 @@ classdef dispmap_globalstereo < dispmap_super
 			init_solution(self);
 		end
 	end
+	methods
+		function corr = segpln_wta(self)
+			% The winner-takes-all window-matching disparity map SegPln fits its planes to, on the GPU.
+			ims = cellfun(@double, self.images, 'UniformOutput', false);
+			corr = sb_builders_mex('segpln_wta', cat(4, ims{:}), permute(self.P(:,:,:), [2 1 3]), self.disps, ...
+				self.options.window, self.options.col_thresh, 0.07);
+		end
+	end
 	methods (Access = protected)
 		function init_solution(self)
 			a = zeros(4, prod(self.sz));
@@ -58,9 +66,8 @@ classdef dispmap_globalstereo < dispmap_super
 			self.options.planar = 0;
 			segment = vgg_segment_ms(ref, self.options.seg_params(1), self.options.seg_params(2), self.options.seg_params(3));
 			self.improve = (self.options.improve > 0);
-			same = segment(self.neighborhood.ind1) == segment(self.neighborhood.ind2);
-			EW = same(:)' * self.options.lambda_h + ~same(:)' * self.options.lambda_l;
-			EW = EW * (numel(self.images) / ((self.options.connect == 8) + 1));
+			EW = sb_builders_mex('smooth_weights', uint32(segment), self.options.lambda_h, self.options.lambda_l, ...
+				numel(self.images) / ((self.options.connect == 8) + 1));
 			self.ephoto = @(F) log(2) - log(exp(sum(F .^ 2, 2) * (-1 / (self.options.col_thresh * colors))) + 1);
 			self.smooth_weights = EW;
 			if (self.smoothness_kernel == 2)

@@ -11,6 +11,7 @@ classdef dispmap_super < handle
 		maxiter = 1000;      % TRW-S iterations / exhaustive binary fusion rounds
 		max_relgap = 1e-4;   % TRW-S relative duality gap
 		improve = false;     % run QPBO-I on unlabelled nodes
+		device_loop = true;  % binary_fuse_until_convergence as ONE library call (fields stay on the GPU between moves)
 	end
 	properties (SetAccess = protected)
 		sz;
@@ -75,6 +76,23 @@ classdef dispmap_super < handle
 			nrand = self.maxiter * 5;
 			ids = [1:np, randi([1 np], nrand, 1)'];
 			ids(diff(ids) == 0) = [];           % drop immediate repeats
+			if self.device_loop && ~show_steps
+				% the whole loop on device-resident fields; the visiting order is the one drawn above
+				N = prod(self.sz);
+				U = zeros(N, np);
+				for l = 1:np
+					if (~isequal(size(proposal_cell{l}), size(self.assignment)))
+						error('Binary fusion: Proposals is of wrong size');
+					end
+					U(:, l) = unary_cost(self, proposal_cell{l});
+				end
+				[fused, E] = sb_builders_mex('fuse_until_convergence', self.sz, self.smoothness_kernel, cat(3, proposal_cell{:}), U, ...
+					self.assignment, unary_cost(self, self.assignment), self.smooth_weights, self.tol, self.dnorm(1), self.dnorm(2), ...
+					double(self.improve), self.maxiter, int32(ids));
+				self.assignment = fused;
+				number_of_iterations = numel(E);
+				return;
+			end
 			E = energy(self);
 			stale = false(np, 1);               % proposals tried since the last improvement
 			for iter = 1:self.maxiter

@@ -9,6 +9,10 @@
 //   [E00,E01,E10,E11] = sb_builders_mex('pairwise_tables', sz, kernel, assignment, proposal, weights, tol, d_min, d_step)
 //   [q,qprim] = sb_builders_mex('fusion_positions', sz, proposals(4 x N x L), d_min, d_step)
 //   e = sb_builders_mex('energy', sz, kernel, unary, assignment, weights, tol, d_min, d_step)
+//   [corr, score] = sb_builders_mex('segpln_wta', images(H x W x C x n), P(3 x 4 x n), disps, window, col_thresh, min_corr)
+//   w = sb_builders_mex('smooth_weights', segment(H x W uint32), lambda_h, lambda_l, scale)
+//   [assignment, E, unary] = sb_builders_mex('fuse_until_convergence', sz, kernel, proposals(4 x N x n), unaries(N x n),
+//                                assignment, unary, weights, tol, d_min, d_step, improve, maxiter, ids(int32))
 // Each forwards to the entry point of the same name in include/stereo_b200.h.
 #include "sb_mex_common.h"
 
@@ -88,6 +92,43 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         plhs[0] = mxCreateDoubleScalar(0);
         sb_mex_check(sb_energy(H, W, (int)scalar(a[1]), mxGetPr(a[2]), mxGetPr(a[3]), mxGetPr(a[4]), scalar(a[5]), scalar(a[6]),
                                scalar(a[7]), mxGetPr(plhs[0])));
+    } else if (!strcmp(op, "segpln_wta")) {
+        SB_MEX_ASSERT(n == 6 && nlhs <= 2);
+        const mwSize nd = mxGetNumberOfDimensions(a[0]);
+        const mwSize *d = mxGetDimensions(a[0]);
+        const int H = (int)d[0], W = (int)d[1], C = nd >= 3 ? (int)d[2] : 1, ni = nd >= 4 ? (int)d[3] : 1;
+        SB_MEX_ASSERT(mxGetNumberOfElements(a[1]) == (size_t)12 * ni);
+        const int D = (int)mxGetNumberOfElements(a[2]), w = (int)scalar(a[3]);
+        plhs[0] = sb_mex_matrix(H, W);
+        mxArray *score = sb_mex_matrix(H - 2 * w, W - 2 * w);
+        sb_mex_check(sb_segpln_wta(H, W, C, ni, mxGetPr(a[0]), mxGetPr(a[1]), D, mxGetPr(a[2]), w, scalar(a[4]), scalar(a[5]),
+                                   mxGetPr(plhs[0]), mxGetPr(score)));
+        if (nlhs == 2) plhs[1] = score; else mxDestroyArray(score);
+    } else if (!strcmp(op, "smooth_weights")) {
+        SB_MEX_ASSERT(n == 4 && mxGetClassID(a[0]) == mxUINT32_CLASS);
+        const int H = (int)mxGetM(a[0]), W = (int)mxGetN(a[0]);
+        plhs[0] = sb_mex_matrix(1, 2 * ((mwSize)(H - 1) * W + (mwSize)H * (W - 1)));
+        sb_mex_check(sb_smooth_weights(H, W, (const uint32_t *)mxGetData(a[0]), scalar(a[1]), scalar(a[2]), scalar(a[3]),
+                                       mxGetPr(plhs[0])));
+    } else if (!strcmp(op, "fuse_until_convergence")) {
+        SB_MEX_ASSERT(n == 13 && nlhs <= 3 && mxGetClassID(a[12]) == mxINT32_CLASS);
+        const int H = (int)mxGetPr(a[0])[0], W = (int)mxGetPr(a[0])[1];
+        const size_t N = (size_t)H * W;
+        const int np = (int)(mxGetNumberOfElements(a[2]) / (4 * N));
+        SB_MEX_ASSERT(np >= 1 && mxGetNumberOfElements(a[3]) == N * np && mxGetNumberOfElements(a[4]) == 4 * N &&
+                      mxGetNumberOfElements(a[5]) == N);
+        const int maxiter = (int)scalar(a[11]);
+        plhs[0] = mxDuplicateArray(a[4]);              // the library fuses in place: work on copies of the inputs
+        mxArray *un = mxDuplicateArray(a[5]);
+        mxArray *E = sb_mex_matrix(1, (mwSize)maxiter + 1);
+        int ne = 0;
+        sb_mex_check(sb_binary_fuse_until_convergence_grid(H, W, (int)scalar(a[1]), np, mxGetPr(a[2]), mxGetPr(a[3]), mxGetPr(plhs[0]),
+                                                           mxGetPr(un), mxGetPr(a[6]), scalar(a[7]), scalar(a[8]), scalar(a[9]),
+                                                           (int)scalar(a[10]), maxiter, (const int32_t *)mxGetData(a[12]),
+                                                           (int64_t)mxGetNumberOfElements(a[12]), 0, mxGetPr(E), &ne, NULL));
+        mxSetN(E, (mwSize)ne);
+        if (nlhs >= 2) plhs[1] = E; else mxDestroyArray(E);
+        if (nlhs >= 3) plhs[2] = un; else mxDestroyArray(un);
     } else {
         mexErrMsgTxt("sb_builders_mex: unknown operation");
     }

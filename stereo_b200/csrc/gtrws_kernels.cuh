@@ -513,6 +513,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MB) gsweep_kernel(const GProblem<
     typedef StageLayout<REAL, K> SL;
     constexpr int LP = 32 * K;
     constexpr int PD = NS - 1;   // bulk copies are issued PD steps ahead
+    constexpr bool EARLY = MB == 1 && sizeof(REAL) == 4 && gsweep_min_blocks<REAL, K>() > 1;   // latency build (see take_operands)
     const int lane = threadIdx.x & 31;
     // (warp w issues from scheduler w & 3: the term warps 2, 3 of send slot 1 -- the sends to the next node of the strip,
     // i.e. the dependent chain, gtrws_plan.cpp -- have their schedulers to themselves; the helpers share with slot 0)
@@ -633,6 +634,76 @@ __global__ void __launch_bounds__(CTA_THREADS, MB) gsweep_kernel(const GProblem<
                 const REAL gamma = inv_small<REAL>(g.gamma_den);
                 const unsigned char *sp = stage_ptr(st);
                 const REAL *NF = reinterpret_cast<const REAL *>(sp + SL::OFF_NF);
+                // ---- my send term: pair in send slot `slot`, term j of it
+                const int d = dir_with_role(g.roles, ROLE_SEND0 + slot);
+                const bool vert = vertical(d);
+                const int sd = side_of(d);
+                const bool tail = (j == sd);
+                const bool to_next = (d == g.next_dir);
+                const long long pair = pair_of(g.u, d < 0 ? 0 : d, W);
+                const long long term = 2 * pair + j;
+                const int peer = d < 0 ? -1 : (int)((g.peer >> (8 * d)) & 255u) - 1;   // -1 local, 0 rank - 1, 1 rank + 1
+                REAL alpha = REAL(0);
+                if (d >= 0) alpha = __ldg(p.alpha + term);
+                // operands of the update, from the stage ring
+                REAL m[K], s[K], x[K];
+                uint8_t rk[K], cn[K];
+                auto take_operands = [&]() {
+                    const REAL *MS = reinterpret_cast<const REAL *>(sp + SL::OFF_MS) + (size_t)(slot * 2 + j) * LP;
+                    lrow_lds<REAL, K>(m, MS, lane);
+#pragma unroll
+                    for (int k = 0; k < K; k++) m[k] = Tag<REAL>::val(m[k]);
+                    REAL own_me[K], g_me[K], own_nb[K], g_nb[K];
+                    lrow_lds<REAL, K>(own_me, NF + NF_OWN * LP, lane);
+                    const REAL *nb_own, *nb_g;
+                    if (to_next) {
+                        // the receiver is the next node of the strip: its rows are (or will shortly be) in the next stage
+                        const bool wrap = st + 1 == NS;
+                        const int stn = wrap ? 0 : st + 1;
+                        record(fs, node, 4, stn);
+                        mbar_wait(bar_full + stn, ph ^ (unsigned)wrap);
+                        record(fs, node, 5, stn);
+                        const REAL *NFn = reinterpret_cast<const REAL *>(stage_ptr(stn) + SL::OFF_NF);
+                        nb_own = NFn + NF_OWN * LP;
+                        nb_g = NFn + (vert ? NF_GY : NF_GX) * LP;
+                    } else {
+                        const REAL *XN = reinterpret_cast<const REAL *>(sp + SL::OFF_XN) + (size_t)(slot * 2) * LP;
+                        nb_own = XN + (vert ? 0 : 1) * LP;
+                        nb_g = XN + (vert ? 1 : 0) * LP;
+                    }
+                    lrow_lds<REAL, K>(own_nb, nb_own, lane);
+                    const uint8_t *PB = sp + SL::OFF_PB + (size_t)slot * 3 * LP;
+                    if (tail) {
+                        // my positions: my planes at the receiver's point (qprim); receiver's: its own (q)
+                        lrow_lds<REAL, K>(g_me, NF + (vert ? NF_GY : NF_GX) * LP, lane);
+#pragma unroll
+                        for (int k = 0; k < K; k++) {
+                            s[k] = sd == 0 ? own_me[k] + g_me[k] : own_me[k] - g_me[k];
+                            x[k] = own_nb[k];
+                        }
+                        lrow_ldb<REAL, K>(rk, PB + 2 * LP, lane);
+                        lrow_ldb<REAL, K>(cn, PB + 0 * LP, lane);
+                    } else {
+                        // I am the head: my own disparities (q); receiver's planes at my point (qprim)
+                        lrow_lds<REAL, K>(g_nb, nb_g, lane);
+#pragma unroll
+                        for (int k = 0; k < K; k++) {
+                            s[k] = own_me[k];
+                            x[k] = sd == 0 ? own_nb[k] - g_nb[k] : own_nb[k] + g_nb[k];
+                        }
+                        lrow_ldb<REAL, K>(rk, sp + SL::OFF_NB, lane);
+                        lrow_ldb<REAL, K>(cn, PB + 1 * LP, lane);
+                    }
+                };
+                // Latency build: the operands do not depend on the chain (carry rows, hand-over), so they are taken
+                // BEFORE the step's waits -- the stage was filled two steps ago -- and only the node total, the update
+                // and the stores remain behind the previous node.  (The throughput build has no registers to hold them.)
+                if constexpr (EARLY) {
+                    if (d >= 0) {
+                        mbar_wait(bar_full + st, ph);
+                        take_operands();
+                    }
+                }
                 // ---- rows of this node are ready (helper), every term warp has finished the previous step
                 tick(6);
                 record(fs, node, 1, (int)g.roles);
@@ -714,67 +785,8 @@ __global__ void __launch_bounds__(CTA_THREADS, MB) gsweep_kernel(const GProblem<
                     if ((g.flags & GF_SAVE) && w == 0) save_total<REAL, K>(p.save + (size_t)g.save * LP * (sizeof(REAL) / 4), Di, lane, p.epoch);
                 }
                 if (prof_on) { tclk += (long long)(Di[0] != Di[0]); tick(2); }
-                // ---- my send term: pair in send slot `slot`, term j of it
-                const int d = dir_with_role(g.roles, ROLE_SEND0 + slot);
                 if (d >= 0) {
-                    const bool vert = vertical(d);
-                    const int sd = side_of(d);
-                    const bool tail = (j == sd);
-                    const bool to_next = (d == g.next_dir);
-                    const long long pair = pair_of(g.u, d, W);
-                    const long long term = 2 * pair + j;
-                    const int peer = (int)((g.peer >> (8 * d)) & 255u) - 1;   // -1 local, 0 rank - 1, 1 rank + 1
-                    const REAL alpha = __ldg(p.alpha + term);
-                    // operands from the stage ring
-                    REAL m[K], s[K], x[K];
-                    uint8_t rk[K], cn[K];
-                    {
-                        const REAL *MS = reinterpret_cast<const REAL *>(sp + SL::OFF_MS) + (size_t)(slot * 2 + j) * LP;
-                        lrow_lds<REAL, K>(m, MS, lane);
-#pragma unroll
-                        for (int k = 0; k < K; k++) m[k] = Tag<REAL>::val(m[k]);
-                        REAL own_me[K], g_me[K], own_nb[K], g_nb[K];
-                        lrow_lds<REAL, K>(own_me, NF + NF_OWN * LP, lane);
-                        const REAL *nb_own, *nb_g;
-                        if (to_next) {
-                            // the receiver is the next node of the strip: its rows are (or will shortly be) in the next stage
-                            const bool wrap = st + 1 == NS;
-                            const int stn = wrap ? 0 : st + 1;
-                            record(fs, node, 4, stn);
-                            mbar_wait(bar_full + stn, ph ^ (unsigned)wrap);
-                            record(fs, node, 5, stn);
-                            const REAL *NFn = reinterpret_cast<const REAL *>(stage_ptr(stn) + SL::OFF_NF);
-                            nb_own = NFn + NF_OWN * LP;
-                            nb_g = NFn + (vert ? NF_GY : NF_GX) * LP;
-                        } else {
-                            const REAL *XN = reinterpret_cast<const REAL *>(sp + SL::OFF_XN) + (size_t)(slot * 2) * LP;
-                            nb_own = XN + (vert ? 0 : 1) * LP;
-                            nb_g = XN + (vert ? 1 : 0) * LP;
-                        }
-                        lrow_lds<REAL, K>(own_nb, nb_own, lane);
-                        const uint8_t *PB = sp + SL::OFF_PB + (size_t)slot * 3 * LP;
-                        if (tail) {
-                            // my positions: my planes at the receiver's point (qprim); receiver's: its own (q)
-                            lrow_lds<REAL, K>(g_me, NF + (vert ? NF_GY : NF_GX) * LP, lane);
-#pragma unroll
-                            for (int k = 0; k < K; k++) {
-                                s[k] = sd == 0 ? own_me[k] + g_me[k] : own_me[k] - g_me[k];
-                                x[k] = own_nb[k];
-                            }
-                            lrow_ldb<REAL, K>(rk, PB + 2 * LP, lane);
-                            lrow_ldb<REAL, K>(cn, PB + 0 * LP, lane);
-                        } else {
-                            // I am the head: my own disparities (q); receiver's planes at my point (qprim)
-                            lrow_lds<REAL, K>(g_nb, nb_g, lane);
-#pragma unroll
-                            for (int k = 0; k < K; k++) {
-                                s[k] = own_me[k];
-                                x[k] = sd == 0 ? own_nb[k] - g_nb[k] : own_nb[k] + g_nb[k];
-                            }
-                            lrow_ldb<REAL, K>(rk, sp + SL::OFF_NB, lane);
-                            lrow_ldb<REAL, K>(cn, PB + 1 * LP, lane);
-                        }
-                    }
+                    if constexpr (!EARLY) take_operands();
                     // the stage of this step is no longer needed by this warp
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_free + st);

@@ -74,9 +74,10 @@ typedef struct sb_trws_options {
                              to the ranks; 1 = contiguous bands); 0 = default (1: more blocks shorten the pipeline fill but
                              add NVLink hand-overs to the critical path -- measured slower on 8 GPUs) */
     int    latency_mode;  /* grid-native entry: 0 = automatic, 1 = always, -1 = never run the LATENCY build of the sweep
-                             kernel (one strip walker per SM, registers uncapped: shorter node steps, less throughput).
-                             Automatic: banded runs whose ranks hold so few nodes that the pass ends with the DAG's
-                             critical path (nodes per SM <= 1.25 (H + W)), DESIGN.md 6 */
+                             kernel (at most two strip walkers per SM, no register spills, operands taken ahead of the
+                             dependent chain: shorter node steps, ~9 % less throughput).  Automatic: when a rank's nodes per SM
+                             are fewer than 3 (H + W) (6 (H + W) in a banded run), i.e. when the pass ends with the DAG's
+                             critical path rather than with the walkers' work, DESIGN.md 4 / 6 */
     int    reserved[4];
 } sb_trws_options;
 

@@ -502,9 +502,11 @@ template <typename REAL, int K> __host__ __device__ constexpr int gsweep_min_blo
     return K <= 4 ? 4 : K <= 6 ? 3 : 2;
 }
 
-// MB = resident CTAs per SM the registers are budgeted for: gsweep_min_blocks (throughput: as many strip walkers per SM
-// as pay) or 1 (latency: no register cap, no spills, one walker per SM -- for passes that run at the DAG's critical
-// path, i.e. the column-banded multi-GPU sweeps with few nodes per rank; gtrws_solve.cu picks)
+// MB = resident CTAs per SM the registers are budgeted for: gsweep_min_blocks (throughput build: as many strip walkers per
+// SM as pay) or at most 2 (latency build: <= 168 registers, no spills, operands taken before the step's waits -- shorter
+// node steps for passes that run at the DAG's critical path, i.e. the column-banded multi-GPU sweeps; gtrws_solve.cu picks).
+// Measured at K = 6 (1980 x 2880 x 192 / its 360-column band alone): MB 3: 38.1 / 12.1 ms per pass, MB 2 + early operands:
+// 41.5 / 11.1 ms, MB 1 + early operands: 63.1 / 12.3 ms.
 template <typename REAL, int K, int KERN, int PASS, int NS, int MB>
 __global__ void __launch_bounds__(CTA_THREADS, MB) gsweep_kernel(const GProblem<REAL> p)
 {
@@ -513,7 +515,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MB) gsweep_kernel(const GProblem<
     typedef StageLayout<REAL, K> SL;
     constexpr int LP = 32 * K;
     constexpr int PD = NS - 1;   // bulk copies are issued PD steps ahead
-    constexpr bool EARLY = MB == 1 && sizeof(REAL) == 4 && gsweep_min_blocks<REAL, K>() > 1;   // latency build (see take_operands)
+    constexpr bool EARLY = sizeof(REAL) == 4 && (MB <= 2 || K <= 2);   // where the registers hold them without spills (see take_operands)   // latency build (see take_operands)
     const int lane = threadIdx.x & 31;
     // (warp w issues from scheduler w & 3: the term warps 2, 3 of send slot 1 -- the sends to the next node of the strip,
     // i.e. the dependent chain, gtrws_plan.cpp -- have their schedulers to themselves; the helpers share with slot 0)

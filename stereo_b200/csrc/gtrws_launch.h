@@ -13,7 +13,7 @@ struct GSweepLaunch {
     int pass;            // PASS_FWD / PASS_BWD
     const void *problem; // GProblem<float> or GProblem<double>, host copy
     int grid;            // persistent CTAs (all co-resident)
-    int lat;             // 1: the latency build (one CTA per SM, registers uncapped)
+    int lat;             // 1: the latency build (at most two CTAs per SM, early operands)
     cudaStream_t stream;
 };
 

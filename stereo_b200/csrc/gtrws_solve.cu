@@ -335,7 +335,7 @@ struct Solver : SolverBase {
     void *peer_ptr[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     GProblem<REAL> P;
     int grid_fwd = 1, grid_bwd = 1;
-    int lat = 0;               // 1: latency build of the sweep (one CTA per SM, registers uncapped)
+    int lat = 0;               // 1: latency build of the sweep (at most two CTAs per SM, no spills, early operands)
     bool isolate = false;
     unsigned launch_epoch = 0, pass_counter = 0;
     Ctrl *hc = nullptr;   // pinned
@@ -413,11 +413,13 @@ struct Solver : SolverBase {
             SB_CUDA(cudaHostAlloc((void **)&rec_host, (size_t)rec_ctas * 6 * 4 * sizeof(int), cudaHostAllocMapped));
             SB_CUDA(cudaHostGetDevicePointer((void **)&P.rec, rec_host, 0));
         }
-        // Throughput or latency build?  A rank of a banded run with few nodes finishes its rows long before the DAG's
-        // critical path (the ring chain, then H + W dependent node steps) lets the pass end: there one walker per SM
-        // with uncapped registers (shorter node steps) wins, where a single GPU wants as many walkers as fit.
-        // The walkers of a latency pass have Nloc / SMs node steps each; the critical path of the rows is H + W.
-        lat = world > 1 && (double)Nloc / num_sms <= 1.25 * (double)(H + W);
+        // Throughput or latency build?  A pass cannot end before the DAG's critical path (the ring chain, then H + W
+        // dependent node steps; across ranks also the pipeline fill): when the walkers have few node steps each next
+        // to that, the build with the shorter node step wins (two walkers per SM, operands taken ahead of the chain),
+        // where a large grid on one GPU wants as many walkers as fit.  Measured on one B200 (ms per pass, throughput /
+        // latency build): 375x450x64 2.60 / 2.44, 540x960x128 5.68 / 5.48, 1980x360x192 12.2 / 11.2, 1080x1920x128
+        // 13.7 / 15.3, 1980x2880x192 38.1 / 41.5 -- the break-even is near 3 (H + W) node steps per SM.
+        lat = (double)Nloc / num_sms <= (world > 1 ? 6.0 : 3.0) * (double)(H + W);
         if (opt.latency_mode) lat = opt.latency_mode > 0;
         if (const char *e = getenv("SB_GTRWS_LAT")) lat = atoi(e) != 0;
         auto grid_for = [&](int pass) {

@@ -192,11 +192,13 @@ def test_column_bands_one_gpu(H, W, L, it, world, blocks, kernel):
 
 
 @pytest.mark.parametrize("kernel", [1, 2])
-@pytest.mark.parametrize("H,W,L,it,world", [(24, 31, 16, 5, 1), (18, 44, 64, 4, 2), (40, 64, 100, 3, 4), (21, 60, 192, 3, 3), (14, 48, 250, 2, 2)])
+@pytest.mark.parametrize("H,W,L,it,world", [(24, 31, 16, 5, 1), (18, 44, 64, 4, 1), (33, 40, 100, 3, 1), (21, 60, 192, 3, 1), (14, 48, 250, 2, 1),
+                                            (18, 44, 64, 4, 2), (40, 64, 100, 3, 4), (21, 60, 192, 3, 3), (14, 48, 250, 2, 2)])
 def test_latency_build(H, W, L, it, world, kernel):
-    """sb_trws_options.latency_mode = 1: the sweep kernel built for one strip walker per SM (registers uncapped), which
-    the banded runs pick on their own when a rank holds few nodes.  Same DAG, same arithmetic: identical labels / energy /
-    bound to the throughput build (single rank), and the banded sweep on it agrees with the single-rank sweep."""
+    """sb_trws_options.latency_mode: the sweep kernel built for at most two strip walkers per SM (no spills, operands taken
+    ahead of the dependent chain), which small grids and banded runs pick on their own, against the throughput build
+    (latency_mode = -1).  Same DAG, same arithmetic: identical labels / energy / bound on a single rank, and the banded
+    sweep on the latency build agrees with the single-rank sweep on the throughput build."""
     from stereo_b200.gridsolver import TrwsGridLocalGroup
     pr = synth.trws_problem(H, W, L, seed=3 * H + W + world, kernel=kernel)
     ref = TrwsGrid(kernel, H, W, L, pr["tol"], dict(latency_mode=-1))

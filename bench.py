@@ -593,6 +593,9 @@ def main():
                 "algorithmic_bytes_per_launch": algo_bytes / world, "avg_launch_ms": avg_kernel_ms,
                 "launches_timed": int(k_n), "peak_source": peak_src + (f" x {world} GPUs" if world > 1 else ""),
                 "kernel_share_of_step": k_ms / t_ms,
+                "kernel_build": ("latency (at most 2 strip walkers per SM, operands ahead of the chain)" if info.get("latency_build")
+                                 else "throughput (as many strip walkers per SM as fit)"),
+                "ctas": [info["ctas_fwd"], info["ctas_bwd"]],
                 "note": "64*L*N bytes per pass (SURVEY 8(d)); positions are recomputed from 3 plane rows per node, rank / "
                         "merge-count bytes add 8*L*N per pass"}
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

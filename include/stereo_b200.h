@@ -403,6 +403,18 @@ SB_API int sb_interp2_linear(const double *A, int h, int w, int col, const doubl
  *   corr     H x W: the winning disparity per pixel;  score (may be null)  (H - 2 window) x (W - 2 window): info.corr */
 SB_API int sb_segpln_wta(int H, int W, int C, int n_images, const double *images, const double *P, int D,
                   const double *disps, int window, double col_thresh, double min_corr, double *corr, double *score);
+/* dispmap_ncc.generate_new_plane_RANSAC + fit_plane_to_points (dispmap_ncc.m:48-91; SURVEY 8(f) rank 1, the
+ * dispmap_ncc producer of proposal plane fields): the plane through the points [col; row; disp(row, col)] within radius r
+ * of (x, y) -- normal = right singular vector of the smallest singular value of the centred point matrix, re-weighted
+ * 20 times by sqrt(|residual|) for kernel 1 (IRLS, :76-83), once for kernel 2 --, p(4) = -(p(1:3)' * mean), p / p(3).
+ * Computed as the eigenvector of the smallest eigenvalue of the 3 x 3 scatter matrix (fp64 block reductions, Jacobi):
+ * agrees with the SVD form to rounding (the sign of V(:, end) cancels in p / p(3)).
+ *   disp       H x W doubles (best_disp_from_ncc);  on_device != 0: `disp` and `proposal` are device pointers
+ *   plane      4 doubles [a; b; 1; d0];  proposal (may be null) 4 x N: repmat(p, [1 N]) (:65), so that a fusion loop
+ *              gets its proposal field without it ever being a host array;  n_points (may be null) points used
+ * Fewer than 3 points within the radius: SB_EINVAL. */
+SB_API int sb_plane_from_disparity(int H, int W, const double *disp, double x, double y, double r, int kernel,
+                            int on_device, double *plane, double *proposal, double *n_points);
 /* dispmap_globalstereo.preprocess, the part after the segmentation (dispmap_globalstereo.m:396-401):
  * weights[p] = scale * (lambda_h if the two pixels of term p lie in the same segment else lambda_l), with
  * scale = num_in / ((connect == 8) + 1), terms in dispmap_super.construct_neighborhood order.  segment: H x W uint32

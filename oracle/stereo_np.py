@@ -259,6 +259,34 @@ def segpln_wta(images, P, disps, window, col_thresh, interp2, min_corr=0.07):
     return np.pad(out, w, mode="symmetric"), vol
 
 
+def fit_plane_to_points(points, kernel):
+    """dispmap_ncc.fit_plane_to_points (dispmap_ncc.m:67-91), literally (SVD, 20 IRLS rounds for kernel 1)."""
+    points = np.asarray(points, dtype=np.float64)
+    c = points.mean(axis=1, keepdims=True)
+    cost = -(points - c).T
+    p = np.zeros(4)
+    if kernel == 1:
+        w = np.ones(cost.shape[0])
+        for _ in range(20):
+            V = np.linalg.svd(w[:, None] * cost, full_matrices=False)[2].T
+            p[:3] = V[:, -1]
+            w = np.sqrt(np.abs(cost @ V[:, -1]))
+    else:
+        V = np.linalg.svd(cost, full_matrices=False)[2].T
+        p[:3] = V[:, -1]
+    p[3] = -(p[:3] @ points[:3].mean(axis=1))
+    return p / p[2]
+
+
+def generate_new_plane(best_disp, x, y, r, kernel):
+    """dispmap_ncc.generate_new_plane_RANSAC (dispmap_ncc.m:48-66) -> (plane 4, proposal 4 x N)."""
+    H, W = best_disp.shape
+    pts = get_points(H, W)
+    ids = np.sqrt((pts[0] - x) ** 2 + (pts[1] - y) ** 2) < r
+    p = fit_plane_to_points(np.vstack([pts[:, ids], best_disp.reshape(-1, order="F")[ids][None]]), kernel)
+    return p, np.repeat(p[:, None], H * W, axis=1)
+
+
 def smooth_weights(H, W, segment, lambda_h, lambda_l, scale):
     """dispmap_globalstereo.m:396-400."""
     ind1, ind2 = construct_neighborhood(H, W)

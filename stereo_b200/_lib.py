@@ -107,6 +107,7 @@ def lib():
         L.sb_binary_fuse_until_convergence_grid.argtypes = [ip, ip, ip, ip, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                             ctypes.c_void_p, ctypes.c_void_p, dbl, dbl, dbl, ip, ip,
                                                             POINTER(ctypes.c_int32), i64, ip, _dp, POINTER(c_int), _dp]
+        L.sb_plane_from_disparity.argtypes = [ip, ip, ctypes.c_void_p, dbl, dbl, dbl, ip, ip, _dp, ctypes.c_void_p, _dp]
         L.sb_segpln_wta.argtypes = [ip, ip, ip, ip, _dp, _dp, ip, _dp, ip, dbl, dbl, _dp, _dp]
         L.sb_smooth_weights.argtypes = [ip, ip, POINTER(ctypes.c_uint32), dbl, dbl, dbl, _dp]
         L.sb_ncc_volume.argtypes = [ip, ip, ip, _dp, _dp, ip, _dp, ip, _dp]

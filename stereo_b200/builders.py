@@ -160,6 +160,19 @@ def segpln_wta(images, P, disps, window, col_thresh, min_corr=0.07, return_score
     return (corr, score) if return_score else corr
 
 
+def plane_from_disparity(disp, x, y, r, kernel, return_proposal=False):
+    """dispmap_ncc.generate_new_plane_RANSAC + fit_plane_to_points (dispmap_ncc.m:48-91): the plane [a; b; 1; d0] through
+    the points (col, row, disp) within radius r of (x, y); with ``return_proposal`` also the 4 x N field repmat(p, [1 N])."""
+    d = np.asfortranarray(np.asarray(disp, dtype=np.float64))
+    H, W = d.shape
+    plane = np.zeros(4, dtype=np.float64)
+    npts = ctypes.c_double(0)
+    prop = np.zeros((4, H * W), dtype=np.float64, order="F") if return_proposal else None
+    check(lib().sb_plane_from_disparity(H, W, ctypes.c_void_p(d.ctypes.data), float(x), float(y), float(r), int(kernel), 0, _p(plane),
+                                        ctypes.c_void_p(prop.ctypes.data) if return_proposal else None, ctypes.byref(npts)))
+    return (plane, prop) if return_proposal else plane
+
+
 def smooth_weights(segment, lambda_h, lambda_l, scale=1.0):
     """The smoothness weights of dispmap_globalstereo.preprocess (dispmap_globalstereo.m:396-401) from a segment label
     image (H x W integers): scale * lambda_h inside a segment, scale * lambda_l across a boundary, E values in

@@ -392,6 +392,132 @@ __global__ void wta_finish_kernel(const double *__restrict__ best, const int *__
     out[u] = best[i] < min_corr ? 0.0 : disps[best_idx[i]];
 }
 
+// ---- dispmap_ncc.generate_new_plane_RANSAC + fit_plane_to_points (dispmap_ncc.m:48-91) ---------------------------
+// One CTA.  The points are the pixels within radius r of (x, y) with the WTA disparity as third coordinate; the plane
+// normal is the right singular vector of the smallest singular value of the (IRLS-weighted) centred point matrix, i.e.
+// the eigenvector of the smallest eigenvalue of its 3 x 3 scatter matrix (block reduction + Jacobi rotations).
+__device__ void jacobi_min_eigenvector(double S[3][3], double v[3])
+{
+    double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int sweep = 0; sweep < 30; sweep++) {
+        const double off = fabs(S[0][1]) + fabs(S[0][2]) + fabs(S[1][2]);
+        if (off <= 1e-300 || off <= 1e-18 * (fabs(S[0][0]) + fabs(S[1][1]) + fabs(S[2][2]))) break;
+        for (int p = 0; p < 2; p++)
+            for (int q = p + 1; q < 3; q++) {
+                if (S[p][q] == 0.0) continue;
+                const double theta = (S[q][q] - S[p][p]) / (2.0 * S[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < 3; k++) {      // S <- S J
+                    const double a = S[k][p], b = S[k][q];
+                    S[k][p] = c * a - sn * b;
+                    S[k][q] = sn * a + c * b;
+                }
+                for (int k = 0; k < 3; k++) {      // S <- J' S
+                    const double a = S[p][k], b = S[q][k];
+                    S[p][k] = c * a - sn * b;
+                    S[q][k] = sn * a + c * b;
+                }
+                for (int k = 0; k < 3; k++) {
+                    const double a = V[k][p], b = V[k][q];
+                    V[k][p] = c * a - sn * b;
+                    V[k][q] = sn * a + c * b;
+                }
+            }
+    }
+    int m = 0;
+    if (S[1][1] < S[m][m]) m = 1;
+    if (S[2][2] < S[m][m]) m = 2;
+    for (int k = 0; k < 3; k++) v[k] = V[k][m];
+}
+
+constexpr int PF_THREADS = 256;
+__device__ __forceinline__ void block_sum(double *vals, int n, double *scratch)
+{
+    // vals[0..n) per thread -> totals in vals on every thread (n <= 8)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = 0; i < n; i++) {
+        double v = vals[i];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) scratch[warp * 8 + i] = v;
+    }
+    __syncthreads();
+    for (int i = 0; i < n; i++) {
+        double t = 0;
+        for (int w = 0; w < PF_THREADS / 32; w++) t += scratch[w * 8 + i];
+        vals[i] = t;
+    }
+    __syncthreads();
+}
+__global__ void __launch_bounds__(PF_THREADS) plane_fit_kernel(const double *__restrict__ disp, int H, int W, double x, double y,
+                                                                double r, int kernel, double *__restrict__ out /* 4 + count */)
+{
+    __shared__ double scratch[(PF_THREADS / 32) * 8];
+    __shared__ double sv[3];
+    const int c_lo = max(1, (int)floor(x - r)), c_hi = min(W, (int)ceil(x + r));
+    const int r_lo = max(1, (int)floor(y - r)), r_hi = min(H, (int)ceil(y + r));
+    const int bw = max(c_hi - c_lo + 1, 0), bh = max(r_hi - r_lo + 1, 0);
+    const long long box = (long long)bw * bh;
+    auto inside = [&](long long i, double &px, double &py, double &pd) {
+        const int cc = c_lo + (int)(i / bh), rr = r_lo + (int)(i % bh);
+        px = (double)cc; py = (double)rr;
+        const double dx = px - x, dy = py - y;
+        if (!(sqrt(dx * dx + dy * dy) < r)) return false;        // dispmap_ncc.m:57
+        pd = disp[(size_t)(cc - 1) * H + (rr - 1)];
+        return true;
+    };
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long i = threadIdx.x; i < box; i += PF_THREADS) {
+        double px, py, pd;
+        if (inside(i, px, py, pd)) { acc[0] += 1.0; acc[1] += px; acc[2] += py; acc[3] += pd; }
+    }
+    block_sum(acc, 4, scratch);
+    const double n = acc[0];
+    if (n < 3.0) {
+        if (threadIdx.x == 0) { out[0] = out[1] = out[2] = out[3] = 0.0; out[4] = n; }
+        return;
+    }
+    const double mx = acc[1] / n, my = acc[2] / n, md = acc[3] / n;      // c = mean(points, 2) (:68)
+    double v[3] = {0, 0, 0};
+    const int rounds = kernel == 1 ? 20 : 1;                               // :76-87
+    for (int it = 0; it < rounds; it++) {
+        double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (long long i = threadIdx.x; i < box; i += PF_THREADS) {
+            double px, py, pd;
+            if (!inside(i, px, py, pd)) continue;
+            const double a0 = -(px - mx), a1 = -(py - my), a2 = -(pd - md);   // cost_func = -(points - c)' (:71)
+            // w .* cost_func with w = sqrt(|cost_func * V(:, end)|) of the previous round (ones in the first): the scatter
+            // matrix carries w^2
+            const double w2 = it == 0 ? 1.0 : fabs(a0 * v[0] + a1 * v[1] + a2 * v[2]);
+            s[0] += w2 * a0 * a0; s[1] += w2 * a0 * a1; s[2] += w2 * a0 * a2;
+            s[3] += w2 * a1 * a1; s[4] += w2 * a1 * a2; s[5] += w2 * a2 * a2;
+        }
+        block_sum(s, 6, scratch);
+        if (threadIdx.x == 0) {
+            double S[3][3] = {{s[0], s[1], s[2]}, {s[1], s[3], s[4]}, {s[2], s[4], s[5]}};
+            double e[3];
+            jacobi_min_eigenvector(S, e);
+            sv[0] = e[0]; sv[1] = e[1]; sv[2] = e[2];
+        }
+        __syncthreads();
+        v[0] = sv[0]; v[1] = sv[1]; v[2] = sv[2];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double p4 = -(v[0] * mx + v[1] * my + v[2] * md);              // :89
+        out[0] = v[0] / v[2]; out[1] = v[1] / v[2]; out[2] = 1.0; out[3] = p4 / v[2];   // p = p / p(3) (:90)
+        out[4] = n;
+    }
+}
+// proposal = repmat(p, [1 N]) (:65)
+__global__ void plane_repeat_kernel(const double *__restrict__ p4, long long N, double *__restrict__ out)
+{
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= N) return;
+    reinterpret_cast<double2 *>(out)[2 * u] = make_double2(p4[0], p4[1]);
+    reinterpret_cast<double2 *>(out)[2 * u + 1] = make_double2(p4[2], p4[3]);
+}
+
 // dispmap_globalstereo.preprocess, the smoothness weights (dispmap_globalstereo.m:398-401): lambda_h on the terms whose
 // two pixels share a segment, lambda_l on those that cross a segment boundary, both scaled by num_in / (connect == 8 + 1).
 __global__ void smooth_weights_kernel(const unsigned *__restrict__ segment, int H, int W, long long E, double w_same,
@@ -800,6 +926,38 @@ int sb_segpln_wta(int H, int W, int C, int n_images, const double *images, const
         count_launch(3 * D + 1);
         SB_CUDA(cudaMemcpy(corr, out.p, (size_t)N * 8, cudaMemcpyDeviceToHost));
         if (score) SB_CUDA(cudaMemcpy(score, best.p, (size_t)Hi * Wi * 8, cudaMemcpyDeviceToHost));
+    });
+}
+
+int sb_plane_from_disparity(int H, int W, const double *disp, double x, double y, double r, int kernel, int on_device,
+                            double *plane, double *proposal, double *n_points)
+{
+    return guarded([&] {
+        SB_REQUIRE(H >= 1 && W >= 1 && disp && plane, SB_EINVAL, "sb_plane_from_disparity: bad arguments");
+        SB_REQUIRE(kernel == 1 || kernel == 2, SB_EINVAL, "Unkown kernel type");
+        SB_REQUIRE(r > 0, SB_EINVAL, "sb_plane_from_disparity: radius must be positive");
+        require_device();
+        const long long N = (long long)H * W;
+        DevBuf<double> dd, out(5), dprop;
+        const double *d = disp;
+        if (!on_device) { upload(dd, disp, (size_t)N); d = dd.p; }
+        plane_fit_kernel<<<1, PF_THREADS>>>(d, H, W, x, y, r, kernel, out.p);
+        SB_CUDA(cudaGetLastError());
+        count_launch();
+        double h[5];
+        SB_CUDA(cudaMemcpy(h, out.p, sizeof(h), cudaMemcpyDeviceToHost));
+        if (n_points) *n_points = h[4];
+        SB_REQUIRE(h[4] >= 3.0, SB_EINVAL, "sb_plane_from_disparity: %d points within the radius (at least 3 needed)", (int)h[4]);
+        for (int i = 0; i < 4; i++) plane[i] = h[i];
+        if (proposal) {
+            double *dst = proposal;
+            if (!on_device) { dprop.alloc((size_t)N * 4); dst = dprop.p; }
+            plane_repeat_kernel<<<blocks_for(N), 256>>>(out.p, N, dst);
+            SB_CUDA(cudaGetLastError());
+            count_launch();
+            if (!on_device) SB_CUDA(cudaMemcpy(proposal, dst, (size_t)N * 4 * 8, cudaMemcpyDeviceToHost));
+            else SB_CUDA(cudaDeviceSynchronize());
+        }
     });
 }
 

@@ -250,6 +250,11 @@ class dispmap_ncc(dispmap_super):
     def best_disp_from_ncc(self):
         return self._vol.best_disp()
 
+    def generate_new_plane_RANSAC(self, x, y, r):
+        """dispmap_ncc.m:48-66: the plane fitted to the WTA disparities within radius r of (x, y), as a 4 x N proposal."""
+        _, prop = builders.plane_from_disparity(self.best_disp_from_ncc(), x, y, r, self.smoothness_kernel, return_proposal=True)
+        return prop
+
     def init_solution(self):
         """dispmap_ncc.m:199-207."""
         best = self.best_disp_from_ncc()

@@ -33,13 +33,9 @@ classdef dispmap_ncc < dispmap_super
 			update_energy(self);
 		end
 		function proposal = generate_new_plane_RANSAC(self, x, y, r)
-			% Plane through the WTA disparities within radius r of (x, y) (host side: an SVD of a
-			% handful of points, dispmap_ncc.m:48-92 -- proposal generation is outside the GPU hot path).
-			points = get_points(self);
-			best_disp = best_disp_from_ncc(self);
-			ids = hypot(points(1,:) - x, points(2,:) - y) < r;
-			p = fit_plane_to_points(self, [points(:, ids); best_disp(ids)]);
-			proposal = repmat(p, [1 size(self.assignment, 2)]);
+			% Plane through the WTA disparities within radius r of (x, y), fitted and replicated on the GPU
+			% (sb_plane_from_disparity; fit_plane_to_points below is the host form of the same fit).
+			[~, proposal] = sb_builders_mex('plane_from_disparity', best_disp_from_ncc(self), x, y, r, self.smoothness_kernel);
 		end
 		function p = fit_plane_to_points(self, points)
 			n = size(points, 2);

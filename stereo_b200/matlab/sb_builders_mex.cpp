@@ -11,6 +11,7 @@
 //   e = sb_builders_mex('energy', sz, kernel, unary, assignment, weights, tol, d_min, d_step)
 //   [corr, score] = sb_builders_mex('segpln_wta', images(H x W x C x n), P(3 x 4 x n), disps, window, col_thresh, min_corr)
 //   w = sb_builders_mex('smooth_weights', segment(H x W uint32), lambda_h, lambda_l, scale)
+//   [p, proposal] = sb_builders_mex('plane_from_disparity', best_disp(H x W), x, y, r, kernel)
 //   [assignment, E, unary] = sb_builders_mex('fuse_until_convergence', sz, kernel, proposals(4 x N x n), unaries(N x n),
 //                                assignment, unary, weights, tol, d_min, d_step, improve, maxiter, ids(int32))
 // Each forwards to the entry point of the same name in include/stereo_b200.h.
@@ -104,6 +105,14 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         sb_mex_check(sb_segpln_wta(H, W, C, ni, mxGetPr(a[0]), mxGetPr(a[1]), D, mxGetPr(a[2]), w, scalar(a[4]), scalar(a[5]),
                                    mxGetPr(plhs[0]), mxGetPr(score)));
         if (nlhs == 2) plhs[1] = score; else mxDestroyArray(score);
+    } else if (!strcmp(op, "plane_from_disparity")) {
+        SB_MEX_ASSERT(n == 5 && nlhs <= 2);
+        const int H = (int)mxGetM(a[0]), W = (int)mxGetN(a[0]);
+        plhs[0] = sb_mex_matrix(4, 1);
+        mxArray *prop = nlhs == 2 ? sb_mex_matrix(4, (mwSize)H * W) : NULL;
+        sb_mex_check(sb_plane_from_disparity(H, W, mxGetPr(a[0]), scalar(a[1]), scalar(a[2]), scalar(a[3]), (int)scalar(a[4]), 0,
+                                             mxGetPr(plhs[0]), prop ? mxGetPr(prop) : NULL, NULL));
+        if (prop) plhs[1] = prop;
     } else if (!strcmp(op, "smooth_weights")) {
         SB_MEX_ASSERT(n == 4 && mxGetClassID(a[0]) == mxUINT32_CLASS);
         const int H = (int)mxGetM(a[0]), W = (int)mxGetN(a[0]);

@@ -198,6 +198,28 @@ def test_segpln_wta_volume(n_images, window):
         assert np.median(np.abs(corr[inner][found] / 4.0 - dtrue[inner][found])) <= 1.0
 
 
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("x,y,r", [(20.0, 15.0, 6.0), (3.0, 2.0, 5.5), (47.5, 30.2, 9.0), (25.0, 18.0, 2.0)])
+def test_plane_from_disparity(x, y, r, kernel):
+    """dispmap_ncc.generate_new_plane_RANSAC / fit_plane_to_points (dispmap_ncc.m:48-91) against the literal SVD / IRLS
+    restatement: same plane to rounding (eigenvector of the scatter matrix == right singular vector, the sign cancels)."""
+    H, W = 36, 52
+    rng = np.random.default_rng(5)
+    cc, rr = np.meshgrid(np.arange(1, W + 1), np.arange(1, H + 1))
+    disp = 4.0 + 0.11 * cc - 0.07 * rr + rng.normal(0, 0.3, size=(H, W))
+    disp[rng.random((H, W)) < 0.05] += 6.0                      # outliers: what the IRLS rounds are for
+    plane, prop = builders.plane_from_disparity(disp, x, y, r, kernel, return_proposal=True)
+    ref, rprop = _np().generate_new_plane(disp, x, y, r, kernel)
+    assert plane[2] == 1.0
+    assert np.allclose(plane, ref, rtol=2e-7, atol=1e-9), (plane, ref)
+    assert prop.shape == (4, H * W) and np.array_equal(prop, np.repeat(plane[:, None], H * W, axis=1))
+    if r >= 5 and kernel == 2:
+        # the least-squares plane is close to the generating one, d = -(a x + b y + d0), despite the outliers
+        assert abs(-plane[0] - 0.11) < 0.08 and abs(-plane[1] + 0.07) < 0.08
+    with pytest.raises(sb._lib.SbError):
+        builders.plane_from_disparity(disp, 10.0, 10.0, 0.5, kernel)     # one point within the radius
+
+
 def test_smooth_weights_from_segments():
     """dispmap_globalstereo.preprocess (:396-401): lambda_h inside a segment, lambda_l across, scaled by the image count."""
     H, W = 13, 17

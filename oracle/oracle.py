@@ -208,3 +208,53 @@ def interp2_linear(A, X, Y, oobv, kind="reference"):
     if rc != 0:
         raise RuntimeError("oracle interp2 failed")
     return out.T.copy()
+
+
+# ----------------------------------------------------------------------------- builders gateway
+class _GwArray(ctypes.Structure):
+    _fields_ = [("classid", ctypes.c_int), ("ndim", ctypes.c_int), ("dims", ctypes.c_int * 4), ("data", ctypes.c_void_p)]
+
+
+# mxClassID values of oracle/mex_shim/mex.h
+_MX = {np.dtype(np.float64): 6, np.dtype(np.int32): 12, np.dtype(np.uint32): 13}
+_MX_BACK = {6: np.float64, 12: np.int32, 13: np.uint32}
+
+
+def builders_gateway(op, *args, nlhs=1):
+    """sb_builders_mex(op, args...) with `nlhs` outputs, through the product's MATLAB gateway compiled against the mex.h
+    stand-in (oracle/gw_builders_driver.cpp).  Arguments: numbers (1 x 1 doubles) or NumPy arrays of float64 / int32 /
+    uint32 with up to 4 dimensions, handed over in MATLAB (column-major) order.  Returns a list of NumPy arrays (copies),
+    MATLAB shapes; raises RuntimeError with the mexErrMsgTxt text."""
+    lib_ = _gateway("builders")
+    lib_.gw_builders_call.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(_GwArray), ctypes.c_int, ctypes.POINTER(_GwArray)]
+    lib_.gw_builders_last_error.restype = ctypes.c_char_p
+    keep = []
+    arr = (_GwArray * max(len(args), 1))()
+    for i, a in enumerate(args):
+        a = np.asarray(a)
+        if a.dtype not in _MX:
+            a = a.astype(np.float64)
+        if a.ndim == 0:
+            a = a.reshape(1, 1)
+        if a.ndim == 1:
+            a = a.reshape(1, -1)
+        a = np.asfortranarray(a)
+        keep.append(a)
+        arr[i].classid = _MX[a.dtype]
+        arr[i].ndim = a.ndim
+        for k in range(4):
+            arr[i].dims[k] = a.shape[k] if k < a.ndim else 1
+        arr[i].data = a.ctypes.data
+    outs = (_GwArray * max(nlhs, 1))()
+    rc = lib_.gw_builders_call(op.encode(), len(args), arr, nlhs, outs)
+    if rc != 0:
+        raise RuntimeError(lib_.gw_builders_last_error().decode("utf-8", "replace"))
+    res = []
+    for i in range(nlhs):
+        o = outs[i]
+        shape = tuple(o.dims[k] for k in range(o.ndim))
+        n = int(np.prod(shape))
+        dt = _MX_BACK[o.classid]
+        buf = (ctypes.c_char * (n * np.dtype(dt).itemsize)).from_address(o.data) if n else b""
+        res.append(np.frombuffer(buf, dtype=dt, count=n).reshape(shape, order="F").copy())
+    return res

@@ -49,7 +49,7 @@ using trws::MODE_ROUND;
 // instructions even when switched off at run time (predicated-off instructions still issue), so they are compiled
 // in only by  make EXTRA=-DSB_GTRWS_DIAG=1  (profiles/r2_phase_counters_cfg5.txt came from such a build).
 #ifndef SB_GTRWS_DIAG
-#define SB_GTRWS_DIAG 0
+#define SB_GTRWS_DIAG SB_TRWS_DIAG
 #endif
 constexpr bool DIAG = SB_GTRWS_DIAG != 0;
 

@@ -42,6 +42,13 @@ namespace trws {
 enum { PASS_FWD = 0, PASS_BWD = 1 };
 enum { MODE_SEND = 1, MODE_ROUND = 2 };
 
+// Phase counters (SB_TRWS_PROFILE) are compiled in only by  make EXTRA=-DSB_TRWS_DIAG=1 : switched off at run time
+// they still issue (predicated-off instructions take issue slots) -- 10-16 % per pass on the grid sweep, measured.
+#ifndef SB_TRWS_DIAG
+#define SB_TRWS_DIAG 0
+#endif
+constexpr bool TDIAG = SB_TRWS_DIAG != 0;
+
 template <typename REAL> struct Lim;
 template <> struct Lim<float> { static __host__ __device__ float big() { return 1e30f; } };
 template <> struct Lim<double> { static __host__ __device__ double big() { return 1e300; } };
@@ -822,9 +829,10 @@ __global__ void __launch_bounds__(cta_threads(NHW), (sizeof(REAL) == 4 && K <= 4
                     unsigned valid = 0;
 #pragma unroll
                     for (int k = 0; k < K; k++) valid |= (lane * K + k < p.L ? 1u : 0u) << k;
-                    if constexpr (KERN == 1)
-                        vmin = update_linear<REAL, K>(gamma, o.alpha, p.lambda, valid, lane, Di, o.m, o.s, rk, o.x, cn, P);
-                    else
+                    if constexpr (KERN == 1) {
+                        if (p.L == LP) vmin = update_linear<REAL, K, true>(gamma, o.alpha, p.lambda, valid, lane, Di, o.m, o.s, rk, o.x, cn, P);
+                        else vmin = update_linear<REAL, K, false>(gamma, o.alpha, p.lambda, valid, lane, Di, o.m, o.s, rk, o.x, cn, P);
+                    } else
                         vmin = update_quadratic<REAL, K>(gamma, o.alpha, p.lambda, valid, p.L, lane, Di, o.m, o.s, rk, o.x, cn, P);
                     if constexpr (MBOX) {
                         if (!to_next) {   // the receiver is in another strip: it polls these words
@@ -852,7 +860,7 @@ __global__ void __launch_bounds__(cta_threads(NHW), (sizeof(REAL) == 4 && K <= 4
 
             // optional phase timers (SB_TRWS_PROFILE): term warp 0 -> prof[0..3] = wait FULL, read rows +
             // rounding, update + stores, nodes
-            const bool prof_on = (p.prof != nullptr) && w == 0;
+            const bool prof_on = TDIAG && (p.prof != nullptr) && w == 0;
             long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             long long tclk = prof_on ? clock64() : 0;
             auto tick = [&](int which) {
@@ -1020,7 +1028,7 @@ __global__ void __launch_bounds__(cta_threads(NHW), (sizeof(REAL) == 4 && K <= 4
             int sg = sg0, seg_start = 0;    // segment of the current node and the strip index of its first node
             int loaded = -1;
             int seg_n = __ldg(&segs[sg].n);
-            const bool prof_on = (p.prof != nullptr) && hid == 0;
+            const bool prof_on = TDIAG && (p.prof != nullptr) && hid == 0;
             long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             long long tclk = prof_on ? clock64() : 0;
             auto tick = [&](int which) {
@@ -1242,10 +1250,10 @@ __global__ void __launch_bounds__(cta_threads(NHW), (sizeof(REAL) == 4 && K <= 4
                 for (int o = 2; o > 0; o >>= 1) c = min(c, __shfl_xor_sync(0xffffffffu, c, o));
                 c = __shfl_sync(0xffffffffu, c, 0);
                 if (c > published) {
-                    const long long t0 = p.prof ? clock64() : 0;
+                    const long long t0 = (TDIAG && p.prof) ? clock64() : 0;
                     if (lane == 0) publish_flag(p.progress + gid, c);
                     __syncwarp();
-                    if (p.prof && lane == 0) {
+                    if (TDIAG && p.prof && lane == 0) {
                         atomicAdd((unsigned long long *)p.prof + (fs == 0 ? 0 : 16) + 12, (unsigned long long)(clock64() - t0));
                         atomicAdd((unsigned long long *)p.prof + (fs == 0 ? 0 : 16) + 13, 1ull);
                         atomicAdd((unsigned long long *)p.prof + (fs == 0 ? 0 : 16) + 14, (unsigned long long)(c - published));

@@ -308,6 +308,8 @@ struct Solver : SolverBase {
             std::memset(rec_host, 0xff, (size_t)rec_ctas * 8 * 4 * sizeof(int));
             SB_CUDA(cudaHostGetDevicePointer((void **)&P.rec, rec_host, 0));
         }
+        if (getenv("SB_TRWS_PROFILE") && !TDIAG)
+            fprintf(stderr, "[stereo_b200] SB_TRWS_PROFILE needs the diagnostics build: make -C stereo_b200/csrc clean all EXTRA=-DSB_TRWS_DIAG=1\n");
         if (getenv("SB_TRWS_PROFILE")) {
             dProf.alloc(64);
             SB_CUDA(cudaMemsetAsync(dProf.p, 0, 64 * sizeof(long long), stream));

@@ -341,6 +341,27 @@ def extras():
                                 "fusion_stats": dm.last_fusion_stats}
     except Exception as ex:
         out["cfg1_pipeline_error"] = str(ex)[:200]
+    # dispmap_super.binary_fuse_until_convergence (dispmap_super.m:85-152) at the same shape: the loop as ONE library call on
+    # device-resident fields (sb_binary_fuse_until_convergence_grid) against one gateway round trip per fusion move
+    try:
+        props = []
+        for d in (6.0, 14.0, 22.0, 30.0, 38.0, 46.0):
+            pp = np.zeros((4, h1 * w1))
+            pp[2] = 1
+            pp[3] = -d
+            props.append(pp)
+        res = {}
+        for name, dev_loop in (("per_fusion_loop", False), ("one_call_device_loop", True)):
+            dmf = sb.dispmap_ncc([a0, a1], lv, 1, 40.0, 8.0 * 4, patchsize=2)
+            dmf.maxiter = 10
+            dmf.device_loop = dev_loop
+            t0 = time.perf_counter()
+            n_e = dmf.binary_fuse_until_convergence(props, rng=np.random.default_rng(7))
+            res[name] = {"ms": (time.perf_counter() - t0) * 1e3, "energies": n_e, "final_energy": dmf.energy()}
+        out["fusion_schedule"] = {"workload": f"{h1}x{w1}, 6 fronto-parallel proposals, maxiter 10 (dispmap_ncc, kernel 1)", **res,
+                                  "same_energies": res["per_fusion_loop"]["final_energy"] == res["one_call_device_loop"]["final_energy"]}
+    except Exception as ex:
+        out["fusion_schedule_error"] = str(ex)[:200]
     return out
 
 

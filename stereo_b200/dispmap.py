@@ -325,6 +325,44 @@ class dispmap_globalstereo(dispmap_super):
         P = np.transpose(self.P, (1, 0, 2))        # :66 (back to 3 x 4 x n)
         return builders.segpln_wta(self.images, P, self.disps, self.options["window"], self.options["col_thresh"])
 
+    def segpln(self, segments, rng=None, corr=None):
+        """dispmap_globalstereo.segpln (dispmap_globalstereo.m:60-201) with the segmentations injected: ``segments`` is a
+        list of H x W label images (the reference computes 14 of them with vgg_segment_ms / vgg_segment_gb, :118-135).
+        The window-matching WTA disparity comes from the GPU (sb_segpln_wta); the per-segment plane fits stay host glue
+        exactly as in the reference -- RANSAC over random point triples (rplane, :417-453; the random stream is ``rng``
+        here, MATLAB's randperm there), least squares on the inliers, the plane written to every pixel of the segment.
+        Returns the proposal cell: one 4 x N plane field per segmentation."""
+        rng = rng or np.random.default_rng()
+        H, W = self.sz
+        if corr is None:
+            corr = self.segpln_wta()
+        with np.errstate(divide="ignore", invalid="ignore"):
+            z = 1.0 / np.asarray(corr, dtype=np.float64).reshape(-1, order="F")             # :142
+            pts = self.get_points()
+            WC = np.stack([z * pts[0], z * pts[1], z], axis=1)                               # :143-144
+        proposals = []
+        for seg in segments:
+            seg = np.asarray(seg).reshape(-1, order="F")
+            prop = np.zeros((4, H * W))
+            prop[2] = 1.0                                                                   # :162-164 (0 disparity)
+            for a in range(1, int(seg.max()) + 1):                                          # :171
+                M = seg == a
+                Np = WC[M]
+                Np = Np[Np[:, 2] != 0]                                                      # :175
+                local = Np
+                if Np.shape[0] > 3:
+                    local = Np[_rplane(Np, 0.1, rng)]                                       # :178-182
+                if local.shape[0] > 2:
+                    with np.errstate(all="ignore"):
+                        try:
+                            n_ = np.linalg.lstsq(local, -np.ones(local.shape[0]), rcond=None)[0]   # :186
+                        except np.linalg.LinAlgError:
+                            n_ = np.full(3, np.nan)
+                    prop[:, M] = np.array([n_[0], n_[1], 1.0, n_[2]])[:, None]              # :191-192
+            prop[~np.isfinite(prop)] = 1e-100                                               # :197-200
+            proposals.append(prop)
+        return proposals
+
     def init_solution(self):
         a = np.zeros((4, self.sz[0] * self.sz[1]))
         a[2] = 1
@@ -335,3 +373,35 @@ class dispmap_globalstereo(dispmap_super):
         """dispmap_globalstereo.m:355-375."""
         return builders.photo_unary(self.images[0], self.images[1], self.P[:, :, 1], assignment, self.d_min,
                                     self.d_step, self.options["col_thresh"])
+
+
+def _nsamples(ni, pt_num, pf, conf):
+    """dispmap_globalstereo.nsamples (dispmap_globalstereo.m:454-466)."""
+    q = np.prod(np.arange(ni - pf + 1, ni + 1) / np.arange(pt_num - pf + 1, pt_num + 1))
+    cnt = 1.0 if (1 - q) < np.finfo(float).eps else np.log(1 - 0.95 if conf is None else 1 - conf) / np.log(1 - q)
+    return max(cnt, 1.0)
+
+
+def _rplane(pts, th, rng):
+    """dispmap_globalstereo.rplane (dispmap_globalstereo.m:417-453): RANSAC inliers of the plane pts * N = -1."""
+    n = pts.shape[0]
+    max_i, max_sam, no_sam = 3, 500.0, 0
+    inls = np.zeros(n, dtype=bool)
+    with np.errstate(all="ignore"):
+        while no_sam < max_sam:
+            no_sam += 1
+            sam = rng.permutation(n)[:3]
+            try:
+                N = np.linalg.solve(pts[sam], -np.ones(3))
+            except np.linalg.LinAlgError:
+                continue
+            v = np.abs(pts @ N + 1) < th
+            no_i = int(v.sum())
+            if max_i < no_i:
+                N = np.linalg.lstsq(pts[v], -np.ones(no_i), rcond=None)[0]
+                v = np.abs(pts @ N + 1) < th
+                if v.sum() > inls.sum():
+                    inls = v
+                    max_i = no_i
+                    max_sam = min(max_sam, _nsamples(int(inls.sum()), n, 3, 0.95))
+    return inls

@@ -239,6 +239,33 @@ def test_smooth_weights_from_segments():
     assert w.shape == (H, W) and set(np.unique(w)).issubset(set(dm.disps) | {0.0})
 
 
+def test_segpln_proposals_with_injected_segments():
+    """dispmap_globalstereo.segpln (dispmap_globalstereo.m:60-201) in the Python mirror: WTA volume on the GPU, per-segment
+    RANSAC + least-squares planes as host glue (like the reference), segmentations injected: one plane per segment, finite
+    (NaN / Inf -> 1e-100 like :197-200), and the proposal cell feeds binary_fuse_until_convergence."""
+    H, W = 40, 60
+    im0, im1, _ = synth.stereo_pair(H, W, 6, seed=9)
+    opts = dict(smoothness_kernel=1, disp_thresh=0.02, lambda_h=5.0, lambda_l=0.5, col_thresh=30.0, improve=0, window=2)
+    P = np.zeros((3, 4, 2))
+    P[:, :3, 0] = np.eye(3)
+    P[:, :3, 1] = np.eye(3)
+    P[0, 3, 1] = -0.25
+    dm = sb.dispmap_globalstereo([im0, im1], P, [0, 8], 4, opts, rng=np.random.default_rng(0))
+    seg_a = (1 + (np.arange(H)[:, None] // 20) * 3 + (np.arange(W)[None, :] // 20)).astype(np.uint32)     # 2 x 3 blocks
+    seg_b = np.ones((H, W), dtype=np.uint32)
+    props = dm.segpln([seg_a, seg_b], rng=np.random.default_rng(1))
+    assert len(props) == 2 and all(p.shape == (4, H * W) and np.isfinite(p).all() for p in props)
+    for seg, p in zip((seg_a, seg_b), props):
+        flat = seg.reshape(-1, order="F")
+        for a in np.unique(flat):
+            assert np.ptp(p[:, flat == a], axis=1).max() == 0          # one plane per segment
+    # the proposals are usable: fusing them never raises the energy
+    e0 = dm.energy()
+    dm.maxiter = 4
+    dm.binary_fuse_until_convergence(props, rng=np.random.default_rng(2))
+    assert dm.energy() <= e0 * (1 + 1e-12)
+
+
 @pytest.mark.parametrize("kernel", [1, 2])
 def test_binary_fuse_until_convergence_device_loop(kernel):
     """dispmap_super.binary_fuse_until_convergence (dispmap_super.m:85-152): the one-call loop over device-resident

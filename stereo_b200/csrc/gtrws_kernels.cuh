@@ -490,9 +490,10 @@ template <typename REAL, int K, int NS> __host__ __device__ constexpr size_t gsw
 // the four term warps among themselves (carry rows of the previous step are complete)
 template <int ID> __device__ __forceinline__ void term_sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(NTW * 32) : "memory"); }
 
-// resident CTAs per SM the register budget is set for
-// resident CTAs per SM the register budget is set for (setmaxnreg re-division between the term warpgroup and the
-// helpers was tried: ptxas 12.9 keeps allocating under the launch cap and spills, so the budget is uniform)
+// resident CTAs per SM the register budget of the throughput build is set for (setmaxnreg re-division between the term
+// warpgroup and the helpers was tried: ptxas 12.9 keeps allocating under the launch cap and spills, so the budget is
+// uniform).  The register file is per scheduler (16 K registers): 3 CTAs x 6 warps put 5 warps on one scheduler => 96
+// registers per thread, 2 CTAs => 168, 4 CTAs => 80.
 template <typename REAL, int K> __host__ __device__ constexpr int gsweep_min_blocks()
 {
     if (sizeof(REAL) == 8) return K <= 2 ? 2 : 1;
@@ -515,7 +516,9 @@ __global__ void __launch_bounds__(CTA_THREADS, MB) gsweep_kernel(const GProblem<
     typedef StageLayout<REAL, K> SL;
     constexpr int LP = 32 * K;
     constexpr int PD = NS - 1;   // bulk copies are issued PD steps ahead
-    constexpr bool EARLY = sizeof(REAL) == 4 && (MB <= 2 || K <= 2);   // where the registers hold them without spills (see take_operands)   // latency build (see take_operands)
+    // operands ahead of the chain (take_operands) where the registers hold them without spills: the latency builds and the
+    // throughput builds of K <= 2 and K = 8; with 100-340 B of spills (K = 4, 6 under the 3- / 4-CTA caps) it LOSES 5-20 %
+    constexpr bool EARLY = sizeof(REAL) == 4 && (MB <= 2 || K <= 2);
     const int lane = threadIdx.x & 31;
     // (warp w issues from scheduler w & 3: the term warps 2, 3 of send slot 1 -- the sends to the next node of the strip,
     // i.e. the dependent chain, gtrws_plan.cpp -- have their schedulers to themselves; the helpers share with slot 0)

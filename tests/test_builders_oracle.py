@@ -64,3 +64,20 @@ def test_smooth_weights_restatement():
     for p in range(ind1.size):
         assert got[p] == (4.0 if flat[ind1[p] - 1] == flat[ind2[p] - 1] else 0.25) * 2.0
     assert got.size == 2 * ((H - 1) * W + H * (W - 1))
+
+
+def test_segpln_host_glue_ransac():
+    """The host glue of the Python mirror's segpln: dispmap_globalstereo.rplane / nsamples (dispmap_globalstereo.m:417-466)
+    restated over a NumPy generator -- on points of one plane plus gross outliers the inlier set is the plane."""
+    from stereo_b200.dispmap import _nsamples, _rplane
+    rng = np.random.default_rng(0)
+    N = np.array([0.01, -0.02, -0.5])
+    P = rng.random((200, 3)) * np.array([50, 40, 1]) + np.array([0, 0, 1.5])
+    P[:, 2] = (-1 - P[:, 0] * N[0] - P[:, 1] * N[1]) / N[2]
+    P[:40, 2] += rng.normal(0, 2, 40)
+    inl = _rplane(P, 0.1, rng)
+    assert inl[40:].all() and inl[:40].sum() <= 10
+    # nsamples: log(1 - conf) / log(1 - q) with q = prod((ni-2:ni) ./ (n-2:n)), at least 1
+    q = (148 / 198) * (149 / 199) * (150 / 200)
+    assert abs(_nsamples(150, 200, 3, 0.95) - np.log(0.05) / np.log(1 - q)) < 1e-12
+    assert _nsamples(200, 200, 3, 0.95) == 1.0

@@ -63,3 +63,41 @@ int gw_builders_call(const char *op, int nargs, const GwArray *args, int nlhs, G
 }
 
 } // extern "C"
+
+#ifdef SB_GW_GRID
+// sb_grid_mex(kernel, sz, proposals, unary, weights, tol, dnorm, options) (stereo_b200/matlab/sb_grid_mex.cpp) with the
+// arguments MATLAB would pass: int32 kernel, 4 x N x L proposals, N x L unaries, an options struct.
+extern "C" int gw_grid_solve(int kernel, int H, int W, int L, const double *proposals, const double *unary, const double *weights,
+                             double tol, double d_min, double d_step, double maxiter, double max_relgap, double *labels,
+                             double *energy, double *lower_bound, double *iterations)
+{
+    const int N = H * W, E = 2 * ((H - 1) * W + H * (W - 1));
+    int32_t k = kernel;
+    double sz[2] = {(double)H, (double)W}, dn[2] = {d_min, d_step};
+    mwSize d11[2] = {1, 1}, d12[2] = {1, 2}, dP[3] = {4, N, L}, dU[2] = {N, L}, dW[2] = {1, E};
+    mxArray *a[7] = {sb_mxWrap(&k, mxINT32_CLASS, 2, d11),          sb_mxWrap(sz, mxDOUBLE_CLASS, 2, d12),
+                     sb_mxWrap((void *)proposals, mxDOUBLE_CLASS, 3, dP), sb_mxWrap((void *)unary, mxDOUBLE_CLASS, 2, dU),
+                     sb_mxWrap((void *)weights, mxDOUBLE_CLASS, 2, dW),   sb_mxWrap(&tol, mxDOUBLE_CLASS, 2, d11),
+                     sb_mxWrap(dn, mxDOUBLE_CLASS, 2, d12)};
+    mxArray *opt = sb_mxCreateStruct();
+    sb_mxAddField(opt, "maxiter", mxCreateDoubleScalar(maxiter));
+    sb_mxAddField(opt, "max_relgap", mxCreateDoubleScalar(max_relgap));
+    const mxArray *prhs[8] = {a[0], a[1], a[2], a[3], a[4], a[5], a[6], opt};
+    mxArray *plhs[4] = {0, 0, 0, 0};
+    int rc = 0;
+    try {
+        mexFunction(4, plhs, 8, prhs);
+        memcpy(labels, mxGetPr(plhs[0]), sizeof(double) * (size_t)N);
+        *energy = mxGetScalar(plhs[1]);
+        *lower_bound = mxGetScalar(plhs[2]);
+        *iterations = mxGetScalar(plhs[3]);
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        rc = -1;
+    }
+    for (int i = 0; i < 4; i++) mxDestroyArray(plhs[i]);
+    mxDestroyArray(opt);
+    for (int i = 0; i < 7; i++) mxDestroyArray(a[i]);
+    return rc;
+}
+#endif

@@ -258,3 +258,28 @@ def builders_gateway(op, *args, nlhs=1):
         buf = (ctypes.c_char * (n * np.dtype(dt).itemsize)).from_address(o.data) if n else b""
         res.append(np.frombuffer(buf, dtype=dt, count=n).reshape(shape, order="F").copy())
     return res
+
+
+def grid_gateway_solve(kernel, H, W, proposals, unary, weights, tol, d_min=0.0, d_step=1.0, maxiter=1000, max_relgap=0.0):
+    """sb_grid_mex(kernel, sz, proposals, unary, weights, tol, dnorm, options) through the product's grid-native MATLAB gateway
+    (stereo_b200/matlab/sb_grid_mex.cpp behind the mex.h stand-in).  proposals: L x 4 x N, unary: L x N, weights: E.
+    Returns (labels N, energy, lower_bound, iterations); raises RuntimeError with the mexErrMsgTxt text."""
+    lib_ = _gateway("grid")
+    proposals = np.asarray(proposals, dtype=np.float64)
+    L = proposals.shape[0]
+    N = int(H) * int(W)
+    assert proposals.shape == (L, 4, N)
+    pl = np.ascontiguousarray(proposals.transpose(0, 2, 1))          # label-major, each label a MATLAB 4 x N array
+    un = np.ascontiguousarray(np.asarray(unary, dtype=np.float64).reshape(L, N))
+    wt = np.ascontiguousarray(np.asarray(weights, dtype=np.float64).reshape(-1))
+    labels = np.zeros(N, dtype=np.float64)
+    e, lb, it = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib_.gw_grid_solve.argtypes = [ctypes.c_int] * 4 + [dp, dp, dp] + [ctypes.c_double] * 5 + [dp, dp, dp, dp]
+    lib_.gw_builders_last_error.restype = ctypes.c_char_p
+    rc = lib_.gw_grid_solve(int(kernel), int(H), int(W), L, pl.ctypes.data_as(dp), un.ctypes.data_as(dp), wt.ctypes.data_as(dp),
+                            float(tol), float(d_min), float(d_step), float(maxiter), float(max_relgap), labels.ctypes.data_as(dp),
+                            ctypes.byref(e), ctypes.byref(lb), ctypes.byref(it))
+    if rc != 0:
+        raise RuntimeError(lib_.gw_builders_last_error().decode("utf-8", "replace"))
+    return labels, e.value, lb.value, it.value

@@ -12,6 +12,8 @@ classdef dispmap_super < handle
 		max_relgap = 1e-4;   % TRW-S relative duality gap
 		improve = false;     % run QPBO-I on unlabelled nodes
 		device_loop = true;  % binary_fuse_until_convergence as ONE library call (fields stay on the GPU between moves)
+		grid_native = false; % true: simultaneous_fusion through sb_grid_mex -- no L x E arrays (q, qprim) are ever built;
+		                     % needed once they stop fitting (BASELINE configs 4-5)
 	end
 	properties (SetAccess = protected)
 		sz;
@@ -124,11 +126,19 @@ classdef dispmap_super < handle
 				unary(l, :) = unary_cost(self, proposal_cell{l});
 			end
 			stack = cat(3, proposal_cell{:});   % 4 x N x L
-			[q, qprim] = sb_builders_mex('fusion_positions', self.sz, stack, self.dnorm(1), self.dnorm(2));
 			options_struct.maxiter = self.maxiter;
 			options_struct.max_relgap = self.max_relgap;
-			[labels, e, lb, iterations] = trws(int32(self.smoothness_kernel), unary, connectivity(self), q, qprim, ...
-				self.smooth_weights(:), self.tol, options_struct);
+			if self.grid_native
+				% the solver takes what this method holds (plane fields, unary slabs, weights) and recomputes the label
+				% positions on the GPU: 45 bytes per label and pixel there, nothing of size L x E anywhere
+				compile('sb_grid_mex.cpp', 'sb_grid_mex');
+				[labels, e, lb, iterations] = sb_grid_mex(int32(self.smoothness_kernel), self.sz, stack, unary', ...
+					self.smooth_weights(:), self.tol, self.dnorm, options_struct);
+			else
+				[q, qprim] = sb_builders_mex('fusion_positions', self.sz, stack, self.dnorm(1), self.dnorm(2));
+				[labels, e, lb, iterations] = trws(int32(self.smoothness_kernel), unary, connectivity(self), q, qprim, ...
+					self.smooth_weights(:), self.tol, options_struct);
+			end
 			fused = zeros(size(proposal_cell{1}));
 			for l = 1:L
 				pick = (labels == l);
